@@ -1,0 +1,173 @@
+/*
+ * nawsod.h -- C ABI of libnawsod.so: the B200 (sm_100a) implementation of NA-fWebSOD's
+ * per-proposal head.  This is the drop-in boundary: every entry
+ * point replaces one Caffe2 operator (or one fused run of operators) of the reference and
+ * keeps that operator's blob order and argument meaning.  Citations are relative to
+ * /root/reference/detectron.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host;
+ *   - the caller owns all memory; the library never allocates device memory and keeps no
+ *     hidden state between calls (the reference SGD op's iter_count_ is an explicit argument);
+ *   - `stream` is a cudaStream_t passed as void*; calls are stream-ordered, re-entrant and
+ *     never synchronise the device;
+ *   - return value: NAWSOD_OK or an error code; nawsod_last_error() gives the message for
+ *     the calling thread (the Python host raises RuntimeError, mirroring CAFFE_ENFORCE);
+ *   - there is no CPU fallback: without a CUDA device every compute entry fails.
+ */
+#ifndef NAWSOD_H_
+#define NAWSOD_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+  NAWSOD_OK = 0,
+  NAWSOD_ERR_ARG = 1,         /* null pointer / bad enum / negative size      */
+  NAWSOD_ERR_SHAPE = 2,       /* shape constraint violated                    */
+  NAWSOD_ERR_ALIGN = 3,       /* pointer not 16-byte aligned where required   */
+  NAWSOD_ERR_UNSUPPORTED = 4, /* combination not implemented                  */
+  NAWSOD_ERR_CUDA = 5         /* CUDA runtime / launch failure                */
+};
+
+enum { NAWSOD_F32 = 0, NAWSOD_BF16 = 1 };
+
+/* Feature-map / pooled-feature layouts.
+ *   NCHW : the reference's layout.  X [N,C,H,W]; pooled Y [R,C,PH,PW] (FC K-index c*49+ph*7+pw).
+ *   NHWC : channels-last.            X [N,H,W,C]; pooled Y [R,PH,PW,C] (FC K-index (ph*7+pw)*C+c). */
+enum { NAWSOD_NCHW = 0, NAWSOD_NHWC = 1 };
+
+const char* nawsod_last_error(void);
+int nawsod_version(void);
+/* Tuning knob for benchmarks ("pool_slab_bytes", "pool_chunks", ...); unknown keys fail. */
+int nawsod_set_tuning(const char* key, int64_t value);
+
+/* ---------------------------------------------------------------------------------------
+ * Layout helpers (no reference counterpart: the reference is NCHW end to end).
+ * in [B,rows,cols] -> out [B,cols,rows]; 4-byte elements (float / int32), optional
+ * conversion of a float source to bf16 on the way out (out_dtype).
+ * ------------------------------------------------------------------------------------- */
+int nawsod_transpose_batched(const void* in, int64_t B, int64_t rows, int64_t cols,
+                             void* out, int out_dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * a1 + a3: RoIPoolF([X, rois] -> [Y, argmax]; pooled_h, pooled_w, spatial_scale)
+ *   replaces Caffe2 RoIPoolF as wired by modeling/detector.py:321-329 (arithmetic:
+ *   ops/roi_loop_pool_op.cu:19-102 with RoIPoolF's deltas), optionally
+ *   fused with RoIFeatureBoost([Y, S] -> Y) (ops/roi_feature_boost_op.cc:8-35,
+ *   modeling/wsl_heads.py:668).
+ *   X      : feature map, x_dtype / x_layout.
+ *   rois   : [R,5] float (batch_idx, x1, y1, x2, y2) in network-input pixels.
+ *   boost  : [R] float (obn_scores + 1) or NULL for plain RoIPoolF.
+ *   Y      : pooled features, y_dtype / y_layout.  argmax: int32, same layout as Y, or NULL
+ *            (is_test).  argmax is h*W+w inside the image plane, -1 for an empty bin.
+ *   Bit-exact with the reference for x_dtype = y_dtype = F32 (any layout).
+ * ------------------------------------------------------------------------------------- */
+int nawsod_roi_pool_f_fwd(const void* X, int x_dtype, int x_layout, const float* rois,
+                          const float* boost, int N, int C, int H, int W, int R,
+                          float spatial_scale, int pooled_h, int pooled_w, void* Y,
+                          int y_dtype, int y_layout, int32_t* argmax, void* stream);
+
+/* a2 (+a3 gradient): RoIPoolFGradient([X, rois, argmax, dY] -> dX)
+ *   (ops/roi_loop_pool_op.cu:105-140, zero fill :199-201; grad maker ops/roi_loop_pool_op.cc:85-96)
+ *   optionally fused with RoIFeatureBoostGradient (ops/roi_feature_boost_op.cc:37-64): the
+ *   incoming dY is multiplied by boost[r] first.  dX is float, zero-filled by the call. */
+int nawsod_roi_pool_f_bwd(const void* dY, int dy_dtype, int y_layout, const int32_t* argmax,
+                          const float* rois, const float* boost, int N, int C, int H, int W,
+                          int R, int pooled_h, int pooled_w, float* dX, int dx_layout,
+                          void* stream);
+
+/* a3 stand-alone: RoIFeatureBoost([X, S] -> Y), in-place allowed (Y == X)
+ *   (ops/roi_feature_boost_op.cc:8-35; its gradient is the same call on dY, :37-64). */
+int nawsod_roi_feature_boost(const float* X, const float* S, int R, int64_t feature_size,
+                             float* Y, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * a4: FC stack GEMMs on the tcgen05 tensor cores (Caffe2 FC / Relu / Dropout as wired by
+ *   modeling/wsl_heads.py:674-679 and modeling/webly_heads.py:490-498).
+ *
+ * nawsod_fc_fwd:  Y[M,N] = epilogue( A[M,K] . W[N,K]^T + bias[N] )
+ *   epilogue flags: NAWSOD_FC_RELU, NAWSOD_FC_DROPOUT (Y *= mask[M,N] * 2, mask uint8 0/1).
+ * nawsod_fc_bwd_x: dA[M,K] = dY[M,N] . W[N,K], then optional relu'/dropout of the layer below:
+ *   dA *= (act_below[M,K] > 0) and dA *= mask_below[M,K] * 2.
+ * nawsod_fc_bwd_w: dW[N,K] (float) = dY[M,N]^T . A[M,K];  db[N] (float) = sum_m dY (or NULL).
+ *   ab_dtype: NAWSOD_BF16 (bf16 operands, fp32 accumulate) or NAWSOD_F32 (TF32 tensor path).
+ *   workspace: opaque device scratch of at least nawsod_fc_workspace_bytes() bytes.
+ * ------------------------------------------------------------------------------------- */
+enum { NAWSOD_FC_RELU = 1, NAWSOD_FC_DROPOUT = 2, NAWSOD_FC_ACCUMULATE = 4 };
+
+int64_t nawsod_fc_workspace_bytes(void);
+
+int nawsod_fc_fwd(const void* A, const void* W, const float* bias, const uint8_t* mask,
+                  int M, int N, int K, int ab_dtype, void* Y, int y_dtype, int flags,
+                  void* workspace, void* stream);
+
+int nawsod_fc_bwd_x(const void* dY, const void* W, const void* act_below,
+                    const uint8_t* mask_below, int M, int N, int K, int ab_dtype, void* dA,
+                    int da_dtype, int flags, void* workspace, void* stream);
+
+int nawsod_fc_bwd_w(const void* dY, const void* A, int M, int N, int K, int ab_dtype,
+                    float* dW, float* db, int flags, void* workspace, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * a5..a9: the two-stream MIL head, noise-aware class weights, weighted multi-label CE and
+ * the whole backward to the fc8 logits, as ONE fused kernel
+ *   (modeling/wsl_heads.py:49-55,213-227; modeling/webly_heads.py:32-74,123-197,265-391;
+ *    ops/roi_iou_op.cu:28-62; ops/cross_entropy_wsl_op.cc:88-180).
+ *   fc8c, fc8d          : [R,C] float logits of the clean stack.
+ *   nfc8c, nfc8d        : [R,C] float logits of the noisy stack, or both NULL (plain WSDDN).
+ *   rois                : [R,5]; rois of image b are rows roi_offsets_host[b]..[b+1]
+ *                         (contiguous per image, the order contract of ops/roi_score_reshape_op.cc:30-44).
+ *   roi_offsets         : [B+1] int32 DEVICE array.
+ *   labels_oh           : [B,C] float (may be soft: mixup).
+ *   flags               : NAWSOD_MIL_ENTROPY (WEBLY.ENTROPY), NAWSOD_MIL_MEAN (WSL.MEAN_LOSS),
+ *                         NAWSOD_MIL_BACKWARD (also produce d_*).
+ * outputs (any may be NULL except loss when BACKWARD is off):
+ *   rois_pred[R,C], cls_prob[B,C], rois_pred_noise[R,C], cls_prob_noise[B,C],
+ *   class_weight[B,C], class_weight_noise[B,C], loss[B,2] (loss_cls, loss_cls_noise per image),
+ *   d_fc8c, d_fc8d, d_nfc8c, d_nfc8d [R,C] (loss-gradient seed 1.0 each, utils/blob.py:167-173).
+ *   workspace: device scratch >= nawsod_mil_workspace_bytes(R, C, B).
+ * ------------------------------------------------------------------------------------- */
+enum { NAWSOD_MIL_ENTROPY = 1, NAWSOD_MIL_MEAN = 2, NAWSOD_MIL_BACKWARD = 4 };
+
+int64_t nawsod_mil_workspace_bytes(int R, int C, int B);
+
+int nawsod_mil_head_fwd_bwd(const float* fc8c, const float* fc8d, const float* nfc8c,
+                            const float* nfc8d, const float* rois, const int32_t* roi_offsets,
+                            const float* labels_oh, int R, int C, int B, int flags,
+                            float* rois_pred, float* cls_prob, float* rois_pred_noise,
+                            float* cls_prob_noise, float* class_weight,
+                            float* class_weight_noise, float* loss, float* d_fc8c,
+                            float* d_fc8d, float* d_nfc8c, float* d_nfc8d, void* workspace,
+                            void* stream);
+
+/* a7 stand-alone: RoIIoU([rois] -> [J]) (ops/roi_iou_op.cc:11-18, ops/roi_iou_op.cu:28-84). J [R,R]. */
+int nawsod_roi_iou(const float* rois, int R, float* J, void* stream);
+
+/* a8 stand-alone: [Weighted]CrossEntropyWithLogits([X, L(, W)] -> [Y]; is_mean) and gradient
+ *   ([X, L(, W), dY] -> [dX]) (ops/cross_entropy_wsl_op.cc:8-180).  X, L, W: [N,C]; W may be NULL. */
+int nawsod_cross_entropy_fwd(const float* X, const float* L, const float* Wt, int N, int C,
+                             int is_mean, float* Y, void* stream);
+int nawsod_cross_entropy_bwd(const float* X, const float* L, const float* Wt, const float* dY,
+                             int N, int C, int is_mean, float* dX, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * a10: ACMWeightDecayMomentumSGDUpdate([g, m, lr, p, acc] -> [g, m, p, acc])
+ *   (ops/acm_weightdecay_momentum_sgd_op.h:48-112, wired by modeling/optimizer_wsl.py:96-137),
+ *   fused into one pass.  In place on m, p, acc.  `lr` is a 1-element DEVICE float
+ *   (the reference's `lr` blob).  iter_count = number of calls already made on this
+ *   parameter (call 0 zero-initialises m and acc, .h:62-69).  p_bf16 (optional) receives
+ *   a bf16 copy of the updated parameter for the tensor-core GEMMs.
+ * ------------------------------------------------------------------------------------- */
+int nawsod_sgd_update(const float* g, float* m, const float* lr, float* p, float* acc,
+                      int64_t n, float momentum, float weight_decay, float lr_mult,
+                      int iter_size, int gpu_num, int64_t iter_count, void* p_bf16,
+                      void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NAWSOD_H_ */

@@ -1,0 +1,73 @@
+"""ctypes binding of libnawsod.so (the C ABI declared in include/nawsod.h).
+
+The library is the product; this module only marshals pointers.  If the shared object is
+missing or a call fails, a RuntimeError is raised -- there is no CPU or PyTorch fallback."""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libnawsod.so")
+
+F32, BF16 = 0, 1
+NCHW, NHWC = 0, 1
+FC_RELU, FC_DROPOUT, FC_ACCUMULATE = 1, 2, 4
+MIL_ENTROPY, MIL_MEAN, MIL_BACKWARD = 1, 2, 4
+
+_c = ctypes
+_vp, _i, _i64, _f = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_float
+
+# name -> (restype, argtypes); must list every symbol include/nawsod.h declares
+PROTOTYPES = {
+    "nawsod_last_error": (_c.c_char_p, []),
+    "nawsod_version": (_i, []),
+    "nawsod_set_tuning": (_i, [_c.c_char_p, _i64]),
+    "nawsod_transpose_batched": (_i, [_vp, _i64, _i64, _i64, _vp, _i, _vp]),
+    "nawsod_roi_pool_f_fwd": (_i, [_vp, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _i, _vp, _i, _i, _vp, _vp]),
+    "nawsod_roi_pool_f_bwd": (_i, [_vp, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp]),
+    "nawsod_roi_feature_boost": (_i, [_vp, _vp, _i, _i64, _vp, _vp]),
+    "nawsod_fc_workspace_bytes": (_i64, []),
+    "nawsod_fc_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _vp, _vp]),
+    "nawsod_fc_bwd_x": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _vp, _vp]),
+    "nawsod_fc_bwd_w": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
+    "nawsod_mil_workspace_bytes": (_i64, [_i, _i, _i]),
+    "nawsod_mil_head_fwd_bwd": (_i, [_vp] * 7 + [_i, _i, _i, _i] + [_vp] * 13),
+    "nawsod_roi_iou": (_i, [_vp, _i, _vp, _vp]),
+    "nawsod_cross_entropy_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "nawsod_cross_entropy_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "nawsod_sgd_update": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _f, _f, _f, _i, _i, _i64, _vp, _vp]),
+}
+
+_lib = None
+
+
+def load():
+    """dlopen libnawsod.so (once) and attach prototypes.  Raises if it is not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "libnawsod.so is not built (%s): run `python na-fwebsod_b200/build.py` or "
+                "__graft_entry__.build(); there is no fallback path" % LIB_PATH)
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(lib, name)          # AttributeError if the symbol is not exported
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(rc: int):
+    if rc != 0:
+        msg = load().nawsod_last_error()
+        raise RuntimeError("libnawsod error %d: %s" % (rc, msg.decode() if msg else "?"))
+
+
+def call(name: str, *args):
+    check(getattr(load(), name)(*args))
+
+
+def set_tuning(key: str, value: int):
+    call("nawsod_set_tuning", key.encode(), int(value))

@@ -1,0 +1,451 @@
+// RoIPoolF (+ fused RoIFeatureBoost) forward and backward for sm_100a.
+//
+// Replaces Caffe2 RoIPoolF / RoIPoolFGradient as wired by detectron/modeling/detector.py:321-329
+// and RoIFeatureBoost (detectron/ops/roi_feature_boost_op.cc:8-64).  The bin arithmetic follows
+// detectron/ops/roi_loop_pool_op.cu:41-100 with RoIPoolF's deltas (stride-5 rois, no inner
+// rectangle, maxval = empty ? 0 : -FLT_MAX) and is bit-exact in fp32.
+//
+// Forward design (HBM-write bound: 2 x 100 KB written per RoI, the map is L2 resident):
+//   the map is channels-last; a CTA owns one (image, channel slab) and stages the whole
+//   H*W x SC slab in shared memory once (16-byte cp.async), then walks a chunk of RoIs.  A
+//   work item is (RoI, 16-byte channel vector): it scans each bin's window out of shared
+//   memory with 16-byte loads in the reference's (h, w) order with strict '>' so the argmax
+//   tie-break is identical, and writes 16-byte vectors of Y / argmax in pooled-NHWC order
+//   ([R, PH, PW, C]).  Maps too large for shared memory take the same code path reading the
+//   (L2-resident) map directly.
+#include <algorithm>
+#include <cfloat>
+#include "common.cuh"
+
+namespace nawsod {
+namespace {
+
+struct PoolParams {
+  const void* X;        // channels-last map [N, H, W, C]
+  const float* rois;    // [R, 5]
+  const float* boost;   // [R] or null
+  int N, C, H, W, R, PH, PW;
+  float scale;
+  int SC;               // channels per slab (multiple of VEC, divides C)
+  int rois_per_chunk;
+  void* Y;              // [R, PH, PW, C]
+  int32_t* argmax;      // same layout or null
+};
+
+template <typename T> struct Vec;
+template <> struct Vec<float> {
+  static constexpr int N = 4;
+  __device__ static __forceinline__ void unpack(const uint4& q, float (&v)[4]) {
+    v[0] = __uint_as_float(q.x); v[1] = __uint_as_float(q.y);
+    v[2] = __uint_as_float(q.z); v[3] = __uint_as_float(q.w);
+  }
+};
+template <> struct Vec<__nv_bfloat16> {
+  static constexpr int N = 8;
+  __device__ static __forceinline__ void unpack(const uint4& q, float (&v)[8]) {
+    v[0] = __uint_as_float(q.x << 16); v[1] = __uint_as_float(q.x & 0xffff0000u);
+    v[2] = __uint_as_float(q.y << 16); v[3] = __uint_as_float(q.y & 0xffff0000u);
+    v[4] = __uint_as_float(q.z << 16); v[5] = __uint_as_float(q.z & 0xffff0000u);
+    v[6] = __uint_as_float(q.w << 16); v[7] = __uint_as_float(q.w & 0xffff0000u);
+  }
+};
+
+template <int VEC>
+__device__ __forceinline__ void store_vals(float* dst, const float (&v)[VEC]) {
+#pragma unroll
+  for (int k = 0; k < VEC; k += 4)
+    *reinterpret_cast<float4*>(dst + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
+}
+template <int VEC>
+__device__ __forceinline__ void store_vals(__nv_bfloat16* dst, const float (&v)[VEC]) {
+  uint32_t w[VEC / 2];
+#pragma unroll
+  for (int k = 0; k < VEC; k += 2) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(v[k], v[k + 1]);
+    w[k / 2] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  if (VEC == 4) *reinterpret_cast<uint2*>(dst) = make_uint2(w[0], w[1]);
+  else *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[VEC / 2 - 2], w[VEC / 2 - 1]);
+}
+template <int VEC>
+__device__ __forceinline__ void store_idx(int32_t* dst, const int (&v)[VEC]) {
+#pragma unroll
+  for (int k = 0; k < VEC; k += 4)
+    *reinterpret_cast<int4*>(dst + k) = make_int4(v[k], v[k + 1], v[k + 2], v[k + 3]);
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  uint32_t s = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gsrc));
+}
+
+template <typename TIn, typename TOut, bool kSmem>
+__global__ void __launch_bounds__(512) roi_pool_fwd_kernel(const PoolParams p) {
+  constexpr int VEC = Vec<TIn>::N;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int slab = blockIdx.x, chunk = blockIdx.y, n = blockIdx.z;
+  const int HW = p.H * p.W;
+  const int vpr = p.SC / VEC;   // 16-byte vectors per RoI in this slab
+  const TIn* gbase = static_cast<const TIn*>(p.X) + (size_t)n * HW * p.C + (size_t)slab * p.SC;
+
+  const TIn* src;
+  int row_stride;   // elements between consecutive cells
+  if (kSmem) {
+    TIn* s = reinterpret_cast<TIn*>(smem_raw);
+    const int total = HW * vpr;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+      const int cell = i / vpr, v = i - cell * vpr;
+      cp_async16(s + (size_t)cell * p.SC + v * VEC, gbase + (size_t)cell * p.C + v * VEC);
+    }
+    asm volatile("cp.async.commit_group;\n" ::);
+    asm volatile("cp.async.wait_group 0;\n" ::);
+    __syncthreads();
+    src = s;
+    row_stride = p.SC;
+  } else {
+    src = gbase;
+    row_stride = p.C;
+  }
+
+  const int r0 = chunk * p.rois_per_chunk;
+  const int r1 = min(p.R, r0 + p.rois_per_chunk);
+  const int items = (r1 - r0) * vpr;
+  TOut* Y = static_cast<TOut*>(p.Y);
+  const int W = p.W, H = p.H;
+
+  for (int item = threadIdx.x; item < items; item += blockDim.x) {
+    const int rl = item / vpr, v = item - rl * vpr;
+    const int r = r0 + rl;
+    const float* roi = p.rois + (size_t)r * 5;
+    if (static_cast<int>(roi[0]) != n) continue;
+    // detectron/ops/roi_loop_pool_op.cu:42-57
+    const int roi_start_w = static_cast<int>(roundf(roi[1] * p.scale));
+    const int roi_start_h = static_cast<int>(roundf(roi[2] * p.scale));
+    const int roi_end_w = static_cast<int>(roundf(roi[3] * p.scale));
+    const int roi_end_h = static_cast<int>(roundf(roi[4] * p.scale));
+    const int roi_width = max(roi_end_w - roi_start_w + 1, 1);
+    const int roi_height = max(roi_end_h - roi_start_h + 1, 1);
+    const float bin_size_h = __fdiv_rn(static_cast<float>(roi_height), static_cast<float>(p.PH));
+    const float bin_size_w = __fdiv_rn(static_cast<float>(roi_width), static_cast<float>(p.PW));
+    const float s = p.boost ? p.boost[r] : 1.0f;
+    const TIn* vsrc = src + v * VEC;
+    const size_t out_base = (size_t)r * p.PH * p.PW * p.C + (size_t)slab * p.SC + v * VEC;
+
+    for (int ph = 0; ph < p.PH; ++ph) {
+      int hstart = static_cast<int>(floorf(__fmul_rn(static_cast<float>(ph), bin_size_h)));
+      int hend = static_cast<int>(ceilf(__fmul_rn(static_cast<float>(ph + 1), bin_size_h)));
+      hstart = min(max(hstart + roi_start_h, 0), H);
+      hend = min(max(hend + roi_start_h, 0), H);
+      for (int pw = 0; pw < p.PW; ++pw) {
+        int wstart = static_cast<int>(floorf(__fmul_rn(static_cast<float>(pw), bin_size_w)));
+        int wend = static_cast<int>(ceilf(__fmul_rn(static_cast<float>(pw + 1), bin_size_w)));
+        wstart = min(max(wstart + roi_start_w, 0), W);
+        wend = min(max(wend + roi_start_w, 0), W);
+        const bool is_empty = (hend <= hstart) || (wend <= wstart);
+        float maxv[VEC];
+        int maxi[VEC];
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) { maxv[k] = is_empty ? 0.f : -FLT_MAX; maxi[k] = -1; }
+        if (!is_empty) {
+          // (h, w) row-major scan, flattened so lanes of different RoIs diverge on area only
+          const int bw = wend - wstart;
+          const int cells = (hend - hstart) * bw;
+          int w = wstart, idx = hstart * W + wstart;
+          const int row_skip = W - bw;
+          for (int t = 0; t < cells; ++t) {
+            const uint4 q = *reinterpret_cast<const uint4*>(vsrc + (size_t)idx * row_stride);
+            float x[VEC];
+            Vec<TIn>::unpack(q, x);
+#pragma unroll
+            for (int k = 0; k < VEC; ++k)
+              if (x[k] > maxv[k]) { maxv[k] = x[k]; maxi[k] = idx; }
+            ++w; ++idx;
+            if (w == wend) { w = wstart; idx += row_skip; }
+          }
+        }
+        if (p.boost) {
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) maxv[k] = __fmul_rn(maxv[k], s);
+        }
+        const size_t o = out_base + (size_t)(ph * p.PW + pw) * p.C;
+        store_vals<VEC>(Y + o, maxv);
+        if (p.argmax) store_idx<VEC>(p.argmax + o, maxi);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Backward.  NHWC: dX[b, argmax, c] += dY[r, bin, c] (lanes = channels: coalesced reads, one
+// red per element).  NCHW: lanes = consecutive (c, bin): neighbouring bins often share their
+// argmax cell, so lanes with the same target address are combined with __match_any_sync and
+// one lane issues the red ("warp-aggregated atomics keyed on the argmax").
+// ---------------------------------------------------------------------------------------------
+template <typename TDy>
+__device__ __forceinline__ float load_dy(const TDy* p, size_t i);
+template <> __device__ __forceinline__ float load_dy<float>(const float* p, size_t i) { return p[i]; }
+template <> __device__ __forceinline__ float load_dy<__nv_bfloat16>(const __nv_bfloat16* p, size_t i) {
+  return __bfloat162float(p[i]);
+}
+
+template <typename TDy>
+__global__ void __launch_bounds__(256) roi_pool_bwd_nhwc_kernel(const TDy* __restrict__ dY,
+                                                               const int32_t* __restrict__ argmax,
+                                                               const float* __restrict__ rois,
+                                                               const float* __restrict__ boost, int C, int HW,
+                                                               int bins, size_t total, float* __restrict__ dX) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int a = argmax[i];
+    if (a < 0) continue;
+    const int c = static_cast<int>(i % C);
+    const size_t r = i / ((size_t)C * bins);
+    const int b = static_cast<int>(rois[r * 5]);
+    float g = load_dy<TDy>(dY, i);
+    if (boost) g *= boost[r];
+    atomicAdd(dX + ((size_t)b * HW + a) * C + c, g);
+  }
+}
+
+template <typename TDy>
+__global__ void __launch_bounds__(256) roi_pool_bwd_nchw_kernel(const TDy* __restrict__ dY,
+                                                               const int32_t* __restrict__ argmax,
+                                                               const float* __restrict__ rois,
+                                                               const float* __restrict__ boost, int C, int HW,
+                                                               int bins, size_t total, float* __restrict__ dX) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  // total is padded by the caller's loop bound so that whole warps stay converged
+  const size_t padded = (total + 31) / 32 * 32;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < padded; i += stride) {
+    long long key = -1;
+    float g = 0.f;
+    if (i < total) {
+      const int a = argmax[i];
+      if (a >= 0) {
+        const size_t rc = i / bins;               // r * C + c
+        const size_t r = rc / C;
+        const int c = static_cast<int>(rc - r * C);
+        const int b = static_cast<int>(rois[r * 5]);
+        key = ((long long)b * C + c) * HW + a;
+        g = load_dy<TDy>(dY, i);
+        if (boost) g *= boost[r];
+      }
+    }
+    const unsigned peers = __match_any_sync(0xffffffffu, key);
+    if (key >= 0) {
+      const int lane = threadIdx.x & 31;
+      const int leader = __ffs(peers) - 1;
+      float sum = 0.f;
+      // fixed lane order -> deterministic partial sums inside the warp
+      for (unsigned m = peers; m; m &= m - 1) {
+        const int src = __ffs(m) - 1;
+        sum += __shfl_sync(peers, g, src);
+      }
+      if (lane == leader) atomicAdd(dX + key, sum);
+    }
+  }
+}
+
+__global__ void boost_kernel(const float* __restrict__ X, const float* __restrict__ S, int64_t F4, int64_t total4,
+                             float* __restrict__ Y) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float s = S[i / F4];
+    float4 v = reinterpret_cast<const float4*>(X)[i];
+    v.x *= s; v.y *= s; v.z *= s; v.w *= s;
+    reinterpret_cast<float4*>(Y)[i] = v;
+  }
+}
+__global__ void boost_kernel_scalar(const float* __restrict__ X, const float* __restrict__ S, int64_t F, int64_t total,
+                                    float* __restrict__ Y) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+    Y[i] = X[i] * S[i / F];
+}
+
+// Batched transpose of 4-byte elements: in [B, rows, cols] -> out [B, cols, rows].
+template <typename TOut>
+__global__ void transpose_kernel(const uint32_t* __restrict__ in, int64_t rows, int64_t cols, TOut* __restrict__ out) {
+  __shared__ uint32_t tile[32][33];
+  const int64_t b = blockIdx.z;
+  const uint32_t* src = in + b * rows * cols;
+  TOut* dst = out + b * rows * cols;
+  const int64_t c0 = (int64_t)blockIdx.x * 32, r0 = (int64_t)blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int64_t r = r0 + j, c = c0 + threadIdx.x;
+    if (r < rows && c < cols) tile[j][threadIdx.x] = src[r * cols + c];
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int64_t c = c0 + j, r = r0 + threadIdx.x;
+    if (r < rows && c < cols) {
+      const uint32_t w = tile[threadIdx.x][j];
+      if (sizeof(TOut) == 4) reinterpret_cast<uint32_t*>(dst)[c * rows + r] = w;
+      else reinterpret_cast<__nv_bfloat16*>(dst)[c * rows + r] = __float2bfloat16_rn(__uint_as_float(w));
+    }
+  }
+}
+
+template <typename TIn, typename TOut>
+int launch_pool_fwd(const PoolParams& p, bool use_smem, size_t smem_bytes, dim3 grid, int threads, cudaStream_t st) {
+  if (use_smem) {
+    auto k = roi_pool_fwd_kernel<TIn, TOut, true>;
+    NAWSOD_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    k<<<grid, threads, smem_bytes, st>>>(p);
+  } else {
+    roi_pool_fwd_kernel<TIn, TOut, false><<<grid, threads, 0, st>>>(p);
+  }
+  NAWSOD_LAUNCH_OK();
+  return NAWSOD_OK;
+}
+
+}  // namespace
+}  // namespace nawsod
+
+using namespace nawsod;
+
+extern "C" int nawsod_transpose_batched(const void* in, int64_t B, int64_t rows, int64_t cols, void* out,
+                                        int out_dtype, void* stream) {
+  NAWSOD_REQUIRE(in && out, NAWSOD_ERR_ARG, "transpose: null pointer");
+  NAWSOD_REQUIRE(B >= 0 && rows >= 0 && cols >= 0, NAWSOD_ERR_SHAPE, "transpose: negative size");
+  NAWSOD_REQUIRE(out_dtype == NAWSOD_F32 || out_dtype == NAWSOD_BF16, NAWSOD_ERR_ARG, "transpose: bad out_dtype");
+  if (B == 0 || rows == 0 || cols == 0) return NAWSOD_OK;
+  NAWSOD_REQUIRE(B <= 65535, NAWSOD_ERR_SHAPE, "transpose: batch %lld > 65535", (long long)B);
+  dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32), (unsigned)B), block(32, 8);
+  NAWSOD_REQUIRE(grid.y <= 65535, NAWSOD_ERR_SHAPE, "transpose: too many rows");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (out_dtype == NAWSOD_F32)
+    transpose_kernel<uint32_t><<<grid, block, 0, st>>>(static_cast<const uint32_t*>(in), rows, cols,
+                                                       static_cast<uint32_t*>(out));
+  else
+    transpose_kernel<__nv_bfloat16><<<grid, block, 0, st>>>(static_cast<const uint32_t*>(in), rows, cols,
+                                                            static_cast<__nv_bfloat16*>(out));
+  NAWSOD_LAUNCH_OK();
+  return NAWSOD_OK;
+}
+
+// Forward on a channels-last map into pooled-NHWC output (the native fast path).
+static int pool_fwd_nhwc(const void* X, int x_dtype, const float* rois, const float* boost, int N, int C, int H, int W,
+                         int R, float scale, int PH, int PW, void* Y, int y_dtype, int32_t* argmax, cudaStream_t st) {
+  const int esize = x_dtype == NAWSOD_F32 ? 4 : 2;
+  const int VEC = 16 / esize;
+  NAWSOD_REQUIRE(C % VEC == 0, NAWSOD_ERR_SHAPE, "roi_pool_f: C=%d must be a multiple of %d", C, VEC);
+  NAWSOD_REQUIRE(aligned16(X) && aligned16(Y) && (!argmax || aligned16(argmax)), NAWSOD_ERR_ALIGN,
+                 "roi_pool_f: X, Y and argmax must be 16-byte aligned");
+  NAWSOD_REQUIRE(N <= 65535, NAWSOD_ERR_SHAPE, "roi_pool_f: N too large");
+  // pick the channel slab: the largest divisor of C (multiple of VEC) whose H*W*SC slab fits the budget
+  const int64_t budget = get_tuning("pool_slab_bytes", 100 * 1024);
+  const int64_t hard = 200 * 1024;
+  const bool force_global = get_tuning("pool_force_global", 0) != 0;
+  int SC = 0;
+  for (int64_t lim : {budget, hard}) {
+    if (force_global || SC) break;
+    for (int cand = C; cand >= VEC; --cand) {
+      if (C % cand || cand % VEC) continue;
+      if ((int64_t)H * W * cand * esize <= lim) { SC = cand; break; }
+    }
+  }
+  const bool use_smem = SC > 0;
+  if (!use_smem) {
+    SC = C;
+    for (int cand = 128 * VEC / 4; cand >= VEC; cand /= 2)
+      if (C % cand == 0) { SC = cand; break; }
+  }
+  const size_t smem_bytes = use_smem ? (size_t)H * W * SC * esize : 0;
+  const int slabs = C / SC;
+  const int ctas_per_sm = use_smem ? (int)std::max<int64_t>(1, std::min<int64_t>(4, (220 * 1024) / (int64_t)(smem_bytes + 1024))) : 4;
+  int threads = (int)get_tuning("pool_threads", use_smem ? (ctas_per_sm >= 2 ? 256 : 512) : 128);
+  int chunks = (int)get_tuning("pool_chunks", 0);
+  if (chunks <= 0) {
+    const int64_t slots = (int64_t)sm_count() * ctas_per_sm;
+    const int64_t base = (int64_t)slabs * N;
+    chunks = (int)std::max<int64_t>(1, (2 * slots + base - 1) / base);
+    // never make chunks so small that a CTA has less than one pass of work items
+    const int64_t max_chunks = std::max<int64_t>(1, ((int64_t)R * (SC / VEC) + threads - 1) / threads);
+    if (!use_smem) chunks = (int)max_chunks;
+    chunks = (int)std::min<int64_t>(chunks, max_chunks);
+  }
+  chunks = std::min(chunks, 65535);
+  PoolParams p;
+  p.X = X; p.rois = rois; p.boost = boost;
+  p.N = N; p.C = C; p.H = H; p.W = W; p.R = R; p.PH = PH; p.PW = PW;
+  p.scale = scale; p.SC = SC; p.rois_per_chunk = (R + chunks - 1) / chunks;
+  p.Y = Y; p.argmax = argmax;
+  dim3 grid(slabs, chunks, N);
+  if (x_dtype == NAWSOD_F32 && y_dtype == NAWSOD_F32)
+    return launch_pool_fwd<float, float>(p, use_smem, smem_bytes, grid, threads, st);
+  if (x_dtype == NAWSOD_F32 && y_dtype == NAWSOD_BF16)
+    return launch_pool_fwd<float, __nv_bfloat16>(p, use_smem, smem_bytes, grid, threads, st);
+  if (x_dtype == NAWSOD_BF16 && y_dtype == NAWSOD_BF16)
+    return launch_pool_fwd<__nv_bfloat16, __nv_bfloat16>(p, use_smem, smem_bytes, grid, threads, st);
+  if (x_dtype == NAWSOD_BF16 && y_dtype == NAWSOD_F32)
+    return launch_pool_fwd<__nv_bfloat16, float>(p, use_smem, smem_bytes, grid, threads, st);
+  set_error("roi_pool_f: unsupported dtype combination");
+  return NAWSOD_ERR_UNSUPPORTED;
+}
+
+extern "C" int nawsod_roi_pool_f_fwd(const void* X, int x_dtype, int x_layout, const float* rois, const float* boost,
+                                     int N, int C, int H, int W, int R, float spatial_scale, int pooled_h,
+                                     int pooled_w, void* Y, int y_dtype, int y_layout, int32_t* argmax,
+                                     void* stream) {
+  NAWSOD_REQUIRE(N >= 0 && C > 0 && H > 0 && W > 0 && R >= 0 && pooled_h > 0 && pooled_w > 0, NAWSOD_ERR_SHAPE,
+                 "roi_pool_f: bad shape N=%d C=%d H=%d W=%d R=%d pooled=%dx%d", N, C, H, W, R, pooled_h, pooled_w);
+  NAWSOD_REQUIRE((x_dtype == NAWSOD_F32 || x_dtype == NAWSOD_BF16) && (y_dtype == NAWSOD_F32 || y_dtype == NAWSOD_BF16),
+                 NAWSOD_ERR_ARG, "roi_pool_f: bad dtype");
+  NAWSOD_REQUIRE(x_layout == NAWSOD_NHWC, NAWSOD_ERR_UNSUPPORTED,
+                 "roi_pool_f: the kernel consumes a channels-last map; convert NCHW with nawsod_transpose_batched");
+  NAWSOD_REQUIRE(y_layout == NAWSOD_NHWC, NAWSOD_ERR_UNSUPPORTED,
+                 "roi_pool_f: the kernel emits pooled-NHWC; convert with nawsod_transpose_batched for NCHW");
+  if (R == 0 || N == 0) return NAWSOD_OK;   // empty rois: nothing to write (roi_loop_pool_op.cu:149-158)
+  NAWSOD_REQUIRE(X && rois && Y, NAWSOD_ERR_ARG, "roi_pool_f: null pointer");
+  NAWSOD_REQUIRE((int64_t)H * W < (1ll << 31) / 4, NAWSOD_ERR_SHAPE, "roi_pool_f: map too large");
+  return pool_fwd_nhwc(X, x_dtype, rois, boost, N, C, H, W, R, spatial_scale, pooled_h, pooled_w, Y, y_dtype, argmax,
+                       static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int nawsod_roi_pool_f_bwd(const void* dY, int dy_dtype, int y_layout, const int32_t* argmax,
+                                     const float* rois, const float* boost, int N, int C, int H, int W, int R,
+                                     int pooled_h, int pooled_w, float* dX, int dx_layout, void* stream) {
+  NAWSOD_REQUIRE(N >= 0 && C > 0 && H > 0 && W > 0 && R >= 0 && pooled_h > 0 && pooled_w > 0, NAWSOD_ERR_SHAPE,
+                 "roi_pool_f_grad: bad shape");
+  NAWSOD_REQUIRE(dy_dtype == NAWSOD_F32 || dy_dtype == NAWSOD_BF16, NAWSOD_ERR_ARG, "roi_pool_f_grad: bad dtype");
+  NAWSOD_REQUIRE(y_layout == dx_layout && (y_layout == NAWSOD_NCHW || y_layout == NAWSOD_NHWC), NAWSOD_ERR_UNSUPPORTED,
+                 "roi_pool_f_grad: dY/argmax and dX must share one layout (NCHW or NHWC)");
+  NAWSOD_REQUIRE(dX || N == 0, NAWSOD_ERR_ARG, "roi_pool_f_grad: null dX");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (N > 0) NAWSOD_CUDA_OK(cudaMemsetAsync(dX, 0, (size_t)N * C * H * W * sizeof(float), st));
+  if (R == 0 || N == 0) return NAWSOD_OK;
+  NAWSOD_REQUIRE(dY && argmax && rois, NAWSOD_ERR_ARG, "roi_pool_f_grad: null pointer");
+  const int bins = pooled_h * pooled_w;
+  const size_t total = (size_t)R * C * bins;
+  const int threads = 256;
+  const int blocks = (int)std::min<size_t>((total + threads - 1) / threads, (size_t)sm_count() * 32);
+#define NAWSOD_BWD(KERNEL, T)                                                                               \
+  KERNEL<T><<<blocks, threads, 0, st>>>(static_cast<const T*>(dY), argmax, rois, boost, C, H * W, bins, total, dX)
+  if (y_layout == NAWSOD_NHWC) {
+    if (dy_dtype == NAWSOD_F32) NAWSOD_BWD(roi_pool_bwd_nhwc_kernel, float);
+    else NAWSOD_BWD(roi_pool_bwd_nhwc_kernel, __nv_bfloat16);
+  } else {
+    if (dy_dtype == NAWSOD_F32) NAWSOD_BWD(roi_pool_bwd_nchw_kernel, float);
+    else NAWSOD_BWD(roi_pool_bwd_nchw_kernel, __nv_bfloat16);
+  }
+#undef NAWSOD_BWD
+  NAWSOD_LAUNCH_OK();
+  return NAWSOD_OK;
+}
+
+extern "C" int nawsod_roi_feature_boost(const float* X, const float* S, int R, int64_t feature_size, float* Y,
+                                        void* stream) {
+  NAWSOD_REQUIRE(R >= 0 && feature_size >= 0, NAWSOD_ERR_SHAPE, "roi_feature_boost: negative size");
+  if (R == 0 || feature_size == 0) return NAWSOD_OK;
+  NAWSOD_REQUIRE(X && S && Y, NAWSOD_ERR_ARG, "roi_feature_boost: null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t total = (int64_t)R * feature_size;
+  if (feature_size % 4 == 0 && aligned16(X) && aligned16(Y)) {
+    const int64_t total4 = total / 4;
+    const int blocks = (int)std::min<int64_t>((total4 + 255) / 256, (int64_t)sm_count() * 16);
+    boost_kernel<<<blocks, 256, 0, st>>>(X, S, feature_size / 4, total4, Y);
+  } else {
+    const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)sm_count() * 16);
+    boost_kernel_scalar<<<blocks, 256, 0, st>>>(X, S, feature_size, total, Y);
+  }
+  NAWSOD_LAUNCH_OK();
+  return NAWSOD_OK;
+}

@@ -1,0 +1,111 @@
+// ACMWeightDecayMomentumSGDUpdate fused into one pass (row a10 of SURVEY.md section 8).
+//
+// Replaces detectron/ops/acm_weightdecay_momentum_sgd_op.h:48-112 (five math:: passes + the
+// MomentumSGDMultKernel of acm_weightdecay_momentum_sgd_op_gpu.cu:7-33) as wired per parameter
+// blob by detectron/modeling/optimizer_wsl.py:96-137.  HBM-bound: with iter_size == 1 it reads
+// g, m, p and writes m, p (+ an optional bf16 shadow of p for the tensor-core GEMMs): 20-22 B/param.
+#include <algorithm>
+#include "common.cuh"
+
+namespace nawsod {
+namespace {
+
+struct SgdArgs {
+  const float* g; float* m; const float* lr; float* p; float* acc; __nv_bfloat16* p_bf16;
+  int64_t n;
+  float momentum, weight_decay, lr_mult, inv_norm;
+  int first_call;   // iter_count == 0: m and acc start from zero whatever the buffers hold (.h:62-69)
+  int do_update;    // (iter_count + 1) % iter_size == 0
+  int use_acc;      // iter_size > 1 or acc buffer given
+};
+
+// Per-element arithmetic in the reference's order (no FMA contraction across its separate passes):
+//   acc = g + acc                        (.h:72-75)
+//   acc = acc * (1 / (iter_size*gpu_num)) (.h:79-84)
+//   acc = acc + wd * p                   (.h:88-90, Axpy)
+//   v   = LR * acc + momentum * m        (.h:19)
+//   m = v; p = p - v; acc = 0            (.h:20-21, 30, 106-109)
+__device__ __forceinline__ void sgd_elem(float g, float& m, float& p, float& acc, const SgdArgs& a, float LR) {
+  float ac = __fadd_rn(g, acc);
+  if (a.do_update) {
+    ac = __fmul_rn(ac, a.inv_norm);
+    ac = __fadd_rn(ac, __fmul_rn(a.weight_decay, p));
+    const float v = __fadd_rn(__fmul_rn(LR, ac), __fmul_rn(a.momentum, m));
+    m = v;
+    p = __fsub_rn(p, v);
+    ac = 0.f;
+  }
+  acc = ac;
+}
+
+__global__ void __launch_bounds__(256) sgd_kernel(const SgdArgs a) {
+  const float LR = __fmul_rn(a.lr[0], a.lr_mult);
+  const int64_t n4 = a.n / 4;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (int64_t i = t0; i < n4; i += stride) {
+    const float4 g = reinterpret_cast<const float4*>(a.g)[i];
+    float4 m = a.first_call ? make_float4(0.f, 0.f, 0.f, 0.f) : reinterpret_cast<const float4*>(a.m)[i];
+    float4 p = reinterpret_cast<const float4*>(a.p)[i];
+    float4 c = (a.first_call || !a.use_acc) ? make_float4(0.f, 0.f, 0.f, 0.f)
+                                            : reinterpret_cast<const float4*>(a.acc)[i];
+    sgd_elem(g.x, m.x, p.x, c.x, a, LR);
+    sgd_elem(g.y, m.y, p.y, c.y, a, LR);
+    sgd_elem(g.z, m.z, p.z, c.z, a, LR);
+    sgd_elem(g.w, m.w, p.w, c.w, a, LR);
+    if (a.do_update || a.first_call) reinterpret_cast<float4*>(a.m)[i] = m;
+    if (a.do_update) {
+      reinterpret_cast<float4*>(a.p)[i] = p;
+      if (a.p_bf16) {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(p.x, p.y), hi = __floats2bfloat162_rn(p.z, p.w);
+        reinterpret_cast<uint2*>(a.p_bf16)[i] =
+            make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+      }
+    }
+    if (a.use_acc) reinterpret_cast<float4*>(a.acc)[i] = c;
+  }
+  // tail (n % 4)
+  for (int64_t i = n4 * 4 + t0; i < a.n; i += stride) {
+    float m = a.first_call ? 0.f : a.m[i];
+    float p = a.p[i];
+    float c = (a.first_call || !a.use_acc) ? 0.f : a.acc[i];
+    sgd_elem(a.g[i], m, p, c, a, LR);
+    if (a.do_update || a.first_call) a.m[i] = m;
+    if (a.do_update) {
+      a.p[i] = p;
+      if (a.p_bf16) a.p_bf16[i] = __float2bfloat16_rn(p);
+    }
+    if (a.use_acc) a.acc[i] = c;
+  }
+}
+
+}  // namespace
+}  // namespace nawsod
+
+using namespace nawsod;
+
+extern "C" int nawsod_sgd_update(const float* g, float* m, const float* lr, float* p, float* acc, int64_t n,
+                                 float momentum, float weight_decay, float lr_mult, int iter_size, int gpu_num,
+                                 int64_t iter_count, void* p_bf16, void* stream) {
+  NAWSOD_REQUIRE(n >= 0, NAWSOD_ERR_SHAPE, "sgd_update: negative n");
+  NAWSOD_REQUIRE(iter_size >= 1 && gpu_num >= 1 && iter_count >= 0, NAWSOD_ERR_ARG,
+                 "sgd_update: need iter_size >= 1, gpu_num >= 1, iter_count >= 0");
+  if (n == 0) return NAWSOD_OK;
+  NAWSOD_REQUIRE(g && m && lr && p, NAWSOD_ERR_ARG, "sgd_update: null pointer");
+  NAWSOD_REQUIRE(acc || iter_size == 1, NAWSOD_ERR_ARG, "sgd_update: acc buffer required when iter_size > 1");
+  NAWSOD_REQUIRE(aligned16(g) && aligned16(m) && aligned16(p) && (!acc || aligned16(acc)) &&
+                     (!p_bf16 || (reinterpret_cast<uintptr_t>(p_bf16) & 7u) == 0),
+                 NAWSOD_ERR_ALIGN, "sgd_update: buffers must be 16-byte aligned");
+  SgdArgs a;
+  a.g = g; a.m = m; a.lr = lr; a.p = p; a.acc = acc; a.p_bf16 = static_cast<__nv_bfloat16*>(p_bf16);
+  a.n = n; a.momentum = momentum; a.weight_decay = weight_decay; a.lr_mult = lr_mult;
+  a.inv_norm = static_cast<float>(1.0 / (static_cast<double>(iter_size) * gpu_num));   // T(1.0 / (iter_size_ * gpu_num_))
+  a.first_call = iter_count == 0;
+  a.do_update = ((iter_count + 1) % iter_size) == 0;
+  a.use_acc = acc != nullptr;
+  const int64_t work = std::max<int64_t>(n / 4, 1);
+  const int blocks = (int)std::min<int64_t>((work + 255) / 256, (int64_t)sm_count() * 16);
+  sgd_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  NAWSOD_LAUNCH_OK();
+  return NAWSOD_OK;
+}

@@ -1,0 +1,308 @@
+"""Operator-level mirror of the reference's Caffe2 ops on the hot path.
+
+Each function keeps the reference operator's name, blob order and argument meaning
+(``[inputs] -> [outputs]; args``) and calls the C ABI of libnawsod.so on the current CUDA
+stream.  Tensors are torch CUDA tensors used as device-memory handles only; no arithmetic is
+done by PyTorch here.  Errors surface as RuntimeError (the reference's CAFFE_ENFORCE ->
+RuntimeError pattern, detectron/tests/test_zero_even_op.py:48-51).
+
+Citations are relative to /root/reference/detectron.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import BF16, F32, NCHW, NHWC
+
+_DT = {torch.float32: F32, torch.bfloat16: BF16}
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _req(t, name, dtype=None, ndim=None):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError("%s must be a CUDA tensor (libnawsod has no CPU path)" % name)
+    if not t.is_contiguous():
+        raise RuntimeError("%s must be contiguous" % name)
+    if dtype is not None and t.dtype not in (dtype if isinstance(dtype, tuple) else (dtype,)):
+        raise RuntimeError("%s has dtype %s, expected %s" % (name, t.dtype, dtype))
+    if ndim is not None and t.dim() != ndim:
+        raise RuntimeError("%s must be %d-d, got shape %s" % (name, ndim, tuple(t.shape)))
+    return t
+
+
+def _layout(s):
+    if s in (NCHW, "NCHW"):
+        return NCHW
+    if s in (NHWC, "NHWC"):
+        return NHWC
+    raise RuntimeError("unknown layout %r" % (s,))
+
+
+def transpose_batched(src, out_dtype=None):
+    """[B, rows, cols] -> [B, cols, rows] for 4-byte elements (float32 / int32); a float32
+    source may be converted to bfloat16 on the way out."""
+    _req(src, "src", (torch.float32, torch.int32), 3)
+    B, rows, cols = src.shape
+    out_dtype = out_dtype or src.dtype
+    if out_dtype not in (src.dtype, torch.bfloat16) or (out_dtype == torch.bfloat16 and src.dtype != torch.float32):
+        raise RuntimeError("transpose_batched: unsupported conversion %s -> %s" % (src.dtype, out_dtype))
+    out = torch.empty((B, cols, rows), dtype=out_dtype, device=src.device)
+    _lib.call("nawsod_transpose_batched", _ptr(src), B, rows, cols, _ptr(out),
+              BF16 if out_dtype == torch.bfloat16 else F32, _stream())
+    return out
+
+
+def to_channels_last(X, dtype=None):
+    """NCHW float32 map -> NHWC (optionally bfloat16) with the library's transpose kernel."""
+    _req(X, "X", torch.float32, 4)
+    N, C, H, W = X.shape
+    return transpose_batched(X.view(N, C, H * W), dtype).view(N, H, W, C)
+
+
+# --------------------------------------------------------------------------------------------
+# RoIPoolF / RoIPoolFGradient / RoIFeatureBoost
+# --------------------------------------------------------------------------------------------
+def RoIPoolF(X, rois, *, pooled_h=7, pooled_w=7, spatial_scale=1.0 / 16, is_test=False, boost=None,
+             x_layout="NCHW", y_layout="NCHW", out_dtype=None):
+    """``RoIPoolF([X, rois] -> [Y, argmax]; pooled_h, pooled_w, spatial_scale)``
+    (modeling/detector.py:321-329; ``sampling_ratio`` is ignored there too).
+
+    Defaults reproduce the reference blobs exactly: X [N,C,H,W] float32, Y [R,C,ph,pw],
+    argmax int32 (None when ``is_test``).  ``x_layout='NHWC'`` / ``y_layout='NHWC'`` select the
+    native channels-last kernel directly (X [N,H,W,C], Y [R,ph,pw,C]); the NCHW defaults go
+    through the library's transpose kernels around the same pooling kernel, so values and
+    argmax are bit-identical in every layout.  ``boost`` ([R] or [R,1], obn_scores+1) fuses
+    ``RoIFeatureBoost`` (modeling/wsl_heads.py:668) into the epilogue.
+    """
+    xl, yl = _layout(x_layout), _layout(y_layout)
+    _req(X, "X", (torch.float32, torch.bfloat16), 4)
+    _req(rois, "rois", torch.float32, 2)
+    if rois.shape[1] != 5:
+        raise RuntimeError("rois must be [R,5], got %s" % (tuple(rois.shape),))
+    if boost is not None:
+        _req(boost, "boost", torch.float32)
+        if boost.numel() != rois.shape[0]:
+            raise RuntimeError("boost must have one entry per RoI")
+    if xl == NCHW:
+        if X.dtype != torch.float32:
+            raise RuntimeError("an NCHW map must be float32 (the reference layout)")
+        N, C, H, W = X.shape
+        Xcl = to_channels_last(X)
+    else:
+        N, H, W, C = X.shape
+        Xcl = X
+    R = rois.shape[0]
+    out_dtype = out_dtype or (torch.float32 if xl == NCHW else X.dtype)
+    if yl == NCHW and out_dtype != torch.float32:
+        raise RuntimeError("pooled NCHW output is float32 only")
+    Y = torch.empty((R, pooled_h, pooled_w, C), dtype=out_dtype, device=X.device)
+    A = None if is_test else torch.empty((R, pooled_h, pooled_w, C), dtype=torch.int32, device=X.device)
+    _lib.call("nawsod_roi_pool_f_fwd", _ptr(Xcl), _DT[Xcl.dtype], NHWC, _ptr(rois), _ptr(boost), N, C, H, W, R,
+              float(spatial_scale), pooled_h, pooled_w, _ptr(Y), _DT[out_dtype], NHWC, _ptr(A), _stream())
+    if yl == NCHW:
+        bins = pooled_h * pooled_w
+        Y = transpose_batched(Y.view(R, bins, C)).view(R, C, pooled_h, pooled_w)
+        if A is not None:
+            A = transpose_batched(A.view(R, bins, C)).view(R, C, pooled_h, pooled_w)
+    return Y, A
+
+
+def RoIPoolFGradient(X, rois, argmax, dY, *, boost=None, layout="NCHW"):
+    """``RoIPoolFGradient([X, rois, argmax, dY] -> dX)`` (grad maker ops/roi_loop_pool_op.cc:85-96).
+    X is only consulted for its shape, as in the reference.  layout: layout of X/dX and of
+    dY/argmax (NCHW: [N,C,H,W] / [R,C,ph,pw]; NHWC: [N,H,W,C] / [R,ph,pw,C])."""
+    lay = _layout(layout)
+    _req(argmax, "argmax", torch.int32, 4)
+    _req(dY, "dY", (torch.float32, torch.bfloat16), 4)
+    _req(rois, "rois", torch.float32, 2)
+    if tuple(argmax.shape) != tuple(dY.shape):
+        raise RuntimeError("argmax and dY must have the same shape")
+    if lay == NCHW:
+        N, C, H, W = X.shape
+        R, C2, ph, pw = dY.shape
+    else:
+        N, H, W, C = X.shape
+        R, ph, pw, C2 = dY.shape
+    if C2 != C or R != rois.shape[0]:
+        raise RuntimeError("shape mismatch between X, rois and dY")
+    dX = torch.empty(tuple(X.shape), dtype=torch.float32, device=dY.device)
+    _lib.call("nawsod_roi_pool_f_bwd", _ptr(dY), _DT[dY.dtype], lay, _ptr(argmax), _ptr(rois), _ptr(boost), N, C, H, W,
+              R, ph, pw, _ptr(dX), lay, _stream())
+    return dX
+
+
+def RoIFeatureBoost(X, S, out=None):
+    """``RoIFeatureBoost([X, S] -> [Y])``, in place when ``out is X`` (ops/roi_feature_boost_op.cc:8-35,74-82)."""
+    _req(X, "X", torch.float32)
+    _req(S, "S", torch.float32)
+    if S.numel() != S.shape[0] or X.shape[0] != S.shape[0]:      # CAFFE_ENFORCE_EQ(S.dim32(0), S.numel()) ...
+        raise RuntimeError("RoIFeatureBoost: S must be [R] or [R,1] with R == X.shape[0]")
+    Y = torch.empty_like(X) if out is None else out
+    R = X.shape[0]
+    _lib.call("nawsod_roi_feature_boost", _ptr(X), _ptr(S), R, X.numel() // max(R, 1), _ptr(Y), _stream())
+    return Y
+
+
+def RoIFeatureBoostGradient(dY, S, out=None):
+    """``RoIFeatureBoostGradient([dY, S] -> [dX])`` (ops/roi_feature_boost_op.cc:37-64)."""
+    return RoIFeatureBoost(dY, S, out)
+
+
+# --------------------------------------------------------------------------------------------
+# RoIIoU, [Weighted]CrossEntropyWithLogits
+# --------------------------------------------------------------------------------------------
+def RoIIoU(rois):
+    """``RoIIoU([rois] -> [J])`` (ops/roi_iou_op.cc:11-18)."""
+    _req(rois, "rois", torch.float32, 2)              # CAFFE_ENFORCE_EQ(R.dim(), 2)
+    if rois.shape[1] != 5:                            # CAFFE_ENFORCE_EQ(R.dim32(1), 5)
+        raise RuntimeError("RoIIoU: rois must be [R,5]")
+    n = rois.shape[0]
+    J = torch.empty((n, n), dtype=torch.float32, device=rois.device)
+    _lib.call("nawsod_roi_iou", _ptr(rois), n, _ptr(J), _stream())
+    return J
+
+
+def _ce_check(X, L, W):
+    _req(X, "X", torch.float32, 2)                    # CAFFE_ENFORCE_EQ(X.dim(), 2)
+    _req(L, "L", torch.float32)
+    if tuple(X.shape) != tuple(L.shape):              # CAFFE_ENFORCE_EQ(X.sizes(), L.sizes())
+        raise RuntimeError("CrossEntropyWithLogits: X and L shapes differ")
+    if W is not None:
+        _req(W, "W", torch.float32)
+        if tuple(X.shape) != tuple(W.shape):
+            raise RuntimeError("WeightedCrossEntropyWithLogits: X and W shapes differ")
+
+
+def CrossEntropyWithLogits(X, L, *, is_mean=False):
+    """``CrossEntropyWithLogits([X, L] -> [Y]; is_mean)`` (ops/cross_entropy_wsl_op.cc:8-45)."""
+    _ce_check(X, L, None)
+    Y = torch.empty((), dtype=torch.float32, device=X.device)
+    _lib.call("nawsod_cross_entropy_fwd", _ptr(X), _ptr(L), None, X.shape[0], X.shape[1], int(bool(is_mean)), _ptr(Y),
+              _stream())
+    return Y
+
+
+def WeightedCrossEntropyWithLogits(X, L, W, *, is_mean=False):
+    """``WeightedCrossEntropyWithLogits([X, L, W] -> [Y]; is_mean)`` (ops/cross_entropy_wsl_op.cc:88-129)."""
+    _ce_check(X, L, W)
+    Y = torch.empty((), dtype=torch.float32, device=X.device)
+    _lib.call("nawsod_cross_entropy_fwd", _ptr(X), _ptr(L), _ptr(W), X.shape[0], X.shape[1], int(bool(is_mean)),
+              _ptr(Y), _stream())
+    return Y
+
+
+def CrossEntropyWithLogitsGradient(X, L, dY, *, is_mean=False):
+    """``([X, L, dY] -> [dX])`` (ops/cross_entropy_wsl_op.cc:47-85)."""
+    _ce_check(X, L, None)
+    _req(dY, "dY", torch.float32)
+    if dY.numel() != 1:                               # CAFFE_ENFORCE_EQ(dY.numel(), 1)
+        raise RuntimeError("dY must have one element")
+    dX = torch.empty_like(X)
+    _lib.call("nawsod_cross_entropy_bwd", _ptr(X), _ptr(L), None, _ptr(dY), X.shape[0], X.shape[1],
+              int(bool(is_mean)), _ptr(dX), _stream())
+    return dX
+
+
+def WeightedCrossEntropyWithLogitsGradient(X, L, W, dY, *, is_mean=False):
+    """``([X, L, W, dY] -> [dX])`` (ops/cross_entropy_wsl_op.cc:131-180)."""
+    _ce_check(X, L, W)
+    _req(dY, "dY", torch.float32)
+    if dY.numel() != 1:
+        raise RuntimeError("dY must have one element")
+    dX = torch.empty_like(X)
+    _lib.call("nawsod_cross_entropy_bwd", _ptr(X), _ptr(L), _ptr(W), _ptr(dY), X.shape[0], X.shape[1],
+              int(bool(is_mean)), _ptr(dX), _stream())
+    return dX
+
+
+# --------------------------------------------------------------------------------------------
+# fused MIL head + losses (a5..a9)
+# --------------------------------------------------------------------------------------------
+_ws_cache = {}
+
+
+def _workspace(nbytes, device, tag):
+    key = (tag, str(device))
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+        _ws_cache[key] = buf
+    return buf
+
+
+def mil_head(fc8c, fc8d, rois, roi_offsets, labels_oh, nfc8c=None, nfc8d=None, *, entropy=True, is_mean=True,
+             backward=True):
+    """The whole of ``add_wsl_outputs`` + ``add_webly_outputs`` + ``add_webly_losses`` and their
+    gradient ops in one kernel (modeling/wsl_heads.py:23-56,213-227; modeling/webly_heads.py:32-74,
+    123-197,265-391).  ``roi_offsets`` [B+1] int32 (device): rows of image b are
+    roi_offsets[b]:roi_offsets[b+1].  Returns a dict of the reference's blob names."""
+    _req(fc8c, "fc8c", torch.float32, 2)
+    _req(fc8d, "fc8d", torch.float32, 2)
+    _req(rois, "rois", torch.float32, 2)
+    _req(roi_offsets, "roi_offsets", torch.int32, 1)
+    _req(labels_oh, "labels_oh", torch.float32, 2)
+    R, C = fc8c.shape
+    B = labels_oh.shape[0]
+    if tuple(fc8d.shape) != (R, C) or rois.shape[0] != R or labels_oh.shape[1] != C or roi_offsets.numel() != B + 1:
+        raise RuntimeError("mil_head: inconsistent shapes")
+    noise = nfc8c is not None
+    if noise:
+        _req(nfc8c, "nfc8c", torch.float32, 2)
+        _req(nfc8d, "nfc8d", torch.float32, 2)
+        if tuple(nfc8c.shape) != (R, C) or tuple(nfc8d.shape) != (R, C):
+            raise RuntimeError("mil_head: inconsistent noisy logits")
+    dev = fc8c.device
+    new = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
+    out = {"rois_pred": new(R, C), "cls_prob": new(B, C), "loss": new(B, 2)}
+    if noise:
+        out.update(rois_pred_noise=new(R, C), cls_prob_noise=new(B, C))
+        if entropy:
+            out.update(class_weight=new(B, C), class_weight_noise=new(B, C))
+    if backward:
+        out.update(d_fc8c=new(R, C), d_fc8d=new(R, C))
+        if noise:
+            out.update(d_nfc8c=new(R, C), d_nfc8d=new(R, C))
+    flags = (_lib.MIL_ENTROPY if entropy else 0) | (_lib.MIL_MEAN if is_mean else 0) | \
+            (_lib.MIL_BACKWARD if backward else 0)
+    ws = _workspace(_lib.load().nawsod_mil_workspace_bytes(R, C, B), dev, "mil")
+    g = out.get
+    _lib.call("nawsod_mil_head_fwd_bwd", _ptr(fc8c), _ptr(fc8d), _ptr(nfc8c), _ptr(nfc8d), _ptr(rois),
+              _ptr(roi_offsets), _ptr(labels_oh), R, C, B, flags, _ptr(g("rois_pred")), _ptr(g("cls_prob")),
+              _ptr(g("rois_pred_noise")), _ptr(g("cls_prob_noise")), _ptr(g("class_weight")),
+              _ptr(g("class_weight_noise")), _ptr(g("loss")), _ptr(g("d_fc8c")), _ptr(g("d_fc8d")),
+              _ptr(g("d_nfc8c")), _ptr(g("d_nfc8d")), _ptr(ws), _stream())
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# ACMWeightDecayMomentumSGDUpdate
+# --------------------------------------------------------------------------------------------
+def ACMWeightDecayMomentumSGDUpdate(g, m, lr, p, acc, *, momentum=0.9, iter_size=1, gpu_num=1, lr_mult=1.0,
+                                    weight_decay=0.0, iter_count=0, p_bf16=None):
+    """``ACMWeightDecayMomentumSGDUpdate([g, m, lr, p, acc] -> [g, m, p, acc])`` in place
+    (ops/acm_weightdecay_momentum_sgd_op.cc:7-22; wiring modeling/optimizer_wsl.py:127-136).
+    ``iter_count`` replaces the op's hidden ``iter_count_`` member; ``acc`` may be None when
+    iter_size == 1 (the accumulator is then identically zero between calls)."""
+    for t, nme in ((g, "g"), (m, "m"), (p, "p")):
+        _req(t, nme, torch.float32)
+    _req(lr, "lr", torch.float32)
+    if lr.numel() != 1:                               # CAFFE_ENFORCE_EQ(Input(LR).numel(), 1)
+        raise RuntimeError("lr must have one element")
+    if g.numel() != m.numel() or g.numel() != p.numel() or (acc is not None and acc.numel() != g.numel()):
+        raise RuntimeError("g, m, p, acc must have the same number of elements")
+    if p_bf16 is not None:
+        _req(p_bf16, "p_bf16", torch.bfloat16)
+    _lib.call("nawsod_sgd_update", _ptr(g), _ptr(m), _ptr(lr), _ptr(p), _ptr(acc), g.numel(), float(momentum),
+              float(weight_decay), float(lr_mult), int(iter_size), int(gpu_num), int(iter_count), _ptr(p_bf16),
+              _stream())
+    return g, m, p, acc

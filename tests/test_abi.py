@@ -1,0 +1,60 @@
+"""CPU suite: the C-ABI library loads and exports every symbol include/nawsod.h declares
+(no compute calls without a GPU), and the host side fails loudly instead of falling back."""
+import os
+import re
+
+import pytest
+
+import nafwebsod_b200 as pkg
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    hdr = open(os.path.join(ROOT, "include", "nawsod.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return set(re.findall(r"\b(nawsod_[a-z0-9_]+)\s*\(", hdr))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = pkg._lib.load()
+    declared = _declared()
+    assert declared, "no declarations parsed from nawsod.h"
+    assert declared == set(pkg._lib.PROTOTYPES), "ctypes prototypes out of sync with nawsod.h"
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.nawsod_version() >= 100
+
+
+def test_status_codes_and_error_string():
+    lib = pkg._lib.load()
+    assert lib.nawsod_set_tuning(b"no_such_knob", 1) != 0
+    assert b"unknown key" in lib.nawsod_last_error()
+    assert lib.nawsod_set_tuning(b"pool_chunks", 0) == 0
+    # argument validation happens before any CUDA call, so it is testable without a device
+    rc = lib.nawsod_roi_pool_f_fwd(None, 0, 1, None, None, 1, 512, 38, 50, -1, 0.0625, 7, 7, None, 0, 1, None, None)
+    assert rc == 2 and b"bad shape" in lib.nawsod_last_error()
+    rc = lib.nawsod_mil_head_fwd_bwd(*([None] * 7), 10, 500, 1, 0, *([None] * 13))
+    assert rc != 0 and b"C=500" in lib.nawsod_last_error()
+    assert lib.nawsod_mil_workspace_bytes(2000, 20, 1) > 2000 * 20 * 4
+
+
+def test_no_cpu_fallback():
+    import torch
+    from nafwebsod_b200 import ops
+    x = torch.zeros(1, 8, 4, 4)
+    rois = torch.zeros(1, 5)
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        ops.RoIPoolF(x, rois)
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        ops.RoIIoU(rois)
+
+
+def test_product_does_not_import_oracle():
+    pkg_dir = os.path.join(ROOT, "na-fwebsod_b200")
+    for dirpath, _, files in os.walk(pkg_dir):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f
+                assert "oracle/" not in src or f == "build.py", f

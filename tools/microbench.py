@@ -1,0 +1,96 @@
+"""Per-kernel timings on one GPU (CUDA events, L2 flushed between iterations).
+    python tools/microbench.py [pool|poolbwd|mil|sgd|gemm ...]"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import nafwebsod_b200 as pkg  # noqa: E402
+from nafwebsod_b200 import ops  # noqa: E402
+from oracle import nawsod_oracle as O  # noqa: E402
+
+PEAKS = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}
+_flush = None
+
+
+def timeit(fn, iters=20, warmup=3, flush=True):
+    global _flush
+    if _flush is None:
+        _flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    for _ in range(warmup):
+        fn()
+    ts = []
+    for _ in range(iters):
+        if flush:
+            _flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record(); torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    ts.sort()
+    return ts[len(ts) // 2], ts[0]
+
+
+def bench_pool():
+    for (N, R, H, W, dt, train) in [(1, 2000, 38, 50, torch.float32, True), (2, 4000, 38, 50, torch.float32, True),
+                                    (2, 4000, 38, 50, torch.bfloat16, True), (1, 2000, 38, 50, torch.bfloat16, False),
+                                    (1, 4000, 75, 125, torch.float32, True), (1, 4000, 75, 125, torch.bfloat16, False)]:
+        C = 512
+        X = torch.from_numpy(O.synth_conv5(N, C, H, W)).cuda()
+        Xcl = ops.to_channels_last(X, dt)
+        rois = torch.from_numpy(np.concatenate([O.synth_rois(R // N, H * 16, W * 16, b, seed=1 + b) for b in range(N)])).cuda()
+        boost = torch.rand(R, device="cuda") + 1
+        es = 4 if dt == torch.float32 else 2
+        alg = R * (C * 49 * es + (C * 49 * 4 if train else 0) + 20) + N * C * H * W * es
+        for knobs in [dict(), dict(pool_slab_bytes=200 * 1024), dict(pool_slab_bytes=64 * 1024), dict(pool_force_global=1)]:
+            for k, v in knobs.items():
+                pkg.set_tuning(k, v)
+            med, best = timeit(lambda: ops.RoIPoolF(Xcl, rois, boost=boost, is_test=not train, x_layout="NHWC", y_layout="NHWC"))
+            pkg.set_tuning("pool_slab_bytes", 100 * 1024); pkg.set_tuning("pool_force_global", 0)
+            print("pool N=%d R=%d %dx%d %s train=%d %s: med %.1f us best %.1f us  %.0f GB/s (%.1f%% of %.0f)  %.2f M RoIs/s" % (
+                N, R, H, W, str(dt)[6:], train, knobs, med * 1e3, best * 1e3, alg / med / 1e6, 100 * alg / med / 1e6 / PEAKS["hbm_gbs"],
+                PEAKS["hbm_gbs"], R / med / 1e3), flush=True)
+
+
+def bench_poolbwd():
+    N, R, H, W, C = 2, 4000, 38, 50, 512
+    X = torch.from_numpy(O.synth_conv5(N, C, H, W)).cuda()
+    rois = torch.from_numpy(np.concatenate([O.synth_rois(R // N, H * 16, W * 16, b, seed=1 + b) for b in range(N)])).cuda()
+    for lay in ("NHWC", "NCHW"):
+        Y, A = ops.RoIPoolF(X if lay == "NCHW" else ops.to_channels_last(X), rois, x_layout=lay, y_layout=lay)
+        dY = torch.randn_like(Y)
+        Xl = X if lay == "NCHW" else ops.to_channels_last(X)
+        med, best = timeit(lambda: ops.RoIPoolFGradient(Xl, rois, A, dY, layout=lay))
+        alg = R * C * 49 * 8 + N * C * H * W * 4
+        print("poolbwd %s: med %.1f us  %.0f GB/s" % (lay, med * 1e3, alg / med / 1e6), flush=True)
+
+
+def bench_mil():
+    for (R, C, B) in [(4000, 20, 2), (2000, 20, 1), (4000, 80, 1), (8000, 80, 2)]:
+        rois = torch.from_numpy(np.concatenate([O.synth_rois(R // B, 608, 800, b, seed=b) for b in range(B)])).cuda()
+        l = [torch.randn(R, C, device="cuda") for _ in range(4)]
+        L = torch.zeros(B, C, device="cuda"); L[:, 3] = 1
+        offs = torch.tensor([i * (R // B) for i in range(B)] + [R], dtype=torch.int32, device="cuda")
+        for ent in (True, False):
+            med, best = timeit(lambda: ops.mil_head(l[0], l[1], rois, offs, L, l[2], l[3], entropy=ent), flush=False)
+            print("mil R=%d C=%d B=%d entropy=%d: med %.1f us best %.1f us" % (R, C, B, ent, med * 1e3, best * 1e3), flush=True)
+
+
+def bench_sgd():
+    n = 4096 * 25088
+    p, m, g = [torch.randn(n, device="cuda") for _ in range(3)]
+    sh = torch.empty(n, dtype=torch.bfloat16, device="cuda")
+    lr = torch.tensor([1e-3], device="cuda")
+    for shadow in (None, sh):
+        med, best = timeit(lambda: ops.ACMWeightDecayMomentumSGDUpdate(g, m, lr, p, None, weight_decay=5e-4, iter_count=3, p_bf16=shadow), iters=10)
+        byt = n * (20 + (2 if shadow is not None else 0))
+        print("sgd n=%d shadow=%s: med %.1f us  %.0f GB/s (%.1f%%)" % (n, shadow is not None, med * 1e3, byt / med / 1e6, 100 * byt / med / 1e6 / PEAKS["hbm_gbs"]), flush=True)
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["pool", "poolbwd", "mil", "sgd"]
+    for w in which:
+        globals()["bench_" + w]()
