@@ -86,31 +86,45 @@ int nawsod_roi_feature_boost(const float* X, const float* S, int R, int64_t feat
                              float* Y, void* stream);
 
 /* ---------------------------------------------------------------------------------------
- * a4: FC stack GEMMs on the tcgen05 tensor cores (Caffe2 FC / Relu / Dropout as wired by
- *   modeling/wsl_heads.py:674-679 and modeling/webly_heads.py:490-498).
+ * a4: FC stack GEMMs on the tcgen05 tensor cores (Caffe2 FC / Relu / Dropout and their
+ *   gradient ops as wired by modeling/wsl_heads.py:674-679 and modeling/webly_heads.py:490-498).
+ *   Every matrix is row-major with an explicit leading dimension (elements between rows), so
+ *   column slices of a wider buffer (e.g. one stack's half of a fused [R, 8192] activation)
+ *   are addressed without copies.  ab_dtype: NAWSOD_BF16 (bf16 operands, fp32 accumulate) or
+ *   NAWSOD_F32 (operands read as TF32, fp32 accumulate).  Operand base pointers must be
+ *   16-byte aligned and leading dimensions multiples of 16 bytes (TMA).
  *
- * nawsod_fc_fwd:  Y[M,N] = epilogue( A[M,K] . W[N,K]^T + bias[N] )
- *   epilogue flags: NAWSOD_FC_RELU, NAWSOD_FC_DROPOUT (Y *= mask[M,N] * 2, mask uint8 0/1).
- * nawsod_fc_bwd_x: dA[M,K] = dY[M,N] . W[N,K], then optional relu'/dropout of the layer below:
- *   dA *= (act_below[M,K] > 0) and dA *= mask_below[M,K] * 2.
- * nawsod_fc_bwd_w: dW[N,K] (float) = dY[M,N]^T . A[M,K];  db[N] (float) = sum_m dY (or NULL).
- *   ab_dtype: NAWSOD_BF16 (bf16 operands, fp32 accumulate) or NAWSOD_F32 (TF32 tensor path).
- *   workspace: opaque device scratch of at least nawsod_fc_workspace_bytes() bytes.
+ * nawsod_fc_fwd   FC([A, W, b] -> Y) [+ Relu] [+ Dropout]:
+ *     Y[M,N] = epilogue( A[M,K] . W[N,K]^T + bias[N] );  bias may be NULL.
+ *     NAWSOD_FC_RELU: max(.,0).  NAWSOD_FC_DROPOUT: Y *= 2 * mask[M,N] (mask uint8 0/1,
+ *     Caffe2 Dropout ratio 0.5, scale 1/(1-ratio)).
+ * nawsod_fc_bwd_x FCGradient's dX (+ the ReluGradient / DropoutGradient of the layer below):
+ *     dA[M,K] = dY[M,N] . W[N,K];  NAWSOD_FC_RELU: dA *= (act_below[M,K] > 0);
+ *     NAWSOD_FC_DROPOUT: dA *= 2 (and *= mask_below[M,K] when mask_below != NULL; with
+ *     act_below = the post-dropout activation the mask is implied by act_below > 0).
+ * nawsod_fc_bwd_w FCGradient's dW, db:
+ *     dW[N,K] (float) = dY[M,N]^T . A[M,K];  db[N] (float) = sum_m dY[m,:] (db may be NULL).
+ *     NAWSOD_FC_ACCUMULATE: add into dW / db instead of overwriting.
  * ------------------------------------------------------------------------------------- */
 enum { NAWSOD_FC_RELU = 1, NAWSOD_FC_DROPOUT = 2, NAWSOD_FC_ACCUMULATE = 4 };
 
-int64_t nawsod_fc_workspace_bytes(void);
+int nawsod_fc_fwd(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
+                  const uint8_t* mask, int64_t ldmask, int M, int N, int K, int ab_dtype,
+                  void* Y, int64_t ldy, int y_dtype, int flags, void* stream);
 
-int nawsod_fc_fwd(const void* A, const void* W, const float* bias, const uint8_t* mask,
-                  int M, int N, int K, int ab_dtype, void* Y, int y_dtype, int flags,
-                  void* workspace, void* stream);
+int nawsod_fc_bwd_x(const void* dY, int64_t lddy, const void* W, int64_t ldw,
+                    const void* act_below, int64_t ldact, int act_dtype,
+                    const uint8_t* mask_below, int64_t ldmask, int M, int N, int K,
+                    int ab_dtype, void* dA, int64_t ldda, int da_dtype, int flags,
+                    void* stream);
 
-int nawsod_fc_bwd_x(const void* dY, const void* W, const void* act_below,
-                    const uint8_t* mask_below, int M, int N, int K, int ab_dtype, void* dA,
-                    int da_dtype, int flags, void* workspace, void* stream);
+int nawsod_fc_bwd_w(const void* dY, int64_t lddy, const void* A, int64_t lda, int M, int N,
+                    int K, int ab_dtype, float* dW, int64_t lddw, float* db, int flags,
+                    void* stream);
 
-int nawsod_fc_bwd_w(const void* dY, const void* A, int M, int N, int K, int ab_dtype,
-                    float* dW, float* db, int flags, void* workspace, void* stream);
+/* float -> bf16 conversion of a [rows, cols] matrix (operand staging for the GEMMs above). */
+int nawsod_convert_f32_to_bf16(const float* src, int64_t ld_src, int64_t rows, int64_t cols,
+                               void* dst, int64_t ld_dst, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * a5..a9: the two-stream MIL head, noise-aware class weights, weighted multi-label CE and

@@ -27,10 +27,10 @@ PROTOTYPES = {
     "nawsod_roi_pool_f_fwd": (_i, [_vp, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _i, _vp, _i, _i, _vp, _vp]),
     "nawsod_roi_pool_f_bwd": (_i, [_vp, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp]),
     "nawsod_roi_feature_boost": (_i, [_vp, _vp, _i, _i64, _vp, _vp]),
-    "nawsod_fc_workspace_bytes": (_i64, []),
-    "nawsod_fc_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _vp, _vp]),
-    "nawsod_fc_bwd_x": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _vp, _vp]),
-    "nawsod_fc_bwd_w": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
+    "nawsod_fc_fwd": (_i, [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _vp, _i64, _i, _i, _vp]),
+    "nawsod_fc_bwd_x": (_i, [_vp, _i64, _vp, _i64, _vp, _i64, _i, _vp, _i64, _i, _i, _i, _i, _vp, _i64, _i, _i, _vp]),
+    "nawsod_fc_bwd_w": (_i, [_vp, _i64, _vp, _i64, _i, _i, _i, _i, _vp, _i64, _vp, _i, _vp]),
+    "nawsod_convert_f32_to_bf16": (_i, [_vp, _i64, _i64, _i64, _vp, _i64, _vp]),
     "nawsod_mil_workspace_bytes": (_i64, [_i, _i, _i]),
     "nawsod_mil_head_fwd_bwd": (_i, [_vp] * 7 + [_i, _i, _i, _i] + [_vp] * 13),
     "nawsod_roi_iou": (_i, [_vp, _i, _vp, _vp]),

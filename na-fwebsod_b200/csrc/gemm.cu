@@ -1,10 +1,568 @@
-// placeholder: tcgen05 FC GEMMs land here
+// FC-stack GEMMs on the 5th-generation tensor cores (tcgen05 + TMEM) fed by TMA, sm_100a.
+//
+// Replaces Caffe2 FC / FCGradient (cuBLAS sgemm in the reference) + Relu + Dropout and their
+// gradient ops as wired by detectron/modeling/wsl_heads.py:674-679 and
+// detectron/modeling/webly_heads.py:490-498.  One persistent, warp-specialised kernel serves
+// all three GEMM shapes of a layer:
+//     fwd    Y [M,N]  = A[M,K]  . W[N,K]^T     A: K-major,  B = W : K-major
+//     bwd_x  dA[M,K]  = dY[M,N] . W[N,K]       A: K-major,  B = W : MN-major (no transposed copy)
+//     bwd_w  dW[N,K]  = dY[M,N]^T . A[M,K]     A = dY: MN-major, B = A: MN-major
+// so no operand is ever transposed in memory: MN-major operands are described to the tensor
+// core through the UMMA shared-memory descriptor (a_major / b_major bits) and loaded by TMA as
+// 128-byte-wide column panels.
+//
+// Kernel anatomy (192 threads, one CTA per SM, persistent over output tiles):
+//   warp 0      TMA producer: cp.async.bulk.tensor.2d into a kStages-deep 128B-swizzled smem ring
+//   warp 1      MMA issuer: one lane issues tcgen05.mma (M=128, N=BN, K=32 bytes) into a
+//               double-buffered TMEM accumulator (2 x BN fp32 columns); tcgen05.commit releases
+//               smem slots and publishes finished accumulators
+//   warps 2..5  epilogue: tcgen05.ld (32 lanes x 32 columns) -> bias / ReLU / dropout /
+//               ReLU-gradient -> bf16 or fp32 stores; overlaps the next tile's main loop
+#include <cuda.h>
+#include <algorithm>
+#include <mutex>
 #include "common.cuh"
+
+namespace nawsod {
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int kNumThreads = 192;
+constexpr int kSmemBudget = 220 * 1024;
+
+struct EpiParams {
+  void* out; long long ldo; int out_dtype;
+  const float* bias;
+  const uint8_t* mask; long long ldmask;
+  const void* act; long long ldact; int act_dtype;
+  int flags;
+  int M, N, K;          // GEMM dims: out is [M, N], reduction over K
+};
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+template <int ES>
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  if (ES == 2) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+  } else {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+  }
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor bit layout): start>>4 [0,14),
+// LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout SWIZZLE_128B=2 [61,64).
+// layout: 2 = SWIZZLE_128B (16-byte atoms), 1 = SWIZZLE_128B_BASE32B (32-byte atoms; the layout
+// an MN-major operand of 4-byte elements must use: Swizzle<2,5,2>, 4-row k-groups).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= 1ull << 46;
+  d |= static_cast<uint64_t>(layout) << 61;
+  return d;
+}
+
+// Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32=1 [4,6), a/b format
+// (BF16=1, TF32=2) [7,10)/[10,13), a_major bit 15, b_major bit 16 (1 = MN-major),
+// N>>3 [17,23), M>>4 [24,29).
+__host__ __device__ constexpr uint32_t make_idesc(int es, bool a_mn, bool b_mn, int m, int n) {
+  return (1u << 4) | ((es == 2 ? 1u : 2u) << 7) | ((es == 2 ? 1u : 2u) << 10) | ((a_mn ? 1u : 0u) << 15) |
+         ((b_mn ? 1u : 0u) << 16) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
+
+__device__ __forceinline__ float ld_act(const void* act, int act_dtype, size_t i) {
+  return act_dtype == NAWSOD_BF16 ? __bfloat162float(static_cast<const __nv_bfloat16*>(act)[i])
+                                  : static_cast<const float*>(act)[i];
+}
+
+template <int BN, int ES> struct Cfg {
+  static constexpr int BK = 128 / ES;                        // elements per k-block (one 128-byte swizzle atom)
+  static constexpr int UMMA_K = 32 / ES;
+  static constexpr int A_BYTES = BLOCK_M * 128;
+  static constexpr int B_BYTES = BN * 128;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (kSmemBudget / STAGE_BYTES) > 8 ? 8 : (kSmemBudget / STAGE_BYTES);
+  static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+template <int BN, bool A_MN, bool B_MN, int ES>
+__global__ void __launch_bounds__(kNumThreads, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const EpiParams ep) {
+  using C = Cfg<BN, ES>;
+  constexpr int BK = C::BK;
+  constexpr int ATOM = 128 / ES;                 // MN elements per 128-byte panel
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + C::STAGES * C::STAGE_BYTES;
+  // barrier layout (8 bytes each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then the TMEM pointer
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * C::STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * C::STAGES + 2 + a); };
+  const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * C::STAGES + 4);
+  volatile uint32_t* tmem_ptr_generic =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_m = (ep.M + BLOCK_M - 1) / BLOCK_M;
+  const int num_n = (ep.N + BN - 1) / BN;
+  const int num_tiles = num_m * num_n;
+  const int num_kb = (ep.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < C::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"(C::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_generic;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile % num_m) * BLOCK_M, n0 = (tile / num_m) * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t sa = smem_base + stage * C::STAGE_BYTES, sb = sa + C::A_BYTES;
+          mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
+          const int k0 = kb * BK;
+          if (!A_MN) tma_load_2d(sa, &tmA, full_bar(stage), k0, m0);
+          else {
+#pragma unroll
+            for (int a = 0; a < BLOCK_M / ATOM; ++a) tma_load_2d(sa + a * BK * 128, &tmA, full_bar(stage), m0 + a * ATOM, k0);
+          }
+          if (!B_MN) tma_load_2d(sb, &tmB, full_bar(stage), k0, n0);
+          else {
+#pragma unroll
+            for (int a = 0; a < BN / ATOM; ++a) tma_load_2d(sb + a * BK * 128, &tmB, full_bar(stage), n0 + a * ATOM, k0);
+          }
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(ES, A_MN, B_MN, BLOCK_M, BN);
+      // K-major: 8-row groups 1024 B apart (SBO), LBO unused; MN-major: 128-byte panels BK*128 B apart (LBO),
+      // 8-row k-groups 1024 B apart (SBO)
+      constexpr uint32_t a_lbo = A_MN ? BK * 128 : 16, b_lbo = B_MN ? BK * 128 : 16;
+      // 4-byte MN-major operands: 32-byte swizzle atoms, k-groups of 4 rows (512 B apart)
+      constexpr uint32_t a_lay = (A_MN && ES == 4) ? 1 : 2, b_lay = (B_MN && ES == 4) ? 1 : 2;
+      constexpr uint32_t a_sbo = (A_MN && ES == 4) ? 512 : 1024, b_sbo = (B_MN && ES == 4) ? 512 : 1024;
+      constexpr uint32_t a_kstep = A_MN ? (C::UMMA_K * 128) >> 4 : 32 >> 4;   // descriptor start-address step per UMMA_K
+      constexpr uint32_t b_kstep = B_MN ? (C::UMMA_K * 128) >> 4 : 32 >> 4;
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * C::STAGE_BYTES, sb = sa + C::A_BYTES;
+          const uint64_t adesc = make_smem_desc(sa, a_lbo, a_sbo, a_lay), bdesc = make_smem_desc(sb, b_lbo, b_sbo, b_lay);
+#pragma unroll
+          for (int k = 0; k < BK / C::UMMA_K; ++k)
+            tc_mma<ES>(tmem_d, adesc + (uint64_t)(k * a_kstep), bdesc + (uint64_t)(k * b_kstep), idesc, (kb | k) != 0);
+          tc_commit(empty_bar(stage));
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(tfull_bar(acc));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ================= epilogue (warps 2..5) =================
+    const int q = warp & 3;                       // TMEM lane quarter this warp may access
+    int acc = 0; uint32_t acc_phase = 0;
+    const bool vec_ok = ((ep.ldo * (ep.out_dtype == NAWSOD_F32 ? 4 : 2)) % 16 == 0) &&
+                        ((reinterpret_cast<uintptr_t>(ep.out) & 15u) == 0);
+    const bool bias_vec = ep.bias && (reinterpret_cast<uintptr_t>(ep.bias) & 15u) == 0;
+    const bool act_vec = ep.act && (reinterpret_cast<uintptr_t>(ep.act) & 15u) == 0 && (ep.ldact * 2) % 16 == 0;
+    const bool mask_vec = ep.mask && (reinterpret_cast<uintptr_t>(ep.mask) & 15u) == 0 && ep.ldmask % 16 == 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile % num_m) * BLOCK_M, n0 = (tile / num_m) * BN;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const int m = m0 + q * 32 + lane;
+      const bool row_ok = m < ep.M;
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        if (n0 + c >= ep.N) break;                // warp-uniform
+        uint32_t r[32];
+        __syncwarp();                             // tcgen05.ld is .sync.aligned: the warp must be converged
+        tc_ld32(tmem_base + acc * BN + c + (static_cast<uint32_t>(q * 32) << 16), r);
+        tc_wait_ld();
+        const int n = n0 + c;
+        const int ncols = min(32, ep.N - n);
+        if (row_ok) {
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+          const bool full = ncols == 32;
+          if (ep.bias) {
+            if (full && bias_vec) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + n + i));
+                v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) if (i < ncols) v[i] += __ldg(ep.bias + n + i);
+            }
+          }
+          if (ep.flags & NAWSOD_FC_RELU) {
+            if (ep.act) {
+              if (full && act_vec && ep.act_dtype == NAWSOD_BF16) {
+                const uint4* ap = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(ep.act) + (size_t)m * ep.ldact + n);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const uint4 a4 = ap[i];
+                  const uint32_t w[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    // bf16 > 0  <=>  sign bit clear and magnitude non-zero
+                    if (!((w[j] & 0x8000u) == 0 && (w[j] & 0x7FFFu) != 0)) v[i * 8 + j * 2] = 0.f;
+                    if (!((w[j] & 0x80000000u) == 0 && (w[j] & 0x7FFF0000u) != 0)) v[i * 8 + j * 2 + 1] = 0.f;
+                  }
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                  if (i < ncols) v[i] = ld_act(ep.act, ep.act_dtype, (size_t)m * ep.ldact + n + i) > 0.f ? v[i] : 0.f;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+            }
+          }
+          if (ep.flags & NAWSOD_FC_DROPOUT) {
+            if (ep.mask) {
+              if (full && mask_vec) {
+                const uint4* mp = reinterpret_cast<const uint4*>(ep.mask + (size_t)m * ep.ldmask + n);
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                  const uint4 m4 = mp[i];
+                  const uint32_t w[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+                  for (int j = 0; j < 16; ++j)
+                    v[i * 16 + j] *= 2.0f * static_cast<float>((w[j >> 2] >> (8 * (j & 3))) & 0xFFu);
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) if (i < ncols) v[i] *= 2.0f * static_cast<float>(ep.mask[(size_t)m * ep.ldmask + n + i]);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] *= 2.0f;
+            }
+          }
+          if (ep.out_dtype == NAWSOD_F32) {
+            float* o = static_cast<float*>(ep.out) + (size_t)m * ep.ldo + n;
+            if (ep.flags & NAWSOD_FC_ACCUMULATE) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) if (i < ncols) v[i] += o[i];
+            }
+            if (vec_ok && full) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) if (i < ncols) o[i] = v[i];
+            }
+          } else {
+            __nv_bfloat16* o = static_cast<__nv_bfloat16*>(ep.out) + (size_t)m * ep.ldo + n;
+            if (vec_ok && full) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 8) {
+                __nv_bfloat162 h0 = __floats2bfloat162_rn(v[i], v[i + 1]), h1 = __floats2bfloat162_rn(v[i + 2], v[i + 3]);
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(v[i + 4], v[i + 5]), h3 = __floats2bfloat162_rn(v[i + 6], v[i + 7]);
+                *reinterpret_cast<uint4*>(o + i) = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
+                                                              *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) if (i < ncols) o[i] = __float2bfloat16_rn(v[i]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// small helpers: column sums (bias gradient) and float -> bf16 conversion
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ X, long long ld, int M, int N, int rows_per_block,
+                                                    float* __restrict__ out) {
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int n = blockIdx.x * 32 + tx;
+  const int r0 = blockIdx.y * rows_per_block, r1 = min(M, r0 + rows_per_block);
+  float s = 0.f;
+  if (n < N)
+    for (int r = r0 + ty; r < r1; r += 8) {
+      const T x = X[(size_t)r * ld + n];
+      if constexpr (sizeof(T) == 2) s += __uint_as_float(static_cast<uint32_t>(x) << 16);
+      else s += x;
+    }
+  red[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && n < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][tx];
+    atomicAdd(out + n, t);
+  }
+}
+
+__global__ void __launch_bounds__(256) cvt_bf16_kernel(const float* __restrict__ src, long long ld_src, long long rows, long long cols,
+                                                      __nv_bfloat16* __restrict__ dst, long long ld_dst) {
+  const long long total = rows * cols;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols, c = i - r * cols;
+    dst[r * ld_dst + c] = __float2bfloat16_rn(src[r * ld_src + c]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// Row-major matrix [rows, cols] with leading dimension ld; box = [box_rows, box_cols] (cols innermost, 128 bytes).
+int make_tmap(CUtensorMap* map, const void* ptr, int es, long long rows, long long cols, long long ld, int box_rows,
+              int box_cols, bool atom32) {
+  EncodeTiledFn fn = get_encode_fn();
+  NAWSOD_REQUIRE(fn != nullptr, NAWSOD_ERR_CUDA, "cuTensorMapEncodeTiled is not available (no CUDA driver?)");
+  NAWSOD_REQUIRE(aligned16(ptr), NAWSOD_ERR_ALIGN, "fc: operand pointer must be 16-byte aligned");
+  NAWSOD_REQUIRE((ld * es) % 16 == 0 && ld >= cols, NAWSOD_ERR_ALIGN,
+                 "fc: leading dimension %lld (x%d bytes) must be >= cols and a multiple of 16 bytes", ld, es);
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * es};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, es == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr),
+                  gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  NAWSOD_REQUIRE(r == CUDA_SUCCESS, NAWSOD_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d", (int)r);
+  return NAWSOD_OK;
+}
+
+template <int BN, bool A_MN, bool B_MN, int ES>
+int launch_gemm(const void* A, long long lda, const void* B, long long ldb, const EpiParams& ep, cudaStream_t st) {
+  using C = Cfg<BN, ES>;
+  constexpr int ATOM = 128 / ES;
+  CUtensorMap tmA, tmB;
+  int rc;
+  // K-major operand: stored [MN, K]; box [BLOCK rows, BK].  MN-major operand: stored [K, MN]; box [BK rows, ATOM].
+  if (!A_MN) rc = make_tmap(&tmA, A, ES, ep.M, ep.K, lda, BLOCK_M, C::BK, false);
+  else rc = make_tmap(&tmA, A, ES, ep.K, ep.M, lda, C::BK, ATOM, ES == 4);
+  if (rc) return rc;
+  if (!B_MN) rc = make_tmap(&tmB, B, ES, ep.N, ep.K, ldb, BN, C::BK, false);
+  else rc = make_tmap(&tmB, B, ES, ep.K, ep.N, ldb, C::BK, ATOM, ES == 4);
+  if (rc) return rc;
+  auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, ES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    NAWSOD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int num_tiles = ((ep.M + BLOCK_M - 1) / BLOCK_M) * ((ep.N + BN - 1) / BN);
+  const int grid = std::min(num_tiles, sm_count());
+  kern<<<grid, kNumThreads, C::SMEM_BYTES, st>>>(tmA, tmB, ep);
+  NAWSOD_LAUNCH_OK();
+  return NAWSOD_OK;
+}
+
+template <bool A_MN, bool B_MN>
+int dispatch_gemm(const void* A, long long lda, const void* B, long long ldb, const EpiParams& ep, int ab_dtype, cudaStream_t st) {
+  // BN = 256 for wide outputs; narrower tiles only when N itself is narrow (fc8: N = 2C)
+  const int bn = ep.N > 128 ? 256 : (ep.N > 64 ? 128 : 64);
+  if (ab_dtype == NAWSOD_BF16) {
+    if (bn == 256) return launch_gemm<256, A_MN, B_MN, 2>(A, lda, B, ldb, ep, st);
+    if (bn == 128) return launch_gemm<128, A_MN, B_MN, 2>(A, lda, B, ldb, ep, st);
+    return launch_gemm<64, A_MN, B_MN, 2>(A, lda, B, ldb, ep, st);
+  }
+  if (bn == 256) return launch_gemm<256, A_MN, B_MN, 4>(A, lda, B, ldb, ep, st);
+  if (bn == 128) return launch_gemm<128, A_MN, B_MN, 4>(A, lda, B, ldb, ep, st);
+  return launch_gemm<64, A_MN, B_MN, 4>(A, lda, B, ldb, ep, st);
+}
+
+int check_common(const char* who, int M, int N, int K, int ab_dtype) {
+  NAWSOD_REQUIRE(M > 0 && N > 0 && K > 0, NAWSOD_ERR_SHAPE, "%s: need M, N, K > 0 (got %d, %d, %d)", who, M, N, K);
+  NAWSOD_REQUIRE(ab_dtype == NAWSOD_BF16 || ab_dtype == NAWSOD_F32, NAWSOD_ERR_ARG, "%s: bad ab_dtype", who);
+  return NAWSOD_OK;
+}
+
+}  // namespace
+}  // namespace nawsod
+
 using namespace nawsod;
-extern "C" int64_t nawsod_fc_workspace_bytes(void) { return 0; }
-extern "C" int nawsod_fc_fwd(const void*, const void*, const float*, const uint8_t*, int, int, int, int, void*, int, int,
-                             void*, void*) { set_error("fc_fwd: not built"); return NAWSOD_ERR_UNSUPPORTED; }
-extern "C" int nawsod_fc_bwd_x(const void*, const void*, const void*, const uint8_t*, int, int, int, int, void*, int,
-                               int, void*, void*) { set_error("fc_bwd_x: not built"); return NAWSOD_ERR_UNSUPPORTED; }
-extern "C" int nawsod_fc_bwd_w(const void*, const void*, int, int, int, int, float*, float*, int, void*, void*) {
-  set_error("fc_bwd_w: not built"); return NAWSOD_ERR_UNSUPPORTED; }
+
+extern "C" int nawsod_fc_fwd(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, const uint8_t* mask,
+                             int64_t ldmask, int M, int N, int K, int ab_dtype, void* Y, int64_t ldy, int y_dtype, int flags,
+                             void* stream) {
+  if (int rc = check_common("fc_fwd", M, N, K, ab_dtype)) return rc;
+  NAWSOD_REQUIRE(A && W && Y, NAWSOD_ERR_ARG, "fc_fwd: null pointer");
+  NAWSOD_REQUIRE(y_dtype == NAWSOD_F32 || y_dtype == NAWSOD_BF16, NAWSOD_ERR_ARG, "fc_fwd: bad y_dtype");
+  NAWSOD_REQUIRE(!(flags & NAWSOD_FC_ACCUMULATE), NAWSOD_ERR_ARG, "fc_fwd: ACCUMULATE is a bwd_w flag");
+  NAWSOD_REQUIRE(ldy >= N && (!mask || ldmask >= N), NAWSOD_ERR_SHAPE, "fc_fwd: ldy / ldmask smaller than N");
+  EpiParams ep{};
+  ep.out = Y; ep.ldo = ldy; ep.out_dtype = y_dtype; ep.bias = bias; ep.mask = (flags & NAWSOD_FC_DROPOUT) ? mask : nullptr;
+  ep.ldmask = ldmask; ep.act = nullptr; ep.flags = flags; ep.M = M; ep.N = N; ep.K = K;
+  return dispatch_gemm<false, false>(A, lda, W, ldw, ep, ab_dtype, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int nawsod_fc_bwd_x(const void* dY, int64_t lddy, const void* W, int64_t ldw, const void* act_below, int64_t ldact,
+                               int act_dtype, const uint8_t* mask_below, int64_t ldmask, int M, int N, int K, int ab_dtype,
+                               void* dA, int64_t ldda, int da_dtype, int flags, void* stream) {
+  if (int rc = check_common("fc_bwd_x", M, N, K, ab_dtype)) return rc;
+  NAWSOD_REQUIRE(dY && W && dA, NAWSOD_ERR_ARG, "fc_bwd_x: null pointer");
+  NAWSOD_REQUIRE(da_dtype == NAWSOD_F32 || da_dtype == NAWSOD_BF16, NAWSOD_ERR_ARG, "fc_bwd_x: bad da_dtype");
+  NAWSOD_REQUIRE(!(flags & NAWSOD_FC_RELU) || act_below, NAWSOD_ERR_ARG, "fc_bwd_x: RELU needs act_below");
+  NAWSOD_REQUIRE(!(flags & NAWSOD_FC_ACCUMULATE), NAWSOD_ERR_ARG, "fc_bwd_x: ACCUMULATE is a bwd_w flag");
+  NAWSOD_REQUIRE(ldda >= K, NAWSOD_ERR_SHAPE, "fc_bwd_x: ldda smaller than K");
+  EpiParams ep{};
+  // GEMM view: out [M, K] = dY [M, N] . W [N, K]  -> reduction over N, "N" of the GEMM is K
+  ep.out = dA; ep.ldo = ldda; ep.out_dtype = da_dtype; ep.bias = nullptr;
+  ep.mask = (flags & NAWSOD_FC_DROPOUT) ? mask_below : nullptr; ep.ldmask = ldmask;
+  ep.act = (flags & NAWSOD_FC_RELU) ? act_below : nullptr; ep.ldact = ldact; ep.act_dtype = act_dtype;
+  ep.flags = flags; ep.M = M; ep.N = K; ep.K = N;
+  return dispatch_gemm<false, true>(dY, lddy, W, ldw, ep, ab_dtype, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int nawsod_fc_bwd_w(const void* dY, int64_t lddy, const void* A, int64_t lda, int M, int N, int K, int ab_dtype,
+                               float* dW, int64_t lddw, float* db, int flags, void* stream) {
+  if (int rc = check_common("fc_bwd_w", M, N, K, ab_dtype)) return rc;
+  NAWSOD_REQUIRE(dY && A && dW, NAWSOD_ERR_ARG, "fc_bwd_w: null pointer");
+  NAWSOD_REQUIRE(lddw >= K, NAWSOD_ERR_SHAPE, "fc_bwd_w: lddw smaller than K");
+  NAWSOD_REQUIRE(!(flags & (NAWSOD_FC_RELU | NAWSOD_FC_DROPOUT)), NAWSOD_ERR_ARG, "fc_bwd_w: only ACCUMULATE is valid");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  EpiParams ep{};
+  // GEMM view: out [N, K] = dY^T [N, M] . A [M, K] -> reduction over M
+  ep.out = dW; ep.ldo = lddw; ep.out_dtype = NAWSOD_F32; ep.flags = flags; ep.M = N; ep.N = K; ep.K = M;
+  if (int rc = dispatch_gemm<true, true>(dY, lddy, A, lda, ep, ab_dtype, st)) return rc;
+  if (db) {
+    if (!(flags & NAWSOD_FC_ACCUMULATE)) NAWSOD_CUDA_OK(cudaMemsetAsync(db, 0, (size_t)N * sizeof(float), st));
+    const int row_blocks = std::max(1, std::min(64, M / 64));
+    const int rpb = (M + row_blocks - 1) / row_blocks;
+    dim3 grid((N + 31) / 32, row_blocks);
+    if (ab_dtype == NAWSOD_BF16)
+      colsum_kernel<uint16_t><<<grid, 256, 0, st>>>(static_cast<const uint16_t*>(dY), lddy, M, N, rpb, db);
+    else
+      colsum_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(dY), lddy, M, N, rpb, db);
+    NAWSOD_LAUNCH_OK();
+  }
+  return NAWSOD_OK;
+}
+
+extern "C" int nawsod_convert_f32_to_bf16(const float* src, int64_t ld_src, int64_t rows, int64_t cols, void* dst, int64_t ld_dst,
+                                          void* stream) {
+  NAWSOD_REQUIRE(rows >= 0 && cols >= 0 && ld_src >= cols && ld_dst >= cols, NAWSOD_ERR_SHAPE, "convert: bad shape");
+  if (rows == 0 || cols == 0) return NAWSOD_OK;
+  NAWSOD_REQUIRE(src && dst, NAWSOD_ERR_ARG, "convert: null pointer");
+  const long long total = rows * cols;
+  const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)sm_count() * 8);
+  cvt_bf16_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, ld_src, rows, cols, static_cast<__nv_bfloat16*>(dst), ld_dst);
+  NAWSOD_LAUNCH_OK();
+  return NAWSOD_OK;
+}

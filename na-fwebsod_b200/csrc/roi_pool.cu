@@ -303,10 +303,10 @@ using namespace nawsod;
 
 extern "C" int nawsod_transpose_batched(const void* in, int64_t B, int64_t rows, int64_t cols, void* out,
                                         int out_dtype, void* stream) {
-  NAWSOD_REQUIRE(in && out, NAWSOD_ERR_ARG, "transpose: null pointer");
   NAWSOD_REQUIRE(B >= 0 && rows >= 0 && cols >= 0, NAWSOD_ERR_SHAPE, "transpose: negative size");
   NAWSOD_REQUIRE(out_dtype == NAWSOD_F32 || out_dtype == NAWSOD_BF16, NAWSOD_ERR_ARG, "transpose: bad out_dtype");
   if (B == 0 || rows == 0 || cols == 0) return NAWSOD_OK;
+  NAWSOD_REQUIRE(in && out, NAWSOD_ERR_ARG, "transpose: null pointer");
   NAWSOD_REQUIRE(B <= 65535, NAWSOD_ERR_SHAPE, "transpose: batch %lld > 65535", (long long)B);
   dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32), (unsigned)B), block(32, 8);
   NAWSOD_REQUIRE(grid.y <= 65535, NAWSOD_ERR_SHAPE, "transpose: too many rows");

@@ -306,3 +306,102 @@ def ACMWeightDecayMomentumSGDUpdate(g, m, lr, p, acc, *, momentum=0.9, iter_size
               float(weight_decay), float(lr_mult), int(iter_size), int(gpu_num), int(iter_count), _ptr(p_bf16),
               _stream())
     return g, m, p, acc
+
+
+# --------------------------------------------------------------------------------------------
+# FC / FCGradient on the tcgen05 tensor cores (+ fused Relu / Dropout and their gradients)
+# --------------------------------------------------------------------------------------------
+def _mat(t, name):
+    """2-D matrix view: rows, cols, leading dimension (elements).  Column slices are allowed."""
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError("%s must be a CUDA tensor (libnawsod has no CPU path)" % name)
+    if t.dim() != 2 or t.stride(1) != 1:
+        raise RuntimeError("%s must be a row-major 2-d matrix (unit column stride)" % name)
+    return t.shape[0], t.shape[1], t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1])
+
+
+def _ab(dtype):
+    if dtype not in _DT:
+        raise RuntimeError("FC operands must be float32 (TF32 path) or bfloat16, got %s" % dtype)
+    return _DT[dtype]
+
+
+def FC(X, W, b=None, *, relu=False, dropout_mask=None, dropout=False, out=None, out_dtype=None):
+    """``FC([X, W, b] -> Y)`` with W [out, in] (Caffe2 layout), optionally fused with the
+    ``Relu`` and ``Dropout(ratio=0.5, is_test=0)`` that follow it in the head
+    (modeling/wsl_heads.py:674-679).  X may be a column slice of a wider matrix."""
+    M, K, lda = _mat(X, "X")
+    N, K2, ldw = _mat(W, "W")
+    if K != K2 or X.dtype != W.dtype:
+        raise RuntimeError("FC: X [%d,%d] %s and W [%d,%d] %s do not match" % (M, K, X.dtype, N, K2, W.dtype))
+    if b is not None:
+        _req(b, "b", torch.float32)
+        if b.numel() != N:
+            raise RuntimeError("FC: bias must have %d elements" % N)
+    out_dtype = out_dtype or (out.dtype if out is not None else X.dtype)
+    Y = torch.empty((M, N), dtype=out_dtype, device=X.device) if out is None else out
+    _, N2, ldy = _mat(Y, "Y")
+    if N2 != N or Y.shape[0] != M:
+        raise RuntimeError("FC: out has the wrong shape")
+    flags = (_lib.FC_RELU if relu else 0) | (_lib.FC_DROPOUT if (dropout or dropout_mask is not None) else 0)
+    ldm = 0
+    if dropout_mask is not None:
+        if dropout_mask.dtype != torch.uint8:
+            raise RuntimeError("dropout_mask must be uint8 (0/1)")
+        _, _, ldm = _mat(dropout_mask, "dropout_mask")
+    _lib.call("nawsod_fc_fwd", _ptr(X), lda, _ptr(W), ldw, _ptr(b), _ptr(dropout_mask), ldm, M, N, K, _ab(X.dtype),
+              _ptr(Y), ldy, _DT[Y.dtype], flags, _stream())
+    return Y
+
+
+def FCGradientX(dY, W, *, act_below=None, mask_below=None, dropout=False, out=None, out_dtype=None):
+    """dX of ``FCGradient([X, W, dY] -> [dW, db, dX])`` fused with the ``DropoutGradient`` and
+    ``ReluGradient`` of the layer below: dX = (dY . W) * 2[dropout] * (act_below > 0)."""
+    M, N, lddy = _mat(dY, "dY")
+    N2, K, ldw = _mat(W, "W")
+    if N != N2 or dY.dtype != W.dtype:
+        raise RuntimeError("FCGradientX: dY and W do not match")
+    out_dtype = out_dtype or (out.dtype if out is not None else dY.dtype)
+    dX = torch.empty((M, K), dtype=out_dtype, device=dY.device) if out is None else out
+    _, K2, ldda = _mat(dX, "dX")
+    if K2 != K or dX.shape[0] != M:
+        raise RuntimeError("FCGradientX: out has the wrong shape")
+    flags = (_lib.FC_RELU if act_below is not None else 0) | (_lib.FC_DROPOUT if (dropout or mask_below is not None) else 0)
+    ldact, act_dt, ldm = 0, F32, 0
+    if act_below is not None:
+        _, _, ldact = _mat(act_below, "act_below")
+        act_dt = _DT[act_below.dtype]
+    if mask_below is not None:
+        _, _, ldm = _mat(mask_below, "mask_below")
+    _lib.call("nawsod_fc_bwd_x", _ptr(dY), lddy, _ptr(W), ldw, _ptr(act_below), ldact, act_dt, _ptr(mask_below), ldm,
+              M, N, K, _ab(dY.dtype), _ptr(dX), ldda, _DT[dX.dtype], flags, _stream())
+    return dX
+
+
+def FCGradientW(dY, X, *, dW=None, db=None, want_db=True, accumulate=False):
+    """dW, db of ``FCGradient``: dW [N,K] = dY^T . X (float32), db [N] = column sums of dY."""
+    M, N, lddy = _mat(dY, "dY")
+    M2, K, lda = _mat(X, "X")
+    if M != M2 or dY.dtype != X.dtype:
+        raise RuntimeError("FCGradientW: dY and X do not match")
+    if dW is None:
+        dW = torch.empty((N, K), dtype=torch.float32, device=dY.device)
+    _, _, lddw = _mat(dW, "dW")
+    if dW.dtype != torch.float32 or tuple(dW.shape) != (N, K):
+        raise RuntimeError("FCGradientW: dW must be float32 [%d,%d]" % (N, K))
+    if db is None and want_db:
+        db = torch.empty((N,), dtype=torch.float32, device=dY.device)
+    _lib.call("nawsod_fc_bwd_w", _ptr(dY), lddy, _ptr(X), lda, M, N, K, _ab(dY.dtype), _ptr(dW), lddw, _ptr(db),
+              _lib.FC_ACCUMULATE if accumulate else 0, _stream())
+    return dW, db
+
+
+def to_bf16(src, out=None):
+    """float32 [rows, cols] (may be a column slice) -> bfloat16, by the library's conversion kernel."""
+    rows, cols, lds = _mat(src, "src")
+    if src.dtype != torch.float32:
+        raise RuntimeError("to_bf16: source must be float32")
+    dst = torch.empty((rows, cols), dtype=torch.bfloat16, device=src.device) if out is None else out
+    _, _, ldd = _mat(dst, "dst")
+    _lib.call("nawsod_convert_f32_to_bf16", _ptr(src), lds, rows, cols, _ptr(dst), ldd, _stream())
+    return dst

@@ -90,6 +90,33 @@ def bench_sgd():
         print("sgd n=%d shadow=%s: med %.1f us  %.0f GB/s (%.1f%%)" % (n, shadow is not None, med * 1e3, byt / med / 1e6, 100 * byt / med / 1e6 / PEAKS["hbm_gbs"]), flush=True)
 
 
+
+
+def bench_gemm():
+    def run(name, M, N, K, fn, flops=None):
+        med, best = timeit(fn, iters=10, warmup=3, flush=False)
+        fl = flops or 2.0 * M * N * K
+        print("gemm %-22s M=%d N=%d K=%d: med %.1f us best %.1f us  %.0f TFLOP/s (%.1f%% of %.0f)" % (
+            name, M, N, K, med * 1e3, best * 1e3, fl / med / 1e9, 100 * fl / med / 1e9 / PEAKS["bf16_tflops"], PEAKS["bf16_tflops"]), flush=True)
+    bf = torch.bfloat16
+    for (M, N, K) in [(4000, 8192, 25088), (4000, 4096, 4096), (4096, 4096, 4096), (8192, 8192, 8192)]:
+        X = (torch.randn(M, K, device="cuda") * 0.5).to(bf)
+        W = (torch.randn(N, K, device="cuda") * 0.02).to(bf)
+        b = torch.zeros(N, device="cuda")
+        Y = torch.empty(M, N, device="cuda", dtype=bf)
+        run("fwd bias+relu", M, N, K, lambda: ops.FC(X, W, b, relu=True, dropout=True, out=Y))
+        run("torch.matmul (cuBLAS)", M, N, K, lambda: torch.matmul(X, W.t()))
+        if K <= 8192:
+            dA = torch.empty(M, K, device="cuda", dtype=bf)
+            run("bwd_x", M, N, K, lambda: ops.FCGradientX(Y, W, act_below=X, dropout=True, out=dA))
+        dW = torch.empty(N, K, device="cuda")
+        run("bwd_w", M, N, K, lambda: ops.FCGradientW(Y, X, dW=dW, want_db=False))
+        del X, W, Y, dW
+    Xf = torch.randn(4000, 4096, device="cuda"); Wf = torch.randn(4096, 4096, device="cuda") * 0.02
+    Yf = torch.empty(4000, 4096, device="cuda")
+    run("fwd tf32", 4000, 4096, 4096, lambda: ops.FC(Xf, Wf, None, out=Yf))
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["pool", "poolbwd", "mil", "sgd"]
     for w in which:
