@@ -96,8 +96,9 @@ int nawsod_roi_feature_boost(const float* X, const float* S, int R, int64_t feat
  *
  * nawsod_fc_fwd   FC([A, W, b] -> Y) [+ Relu] [+ Dropout]:
  *     Y[M,N] = epilogue( A[M,K] . W[N,K]^T + bias[N] );  bias may be NULL.
- *     NAWSOD_FC_RELU: max(.,0).  NAWSOD_FC_DROPOUT: Y *= 2 * mask[M,N] (mask uint8 0/1,
- *     Caffe2 Dropout ratio 0.5, scale 1/(1-ratio)).
+ *     NAWSOD_FC_RELU: max(.,0).  NAWSOD_FC_DROPOUT: Y *= 2 * keep[M,N] (Caffe2 Dropout ratio 0.5,
+ *     scale 1/(1-ratio)); keep = mask (uint8 0/1) when mask != NULL (injected, for parity runs),
+ *     else a counter-based hash of (dropout_seed, m, n) when dropout_seed != 0, else 1.
  * nawsod_fc_bwd_x FCGradient's dX (+ the ReluGradient / DropoutGradient of the layer below):
  *     dA[M,K] = dY[M,N] . W[N,K];  NAWSOD_FC_RELU: dA *= (act_below[M,K] > 0);
  *     NAWSOD_FC_DROPOUT: dA *= 2 (and *= mask_below[M,K] when mask_below != NULL; with
@@ -105,12 +106,14 @@ int nawsod_roi_feature_boost(const float* X, const float* S, int R, int64_t feat
  * nawsod_fc_bwd_w FCGradient's dW, db:
  *     dW[N,K] (float) = dY[M,N]^T . A[M,K];  db[N] (float) = sum_m dY[m,:] (db may be NULL).
  *     NAWSOD_FC_ACCUMULATE: add into dW / db instead of overwriting.
+ * NAWSOD_FC_ROUND_TF32 (fwd / bwd_x, float outputs): round the stored values to the nearest
+ *     TF32 so that the next GEMM's tensor-core truncation is exact (keeps the fp32 path unbiased).
  * ------------------------------------------------------------------------------------- */
-enum { NAWSOD_FC_RELU = 1, NAWSOD_FC_DROPOUT = 2, NAWSOD_FC_ACCUMULATE = 4 };
+enum { NAWSOD_FC_RELU = 1, NAWSOD_FC_DROPOUT = 2, NAWSOD_FC_ACCUMULATE = 4, NAWSOD_FC_ROUND_TF32 = 8 };
 
 int nawsod_fc_fwd(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
-                  const uint8_t* mask, int64_t ldmask, int M, int N, int K, int ab_dtype,
-                  void* Y, int64_t ldy, int y_dtype, int flags, void* stream);
+                  const uint8_t* mask, int64_t ldmask, uint64_t dropout_seed, int M, int N, int K,
+                  int ab_dtype, void* Y, int64_t ldy, int y_dtype, int flags, void* stream);
 
 int nawsod_fc_bwd_x(const void* dY, int64_t lddy, const void* W, int64_t ldw,
                     const void* act_below, int64_t ldact, int act_dtype,
@@ -122,17 +125,21 @@ int nawsod_fc_bwd_w(const void* dY, int64_t lddy, const void* A, int64_t lda, in
                     int K, int ab_dtype, float* dW, int64_t lddw, float* db, int flags,
                     void* stream);
 
-/* float -> bf16 conversion of a [rows, cols] matrix (operand staging for the GEMMs above). */
+/* Operand staging for the GEMMs above: float -> bf16, and float -> nearest-TF32 (kept in a
+ * float container; dst may alias src) of a [rows, cols] matrix. */
 int nawsod_convert_f32_to_bf16(const float* src, int64_t ld_src, int64_t rows, int64_t cols,
                                void* dst, int64_t ld_dst, void* stream);
+int nawsod_round_to_tf32(const float* src, int64_t ld_src, int64_t rows, int64_t cols,
+                         float* dst, int64_t ld_dst, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * a5..a9: the two-stream MIL head, noise-aware class weights, weighted multi-label CE and
  * the whole backward to the fc8 logits, as ONE fused kernel
  *   (modeling/wsl_heads.py:49-55,213-227; modeling/webly_heads.py:32-74,123-197,265-391;
  *    ops/roi_iou_op.cu:28-62; ops/cross_entropy_wsl_op.cc:88-180).
- *   fc8c, fc8d          : [R,C] float logits of the clean stack.
- *   nfc8c, nfc8d        : [R,C] float logits of the noisy stack, or both NULL (plain WSDDN).
+ *   fc8c, fc8d          : [R,C] float logits of the clean stack, row pitch ld_logits elements
+ *                         (fc8c | fc8d may be the two halves of one fused [R,2C] FC output).
+ *   nfc8c, nfc8d        : [R,C] float logits of the noisy stack (same pitch), or both NULL (plain WSDDN).
  *   rois                : [R,5]; rois of image b are rows roi_offsets_host[b]..[b+1]
  *                         (contiguous per image, the order contract of ops/roi_score_reshape_op.cc:30-44).
  *   roi_offsets         : [B+1] int32 DEVICE array.
@@ -142,7 +149,8 @@ int nawsod_convert_f32_to_bf16(const float* src, int64_t ld_src, int64_t rows, i
  * outputs (any may be NULL except loss when BACKWARD is off):
  *   rois_pred[R,C], cls_prob[B,C], rois_pred_noise[R,C], cls_prob_noise[B,C],
  *   class_weight[B,C], class_weight_noise[B,C], loss[B,2] (loss_cls, loss_cls_noise per image),
- *   d_fc8c, d_fc8d, d_nfc8c, d_nfc8d [R,C] (loss-gradient seed 1.0 each, utils/blob.py:167-173).
+ *   d_fc8c, d_fc8d, d_nfc8c, d_nfc8d [R,C], row pitch ld_grads (loss-gradient seed 1.0 each,
+ *   utils/blob.py:167-173).
  *   workspace: device scratch >= nawsod_mil_workspace_bytes(R, C, B).
  * ------------------------------------------------------------------------------------- */
 enum { NAWSOD_MIL_ENTROPY = 1, NAWSOD_MIL_MEAN = 2, NAWSOD_MIL_BACKWARD = 4 };
@@ -150,13 +158,14 @@ enum { NAWSOD_MIL_ENTROPY = 1, NAWSOD_MIL_MEAN = 2, NAWSOD_MIL_BACKWARD = 4 };
 int64_t nawsod_mil_workspace_bytes(int R, int C, int B);
 
 int nawsod_mil_head_fwd_bwd(const float* fc8c, const float* fc8d, const float* nfc8c,
-                            const float* nfc8d, const float* rois, const int32_t* roi_offsets,
-                            const float* labels_oh, int R, int C, int B, int flags,
+                            const float* nfc8d, int64_t ld_logits, const float* rois,
+                            const int32_t* roi_offsets, const float* labels_oh, int R, int C,
+                            int B, int flags,
                             float* rois_pred, float* cls_prob, float* rois_pred_noise,
                             float* cls_prob_noise, float* class_weight,
                             float* class_weight_noise, float* loss, float* d_fc8c,
-                            float* d_fc8d, float* d_nfc8c, float* d_nfc8d, void* workspace,
-                            void* stream);
+                            float* d_fc8d, float* d_nfc8c, float* d_nfc8d, int64_t ld_grads,
+                            void* workspace, void* stream);
 
 /* a7 stand-alone: RoIIoU([rois] -> [J]) (ops/roi_iou_op.cc:11-18, ops/roi_iou_op.cu:28-84). J [R,R]. */
 int nawsod_roi_iou(const float* rois, int R, float* J, void* stream);
@@ -173,13 +182,14 @@ int nawsod_cross_entropy_bwd(const float* X, const float* L, const float* Wt, co
  *   (ops/acm_weightdecay_momentum_sgd_op.h:48-112, wired by modeling/optimizer_wsl.py:96-137),
  *   fused into one pass.  In place on m, p, acc.  `lr` is a 1-element DEVICE float
  *   (the reference's `lr` blob).  iter_count = number of calls already made on this
- *   parameter (call 0 zero-initialises m and acc, .h:62-69).  p_bf16 (optional) receives
- *   a bf16 copy of the updated parameter for the tensor-core GEMMs.
+ *   parameter (call 0 zero-initialises m and acc, .h:62-69).  p_shadow (optional) receives
+ *   the updated parameter as the tensor-core GEMM operand: bf16 (shadow_dtype NAWSOD_BF16) or
+ *   float rounded to the nearest TF32 (shadow_dtype NAWSOD_F32).
  * ------------------------------------------------------------------------------------- */
 int nawsod_sgd_update(const float* g, float* m, const float* lr, float* p, float* acc,
                       int64_t n, float momentum, float weight_decay, float lr_mult,
-                      int iter_size, int gpu_num, int64_t iter_count, void* p_bf16,
-                      void* stream);
+                      int iter_size, int gpu_num, int64_t iter_count, void* p_shadow,
+                      int shadow_dtype, void* stream);
 
 #ifdef __cplusplus
 }

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libnawsod.so")
 
 F32, BF16 = 0, 1
 NCHW, NHWC = 0, 1
-FC_RELU, FC_DROPOUT, FC_ACCUMULATE = 1, 2, 4
+FC_RELU, FC_DROPOUT, FC_ACCUMULATE, FC_ROUND_TF32 = 1, 2, 4, 8
 MIL_ENTROPY, MIL_MEAN, MIL_BACKWARD = 1, 2, 4
 
 _c = ctypes
@@ -27,16 +27,17 @@ PROTOTYPES = {
     "nawsod_roi_pool_f_fwd": (_i, [_vp, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _i, _vp, _i, _i, _vp, _vp]),
     "nawsod_roi_pool_f_bwd": (_i, [_vp, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp]),
     "nawsod_roi_feature_boost": (_i, [_vp, _vp, _i, _i64, _vp, _vp]),
-    "nawsod_fc_fwd": (_i, [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _vp, _i64, _i, _i, _vp]),
+    "nawsod_fc_fwd": (_i, [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _c.c_uint64, _i, _i, _i, _i, _vp, _i64, _i, _i, _vp]),
     "nawsod_fc_bwd_x": (_i, [_vp, _i64, _vp, _i64, _vp, _i64, _i, _vp, _i64, _i, _i, _i, _i, _vp, _i64, _i, _i, _vp]),
     "nawsod_fc_bwd_w": (_i, [_vp, _i64, _vp, _i64, _i, _i, _i, _i, _vp, _i64, _vp, _i, _vp]),
     "nawsod_convert_f32_to_bf16": (_i, [_vp, _i64, _i64, _i64, _vp, _i64, _vp]),
     "nawsod_mil_workspace_bytes": (_i64, [_i, _i, _i]),
-    "nawsod_mil_head_fwd_bwd": (_i, [_vp] * 7 + [_i, _i, _i, _i] + [_vp] * 13),
+    "nawsod_mil_head_fwd_bwd": (_i, [_vp] * 4 + [_i64] + [_vp] * 3 + [_i, _i, _i, _i] + [_vp] * 11 + [_i64, _vp, _vp]),
     "nawsod_roi_iou": (_i, [_vp, _i, _vp, _vp]),
     "nawsod_cross_entropy_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "nawsod_cross_entropy_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
-    "nawsod_sgd_update": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _f, _f, _f, _i, _i, _i64, _vp, _vp]),
+    "nawsod_round_to_tf32": (_i, [_vp, _i64, _i64, _i64, _vp, _i64, _vp]),
+    "nawsod_sgd_update": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _f, _f, _f, _i, _i, _i64, _vp, _i, _vp]),
 }
 
 _lib = None

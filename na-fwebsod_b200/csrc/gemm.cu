@@ -36,6 +36,7 @@ struct EpiParams {
   const uint8_t* mask; long long ldmask;
   const void* act; long long ldact; int act_dtype;
   int flags;
+  unsigned long long seed;   // counter-based dropout (fwd) when mask == nullptr and seed != 0
   int M, N, K;          // GEMM dims: out is [M, N], reduction over K
 };
 
@@ -123,6 +124,15 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
 __host__ __device__ constexpr uint32_t make_idesc(int es, bool a_mn, bool b_mn, int m, int n) {
   return (1u << 4) | ((es == 2 ? 1u : 2u) << 7) | ((es == 2 ? 1u : 2u) << 10) | ((a_mn ? 1u : 0u) << 15) |
          ((b_mn ? 1u : 0u) << 16) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
+
+// Round-to-nearest TF32 (10-bit mantissa) kept in an fp32 container.  kind::tf32 reads only the
+// upper 19 bits of each operand, i.e. it truncates; feeding it pre-rounded operands removes the
+// systematic under-estimate (~7e-4 per layer) that truncation would add.
+__device__ __forceinline__ float round_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
 }
 
 __device__ __forceinline__ float ld_act(const void* act, int act_dtype, size_t i) {
@@ -321,6 +331,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
                 for (int i = 0; i < 32; ++i) if (i < ncols) v[i] *= 2.0f * static_cast<float>(ep.mask[(size_t)m * ep.ldmask + n + i]);
               }
+            } else if (ep.seed != 0) {
+              // counter-based keep bits: one 64-bit mix per (row, 32-column chunk), one bit per column
+              unsigned long long h = ep.seed ^ (0x9E3779B97F4A7C15ull * (unsigned long long)(m + 1)) ^
+                                     (0xC2B2AE3D27D4EB4Full * (unsigned long long)(n / 32 + 1));
+              h ^= h >> 33; h *= 0xFF51AFD7ED558CCDull; h ^= h >> 33; h *= 0xC4CEB9FE1A85EC53ull; h ^= h >> 33;
+              const uint32_t bits = static_cast<uint32_t>(h);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = ((bits >> i) & 1u) ? v[i] * 2.0f : 0.f;
             } else {
 #pragma unroll
               for (int i = 0; i < 32; ++i) v[i] *= 2.0f;
@@ -331,6 +349,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (ep.flags & NAWSOD_FC_ACCUMULATE) {
 #pragma unroll
               for (int i = 0; i < 32; ++i) if (i < ncols) v[i] += o[i];
+            }
+            if (ep.flags & NAWSOD_FC_ROUND_TF32) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = round_tf32(v[i]);
             }
             if (vec_ok && full) {
 #pragma unroll
@@ -395,6 +417,15 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ X, lo
 #pragma unroll
     for (int k = 0; k < 8; ++k) t += red[k][tx];
     atomicAdd(out + n, t);
+  }
+}
+
+__global__ void __launch_bounds__(256) round_tf32_kernel(const float* __restrict__ src, long long ld_src, long long rows,
+                                                        long long cols, float* __restrict__ dst, long long ld_dst) {
+  const long long total = rows * cols;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols, c = i - r * cols;
+    dst[r * ld_dst + c] = round_tf32(src[r * ld_src + c]);
   }
 }
 
@@ -499,16 +530,17 @@ int check_common(const char* who, int M, int N, int K, int ab_dtype) {
 using namespace nawsod;
 
 extern "C" int nawsod_fc_fwd(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, const uint8_t* mask,
-                             int64_t ldmask, int M, int N, int K, int ab_dtype, void* Y, int64_t ldy, int y_dtype, int flags,
-                             void* stream) {
+                             int64_t ldmask, uint64_t dropout_seed, int M, int N, int K, int ab_dtype, void* Y, int64_t ldy,
+                             int y_dtype, int flags, void* stream) {
   if (int rc = check_common("fc_fwd", M, N, K, ab_dtype)) return rc;
   NAWSOD_REQUIRE(A && W && Y, NAWSOD_ERR_ARG, "fc_fwd: null pointer");
   NAWSOD_REQUIRE(y_dtype == NAWSOD_F32 || y_dtype == NAWSOD_BF16, NAWSOD_ERR_ARG, "fc_fwd: bad y_dtype");
   NAWSOD_REQUIRE(!(flags & NAWSOD_FC_ACCUMULATE), NAWSOD_ERR_ARG, "fc_fwd: ACCUMULATE is a bwd_w flag");
+  NAWSOD_REQUIRE(!(flags & NAWSOD_FC_ROUND_TF32) || y_dtype == NAWSOD_F32, NAWSOD_ERR_ARG, "fc_fwd: ROUND_TF32 needs a float output");
   NAWSOD_REQUIRE(ldy >= N && (!mask || ldmask >= N), NAWSOD_ERR_SHAPE, "fc_fwd: ldy / ldmask smaller than N");
   EpiParams ep{};
   ep.out = Y; ep.ldo = ldy; ep.out_dtype = y_dtype; ep.bias = bias; ep.mask = (flags & NAWSOD_FC_DROPOUT) ? mask : nullptr;
-  ep.ldmask = ldmask; ep.act = nullptr; ep.flags = flags; ep.M = M; ep.N = N; ep.K = K;
+  ep.ldmask = ldmask; ep.act = nullptr; ep.flags = flags; ep.seed = dropout_seed; ep.M = M; ep.N = N; ep.K = K;
   return dispatch_gemm<false, false>(A, lda, W, ldw, ep, ab_dtype, static_cast<cudaStream_t>(stream));
 }
 
@@ -535,7 +567,8 @@ extern "C" int nawsod_fc_bwd_w(const void* dY, int64_t lddy, const void* A, int6
   if (int rc = check_common("fc_bwd_w", M, N, K, ab_dtype)) return rc;
   NAWSOD_REQUIRE(dY && A && dW, NAWSOD_ERR_ARG, "fc_bwd_w: null pointer");
   NAWSOD_REQUIRE(lddw >= K, NAWSOD_ERR_SHAPE, "fc_bwd_w: lddw smaller than K");
-  NAWSOD_REQUIRE(!(flags & (NAWSOD_FC_RELU | NAWSOD_FC_DROPOUT)), NAWSOD_ERR_ARG, "fc_bwd_w: only ACCUMULATE is valid");
+  NAWSOD_REQUIRE(!(flags & (NAWSOD_FC_RELU | NAWSOD_FC_DROPOUT | NAWSOD_FC_ROUND_TF32)), NAWSOD_ERR_ARG,
+                 "fc_bwd_w: only ACCUMULATE is valid");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   EpiParams ep{};
   // GEMM view: out [N, K] = dY^T [N, M] . A [M, K] -> reduction over M
@@ -563,6 +596,18 @@ extern "C" int nawsod_convert_f32_to_bf16(const float* src, int64_t ld_src, int6
   const long long total = rows * cols;
   const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)sm_count() * 8);
   cvt_bf16_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, ld_src, rows, cols, static_cast<__nv_bfloat16*>(dst), ld_dst);
+  NAWSOD_LAUNCH_OK();
+  return NAWSOD_OK;
+}
+
+extern "C" int nawsod_round_to_tf32(const float* src, int64_t ld_src, int64_t rows, int64_t cols, float* dst, int64_t ld_dst,
+                                    void* stream) {
+  NAWSOD_REQUIRE(rows >= 0 && cols >= 0 && ld_src >= cols && ld_dst >= cols, NAWSOD_ERR_SHAPE, "round_to_tf32: bad shape");
+  if (rows == 0 || cols == 0) return NAWSOD_OK;
+  NAWSOD_REQUIRE(src && dst, NAWSOD_ERR_ARG, "round_to_tf32: null pointer");
+  const long long total = rows * cols;
+  const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)sm_count() * 8);
+  round_tf32_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, ld_src, rows, cols, dst, ld_dst);
   NAWSOD_LAUNCH_OK();
   return NAWSOD_OK;
 }

@@ -39,6 +39,7 @@ struct MilParams {
   const float *fc8c, *fc8d, *nfc8c, *nfc8d, *rois, *labels;
   const int32_t* roi_offsets;
   int R, C, B, flags;
+  long long ldl, ldg;   // row pitch of the logit inputs / logit-gradient outputs
   float *rois_pred, *cls_prob, *rois_pred_noise, *cls_prob_noise, *class_weight, *class_weight_noise, *loss;
   float *d_fc8c, *d_fc8d, *d_nfc8c, *d_nfc8d;
   // workspace
@@ -72,7 +73,7 @@ __device__ __forceinline__ void combine_ms(float& m, float& s, float m2, float s
 struct RowProbs { float a_cls[kQ], a_det[kQ], P[kQ]; };
 
 __device__ __forceinline__ void row_probs(const float* __restrict__ lc, const float* __restrict__ nlc,
-                                          const float* __restrict__ ld, const float* __restrict__ nld, int r, int C,
+                                          const float* __restrict__ ld, const float* __restrict__ nld, int r, int C, long long pitch,
                                           const float* colmax, const float* colsum, int lane, RowProbs& o) {
   float xc[kQ], xd[kQ];
   float m = -INFINITY;
@@ -80,9 +81,9 @@ __device__ __forceinline__ void row_probs(const float* __restrict__ lc, const fl
   for (int q = 0; q < kQ; ++q) {
     const int c = lane + 32 * q;
     if (c < C) {
-      xc[q] = lc[(size_t)r * C + c];
-      xd[q] = ld[(size_t)r * C + c];
-      if (nlc) { xc[q] += nlc[(size_t)r * C + c]; xd[q] += nld[(size_t)r * C + c]; }
+      xc[q] = lc[(size_t)r * pitch + c];
+      xd[q] = ld[(size_t)r * pitch + c];
+      if (nlc) { xc[q] += nlc[(size_t)r * pitch + c]; xd[q] += nld[(size_t)r * pitch + c]; }
       m = fmaxf(m, xc[q]);
     } else { xc[q] = -INFINITY; xd[q] = -INFINITY; }
   }
@@ -189,8 +190,8 @@ __global__ void __launch_bounds__(kThreads, 1) mil_head_kernel(const MilParams p
       const int col = tid % C, rl = tid / C;
       if (rl < KR) {
         for (int r = row0 + rl; r < row1; r += KR) {
-          float v = ld[(size_t)r * C + col];
-          if (nld) v += nld[(size_t)r * C + col];
+          float v = ld[(size_t)r * p.ldl + col];
+          if (nld) v += nld[(size_t)r * p.ldl + col];
           if (v > m) { sum = sum * expf(m - v) + 1.f; m = v; }
           else sum += expf(v - m);
         }
@@ -227,7 +228,7 @@ __global__ void __launch_bounds__(kThreads, 1) mil_head_kernel(const MilParams p
     for (int q = 0; q < kQ; ++q) { yacc[0][q] = 0.f; yacc[1][q] = 0.f; }
     for (int r = row0 + warp; r < row1; r += kWarps) {
       RowProbs pr;
-      row_probs(p.fc8c, nullptr, p.fc8d, nullptr, r, C, colmax_s[0], colsum_s[0], lane, pr);
+      row_probs(p.fc8c, nullptr, p.fc8d, nullptr, r, C, p.ldl, colmax_s[0], colsum_s[0], lane, pr);
 #pragma unroll
       for (int q = 0; q < kQ; ++q) {
         const int c = lane + 32 * q;
@@ -249,7 +250,7 @@ __global__ void __launch_bounds__(kThreads, 1) mil_head_kernel(const MilParams p
         p.box[r] = make_int4((int)roi[1], (int)roi[2], (int)roi[3], (int)roi[4]);   // float -> int truncation
       }
       if (noise) {
-        row_probs(p.fc8c, p.nfc8c, p.fc8d, p.nfc8d, r, C, colmax_s[1], colsum_s[1], lane, pr);
+        row_probs(p.fc8c, p.nfc8c, p.fc8d, p.nfc8d, r, C, p.ldl, colmax_s[1], colsum_s[1], lane, pr);
 #pragma unroll
         for (int q = 0; q < kQ; ++q) {
           const int c = lane + 32 * q;
@@ -365,7 +366,7 @@ __global__ void __launch_bounds__(kThreads, 1) mil_head_kernel(const MilParams p
   if (p.flags & NAWSOD_MIL_BACKWARD) {
     for (int r = row0 + warp; r < row1; r += kWarps) {
       RowProbs pr;
-      row_probs(p.fc8c, nullptr, p.fc8d, nullptr, r, C, colmax_s[0], colsum_s[0], lane, pr);
+      row_probs(p.fc8c, nullptr, p.fc8d, nullptr, r, C, p.ldl, colmax_s[0], colsum_s[0], lane, pr);
       float S = 0.f;
 #pragma unroll
       for (int q = 0; q < kQ; ++q) {
@@ -384,7 +385,7 @@ __global__ void __launch_bounds__(kThreads, 1) mil_head_kernel(const MilParams p
         }
       }
       if (noise) {
-        row_probs(p.fc8c, p.nfc8c, p.fc8d, p.nfc8d, r, C, colmax_s[1], colsum_s[1], lane, pr);
+        row_probs(p.fc8c, p.nfc8c, p.fc8d, p.nfc8d, r, C, p.ldl, colmax_s[1], colsum_s[1], lane, pr);
         float Sn = 0.f;
 #pragma unroll
         for (int q = 0; q < kQ; ++q) {
@@ -399,8 +400,8 @@ __global__ void __launch_bounds__(kThreads, 1) mil_head_kernel(const MilParams p
             const float dy = dy_s[1][c];
             const float nc = pr.a_cls[q] * (dy * pr.a_det[q] - Sn);
             const float nd = pr.a_det[q] * (dy * pr.a_cls[q] - dy * y_s[1][c]);
-            p.d_nfc8c[(size_t)r * C + c] = nc;
-            p.d_nfc8d[(size_t)r * C + c] = nd;
+            p.d_nfc8c[(size_t)r * p.ldg + c] = nc;
+            p.d_nfc8d[(size_t)r * p.ldg + c] = nd;
             gc[q] += nc;      // Add fans the gradient out to both summands
             gd[q] += nd;
           }
@@ -410,8 +411,8 @@ __global__ void __launch_bounds__(kThreads, 1) mil_head_kernel(const MilParams p
       for (int q = 0; q < kQ; ++q) {
         const int c = lane + 32 * q;
         if (c < C) {
-          p.d_fc8c[(size_t)r * C + c] = gc[q];
-          p.d_fc8d[(size_t)r * C + c] = gd[q];
+          p.d_fc8c[(size_t)r * p.ldg + c] = gc[q];
+          p.d_fc8d[(size_t)r * p.ldg + c] = gd[q];
         }
       }
     }
@@ -503,11 +504,11 @@ extern "C" int64_t nawsod_mil_workspace_bytes(int R, int C, int B) {
 }
 
 extern "C" int nawsod_mil_head_fwd_bwd(const float* fc8c, const float* fc8d, const float* nfc8c, const float* nfc8d,
-                                       const float* rois, const int32_t* roi_offsets, const float* labels_oh, int R,
-                                       int C, int B, int flags, float* rois_pred, float* cls_prob,
+                                       int64_t ld_logits, const float* rois, const int32_t* roi_offsets,
+                                       const float* labels_oh, int R, int C, int B, int flags, float* rois_pred, float* cls_prob,
                                        float* rois_pred_noise, float* cls_prob_noise, float* class_weight,
                                        float* class_weight_noise, float* loss, float* d_fc8c, float* d_fc8d,
-                                       float* d_nfc8c, float* d_nfc8d, void* workspace, void* stream) {
+                                       float* d_nfc8c, float* d_nfc8d, int64_t ld_grads, void* workspace, void* stream) {
   NAWSOD_REQUIRE(R > 0 && C > 0 && B > 0, NAWSOD_ERR_SHAPE, "mil_head: need R, C, B > 0 (got %d, %d, %d)", R, C, B);
   NAWSOD_REQUIRE(C <= kMaxC, NAWSOD_ERR_UNSUPPORTED, "mil_head: C=%d > %d", C, kMaxC);
   NAWSOD_REQUIRE(B <= kMaxB, NAWSOD_ERR_UNSUPPORTED, "mil_head: B=%d > %d", B, kMaxB);
@@ -520,12 +521,14 @@ extern "C" int nawsod_mil_head_fwd_bwd(const float* fc8c, const float* fc8d, con
                    "mil_head: BACKWARD needs the d_* outputs");
   }
   NAWSOD_REQUIRE(aligned16(workspace), NAWSOD_ERR_ALIGN, "mil_head: workspace must be 16-byte aligned");
+  NAWSOD_REQUIRE(ld_logits >= C && (!(flags & NAWSOD_MIL_BACKWARD) || ld_grads >= C), NAWSOD_ERR_SHAPE,
+                 "mil_head: leading dimensions must be >= C");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const WsLayout w = ws_layout(R, C);
   char* base = static_cast<char*>(workspace);
   MilParams p;
   p.fc8c = fc8c; p.fc8d = fc8d; p.nfc8c = nfc8c; p.nfc8d = nfc8d; p.rois = rois; p.labels = labels_oh;
-  p.roi_offsets = roi_offsets; p.R = R; p.C = C; p.B = B; p.flags = flags;
+  p.roi_offsets = roi_offsets; p.R = R; p.C = C; p.B = B; p.flags = flags; p.ldl = ld_logits; p.ldg = ld_grads;
   p.rois_pred = rois_pred; p.cls_prob = cls_prob; p.rois_pred_noise = rois_pred_noise;
   p.cls_prob_noise = cls_prob_noise; p.class_weight = class_weight; p.class_weight_noise = class_weight_noise;
   p.loss = loss; p.d_fc8c = d_fc8c; p.d_fc8d = d_fc8d; p.d_nfc8c = d_nfc8c; p.d_nfc8d = d_nfc8d;

@@ -11,13 +11,19 @@ namespace nawsod {
 namespace {
 
 struct SgdArgs {
-  const float* g; float* m; const float* lr; float* p; float* acc; __nv_bfloat16* p_bf16;
+  const float* g; float* m; const float* lr; float* p; float* acc; __nv_bfloat16* p_bf16; float* p_tf32;
   int64_t n;
   float momentum, weight_decay, lr_mult, inv_norm;
   int first_call;   // iter_count == 0: m and acc start from zero whatever the buffers hold (.h:62-69)
   int do_update;    // (iter_count + 1) % iter_size == 0
   int use_acc;      // iter_size > 1 or acc buffer given
 };
+
+__device__ __forceinline__ float rna_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
 
 // Per-element arithmetic in the reference's order (no FMA contraction across its separate passes):
 //   acc = g + acc                        (.h:72-75)
@@ -61,6 +67,7 @@ __global__ void __launch_bounds__(256) sgd_kernel(const SgdArgs a) {
         reinterpret_cast<uint2*>(a.p_bf16)[i] =
             make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
       }
+      if (a.p_tf32) reinterpret_cast<float4*>(a.p_tf32)[i] = make_float4(rna_tf32(p.x), rna_tf32(p.y), rna_tf32(p.z), rna_tf32(p.w));
     }
     if (a.use_acc) reinterpret_cast<float4*>(a.acc)[i] = c;
   }
@@ -74,6 +81,7 @@ __global__ void __launch_bounds__(256) sgd_kernel(const SgdArgs a) {
     if (a.do_update) {
       a.p[i] = p;
       if (a.p_bf16) a.p_bf16[i] = __float2bfloat16_rn(p);
+      if (a.p_tf32) a.p_tf32[i] = rna_tf32(p);
     }
     if (a.use_acc) a.acc[i] = c;
   }
@@ -86,7 +94,7 @@ using namespace nawsod;
 
 extern "C" int nawsod_sgd_update(const float* g, float* m, const float* lr, float* p, float* acc, int64_t n,
                                  float momentum, float weight_decay, float lr_mult, int iter_size, int gpu_num,
-                                 int64_t iter_count, void* p_bf16, void* stream) {
+                                 int64_t iter_count, void* p_shadow, int shadow_dtype, void* stream) {
   NAWSOD_REQUIRE(n >= 0, NAWSOD_ERR_SHAPE, "sgd_update: negative n");
   NAWSOD_REQUIRE(iter_size >= 1 && gpu_num >= 1 && iter_count >= 0, NAWSOD_ERR_ARG,
                  "sgd_update: need iter_size >= 1, gpu_num >= 1, iter_count >= 0");
@@ -94,10 +102,14 @@ extern "C" int nawsod_sgd_update(const float* g, float* m, const float* lr, floa
   NAWSOD_REQUIRE(g && m && lr && p, NAWSOD_ERR_ARG, "sgd_update: null pointer");
   NAWSOD_REQUIRE(acc || iter_size == 1, NAWSOD_ERR_ARG, "sgd_update: acc buffer required when iter_size > 1");
   NAWSOD_REQUIRE(aligned16(g) && aligned16(m) && aligned16(p) && (!acc || aligned16(acc)) &&
-                     (!p_bf16 || (reinterpret_cast<uintptr_t>(p_bf16) & 7u) == 0),
+                     (!p_shadow || aligned16(p_shadow)),
                  NAWSOD_ERR_ALIGN, "sgd_update: buffers must be 16-byte aligned");
   SgdArgs a;
-  a.g = g; a.m = m; a.lr = lr; a.p = p; a.acc = acc; a.p_bf16 = static_cast<__nv_bfloat16*>(p_bf16);
+  NAWSOD_REQUIRE(!p_shadow || shadow_dtype == NAWSOD_BF16 || shadow_dtype == NAWSOD_F32, NAWSOD_ERR_ARG,
+                 "sgd_update: shadow_dtype must be NAWSOD_BF16 or NAWSOD_F32 (TF32-rounded)");
+  a.g = g; a.m = m; a.lr = lr; a.p = p; a.acc = acc;
+  a.p_bf16 = (p_shadow && shadow_dtype == NAWSOD_BF16) ? static_cast<__nv_bfloat16*>(p_shadow) : nullptr;
+  a.p_tf32 = (p_shadow && shadow_dtype == NAWSOD_F32) ? static_cast<float*>(p_shadow) : nullptr;
   a.n = n; a.momentum = momentum; a.weight_decay = weight_decay; a.lr_mult = lr_mult;
   a.inv_norm = static_cast<float>(1.0 / (static_cast<double>(iter_size) * gpu_num));   // T(1.0 / (iter_size_ * gpu_num_))
   a.first_call = iter_count == 0;

@@ -1,0 +1,346 @@
+"""Host-side mirror of the reference's WSL / webly head builders for the per-proposal path.
+
+The reference builds a Caffe2 graph with ``add_VGG16_roi_2fc_noise_head`` ->
+``add_webly_outputs`` -> ``add_webly_losses`` (detectron/modeling/webly_heads.py:463-502, 32-74,
+123-216; single-stack WSDDN: detectron/modeling/wsl_heads.py:654-681, 23-56) and runs it with
+``workspace.RunNet``.  Here the same-named functions execute eagerly on a :class:`WeblyHeadModel`
+(the ``model`` argument of the reference builders), each one a short run of libnawsod C-ABI
+calls; blobs keep the reference's names (``rois``, ``obn_scores``, ``labels_oh``, ``roi_feat``,
+``drop7``, ``fc8c`` ... ``cls_prob``, ``loss_cls``, ``loss_cls_noise``) and parameters are
+imported / exported under the reference's names and layouts (``fc6_w`` [4096, 25088] with
+K-index c*49+ph*7+pw, ``_[noisy]_fc6_w``, ``noisy_fc8c_w`` ...).
+
+Device-side layout:
+  * conv5 map channels-last, pooled features [R, 49*C] in (ph, pw, c) order -> fc6 weights are
+    stored K-permuted once at load time;
+  * the two stacks' fc6 are ONE GEMM (W6 = [fc6_w; _[noisy]_fc6_w], N = 8192): the pooled
+    features are read once; fc8c|fc8d of a stack are one GEMM with N = 2C;
+  * all parameters / gradients / momenta live in three flat float32 buffers (weights first,
+    biases last) so the data-parallel all-reduce is a handful of large NCCL calls and the SGD
+    update is two fused kernel launches; bf16 runs keep a flat bf16 shadow of the parameters.
+PyTorch is used for memory, streams and (in dp.py) NCCL plumbing only.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import ops
+
+_ALIGN = 64  # elements; keeps every carved view 256-byte aligned
+
+
+def _round_up(v, a):
+    return (v + a - 1) // a * a
+
+
+class WeblyHeadModel:
+    """State + eager execution of the NA-fWebSOD head (``noise=True``) or plain WSDDN head.
+
+    num_classes follows the reference: it INCLUDES background (cfg.MODEL.NUM_CLASSES), the
+    heads predict ``num_classes - 1`` classes (detectron/modeling/wsl_heads.py:33).
+    """
+
+    def __init__(self, num_classes=21, dim_in=512, roi_size=7, hidden_dim=4096, spatial_scale=1.0 / 16,
+                 noise=True, entropy=True, mean_loss=True, dtype=torch.bfloat16, device="cuda", train=True,
+                 freeze_conv_body=True):
+        if dtype not in (torch.bfloat16, torch.float32):
+            raise RuntimeError("dtype must be bfloat16 or float32 (TF32 tensor path)")
+        self.num_classes = num_classes
+        self.C = num_classes - 1
+        self.dim_in, self.roi_size, self.H = dim_in, roi_size, hidden_dim
+        self.D = dim_in * roi_size * roi_size
+        self.spatial_scale = spatial_scale
+        self.noise, self.entropy, self.mean_loss = noise, entropy, mean_loss
+        self.S = 2 if noise else 1
+        self.dtype, self.device, self.train = dtype, torch.device(device), train
+        self.freeze_conv_body = freeze_conv_body
+        self.tf32 = dtype == torch.float32
+        self.blobs = {}
+        self._buf = {}
+        self.iter_count = 0
+        self._alloc_params()
+
+    # ------------------------------------------------------------------ parameters
+    def _alloc_params(self):
+        S, H, D, C2 = self.S, self.H, self.D, 2 * self.C
+        shapes_w = [("W6", (S * H, D))] + [("W7_%d" % s, (H, H)) for s in range(S)] + \
+                   [("W8_%d" % s, (C2, H)) for s in range(S)]
+        shapes_b = [("b6", (S * H,))] + [("b7_%d" % s, (H,)) for s in range(S)] + [("b8_%d" % s, (C2,)) for s in range(S)]
+        off, self._slices = 0, {}
+        for name, shp in shapes_w:
+            n = int(np.prod(shp))
+            self._slices[name] = (off, n, shp)
+            off = _round_up(off + n, _ALIGN)
+        self.n_weights = off
+        for name, shp in shapes_b:
+            n = int(np.prod(shp))
+            self._slices[name] = (off, n, shp)
+            off = _round_up(off + n, _ALIGN)
+        self.n_total = off
+        z = lambda dt: torch.zeros(self.n_total, dtype=dt, device=self.device)
+        self.flat_param, self.flat_grad, self.flat_mom = z(torch.float32), z(torch.float32), z(torch.float32)
+        # GEMM-operand copy of the parameters: bf16, or float rounded to the nearest TF32
+        self.flat_lp = z(self.dtype)
+        self.lr = torch.zeros(1, dtype=torch.float32, device=self.device)   # the reference's `lr` blob
+        view = lambda flat, k: flat[self._slices[k][0]: self._slices[k][0] + self._slices[k][1]].view(self._slices[k][2])
+        self.p = {k: view(self.flat_param, k) for k in self._slices}       # fp32 masters
+        self.g = {k: view(self.flat_grad, k) for k in self._slices}
+        self.w = {k: view(self.flat_lp, k) for k in self._slices}          # GEMM operands (bf16 shadow or the master)
+
+    def _ref_names(self, s):
+        """Reference blob-name prefixes of stack s (detectron/modeling/webly_heads.py:490-498, 36-55)."""
+        return ("", "") if s == 0 else ("_[noisy]_", "noisy_")
+
+    def _k_permute(self, W_ref):
+        """[O, c*49+bin] (reference, NCHW flatten) -> [O, bin*Cin+c] (pooled-NHWC order)."""
+        O = W_ref.shape[0]
+        bins = self.roi_size * self.roi_size
+        return W_ref.reshape(O, self.dim_in, bins).permute(0, 2, 1).reshape(O, self.D)
+
+    def _k_unpermute(self, W_fast):
+        O = W_fast.shape[0]
+        bins = self.roi_size * self.roi_size
+        return W_fast.reshape(O, bins, self.dim_in).permute(0, 2, 1).reshape(O, self.D)
+
+    def load_reference_params(self, params):
+        """params: dict of reference-named arrays (numpy or torch).  Stack-2 names may be given
+        as the reference writes them (``_[noisy]_fc6_w``, ``noisy_fc8c_w``) or with a plain
+        ``noisy_`` prefix (the oracle's convention)."""
+        def get(*names):
+            for n in names:
+                if n in params:
+                    v = params[n]
+                    return (torch.from_numpy(np.ascontiguousarray(v)) if isinstance(v, np.ndarray) else v).to(
+                        self.device, torch.float32)
+            raise KeyError(names[0])
+        H, C = self.H, self.C
+        for s in range(self.S):
+            a, b = self._ref_names(s)
+            alt = "noisy_" if s else ""
+            self.p["W6"][s * H:(s + 1) * H].copy_(self._k_permute(get(a + "fc6_w", alt + "fc6_w")))
+            self.p["b6"][s * H:(s + 1) * H].copy_(get(a + "fc6_b", alt + "fc6_b"))
+            self.p["W7_%d" % s].copy_(get(a + "fc7_w", alt + "fc7_w"))
+            self.p["b7_%d" % s].copy_(get(a + "fc7_b", alt + "fc7_b"))
+            self.p["W8_%d" % s][:C].copy_(get(b + "fc8c_w"))
+            self.p["W8_%d" % s][C:].copy_(get(b + "fc8d_w"))
+            self.p["b8_%d" % s][:C].copy_(get(b + "fc8c_b"))
+            self.p["b8_%d" % s][C:].copy_(get(b + "fc8d_b"))
+        self.sync_shadow()
+
+    def sync_shadow(self):
+        if self.dtype == torch.bfloat16:
+            ops.to_bf16(self.flat_param.view(1, -1), out=self.flat_lp.view(1, -1))
+        else:
+            ops.round_to_tf32(self.flat_param.view(1, -1), out=self.flat_lp.view(1, -1))
+
+    def _export(self, src):
+        out, H, C = {}, self.H, self.C
+        for s in range(self.S):
+            a, b = self._ref_names(s)
+            out[a + "fc6_w"] = self._k_unpermute(src["W6"][s * H:(s + 1) * H])
+            out[a + "fc6_b"] = src["b6"][s * H:(s + 1) * H]
+            out[a + "fc7_w"], out[a + "fc7_b"] = src["W7_%d" % s], src["b7_%d" % s]
+            out[b + "fc8c_w"], out[b + "fc8d_w"] = src["W8_%d" % s][:C], src["W8_%d" % s][C:]
+            out[b + "fc8c_b"], out[b + "fc8d_b"] = src["b8_%d" % s][:C], src["b8_%d" % s][C:]
+        return out
+
+    def export_reference_params(self):
+        """Parameters under the reference's blob names and layouts (checkpoint contract,
+        detectron/utils/net_wsl.py:140-181)."""
+        return self._export(self.p)
+
+    def export_reference_grads(self):
+        return self._export(self.g)
+
+    # ------------------------------------------------------------------ scratch
+    def _scratch(self, name, shape, dtype):
+        t = self._buf.get(name)
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+            t = torch.empty(shape, dtype=dtype, device=self.device)
+            self._buf[name] = t
+        return t
+
+    # ------------------------------------------------------------------ inputs
+    def FeedBlobs(self, data_conv5, rois, obn_scores, labels_oh=None, roi_offsets=None, x_layout="NHWC"):
+        """Feed the head's input blobs (the contract of detectron/roi_data/wsl.py:20-58 downstream of
+        the frozen conv body): conv5 map, ``rois`` [R,5], ``obn_scores`` [R,1] (already +1,
+        roi_data/wsl.py:101-103), ``labels_oh`` [B,C].  ``roi_offsets`` [B+1] int32 marks the
+        contiguous per-image row ranges (one image when omitted)."""
+        if x_layout == "NCHW":
+            data_conv5 = ops.to_channels_last(data_conv5, self.dtype)
+        elif data_conv5.dtype != self.dtype:
+            raise RuntimeError("channels-last conv5 map must already be %s" % self.dtype)
+        R = rois.shape[0]
+        if roi_offsets is None:
+            roi_offsets = torch.tensor([0, R], dtype=torch.int32, device=self.device)
+        self.blobs.update(conv5=data_conv5, rois=rois, obn_scores=obn_scores.reshape(-1), roi_offsets=roi_offsets)
+        if labels_oh is not None:
+            self.blobs["labels_oh"] = labels_oh
+
+    # ------------------------------------------------------------------ forward pieces
+    def _fc_stack(self, dropout_masks=None, dropout_seed=0, stacks=None):
+        """RoIFeatureTransform -> RoIFeatureBoost -> (fc6 -> Relu -> Dropout -> fc7 -> Relu -> Dropout) per stack."""
+        bl, H = self.blobs, self.H
+        stacks = list(range(self.S)) if stacks is None else stacks
+        need_argmax = self.train and not self.freeze_conv_body
+        roi_feat, argmax = ops.RoIPoolF(bl["conv5"], bl["rois"], pooled_h=self.roi_size, pooled_w=self.roi_size,
+                                        spatial_scale=self.spatial_scale, is_test=not need_argmax,
+                                        boost=bl["obn_scores"], x_layout="NHWC", y_layout="NHWC", out_dtype=self.dtype)
+        R = roi_feat.shape[0]
+        feat = roi_feat.view(R, self.D)
+        if self.tf32:
+            ops.round_to_tf32(feat, out=feat)     # GEMM operand: nearest-TF32 (the stand-alone RoIPoolF op stays exact)
+        bl["roi_feat"], bl["_argmax_roi_feat"] = feat, argmax
+        nS = len(stacks)
+        drop6 = self._scratch("drop6", (R, nS * H), self.dtype)
+        drop7 = self._scratch("drop7", (R, nS * H), self.dtype)
+        # Dropout is active in training when a mask is injected or a seed is given
+        # (DropoutIfTraining, detectron/modeling/wsl_heads.py:1259-1267); otherwise it is the identity.
+        use_drop = self.train and (dropout_masks is not None or dropout_seed != 0)
+        self._dropped = use_drop
+        m6 = m7 = None
+        if use_drop and dropout_masks is not None:
+            names = [("drop6", "drop7"), ("noisy_drop6", "noisy_drop7")]
+            m6 = torch.cat([dropout_masks[names[s][0]] for s in stacks], dim=1).contiguous()
+            m7 = [dropout_masks[names[s][1]] for s in stacks]
+        s0, s1 = stacks[0], stacks[-1] + 1
+        ops.FC(feat, self.w["W6"][s0 * H:s1 * H], self.p["b6"][s0 * H:s1 * H], relu=True, dropout=use_drop,
+               dropout_mask=m6, dropout_seed=(dropout_seed * 4 + 1) if (use_drop and m6 is None) else 0, out=drop6,
+               round_tf32=self.tf32)
+        for i, s in enumerate(stacks):
+            ops.FC(drop6[:, i * H:(i + 1) * H], self.w["W7_%d" % s], self.p["b7_%d" % s], relu=True, dropout=use_drop,
+                   dropout_mask=None if m7 is None else m7[i],
+                   dropout_seed=(dropout_seed * 4 + 2 + s) if (use_drop and m7 is None) else 0,
+                   out=drop7[:, i * H:(i + 1) * H], round_tf32=self.tf32)
+        bl["drop6_cat"], bl["drop7_cat"] = drop6, drop7
+        return drop6, drop7
+
+    def _fc8(self, drop7, stacks=None):
+        """fc8c | fc8d of every stack: one [R, 2C] GEMM per stack (fp32 logits)."""
+        H, C2 = self.H, 2 * self.C
+        stacks = list(range(self.S)) if stacks is None else stacks
+        R = drop7.shape[0]
+        ld = _round_up(C2, 8)
+        logits = self._scratch("logits", (len(stacks), R, ld), torch.float32)
+        for i, s in enumerate(stacks):
+            ops.FC(drop7[:, i * H:(i + 1) * H], self.w["W8_%d" % s], self.p["b8_%d" % s], out=logits[i][:, :C2])
+        self.blobs["fc8_logits"] = logits
+        return logits
+
+    # ------------------------------------------------------------------ the reference's builder names
+    def RunTrainStep(self, dropout_masks=None, dropout_seed=0, need_dX=False):
+        """One fwd+bwd pass of the head on the fed blobs (the slice of ``workspace.RunNet(net)``,
+        detectron/utils/train_wsl.py:59, that lies between conv5 and the parameter gradients).
+        Gradients land in ``self.g`` / ``self.flat_grad``; returns the blob dict."""
+        if not self.train:
+            raise RuntimeError("RunTrainStep on a test-mode model")
+        bl, H, C, C2 = self.blobs, self.H, self.C, 2 * self.C
+        drop6, drop7 = self._fc_stack(dropout_masks, dropout_seed)
+        logits = self._fc8(drop7)
+        R = drop7.shape[0]
+        ld = logits.shape[2]
+        dlog = self._scratch("dlogits", (self.S, R, ld), torch.float32)
+        gout = {"d_fc8c": dlog[0][:, :C], "d_fc8d": dlog[0][:, C:C2]}
+        if self.noise:
+            gout.update(d_nfc8c=dlog[1][:, :C], d_nfc8d=dlog[1][:, C:C2])
+        out = ops.mil_head(logits[0][:, :C], logits[0][:, C:C2], bl["rois"], bl["roi_offsets"], bl["labels_oh"],
+                           logits[1][:, :C] if self.noise else None, logits[1][:, C:C2] if self.noise else None,
+                           entropy=self.entropy, is_mean=self.mean_loss, backward=True, grads_out=gout)
+        bl.update(out)
+        bl["loss_cls"] = out["loss"][:, 0]
+        if self.noise:
+            bl["loss_cls_noise"] = out["loss"][:, 1]
+        # ---- backward (Caffe2 AddGradientOperators order: fc8 -> fc7 -> fc6) ----
+        if self.dtype == torch.bfloat16:
+            dl = self._scratch("dlogits_lp", (self.S, R, ld), torch.bfloat16)
+            ops.to_bf16(dlog.view(self.S * R, ld), out=dl.view(self.S * R, ld))
+        else:
+            dl = self._scratch("dlogits_lp", (self.S, R, ld), torch.float32)
+            ops.round_to_tf32(dlog.view(self.S * R, ld), out=dl.view(self.S * R, ld))
+        d6 = self._scratch("d_fc6", (R, self.S * H), self.dtype)
+        d7 = self._scratch("d_fc7", (R, H), self.dtype)
+        for s in range(self.S):
+            dls = dl[s][:, :C2]
+            a7 = drop7[:, s * H:(s + 1) * H]
+            a6 = drop6[:, s * H:(s + 1) * H]
+            ops.FCGradientW(dls, a7, dW=self.g["W8_%d" % s], db=self.g["b8_%d" % s])
+            ops.FCGradientX(dls, self.w["W8_%d" % s], act_below=a7, dropout=self._dropped, out=d7, round_tf32=self.tf32)
+            ops.FCGradientW(d7, a6, dW=self.g["W7_%d" % s], db=self.g["b7_%d" % s])
+            ops.FCGradientX(d7, self.w["W7_%d" % s], act_below=a6, dropout=self._dropped, out=d6[:, s * H:(s + 1) * H],
+                            round_tf32=self.tf32)
+        ops.FCGradientW(d6, bl["roi_feat"], dW=self.g["W6"], db=self.g["b6"])
+        if need_dX:
+            if bl["_argmax_roi_feat"] is None:
+                raise RuntimeError("need_dX requires freeze_conv_body=False (argmax is not kept otherwise)")
+            d_feat = ops.FCGradientX(d6, self.w["W6"], out_dtype=self.dtype)
+            N, Hh, Ww, Cc = bl["conv5"].shape
+            bl["d_conv5"] = ops.RoIPoolFGradient(bl["conv5"], bl["rois"], bl["_argmax_roi_feat"],
+                                                 d_feat.view(R, self.roi_size, self.roi_size, Cc),
+                                                 boost=bl["obn_scores"], layout="NHWC")
+        return bl
+
+    def RunTestNet(self):
+        """Test-time forward (detectron/core/test_wsl.py:142 ``RunNet``): clean stack only, no dropout;
+        ``cls_prob`` [R, C+1] with column 0 duplicated (detectron/modeling/wsl_heads.py:57-67)."""
+        bl, C, C2 = self.blobs, self.C, 2 * self.C
+        was_train, self.train = self.train, False
+        try:
+            _, drop7 = self._fc_stack(stacks=[0])
+            logits = self._fc8(drop7, stacks=[0])
+        finally:
+            self.train = was_train
+        R = drop7.shape[0]
+        B = bl["roi_offsets"].numel() - 1
+        labels = bl.get("labels_oh")
+        if labels is None:
+            labels = torch.zeros((B, C), dtype=torch.float32, device=self.device)
+        out = ops.mil_head(logits[0][:, :C], logits[0][:, C:C2], bl["rois"], bl["roi_offsets"], labels,
+                           entropy=False, is_mean=self.mean_loss, backward=False)
+        rp = out["rois_pred"]
+        bl["rois_pred"] = rp
+        bl["cls_prob"] = torch.cat([rp[:, :1], rp], dim=1)      # Split/Concat of the reference: a copy, no arithmetic
+        return bl["cls_prob"]
+
+    # ------------------------------------------------------------------ optimizer (single GPU; dp.py adds the all-reduce)
+    def UpdateWorkspaceLr(self, lr):
+        """detectron/modeling/detector.py:509-537: write the `lr` blob."""
+        self.lr.fill_(float(lr))
+
+    def param_update(self, momentum=0.9, weight_decay=5e-4, gpu_num=1, iter_size=1):
+        """``ACMWeightDecayMomentumSGDUpdate`` for every parameter (detectron/modeling/optimizer_wsl.py:96-137):
+        weights wd=5e-4, lr_mult=1; biases wd=0, lr_mult=2.  Two fused launches over the flat buffers."""
+        if iter_size != 1:
+            raise RuntimeError("iter_size > 1 needs an accumulator; use ops.ACMWeightDecayMomentumSGDUpdate directly")
+        nw, nt = self.n_weights, self.n_total
+        lp = self.flat_lp
+        ops.ACMWeightDecayMomentumSGDUpdate(self.flat_grad[:nw], self.flat_mom[:nw], self.lr, self.flat_param[:nw], None,
+                                            momentum=momentum, gpu_num=gpu_num, lr_mult=1.0, weight_decay=weight_decay,
+                                            iter_count=self.iter_count, p_shadow=lp[:nw])
+        ops.ACMWeightDecayMomentumSGDUpdate(self.flat_grad[nw:nt], self.flat_mom[nw:nt], self.lr, self.flat_param[nw:nt],
+                                            None, momentum=momentum, gpu_num=gpu_num, lr_mult=2.0, weight_decay=0.0,
+                                            iter_count=self.iter_count, p_shadow=lp[nw:nt])
+        self.iter_count += 1
+
+
+# ---------------------------------------------------------------------------------------------
+# Reference builder names (eager): the functions a caller of detectron/modeling/*_heads.py knows
+# ---------------------------------------------------------------------------------------------
+def add_VGG16_roi_2fc_head(model, blob_in=None, dim_in=None, spatial_scale=None, prefix=""):
+    """detectron/modeling/wsl_heads.py:654-681 (clean stack only).  Returns (drop7, 4096)."""
+    _, drop7 = model._fc_stack(stacks=[0])
+    return drop7[:, :model.H], model.H
+
+
+def add_VGG16_roi_2fc_noise_head(model, blob_in=None, dim_in=None, spatial_scale=None, prefix="", dropout_masks=None,
+                                 dropout_seed=0):
+    """detectron/modeling/webly_heads.py:463-502.  Returns ([drop7, noisy drop7], [4096, 4096])."""
+    _, drop7 = model._fc_stack(dropout_masks, dropout_seed)
+    H = model.H
+    return [drop7[:, s * H:(s + 1) * H] for s in range(model.S)], [H] * model.S
+
+
+def add_webly_outputs(model, blob_in=None, dim=None, prefix=""):
+    """detectron/modeling/webly_heads.py:32-74 (and wsl_heads.add_wsl_outputs for the clean stack):
+    the fc8 logits; the softmaxes / product are evaluated by ``add_webly_losses``' fused kernel."""
+    return model._fc8(model.blobs["drop7_cat"])

@@ -241,26 +241,27 @@ def _workspace(nbytes, device, tag):
 
 
 def mil_head(fc8c, fc8d, rois, roi_offsets, labels_oh, nfc8c=None, nfc8d=None, *, entropy=True, is_mean=True,
-             backward=True):
+             backward=True, grads_out=None):
     """The whole of ``add_wsl_outputs`` + ``add_webly_outputs`` + ``add_webly_losses`` and their
     gradient ops in one kernel (modeling/wsl_heads.py:23-56,213-227; modeling/webly_heads.py:32-74,
     123-197,265-391).  ``roi_offsets`` [B+1] int32 (device): rows of image b are
-    roi_offsets[b]:roi_offsets[b+1].  Returns a dict of the reference's blob names."""
-    _req(fc8c, "fc8c", torch.float32, 2)
-    _req(fc8d, "fc8d", torch.float32, 2)
+    roi_offsets[b]:roi_offsets[b+1].  The logits may be column slices of wider matrices (all
+    with one common row pitch), e.g. the halves of a fused [R,2C] fc8 output.  ``grads_out``:
+    optional dict of preallocated (possibly sliced) d_fc8c/d_fc8d/d_nfc8c/d_nfc8d tensors.
+    Returns a dict of the reference's blob names."""
+    R, C, ldl = _mat(fc8c, "fc8c")
+    B = labels_oh.shape[0]
+    noise = nfc8c is not None
+    logits = [fc8d] + ([nfc8c, nfc8d] if noise else [])
+    for t in [fc8c] + logits:
+        r2, c2, l2 = _mat(t, "logits")
+        if t.dtype != torch.float32 or (r2, c2, l2) != (R, C, ldl):
+            raise RuntimeError("mil_head: logits must be float32 [R,C] with one common row pitch")
     _req(rois, "rois", torch.float32, 2)
     _req(roi_offsets, "roi_offsets", torch.int32, 1)
     _req(labels_oh, "labels_oh", torch.float32, 2)
-    R, C = fc8c.shape
-    B = labels_oh.shape[0]
-    if tuple(fc8d.shape) != (R, C) or rois.shape[0] != R or labels_oh.shape[1] != C or roi_offsets.numel() != B + 1:
+    if rois.shape[0] != R or labels_oh.shape[1] != C or roi_offsets.numel() != B + 1:
         raise RuntimeError("mil_head: inconsistent shapes")
-    noise = nfc8c is not None
-    if noise:
-        _req(nfc8c, "nfc8c", torch.float32, 2)
-        _req(nfc8d, "nfc8d", torch.float32, 2)
-        if tuple(nfc8c.shape) != (R, C) or tuple(nfc8d.shape) != (R, C):
-            raise RuntimeError("mil_head: inconsistent noisy logits")
     dev = fc8c.device
     new = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
     out = {"rois_pred": new(R, C), "cls_prob": new(B, C), "loss": new(B, 2)}
@@ -268,19 +269,28 @@ def mil_head(fc8c, fc8d, rois, roi_offsets, labels_oh, nfc8c=None, nfc8d=None, *
         out.update(rois_pred_noise=new(R, C), cls_prob_noise=new(B, C))
         if entropy:
             out.update(class_weight=new(B, C), class_weight_noise=new(B, C))
+    ldg = C
     if backward:
-        out.update(d_fc8c=new(R, C), d_fc8d=new(R, C))
-        if noise:
-            out.update(d_nfc8c=new(R, C), d_nfc8d=new(R, C))
+        names = ["d_fc8c", "d_fc8d"] + (["d_nfc8c", "d_nfc8d"] if noise else [])
+        if grads_out is None:
+            out.update({n: new(R, C) for n in names})
+        else:
+            ldg = None
+            for n in names:
+                r2, c2, l2 = _mat(grads_out[n], n)
+                if grads_out[n].dtype != torch.float32 or (r2, c2) != (R, C) or (ldg is not None and l2 != ldg):
+                    raise RuntimeError("mil_head: grads_out tensors must be float32 [R,C] with one row pitch")
+                ldg = l2
+                out[n] = grads_out[n]
     flags = (_lib.MIL_ENTROPY if entropy else 0) | (_lib.MIL_MEAN if is_mean else 0) | \
             (_lib.MIL_BACKWARD if backward else 0)
     ws = _workspace(_lib.load().nawsod_mil_workspace_bytes(R, C, B), dev, "mil")
     g = out.get
-    _lib.call("nawsod_mil_head_fwd_bwd", _ptr(fc8c), _ptr(fc8d), _ptr(nfc8c), _ptr(nfc8d), _ptr(rois),
+    _lib.call("nawsod_mil_head_fwd_bwd", _ptr(fc8c), _ptr(fc8d), _ptr(nfc8c), _ptr(nfc8d), ldl, _ptr(rois),
               _ptr(roi_offsets), _ptr(labels_oh), R, C, B, flags, _ptr(g("rois_pred")), _ptr(g("cls_prob")),
               _ptr(g("rois_pred_noise")), _ptr(g("cls_prob_noise")), _ptr(g("class_weight")),
               _ptr(g("class_weight_noise")), _ptr(g("loss")), _ptr(g("d_fc8c")), _ptr(g("d_fc8d")),
-              _ptr(g("d_nfc8c")), _ptr(g("d_nfc8d")), _ptr(ws), _stream())
+              _ptr(g("d_nfc8c")), _ptr(g("d_nfc8d")), ldg, _ptr(ws), _stream())
     return out
 
 
@@ -288,7 +298,7 @@ def mil_head(fc8c, fc8d, rois, roi_offsets, labels_oh, nfc8c=None, nfc8d=None, *
 # ACMWeightDecayMomentumSGDUpdate
 # --------------------------------------------------------------------------------------------
 def ACMWeightDecayMomentumSGDUpdate(g, m, lr, p, acc, *, momentum=0.9, iter_size=1, gpu_num=1, lr_mult=1.0,
-                                    weight_decay=0.0, iter_count=0, p_bf16=None):
+                                    weight_decay=0.0, iter_count=0, p_shadow=None):
     """``ACMWeightDecayMomentumSGDUpdate([g, m, lr, p, acc] -> [g, m, p, acc])`` in place
     (ops/acm_weightdecay_momentum_sgd_op.cc:7-22; wiring modeling/optimizer_wsl.py:127-136).
     ``iter_count`` replaces the op's hidden ``iter_count_`` member; ``acc`` may be None when
@@ -300,11 +310,11 @@ def ACMWeightDecayMomentumSGDUpdate(g, m, lr, p, acc, *, momentum=0.9, iter_size
         raise RuntimeError("lr must have one element")
     if g.numel() != m.numel() or g.numel() != p.numel() or (acc is not None and acc.numel() != g.numel()):
         raise RuntimeError("g, m, p, acc must have the same number of elements")
-    if p_bf16 is not None:
-        _req(p_bf16, "p_bf16", torch.bfloat16)
+    if p_shadow is not None:
+        _req(p_shadow, "p_shadow", (torch.bfloat16, torch.float32))   # bf16 copy, or float rounded to TF32
     _lib.call("nawsod_sgd_update", _ptr(g), _ptr(m), _ptr(lr), _ptr(p), _ptr(acc), g.numel(), float(momentum),
-              float(weight_decay), float(lr_mult), int(iter_size), int(gpu_num), int(iter_count), _ptr(p_bf16),
-              _stream())
+              float(weight_decay), float(lr_mult), int(iter_size), int(gpu_num), int(iter_count), _ptr(p_shadow),
+              _DT[p_shadow.dtype] if p_shadow is not None else F32, _stream())
     return g, m, p, acc
 
 
@@ -326,7 +336,8 @@ def _ab(dtype):
     return _DT[dtype]
 
 
-def FC(X, W, b=None, *, relu=False, dropout_mask=None, dropout=False, out=None, out_dtype=None):
+def FC(X, W, b=None, *, relu=False, dropout_mask=None, dropout=False, dropout_seed=0, out=None, out_dtype=None,
+       round_tf32=False):
     """``FC([X, W, b] -> Y)`` with W [out, in] (Caffe2 layout), optionally fused with the
     ``Relu`` and ``Dropout(ratio=0.5, is_test=0)`` that follow it in the head
     (modeling/wsl_heads.py:674-679).  X may be a column slice of a wider matrix."""
@@ -343,18 +354,20 @@ def FC(X, W, b=None, *, relu=False, dropout_mask=None, dropout=False, out=None, 
     _, N2, ldy = _mat(Y, "Y")
     if N2 != N or Y.shape[0] != M:
         raise RuntimeError("FC: out has the wrong shape")
-    flags = (_lib.FC_RELU if relu else 0) | (_lib.FC_DROPOUT if (dropout or dropout_mask is not None) else 0)
+    flags = (_lib.FC_RELU if relu else 0) | \
+            (_lib.FC_DROPOUT if (dropout or dropout_mask is not None or dropout_seed) else 0) | \
+            (_lib.FC_ROUND_TF32 if round_tf32 else 0)
     ldm = 0
     if dropout_mask is not None:
         if dropout_mask.dtype != torch.uint8:
             raise RuntimeError("dropout_mask must be uint8 (0/1)")
         _, _, ldm = _mat(dropout_mask, "dropout_mask")
-    _lib.call("nawsod_fc_fwd", _ptr(X), lda, _ptr(W), ldw, _ptr(b), _ptr(dropout_mask), ldm, M, N, K, _ab(X.dtype),
+    _lib.call("nawsod_fc_fwd", _ptr(X), lda, _ptr(W), ldw, _ptr(b), _ptr(dropout_mask), ldm, int(dropout_seed), M, N, K, _ab(X.dtype),
               _ptr(Y), ldy, _DT[Y.dtype], flags, _stream())
     return Y
 
 
-def FCGradientX(dY, W, *, act_below=None, mask_below=None, dropout=False, out=None, out_dtype=None):
+def FCGradientX(dY, W, *, act_below=None, mask_below=None, dropout=False, out=None, out_dtype=None, round_tf32=False):
     """dX of ``FCGradient([X, W, dY] -> [dW, db, dX])`` fused with the ``DropoutGradient`` and
     ``ReluGradient`` of the layer below: dX = (dY . W) * 2[dropout] * (act_below > 0)."""
     M, N, lddy = _mat(dY, "dY")
@@ -366,7 +379,8 @@ def FCGradientX(dY, W, *, act_below=None, mask_below=None, dropout=False, out=No
     _, K2, ldda = _mat(dX, "dX")
     if K2 != K or dX.shape[0] != M:
         raise RuntimeError("FCGradientX: out has the wrong shape")
-    flags = (_lib.FC_RELU if act_below is not None else 0) | (_lib.FC_DROPOUT if (dropout or mask_below is not None) else 0)
+    flags = (_lib.FC_RELU if act_below is not None else 0) | (_lib.FC_DROPOUT if (dropout or mask_below is not None) else 0) | \
+            (_lib.FC_ROUND_TF32 if round_tf32 else 0)
     ldact, act_dt, ldm = 0, F32, 0
     if act_below is not None:
         _, _, ldact = _mat(act_below, "act_below")
@@ -404,4 +418,15 @@ def to_bf16(src, out=None):
     dst = torch.empty((rows, cols), dtype=torch.bfloat16, device=src.device) if out is None else out
     _, _, ldd = _mat(dst, "dst")
     _lib.call("nawsod_convert_f32_to_bf16", _ptr(src), lds, rows, cols, _ptr(dst), ldd, _stream())
+    return dst
+
+
+def round_to_tf32(src, out=None):
+    """float32 -> nearest TF32 value in a float32 container (``out`` may be ``src``)."""
+    rows, cols, lds = _mat(src, "src")
+    if src.dtype != torch.float32:
+        raise RuntimeError("round_to_tf32: source must be float32")
+    dst = torch.empty((rows, cols), dtype=torch.float32, device=src.device) if out is None else out
+    _, _, ldd = _mat(dst, "dst")
+    _lib.call("nawsod_round_to_tf32", _ptr(src), lds, rows, cols, _ptr(dst), ldd, _stream())
     return dst

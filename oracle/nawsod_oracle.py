@@ -361,12 +361,18 @@ def fc_stack_forward(feat, W6, b6, W7, b7, mask6=None, mask7=None):
     return dict(fc6=fc6, drop6=drop6, fc7=fc7, drop7=drop7)
 
 
-def fc_stack_backward(feat, acts, W6, W7, d_drop7, mask6=None, mask7=None, need_dfeat=False):
+def fc_stack_backward(feat, acts, W6, W7, d_drop7, mask6=None, mask7=None, need_dfeat=False,
+                      relu_pattern=None):
+    """relu_pattern: optional (pattern6, pattern7) boolean arrays that replace ``Y > 0`` in the two
+    ReluGradients.  Tests use it to evaluate the gradient arithmetic on the activation pattern
+    of the implementation under test: an element whose pre-activation is within rounding error
+    of zero may legitimately fall on either side of the ReLU, and its gradient then flips
+    between 0 and its full value."""
     d_fc7 = dropout_grad(d_drop7, mask7) if mask7 is not None else d_drop7
-    d_fc7 = relu_grad(acts["fc7"], d_fc7)
+    d_fc7 = relu_grad(acts["fc7"] if relu_pattern is None else relu_pattern[1], d_fc7)
     dW7, db7, d_drop6 = fc_grad(acts["drop6"], W7, d_fc7)
     d_fc6 = dropout_grad(d_drop6, mask6) if mask6 is not None else d_drop6
-    d_fc6 = relu_grad(acts["fc6"], d_fc6)
+    d_fc6 = relu_grad(acts["fc6"] if relu_pattern is None else relu_pattern[0], d_fc6)
     dW6, db6, d_feat = fc_grad(feat, W6, d_fc6)
     out = dict(fc6_w=dW6, fc6_b=db6, fc7_w=dW7, fc7_b=db7)
     if need_dfeat:
@@ -424,7 +430,7 @@ def mil_head_forward_backward(fc8c, fc8d, rois, labels_oh, nfc8c=None, nfc8d=Non
 
 def head_forward_backward(X, rois, obn_scores, labels_oh, params, spatial_scale=1.0 / 16,
                           masks=None, noise=True, entropy=True, is_mean=True, backward=True,
-                          need_dX=False):
+                          need_dX=False, relu_patterns=None):
     """The whole per-proposal head for ONE image (the reference asserts 1 image per GPU,
     modeling/wsl_heads.py:214): RoIPoolF -> RoIFeatureBoost -> fc6/fc7 (x2 stacks if
     ``noise``) -> fc8c/fc8d (+noisy) -> MIL -> noise-aware losses -> gradients of every
@@ -450,9 +456,10 @@ def head_forward_backward(X, rois, obn_scores, labels_oh, params, spatial_scale=
         nfc8d = fc(nacts["drop7"], params["noisy_fc8d_w"], params["noisy_fc8d_b"])
     out = mil_head_forward_backward(fc8c, fc8d, rois, labels_oh, nfc8c, nfc8d,
                                     entropy=entropy, is_mean=is_mean, backward=backward)
-    out.update(roi_feat=feat, argmax=A, fc8c=fc8c, fc8d=fc8d, drop7=acts["drop7"])
+    out.update(roi_feat=feat, argmax=A, fc8c=fc8c, fc8d=fc8d, drop7=acts["drop7"], acts=acts)
     if noise:
-        out.update(nfc8c=nfc8c, nfc8d=nfc8d)
+        out.update(nfc8c=nfc8c, nfc8d=nfc8d, noisy_acts=nacts)
+    relu_patterns = relu_patterns or {}
     if not backward:
         return out
     grads = {}
@@ -460,7 +467,8 @@ def head_forward_backward(X, rois, obn_scores, labels_oh, params, spatial_scale=
     dWd, dbd, dx_d = fc_grad(acts["drop7"], params["fc8d_w"], out["d_fc8d"])
     grads.update(fc8c_w=dWc, fc8c_b=dbc, fc8d_w=dWd, fc8d_b=dbd)
     g = fc_stack_backward(feat, acts, params["fc6_w"], params["fc7_w"], (dx_c + dx_d).astype(F32),
-                          masks.get("drop6"), masks.get("drop7"), need_dfeat=need_dX)
+                          masks.get("drop6"), masks.get("drop7"), need_dfeat=need_dX,
+                          relu_pattern=relu_patterns.get("clean"))
     d_feat = g.pop("d_feat", None)
     grads.update(g)
     if noise:
@@ -469,7 +477,8 @@ def head_forward_backward(X, rois, obn_scores, labels_oh, params, spatial_scale=
         grads.update(noisy_fc8c_w=dWc, noisy_fc8c_b=dbc, noisy_fc8d_w=dWd, noisy_fc8d_b=dbd)
         g = fc_stack_backward(feat, nacts, params["noisy_fc6_w"], params["noisy_fc7_w"],
                               (dx_c + dx_d).astype(F32), masks.get("noisy_drop6"),
-                              masks.get("noisy_drop7"), need_dfeat=need_dX)
+                              masks.get("noisy_drop7"), need_dfeat=need_dX,
+                              relu_pattern=relu_patterns.get("noisy"))
         d_feat_n = g.pop("d_feat", None)
         grads.update({"noisy_" + k: v for k, v in g.items()})
         if need_dX:

@@ -34,7 +34,7 @@ def test_status_codes_and_error_string():
     # argument validation happens before any CUDA call, so it is testable without a device
     rc = lib.nawsod_roi_pool_f_fwd(None, 0, 1, None, None, 1, 512, 38, 50, -1, 0.0625, 7, 7, None, 0, 1, None, None)
     assert rc == 2 and b"bad shape" in lib.nawsod_last_error()
-    rc = lib.nawsod_mil_head_fwd_bwd(*([None] * 7), 10, 500, 1, 0, *([None] * 13))
+    rc = lib.nawsod_mil_head_fwd_bwd(*([None] * 4), 500, *([None] * 3), 10, 500, 1, 0, *([None] * 11), 500, None, None)
     assert rc != 0 and b"C=500" in lib.nawsod_last_error()
     assert lib.nawsod_mil_workspace_bytes(2000, 20, 1) > 2000 * 20 * 4
 

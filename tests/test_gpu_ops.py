@@ -165,7 +165,7 @@ def test_sgd_matches_reference_golden(golden_dir):
             lr = torch.tensor([1e-3 if s < 4 else 1e-4], dtype=torch.float32, device="cuda")
             ops.ACMWeightDecayMomentumSGDUpdate(dev(G[s]), m, lr, p, acc, momentum=0.9, iter_size=int(isz),
                                                 gpu_num=int(gn), lr_mult=lm, weight_decay=wd, iter_count=s,
-                                                p_bf16=shadow)
+                                                p_shadow=shadow)
             assert np.array_equal(p.cpu().numpy(), g["sgd%d_P" % ci][s])       # bit-exact with the reference op
             assert np.array_equal(m.cpu().numpy(), g["sgd%d_M" % ci][s])
             assert np.array_equal(acc.cpu().numpy(), g["sgd%d_A" % ci][s])
@@ -267,5 +267,5 @@ def test_mil_head_plain_wsddn_and_no_entropy():
     _close(o["loss"][0, 0], ref["loss_cls"]); _close(o["loss"][0, 1], ref["loss_cls_noise"])
     for name in ("d_fc8c", "d_fc8d", "d_nfc8c", "d_nfc8d"):
         _close(o[name], ref[name])
-    # size-independent property: image scores are a convex combination -> sum_c cls_prob <= 1, each in [0,1]
-    assert (o["cls_prob"] >= 0).all() and o["cls_prob"].sum() <= 1 + 1e-5
+    # size-independent property: y_c = sum_r a_cls*a_det with sum_r a_det = 1 and a_cls <= 1 -> each y_c in [0,1]
+    assert (o["cls_prob"] >= 0).all() and (o["cls_prob"] <= 1 + 1e-5).all()

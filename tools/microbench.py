@@ -85,7 +85,7 @@ def bench_sgd():
     sh = torch.empty(n, dtype=torch.bfloat16, device="cuda")
     lr = torch.tensor([1e-3], device="cuda")
     for shadow in (None, sh):
-        med, best = timeit(lambda: ops.ACMWeightDecayMomentumSGDUpdate(g, m, lr, p, None, weight_decay=5e-4, iter_count=3, p_bf16=shadow), iters=10)
+        med, best = timeit(lambda: ops.ACMWeightDecayMomentumSGDUpdate(g, m, lr, p, None, weight_decay=5e-4, iter_count=3, p_shadow=shadow), iters=10)
         byt = n * (20 + (2 if shadow is not None else 0))
         print("sgd n=%d shadow=%s: med %.1f us  %.0f GB/s (%.1f%%)" % (n, shadow is not None, med * 1e3, byt / med / 1e6, 100 * byt / med / 1e6 / PEAKS["hbm_gbs"]), flush=True)
 
