@@ -1,0 +1,394 @@
+#!/usr/bin/env python
+"""Headline benchmark: RoIs/sec through the NA-fWebSOD per-proposal head, fwd + bwd (+ gradient
+all-reduce + SGD update), BASELINE.json config 2 per GPU: 2 images x 2000 proposals, 20 classes,
+VGG16 conv5 map 512x38x50, two-stack noise-aware head, bf16 tensor-core path.
+
+    python bench.py --gpus N --steps K --warmup W                 # our arm (N>1: launched by torchrun)
+    python bench.py --impl reference --gpus N --steps K --warmup W # the reference's CPU path (oracle port)
+
+One JSON line on stdout (rank 0).  A "step" is one pass of the hot path over one batch of
+synthetic input.  `value` is measured with the inputs resident in HBM; `e2e` runs the same step
+through the public API from pinned HOST buffers (H2D of the step's inputs and D2H of its loss
+inside the timed region).  Timing: CUDA events on the launching stream, barrier + synchronize
+on both sides, max over ranks.  The working set (>1.5 GB of weights, gradients and activations
+per step) is far larger than the 126 MB L2, so no explicit flush is needed.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "RoIs/sec (fwd+bwd, WSDDN head)"
+UNIT = "RoIs/s"
+IMAGES_PER_GPU, ROIS_PER_IMAGE, NUM_CLASSES = 2, 2000, 21
+C5, H5, W5 = 512, 38, 50
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm=p["hbm_gbs"], tf_burst=p["bf16_tflops"], tf_sustained=p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+def _flops_per_roi(noise=True, C=NUM_CLASSES - 1, D=C5 * 49, H=4096):
+    """fwd 2*(D*H + H*H + 2*H*C), bwd as the reference runs it (no fc6 dX)."""
+    fwd = 2 * (D * H + H * H + 2 * H * C)
+    bwd = 2 * (D * H) + 2 * 2 * (H * H) + 2 * 2 * (2 * H * C)
+    return (fwd + bwd) * (2 if noise else 1)
+
+
+def synth_conv5(n, c, h, w, seed):
+    """Post-ReLU-like conv5_3 map: U[0,1) * Bernoulli(0.5)."""
+    rng = np.random.default_rng(seed)
+    return (rng.random((n, c, h, w), dtype=np.float32) * (rng.random((n, c, h, w)) < 0.5)).astype(np.float32)
+
+
+def synth_rois(r, img_h, img_w, batch_idx, seed):
+    """MCG-like integer boxes, side 16 px .. image/2, as (batch_idx, x1, y1, x2, y2)."""
+    rng = np.random.default_rng(seed)
+    x1 = np.floor(rng.random(r) * (img_w - 17))
+    y1 = np.floor(rng.random(r) * (img_h - 17))
+    bw = np.floor(16 + rng.random(r) * (img_w / 2 - 16))
+    bh = np.floor(16 + rng.random(r) * (img_h / 2 - 16))
+    return np.stack([np.full(r, batch_idx), x1, y1, np.minimum(x1 + bw, img_w - 1), np.minimum(y1 + bh, img_h - 1)],
+                    axis=1).astype(np.float32)
+
+
+def synth_inputs(images, rois_per_image, seed=0):
+    X = synth_conv5(images, C5, H5, W5, seed=seed)
+    rois = np.concatenate([synth_rois(rois_per_image, H5 * 16, W5 * 16, b, seed=seed + 1 + b) for b in range(images)])
+    rng = np.random.default_rng(seed + 100)
+    obn = (rng.random(rois.shape[0]) + 1).astype(np.float32)
+    L = np.zeros((images, NUM_CLASSES - 1), np.float32)
+    for b in range(images):
+        L[b, rng.integers(NUM_CLASSES - 1)] = 1          # webly images are single-label (loader_wsl.py:86-93)
+    offs = np.asarray([b * rois_per_image for b in range(images)] + [rois.shape[0]], np.int32)
+    return X, rois, obn, L, offs
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU leg: the oracle port of the reference's algorithm, timed on this box's host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_head_step(X, rois, obn, L, params, masks):
+    """One fwd+bwd of the head for ONE image with the CPU oracle (C restatement of RoIPoolF with
+    OpenMP + NumPy/BLAS for the FC stack + the MIL / noise-weight / loss restatement)."""
+    from oracle import nawsod_oracle as O
+    from oracle import c_oracle as CO
+    Y, _ = CO.roi_pool_f(X, rois, 1.0 / 16)
+    feat = O.roi_feature_boost(Y, obn).reshape(Y.shape[0], -1)
+    stacks, logits = [], []
+    for pre in ("", "noisy_"):
+        a = O.fc_stack_forward(feat, params[pre + "fc6_w"], params[pre + "fc6_b"], params[pre + "fc7_w"], params[pre + "fc7_b"],
+                               masks[pre + "drop6"], masks[pre + "drop7"])
+        stacks.append(a)
+        logits += [O.fc(a["drop7"], params[pre + "fc8c_w"], params[pre + "fc8c_b"]), O.fc(a["drop7"], params[pre + "fc8d_w"], params[pre + "fc8d_b"])]
+    out = O.mil_head_forward_backward(logits[0], logits[1], rois, L, logits[2], logits[3])
+    for pre, a, dc, dd in (("", stacks[0], out["d_fc8c"], out["d_fc8d"]), ("noisy_", stacks[1], out["d_nfc8c"], out["d_nfc8d"])):
+        _, _, dxc = O.fc_grad(a["drop7"], params[pre + "fc8c_w"], dc)
+        _, _, dxd = O.fc_grad(a["drop7"], params[pre + "fc8d_w"], dd)
+        O.fc_stack_backward(feat, a, params[pre + "fc6_w"], params[pre + "fc7_w"], dxc + dxd, masks[pre + "drop6"], masks[pre + "drop7"])
+    return float(out["loss_cls"]) + float(out["loss_cls_noise"])
+
+
+def cpu_problem(rois_n, seed=0):
+    from oracle import nawsod_oracle as O
+    X, rois, obn, L, _ = synth_inputs(1, rois_n, seed)
+    params = O.synth_params(NUM_CLASSES - 1, C5 * 49, 4096, noise=True, seed=2)
+    rng = np.random.default_rng(3)
+    masks = {k: (rng.random((rois_n, 4096)) < 0.5).astype(np.float32) for k in ("drop6", "drop7", "noisy_drop6", "noisy_drop7")}
+    return X, rois, obn, L, params, masks
+
+
+def run_cpu(steps, warmup, sample_rois):
+    prob = cpu_problem(sample_rois)
+    for _ in range(warmup):
+        cpu_head_step(*prob)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_head_step(*prob)
+    dt = time.perf_counter() - t0
+    return sample_rois * steps / dt, dt / steps
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    sample = 250
+    steps, warmup = max(1, min(args.steps, 10)), max(1, min(args.warmup, 2))
+    value, per = run_cpu(steps, warmup, sample)
+    desc = ("1 image x %d RoIs per step (of the 2 x 2000 workload), 512x38x50 map, 20 classes, two-stack head, fwd+bwd, fp32; "
+            "oracle port of the reference's CPU algorithm (Caffe2 itself is not installable here): C/OpenMP RoIPoolF + NumPy/BLAS") % sample
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+        "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "NA-fWebSOD head fwd+bwd, BASELINE config 2 shapes (2 img x 2000 RoIs, 20 classes, conv5 512x38x50), CPU sample",
+                   "sample": desc},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi sampled DURING the timed region (B200_PROFILING.md 'clocks line')."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.proc, self.path = gpu_index, None, "/tmp/nawsod_clocks_%d.csv" % os.getpid()
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "50"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, smax, reasons, power = [], None, set(), []
+        for ln in open(self.path):
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax = float(f[2]); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": smax, "reasons": ["no samples"]}
+        busy = [c for c, p in zip(sm, power) if p > 0.5 * max(power)] or sm
+        return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm),
+                "power_w_max": max(power)}
+
+
+def gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    import nafwebsod_b200 as pkg
+    from nafwebsod_b200 import _lib
+    from nafwebsod_b200.heads import WeblyHeadModel
+    from nafwebsod_b200.dp import DataParallelHead
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: libnawsod has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+    dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+    noise = args.head == "na"
+
+    # ---- model: random-init weights of the reference architecture (no checkpoints offline) ----
+    model = WeblyHeadModel(NUM_CLASSES, C5, 7, 4096, noise=noise, dtype=dtype, device=dev)
+    g = torch.Generator(device=dev).manual_seed(2)
+    nw = model.n_weights
+    model.flat_param[:nw].normal_(0.0, 0.01, generator=g)          # gauss_fill(0.01); biases stay 0
+    for s in range(model.S):                                        # XavierFill for fc8
+        lim = float(np.sqrt(3.0 / 4096))
+        model.p["W8_%d" % s].uniform_(-lim, lim, generator=g)
+    model.sync_shadow()
+    dp = DataParallelHead(model, fc6_panels=args.fc6_panels)
+    dp.broadcast_parameters()
+    model.UpdateWorkspaceLr(1e-3)
+
+    # ---- this rank's shard of the synthetic batch (weak scaling: 2 images per GPU) ----
+    X, rois, obn, L, offs = synth_inputs(IMAGES_PER_GPU, ROIS_PER_IMAGE, seed=1000 * rank)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    hX, hrois, hobn, hL, hoffs = pin(X), pin(rois), pin(obn), pin(L), pin(offs)
+    h2d_bytes = sum(t.numel() * t.element_size() for t in (hX, hrois, hobn, hL, hoffs))
+    R = rois.shape[0]
+
+    def feed_from_host():
+        model.FeedBlobs(hX.to(dev, non_blocking=True), hrois.to(dev, non_blocking=True), hobn.to(dev, non_blocking=True),
+                        hL.to(dev, non_blocking=True), hoffs.to(dev, non_blocking=True), x_layout="NCHW")
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        sync_all()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(steps):
+            fn(i)
+        b.record()
+        sync_all()
+        ms = torch.tensor([a.elapsed_time(b)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    # ---- resident-input leg (value) ----
+    feed_from_host()                      # inputs now live in HBM (channels-last bf16 map etc.)
+    step_resident = lambda i: dp.step(dropout_seed=i + 1)
+    for i in range(args.warmup):
+        step_resident(i)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    model.profile = {}
+    launches0 = _lib.launch_count
+    ms_total = timed(step_resident, args.steps)
+    launches = _lib.launch_count - launches0
+    prof, model.profile = model.profile, None
+    ms_step = ms_total / args.steps
+    value = world * R * args.steps / (ms_total * 1e-3)
+
+    # ---- end-to-end leg: host buffers in, loss out, every step ----
+    losses = []
+
+    def step_e2e(i):
+        feed_from_host()
+        bl = dp.step(dropout_seed=i + 1)
+        losses.append(bl["loss"].to("cpu", non_blocking=False))      # D2H read of the step's result
+
+    for i in range(max(1, args.warmup // 2)):
+        step_e2e(i)
+    ms_e2e = timed(step_e2e, args.steps)
+    # clocks are sampled across BOTH timed regions (resident + end-to-end) so that short runs still
+    # collect samples under load
+    clocks = sampler.stop() if rank == 0 else None
+    e2e_value = world * R * args.steps / (ms_e2e * 1e-3)
+    d2h_bytes = int(losses[-1].numel() * losses[-1].element_size())
+    assert all(bool(torch.isfinite(l).all()) for l in losses), "non-finite loss in the benchmark"
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel + per-kernel breakdown from the in-run events ----
+    peaks = _peaks()
+    def avg_ms(name):
+        ev = prof.get(name, [])
+        return sum(a.elapsed_time(b) for a, b in ev) / max(len(ev), 1) if ev else None
+    S = model.S
+    es = 2 if dtype == torch.bfloat16 else 4
+    fc6_flops = 2.0 * R * (S * 4096) * (C5 * 49)
+    t_fwd, t_bww, t_pool, t_mil = avg_ms("fc6_fwd"), avg_ms("fc6_bwd_w"), avg_ms("roi_pool_f"), avg_ms("mil_head")
+    n_panels = max(1, len(prof.get("fc6_bwd_w", [])) // max(args.steps, 1))
+    t_bww_total = t_bww * n_panels if t_bww else None
+    pool_bytes = R * (C5 * 49 * es + 20) + IMAGES_PER_GPU * C5 * H5 * W5 * es     # no argmax: conv body frozen (StopGradient)
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("fc6_bwd_w_dram_bytes_per_launch")
+    tensor_peak = peaks["tf_sustained"] * (1.0 if dtype == torch.bfloat16 else 0.5)
+    roofline = {
+        "kernel": "gemm_tcgen05_kernel<256,MN,MN> (fc6 weight gradient, dY^T.X, both stacks fused)",
+        "bound": "tensor", "achieved": fc6_flops / (t_bww_total * 1e-3) / 1e12 if t_bww_total else None, "peak": tensor_peak,
+        "unit": "TFLOP/s", "traffic": traffic, "peak_source": peaks["source"] + ("; sustained bf16" if dtype == torch.bfloat16 else "; TF32 = bf16/2"),
+    }
+    roofline["frac"] = roofline["achieved"] / tensor_peak if roofline["achieved"] else None
+    kernels = {
+        "fc6_fwd": {"ms": t_fwd, "tflops": fc6_flops / (t_fwd * 1e-3) / 1e12 if t_fwd else None,
+                    "frac_tensor": fc6_flops / (t_fwd * 1e-3) / 1e12 / tensor_peak if t_fwd else None},
+        "fc6_bwd_w": {"ms": t_bww_total, "panels": n_panels, "tflops": roofline["achieved"], "frac_tensor": roofline["frac"]},
+        "roi_pool_f": {"ms": t_pool, "gbs": pool_bytes / (t_pool * 1e-3) / 1e9 if t_pool else None,
+                       "frac_hbm": pool_bytes / (t_pool * 1e-3) / 1e9 / peaks["hbm"] if t_pool else None,
+                       "algorithmic_bytes": pool_bytes},
+        "mil_head": {"ms": t_mil},
+        "step_tensor_frac": _flops_per_roi(noise) * R / (ms_step * 1e-3) / 1e12 / tensor_peak,
+    }
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        sample = 250
+        v, per = run_cpu(3, 1, sample)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "3 steps of 1 image x %d RoIs (bounded sample of the 2 x 2000 workload), fp32 oracle port: C/OpenMP RoIPoolF + NumPy/BLAS "
+                         "FC stack + MIL/loss restatement, %.2f s per step" % (sample, per)}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16" if dtype == torch.bfloat16 else "tf32", "data": "synthetic",
+        "config": {"workload": "NA-fWebSOD head fwd+bwd+allreduce+SGD, BASELINE config 2 per GPU: %d images x %d RoIs, %d classes, conv5 %dx%dx%d, "
+                               "RoIPoolF 7x7 @1/16 + boost, %s fc6/fc7 4096, seeded dropout" % (
+                                   IMAGES_PER_GPU, ROIS_PER_IMAGE, NUM_CLASSES - 1, C5, H5, W5, "two-stack (clean + noisy)" if noise else "single-stack"),
+                   "global_rois_per_step": world * R, "parallelism": "dp%d (images sharded by rank, 1 grad all-reduce/step)" % world,
+                   "l2": "working set per step (weights 0.5 GB bf16 + 0.96 GB fp32 grads + activations) >> 126 MB L2; no flush needed",
+                   "fc6_panels": dp.fc6_panels},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": d2h_bytes,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roofline,
+        "kernels": kernels,
+        "cpu_baseline": cpu,
+        "loss": [float(x) for x in losses[-1].flatten().tolist()],
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "tf32"])
+    ap.add_argument("--head", default="na", choices=["na", "wsddn"])
+    ap.add_argument("--fc6-panels", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return reference_arm(args)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus != world:
+        if world == 1 and args.gpus > 1:
+            # convenience: re-launch under torchrun on one node
+            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+                   "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000), os.path.abspath(__file__)] + sys.argv[1:]
+            return subprocess.call(cmd)
+        raise RuntimeError("--gpus %d does not match WORLD_SIZE %d" % (args.gpus, world))
+    return gpu_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

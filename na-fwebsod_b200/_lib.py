@@ -40,6 +40,15 @@ PROTOTYPES = {
     "nawsod_sgd_update": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _f, _f, _f, _i, _i, _i64, _vp, _i, _vp]),
 }
 
+# kernels launched per C-ABI call (bench.py reports the count of OUR kernels in the timed region)
+KERNELS_PER_CALL = {
+    "nawsod_transpose_batched": 1, "nawsod_roi_pool_f_fwd": 1, "nawsod_roi_pool_f_bwd": 1, "nawsod_roi_feature_boost": 1,
+    "nawsod_fc_fwd": 1, "nawsod_fc_bwd_x": 1, "nawsod_fc_bwd_w": 1, "nawsod_convert_f32_to_bf16": 1,
+    "nawsod_round_to_tf32": 1, "nawsod_mil_head_fwd_bwd": 1, "nawsod_roi_iou": 1, "nawsod_cross_entropy_fwd": 1,
+    "nawsod_cross_entropy_bwd": 1, "nawsod_sgd_update": 1,
+}
+launch_count = 0
+
 _lib = None
 
 
@@ -66,8 +75,10 @@ def check(rc: int):
         raise RuntimeError("libnawsod error %d: %s" % (rc, msg.decode() if msg else "?"))
 
 
-def call(name: str, *args):
+def call(name: str, *args, extra_kernels: int = 0):
+    global launch_count
     check(getattr(load(), name)(*args))
+    launch_count += KERNELS_PER_CALL.get(name, 0) + extra_kernels
 
 
 def set_tuning(key: str, value: int):

@@ -58,6 +58,7 @@ class WeblyHeadModel:
         self.tf32 = dtype == torch.float32
         self.blobs = {}
         self._buf = {}
+        self.profile = None        # dict name -> [(start_event, end_event)] when bench.py instruments a run
         self.iter_count = 0
         self._alloc_params()
 
@@ -153,6 +154,17 @@ class WeblyHeadModel:
     def export_reference_grads(self):
         return self._export(self.g)
 
+    def _timed(self, name, fn):
+        """Run fn(); when instrumented, bracket it with CUDA events on the launching stream."""
+        if self.profile is None:
+            return fn()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        r = fn()
+        b.record()
+        self.profile.setdefault(name, []).append((a, b))
+        return r
+
     # ------------------------------------------------------------------ scratch
     def _scratch(self, name, shape, dtype):
         t = self._buf.get(name)
@@ -184,9 +196,9 @@ class WeblyHeadModel:
         bl, H = self.blobs, self.H
         stacks = list(range(self.S)) if stacks is None else stacks
         need_argmax = self.train and not self.freeze_conv_body
-        roi_feat, argmax = ops.RoIPoolF(bl["conv5"], bl["rois"], pooled_h=self.roi_size, pooled_w=self.roi_size,
-                                        spatial_scale=self.spatial_scale, is_test=not need_argmax,
-                                        boost=bl["obn_scores"], x_layout="NHWC", y_layout="NHWC", out_dtype=self.dtype)
+        roi_feat, argmax = self._timed("roi_pool_f", lambda: ops.RoIPoolF(
+            bl["conv5"], bl["rois"], pooled_h=self.roi_size, pooled_w=self.roi_size, spatial_scale=self.spatial_scale,
+            is_test=not need_argmax, boost=bl["obn_scores"], x_layout="NHWC", y_layout="NHWC", out_dtype=self.dtype))
         R = roi_feat.shape[0]
         feat = roi_feat.view(R, self.D)
         if self.tf32:
@@ -205,9 +217,10 @@ class WeblyHeadModel:
             m6 = torch.cat([dropout_masks[names[s][0]] for s in stacks], dim=1).contiguous()
             m7 = [dropout_masks[names[s][1]] for s in stacks]
         s0, s1 = stacks[0], stacks[-1] + 1
-        ops.FC(feat, self.w["W6"][s0 * H:s1 * H], self.p["b6"][s0 * H:s1 * H], relu=True, dropout=use_drop,
-               dropout_mask=m6, dropout_seed=(dropout_seed * 4 + 1) if (use_drop and m6 is None) else 0, out=drop6,
-               round_tf32=self.tf32)
+        self._timed("fc6_fwd", lambda: ops.FC(
+            feat, self.w["W6"][s0 * H:s1 * H], self.p["b6"][s0 * H:s1 * H], relu=True, dropout=use_drop,
+            dropout_mask=m6, dropout_seed=(dropout_seed * 4 + 1) if (use_drop and m6 is None) else 0, out=drop6,
+            round_tf32=self.tf32))
         for i, s in enumerate(stacks):
             ops.FC(drop6[:, i * H:(i + 1) * H], self.w["W7_%d" % s], self.p["b7_%d" % s], relu=True, dropout=use_drop,
                    dropout_mask=None if m7 is None else m7[i],
@@ -229,10 +242,16 @@ class WeblyHeadModel:
         return logits
 
     # ------------------------------------------------------------------ the reference's builder names
-    def RunTrainStep(self, dropout_masks=None, dropout_seed=0, need_dX=False):
+    def RunTrainStep(self, dropout_masks=None, dropout_seed=0, need_dX=False, fc6_panels=1, on_small_grads=None,
+                     on_fc6_panel=None):
         """One fwd+bwd pass of the head on the fed blobs (the slice of ``workspace.RunNet(net)``,
         detectron/utils/train_wsl.py:59, that lies between conv5 and the parameter gradients).
-        Gradients land in ``self.g`` / ``self.flat_grad``; returns the blob dict."""
+        Gradients land in ``self.g`` / ``self.flat_grad``; returns the blob dict.
+
+        Data-parallel hooks (dp.py): the dominant fc6 weight gradient is produced LAST in the
+        backward pass, so it is computed in ``fc6_panels`` row panels and ``on_fc6_panel(r0, r1)``
+        fires after each one (its all-reduce then overlaps the next panel's GEMM);
+        ``on_small_grads()`` fires once the fc7 / fc8 weight gradients are complete."""
         if not self.train:
             raise RuntimeError("RunTrainStep on a test-mode model")
         bl, H, C, C2 = self.blobs, self.H, self.C, 2 * self.C
@@ -244,9 +263,10 @@ class WeblyHeadModel:
         gout = {"d_fc8c": dlog[0][:, :C], "d_fc8d": dlog[0][:, C:C2]}
         if self.noise:
             gout.update(d_nfc8c=dlog[1][:, :C], d_nfc8d=dlog[1][:, C:C2])
-        out = ops.mil_head(logits[0][:, :C], logits[0][:, C:C2], bl["rois"], bl["roi_offsets"], bl["labels_oh"],
-                           logits[1][:, :C] if self.noise else None, logits[1][:, C:C2] if self.noise else None,
-                           entropy=self.entropy, is_mean=self.mean_loss, backward=True, grads_out=gout)
+        out = self._timed("mil_head", lambda: ops.mil_head(
+            logits[0][:, :C], logits[0][:, C:C2], bl["rois"], bl["roi_offsets"], bl["labels_oh"],
+            logits[1][:, :C] if self.noise else None, logits[1][:, C:C2] if self.noise else None,
+            entropy=self.entropy, is_mean=self.mean_loss, backward=True, grads_out=gout))
         bl.update(out)
         bl["loss_cls"] = out["loss"][:, 0]
         if self.noise:
@@ -269,7 +289,16 @@ class WeblyHeadModel:
             ops.FCGradientW(d7, a6, dW=self.g["W7_%d" % s], db=self.g["b7_%d" % s])
             ops.FCGradientX(d7, self.w["W7_%d" % s], act_below=a6, dropout=self._dropped, out=d6[:, s * H:(s + 1) * H],
                             round_tf32=self.tf32)
-        ops.FCGradientW(d6, bl["roi_feat"], dW=self.g["W6"], db=self.g["b6"])
+        if on_small_grads is not None:
+            on_small_grads()
+        rows = self.S * H
+        step = _round_up((rows + fc6_panels - 1) // fc6_panels, 256)
+        for r0 in range(0, rows, step):
+            r1 = min(rows, r0 + step)
+            self._timed("fc6_bwd_w", lambda: ops.FCGradientW(d6[:, r0:r1], bl["roi_feat"], dW=self.g["W6"][r0:r1],
+                                                             db=self.g["b6"][r0:r1]))
+            if on_fc6_panel is not None:
+                on_fc6_panel(r0, r1)
         if need_dX:
             if bl["_argmax_roi_feat"] is None:
                 raise RuntimeError("need_dX requires freeze_conv_body=False (argmax is not kept otherwise)")

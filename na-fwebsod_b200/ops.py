@@ -406,7 +406,7 @@ def FCGradientW(dY, X, *, dW=None, db=None, want_db=True, accumulate=False):
     if db is None and want_db:
         db = torch.empty((N,), dtype=torch.float32, device=dY.device)
     _lib.call("nawsod_fc_bwd_w", _ptr(dY), lddy, _ptr(X), lda, M, N, K, _ab(dY.dtype), _ptr(dW), lddw, _ptr(db),
-              _lib.FC_ACCUMULATE if accumulate else 0, _stream())
+              _lib.FC_ACCUMULATE if accumulate else 0, _stream(), extra_kernels=1 if db is not None else 0)
     return dW, db
 
 
