@@ -15,6 +15,7 @@
 //   (L2-resident) map directly.
 #include <algorithm>
 #include <cfloat>
+#include <type_traits>
 #include "common.cuh"
 
 namespace nawsod {
@@ -79,14 +80,86 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gsrc));
 }
 
-template <typename TIn, typename TOut, bool kSmem>
-__global__ void __launch_bounds__(512) roi_pool_fwd_kernel(const PoolParams p) {
+// Per-bin scanners.  A lane owns VEC channels of one bin; the window is walked in the reference's
+// (h, w) row-major order with strict '>' so ties resolve to the first cell (roi_loop_pool_op.cu:77-95).
+template <bool kArgmax>
+struct ScanF32 {   // fp32 map, VEC = 4
+  float m[4]; int i[4];
+  __device__ __forceinline__ void init(bool empty) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { m[k] = empty ? 0.f : -FLT_MAX; i[k] = -1; }
+  }
+  __device__ __forceinline__ void visit(const uint4& q, int idx) {
+    const float x[4] = {__uint_as_float(q.x), __uint_as_float(q.y), __uint_as_float(q.z), __uint_as_float(q.w)};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (kArgmax) { if (x[k] > m[k]) { m[k] = x[k]; i[k] = idx; } }
+      else m[k] = fmaxf(m[k], x[k]);
+    }
+  }
+  __device__ __forceinline__ void result(bool, float (&v)[4], int (&a)[4]) const {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { v[k] = m[k]; a[k] = i[k]; }
+  }
+};
+
+// bf16 map, VEC = 8: packed bf16x2 compare/select (3 instructions per 2 elements with argmax,
+// 1 per 2 without).  Cell indices are carried as packed u16 pairs (host guarantees H*W <= 65535),
+// 0xFFFF = "never selected".  The running maximum starts at -inf: every finite bf16 beats it,
+// exactly like -FLT_MAX in the fp32 reference.
+template <bool kArgmax>
+struct ScanBF16 {
+  uint32_t m[4]; uint32_t i[4];
+  __device__ __forceinline__ void init(bool) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { m[k] = 0xFF80FF80u; i[k] = 0xFFFFFFFFu; }
+  }
+  __device__ __forceinline__ void visit(const uint4& q, int idx) {
+    const uint32_t x[4] = {q.x, q.y, q.z, q.w};
+    const uint32_t idx2 = static_cast<uint32_t>(idx) * 0x00010001u;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const __nv_bfloat162 xv = *reinterpret_cast<const __nv_bfloat162*>(&x[k]);
+      const __nv_bfloat162 mv = *reinterpret_cast<const __nv_bfloat162*>(&m[k]);
+      if (kArgmax) {
+        const uint32_t gt = __hgt2_mask(xv, mv);                  // 0xFFFF per half where x > m (strict)
+        m[k] = (x[k] & gt) | (m[k] & ~gt);
+        i[k] = (idx2 & gt) | (i[k] & ~gt);
+      } else {
+        const __nv_bfloat162 r = __hmax2(xv, mv);
+        m[k] = *reinterpret_cast<const uint32_t*>(&r);
+      }
+    }
+  }
+  __device__ __forceinline__ void result(bool empty, float (&v)[8], int (&a)[8]) const {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      v[2 * k] = empty ? 0.f : __uint_as_float(m[k] << 16);
+      v[2 * k + 1] = empty ? 0.f : __uint_as_float(m[k] & 0xffff0000u);
+      const uint32_t lo = i[k] & 0xFFFFu, hi = i[k] >> 16;
+      a[2 * k] = (lo == 0xFFFFu) ? -1 : static_cast<int>(lo);
+      a[2 * k + 1] = (hi == 0xFFFFu) ? -1 : static_cast<int>(hi);
+    }
+  }
+};
+
+// Forward.  grid = (channel slabs, RoI chunks, images).  One WARP owns one RoI at a time (fetched
+// dynamically from the CTA's chunk); its 32 lanes are (bin slot, 16-byte channel vector) pairs, so
+// all lanes share the RoI geometry and loop trip counts differ by at most one cell.
+template <typename TIn, typename TOut, bool kSmem, bool kArgmax, bool k7x7>
+__global__ void __launch_bounds__(1024, 1) roi_pool_fwd_kernel(const PoolParams p) {
   constexpr int VEC = Vec<TIn>::N;
+  using Scan = typename std::conditional<sizeof(TIn) == 4, ScanF32<kArgmax>, ScanBF16<kArgmax>>::type;
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ int next_roi;
   const int slab = blockIdx.x, chunk = blockIdx.y, n = blockIdx.z;
   const int HW = p.H * p.W;
-  const int vpr = p.SC / VEC;   // 16-byte vectors per RoI in this slab
+  const int vpr = p.SC / VEC;          // lanes per bin slot (power of two <= 32)
+  const int slots = 32 / vpr;          // bins handled concurrently by one warp
   const TIn* gbase = static_cast<const TIn*>(p.X) + (size_t)n * HW * p.C + (size_t)slab * p.SC;
+  const int r0 = chunk * p.rois_per_chunk;
+  const int r1 = min(p.R, r0 + p.rois_per_chunk);
+  if (threadIdx.x == 0) next_roi = r0;
 
   const TIn* src;
   int row_stride;   // elements between consecutive cells
@@ -99,77 +172,87 @@ __global__ void __launch_bounds__(512) roi_pool_fwd_kernel(const PoolParams p) {
     }
     asm volatile("cp.async.commit_group;\n" ::);
     asm volatile("cp.async.wait_group 0;\n" ::);
-    __syncthreads();
     src = s;
     row_stride = p.SC;
   } else {
     src = gbase;
     row_stride = p.C;
   }
+  __syncthreads();
 
-  const int r0 = chunk * p.rois_per_chunk;
-  const int r1 = min(p.R, r0 + p.rois_per_chunk);
-  const int items = (r1 - r0) * vpr;
-  TOut* Y = static_cast<TOut*>(p.Y);
+  const int lane = threadIdx.x & 31;
+  const int v = lane % vpr, slot = lane / vpr;
   const int W = p.W, H = p.H;
+  const int PH = k7x7 ? 7 : p.PH, PW = k7x7 ? 7 : p.PW;
+  const int bins = PH * PW;
+  const TIn* vsrc = src + v * VEC;
+  const int cell_bytes = row_stride * (int)sizeof(TIn);
+  // Slot grid: slotsW slots across bin columns (a lane keeps ONE column pw when slotsW >= PW, so its
+  // w-bounds are computed once per RoI), slotsH bin rows per round (the h-range is warp-uniform when 1).
+  int slotsW = 1;
+  while (slotsW < PW && slotsW < slots) slotsW <<= 1;
+  const int slotsH = slots / slotsW;
+  const int sw = slot % slotsW, sh = slot / slotsW;
+  const float fPH = static_cast<float>(PH), fPW = static_cast<float>(PW);
 
-  for (int item = threadIdx.x; item < items; item += blockDim.x) {
-    const int rl = item / vpr, v = item - rl * vpr;
-    const int r = r0 + rl;
+  while (true) {
+    int r = 0;
+    if (lane == 0) r = atomicAdd(&next_roi, 1);
+    r = __shfl_sync(0xffffffffu, r, 0);
+    if (r >= r1) break;
     const float* roi = p.rois + (size_t)r * 5;
-    if (static_cast<int>(roi[0]) != n) continue;
+    if (static_cast<int>(__ldg(roi)) != n) continue;
     // detectron/ops/roi_loop_pool_op.cu:42-57
-    const int roi_start_w = static_cast<int>(roundf(roi[1] * p.scale));
-    const int roi_start_h = static_cast<int>(roundf(roi[2] * p.scale));
-    const int roi_end_w = static_cast<int>(roundf(roi[3] * p.scale));
-    const int roi_end_h = static_cast<int>(roundf(roi[4] * p.scale));
+    const int roi_start_w = static_cast<int>(roundf(__ldg(roi + 1) * p.scale));
+    const int roi_start_h = static_cast<int>(roundf(__ldg(roi + 2) * p.scale));
+    const int roi_end_w = static_cast<int>(roundf(__ldg(roi + 3) * p.scale));
+    const int roi_end_h = static_cast<int>(roundf(__ldg(roi + 4) * p.scale));
     const int roi_width = max(roi_end_w - roi_start_w + 1, 1);
     const int roi_height = max(roi_end_h - roi_start_h + 1, 1);
-    const float bin_size_h = __fdiv_rn(static_cast<float>(roi_height), static_cast<float>(p.PH));
-    const float bin_size_w = __fdiv_rn(static_cast<float>(roi_width), static_cast<float>(p.PW));
-    const float s = p.boost ? p.boost[r] : 1.0f;
-    const TIn* vsrc = src + v * VEC;
-    const size_t out_base = (size_t)r * p.PH * p.PW * p.C + (size_t)slab * p.SC + v * VEC;
+    const float bin_size_h = __fdiv_rn(static_cast<float>(roi_height), fPH);
+    const float bin_size_w = __fdiv_rn(static_cast<float>(roi_width), fPW);
+    const float s = p.boost ? __ldg(p.boost + r) : 1.0f;
+    TOut* yrow = static_cast<TOut*>(p.Y) + ((size_t)r * bins * p.C + (size_t)slab * p.SC + v * VEC);
+    int32_t* arow = kArgmax ? p.argmax + ((size_t)r * bins * p.C + (size_t)slab * p.SC + v * VEC) : nullptr;
 
-    for (int ph = 0; ph < p.PH; ++ph) {
+#pragma unroll 1
+    for (int ph = sh; ph < PH; ph += slotsH) {
       int hstart = static_cast<int>(floorf(__fmul_rn(static_cast<float>(ph), bin_size_h)));
       int hend = static_cast<int>(ceilf(__fmul_rn(static_cast<float>(ph + 1), bin_size_h)));
       hstart = min(max(hstart + roi_start_h, 0), H);
       hend = min(max(hend + roi_start_h, 0), H);
-      for (int pw = 0; pw < p.PW; ++pw) {
+#pragma unroll 1
+      for (int pw = sw; pw < PW; pw += slotsW) {
         int wstart = static_cast<int>(floorf(__fmul_rn(static_cast<float>(pw), bin_size_w)));
         int wend = static_cast<int>(ceilf(__fmul_rn(static_cast<float>(pw + 1), bin_size_w)));
         wstart = min(max(wstart + roi_start_w, 0), W);
         wend = min(max(wend + roi_start_w, 0), W);
         const bool is_empty = (hend <= hstart) || (wend <= wstart);
-        float maxv[VEC];
-        int maxi[VEC];
-#pragma unroll
-        for (int k = 0; k < VEC; ++k) { maxv[k] = is_empty ? 0.f : -FLT_MAX; maxi[k] = -1; }
+        Scan sc;
+        sc.init(is_empty);
         if (!is_empty) {
-          // (h, w) row-major scan, flattened so lanes of different RoIs diverge on area only
-          const int bw = wend - wstart;
-          const int cells = (hend - hstart) * bw;
-          int w = wstart, idx = hstart * W + wstart;
-          const int row_skip = W - bw;
-          for (int t = 0; t < cells; ++t) {
-            const uint4 q = *reinterpret_cast<const uint4*>(vsrc + (size_t)idx * row_stride);
-            float x[VEC];
-            Vec<TIn>::unpack(q, x);
-#pragma unroll
-            for (int k = 0; k < VEC; ++k)
-              if (x[k] > maxv[k]) { maxv[k] = x[k]; maxi[k] = idx; }
-            ++w; ++idx;
-            if (w == wend) { w = wstart; idx += row_skip; }
+          int idx0 = hstart * W + wstart;
+          const unsigned char* rowp = reinterpret_cast<const unsigned char*>(vsrc) + (size_t)idx0 * cell_bytes;
+          const int row_bytes = W * cell_bytes;
+#pragma unroll 1
+          for (int h = hstart; h < hend; ++h, idx0 += W, rowp += row_bytes) {
+            const unsigned char* cp = rowp;
+            int idx = idx0;
+#pragma unroll 1
+            for (int w = wstart; w < wend; ++w, ++idx, cp += cell_bytes)
+              sc.visit(*reinterpret_cast<const uint4*>(cp), idx);
           }
         }
+        float maxv[VEC];
+        int maxi[VEC];
+        sc.result(is_empty, maxv, maxi);
         if (p.boost) {
 #pragma unroll
           for (int k = 0; k < VEC; ++k) maxv[k] = __fmul_rn(maxv[k], s);
         }
-        const size_t o = out_base + (size_t)(ph * p.PW + pw) * p.C;
-        store_vals<VEC>(Y + o, maxv);
-        if (p.argmax) store_idx<VEC>(p.argmax + o, maxi);
+        const int o = (ph * PW + pw) * p.C;
+        store_vals<VEC>(yrow + o, maxv);
+        if (kArgmax) store_idx<VEC>(arow + o, maxi);
       }
     }
   }
@@ -283,17 +366,28 @@ __global__ void transpose_kernel(const uint32_t* __restrict__ in, int64_t rows, 
   }
 }
 
-template <typename TIn, typename TOut>
-int launch_pool_fwd(const PoolParams& p, bool use_smem, size_t smem_bytes, dim3 grid, int threads, cudaStream_t st) {
-  if (use_smem) {
-    auto k = roi_pool_fwd_kernel<TIn, TOut, true>;
-    NAWSOD_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-    k<<<grid, threads, smem_bytes, st>>>(p);
-  } else {
-    roi_pool_fwd_kernel<TIn, TOut, false><<<grid, threads, 0, st>>>(p);
-  }
+template <typename TIn, typename TOut, bool kSmem, bool kArgmax, bool k7x7>
+int launch_pool_fwd3(const PoolParams& p, size_t smem_bytes, dim3 grid, int threads, cudaStream_t st) {
+  auto k = roi_pool_fwd_kernel<TIn, TOut, kSmem, kArgmax, k7x7>;
+  if (kSmem) NAWSOD_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+  k<<<grid, threads, smem_bytes, st>>>(p);
   NAWSOD_LAUNCH_OK();
   return NAWSOD_OK;
+}
+
+template <typename TIn, typename TOut, bool kSmem, bool kArgmax>
+int launch_pool_fwd2(const PoolParams& p, size_t smem_bytes, dim3 grid, int threads, cudaStream_t st) {
+  if (p.PH == 7 && p.PW == 7) return launch_pool_fwd3<TIn, TOut, kSmem, kArgmax, true>(p, smem_bytes, grid, threads, st);
+  return launch_pool_fwd3<TIn, TOut, kSmem, kArgmax, false>(p, smem_bytes, grid, threads, st);
+}
+
+template <typename TIn, typename TOut>
+int launch_pool_fwd(const PoolParams& p, bool use_smem, size_t smem_bytes, dim3 grid, int threads, cudaStream_t st) {
+  const bool am = p.argmax != nullptr;
+  if (use_smem) return am ? launch_pool_fwd2<TIn, TOut, true, true>(p, smem_bytes, grid, threads, st)
+                          : launch_pool_fwd2<TIn, TOut, true, false>(p, smem_bytes, grid, threads, st);
+  return am ? launch_pool_fwd2<TIn, TOut, false, true>(p, 0, grid, threads, st)
+            : launch_pool_fwd2<TIn, TOut, false, false>(p, 0, grid, threads, st);
 }
 
 }  // namespace
@@ -330,37 +424,48 @@ static int pool_fwd_nhwc(const void* X, int x_dtype, const float* rois, const fl
   NAWSOD_REQUIRE(aligned16(X) && aligned16(Y) && (!argmax || aligned16(argmax)), NAWSOD_ERR_ALIGN,
                  "roi_pool_f: X, Y and argmax must be 16-byte aligned");
   NAWSOD_REQUIRE(N <= 65535, NAWSOD_ERR_SHAPE, "roi_pool_f: N too large");
-  // pick the channel slab: the largest divisor of C (multiple of VEC) whose H*W*SC slab fits the budget
-  const int64_t budget = get_tuning("pool_slab_bytes", 100 * 1024);
-  const int64_t hard = 200 * 1024;
+  NAWSOD_REQUIRE(x_dtype == NAWSOD_F32 || (int64_t)H * W <= 65535, NAWSOD_ERR_UNSUPPORTED,
+                 "roi_pool_f: a bf16 map is limited to H*W <= 65535 cells (packed 16-bit argmax)");
+  // Channel slab SC = VEC * 2^k lanes-per-bin (<= 32 lanes), dividing C.  Prefer the largest slab whose
+  // H*W*SC tile fits the shared-memory budget; otherwise read the (L2-resident) map directly with a
+  // whole warp of channel vectors per bin.
+  const int64_t budget = std::min<int64_t>(get_tuning("pool_slab_bytes", 200 * 1024), 200 * 1024);
   const bool force_global = get_tuning("pool_force_global", 0) != 0;
   int SC = 0;
-  for (int64_t lim : {budget, hard}) {
-    if (force_global || SC) break;
-    for (int cand = C; cand >= VEC; --cand) {
-      if (C % cand || cand % VEC) continue;
-      if ((int64_t)H * W * cand * esize <= lim) { SC = cand; break; }
+  if (!force_global)
+    for (int lanes = 32; lanes >= 1; lanes >>= 1) {
+      const int cand = lanes * VEC;
+      if (cand > C || C % cand) continue;
+      if ((int64_t)H * W * cand * esize <= budget) { SC = cand; break; }
     }
-  }
   const bool use_smem = SC > 0;
-  if (!use_smem) {
-    SC = C;
-    for (int cand = 128 * VEC / 4; cand >= VEC; cand /= 2)
-      if (C % cand == 0) { SC = cand; break; }
-  }
+  if (!use_smem)
+    for (int lanes = 32; lanes >= 1; lanes >>= 1)
+      if (lanes * VEC <= C && C % (lanes * VEC) == 0) { SC = lanes * VEC; break; }
+  NAWSOD_REQUIRE(SC > 0, NAWSOD_ERR_SHAPE, "roi_pool_f: C=%d has no power-of-two multiple of %d as a divisor", C, VEC);
   const size_t smem_bytes = use_smem ? (size_t)H * W * SC * esize : 0;
   const int slabs = C / SC;
-  const int ctas_per_sm = use_smem ? (int)std::max<int64_t>(1, std::min<int64_t>(4, (220 * 1024) / (int64_t)(smem_bytes + 1024))) : 4;
-  int threads = (int)get_tuning("pool_threads", use_smem ? (ctas_per_sm >= 2 ? 256 : 512) : 128);
+  int threads = (int)get_tuning("pool_threads", 0);
+  if (threads <= 0) threads = use_smem ? 1024 : 256;
+  threads = std::max(32, std::min(1024, threads / 32 * 32));
+  const int warps = threads / 32;
   int chunks = (int)get_tuning("pool_chunks", 0);
   if (chunks <= 0) {
-    const int64_t slots = (int64_t)sm_count() * ctas_per_sm;
+    // ~2 CTAs per SM slot overall; never fewer than one RoI per warp
+    // fill whole waves: choose the chunk count (2..8 waves' worth) whose CTA total wastes the least
+    // of its last wave; never fewer than ~4 RoIs per warp
     const int64_t base = (int64_t)slabs * N;
-    chunks = (int)std::max<int64_t>(1, (2 * slots + base - 1) / base);
-    // never make chunks so small that a CTA has less than one pass of work items
-    const int64_t max_chunks = std::max<int64_t>(1, ((int64_t)R * (SC / VEC) + threads - 1) / threads);
-    if (!use_smem) chunks = (int)max_chunks;
-    chunks = (int)std::min<int64_t>(chunks, max_chunks);
+    const int64_t slots = (int64_t)sm_count() * (use_smem ? 1 : (2048 / threads));
+    const int64_t max_chunks = std::max<int64_t>(1, (int64_t)R / ((use_smem ? 4 : 1) * warps));
+    double best_eff = -1.0;
+    chunks = 1;
+    for (int64_t c = 1; c <= std::min<int64_t>(max_chunks, ((use_smem ? 4 : 8) * slots) / base + 1); ++c) {
+      const int64_t ctas = c * base;
+      const int64_t waves = (ctas + slots - 1) / slots;
+      double eff = (double)ctas / (double)(waves * slots);
+      if (waves < 2) eff *= 0.9;      // a single wave has no slack for uneven RoI costs
+      if (eff > best_eff + 1e-9) { best_eff = eff; chunks = (int)c; }
+    }
   }
   chunks = std::min(chunks, 65535);
   PoolParams p;

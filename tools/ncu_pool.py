@@ -1,0 +1,13 @@
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import nafwebsod_b200 as pkg
+from nafwebsod_b200 import ops
+import bench
+X, rois, obn, L, offs = bench.synth_inputs(1, 2000, 0)
+Xd = torch.from_numpy(X).cuda(); r = torch.from_numpy(rois).cuda(); b = torch.from_numpy(obn).cuda()
+for dt, train in ((torch.float32, True), (torch.bfloat16, False)):
+    Xcl = ops.to_channels_last(Xd, dt)
+    for _ in range(2):
+        ops.RoIPoolF(Xcl, r, boost=b, is_test=not train, x_layout="NHWC", y_layout="NHWC")
+torch.cuda.synchronize()
