@@ -211,6 +211,10 @@ def gpu_arm(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if args.comm_sms > 0:
+            # the persistent GEMMs leave --comm-sms SMs to the NCCL kernels while an exchange is in flight; cap NCCL to match
+            os.environ["NAWSOD_COMM_SMS"] = str(args.comm_sms)
+            os.environ.setdefault("NCCL_MAX_CTAS", str(args.comm_sms))
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
     dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
@@ -225,7 +229,7 @@ def gpu_arm(args):
         lim = float(np.sqrt(3.0 / 4096))
         model.p["W8_%d" % s].uniform_(-lim, lim, generator=g)
     model.sync_shadow()
-    dp = DataParallelHead(model, fc6_panels=args.fc6_panels)
+    dp = DataParallelHead(model, fc6_panels=args.fc6_panels, sync=args.dp_sync)
     dp.broadcast_parameters()
     model.UpdateWorkspaceLr(1e-3)
 
@@ -251,6 +255,7 @@ def gpu_arm(args):
         a.record()
         for i in range(steps):
             fn(i)
+        dp.flush()                      # the last step's parameter exchange belongs to the timed region
         b.record()
         sync_all()
         ms = torch.tensor([a.elapsed_time(b)], device=dev)
@@ -344,10 +349,11 @@ def gpu_arm(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16" if dtype == torch.bfloat16 else "tf32", "data": "synthetic",
-        "config": {"workload": "NA-fWebSOD head fwd+bwd+allreduce+SGD, BASELINE config 2 per GPU: %d images x %d RoIs, %d classes, conv5 %dx%dx%d, "
+        "config": {"workload": "NA-fWebSOD head fwd+bwd+gradient exchange+SGD, BASELINE config 2 per GPU: %d images x %d RoIs, %d classes, conv5 %dx%dx%d, "
                                "RoIPoolF 7x7 @1/16 + boost, %s fc6/fc7 4096, seeded dropout" % (
                                    IMAGES_PER_GPU, ROIS_PER_IMAGE, NUM_CLASSES - 1, C5, H5, W5, "two-stack (clean + noisy)" if noise else "single-stack"),
-                   "global_rois_per_step": world * R, "parallelism": "dp%d (images sharded by rank, 1 grad all-reduce/step)" % world,
+                   "global_rois_per_step": world * R, "parallelism": "dp%d (images sharded by rank; gradient exchange per step: %s)" % (
+                       world, "none" if world == 1 else ("reduce-scatter fp32 grads + sharded SGD + all-gather bf16 operands" if args.dp_sync == "sharded" else "all-reduce fp32 grads + full SGD")),
                    "l2": "working set per step (weights 0.5 GB bf16 + 0.96 GB fp32 grads + activations) >> 126 MB L2; no flush needed",
                    "fc6_panels": dp.fc6_panels},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": d2h_bytes,
@@ -374,6 +380,9 @@ def main():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "tf32"])
     ap.add_argument("--head", default="na", choices=["na", "wsddn"])
     ap.add_argument("--fc6-panels", type=int, default=4)
+    ap.add_argument("--comm-sms", type=int, default=0, help="N>1: SMs the GEMMs leave to NCCL during the exchange (0 = no reservation)")
+    ap.add_argument("--dp-sync", default="sharded", choices=["sharded", "allreduce"],
+                    help="N>1: reduce-scatter + sharded SGD + all-gather (default) or the reference's all-reduce + full SGD")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

@@ -498,7 +498,10 @@ int launch_gemm(const void* A, long long lda, const void* B, long long ldb, cons
     attr_set = true;
   }
   const int num_tiles = ((ep.M + BLOCK_M - 1) / BLOCK_M) * ((ep.N + BN - 1) / BN);
-  const int grid = std::min(num_tiles, sm_count());
+  // gemm_max_ctas: leave SMs to concurrently running collectives (a persistent one-CTA-per-SM grid
+  // would otherwise wait behind them, or they behind it)
+  const int cap = (int)get_tuning("gemm_max_ctas", 0);
+  const int grid = std::min(num_tiles, cap > 0 ? std::min(cap, sm_count()) : sm_count());
   kern<<<grid, kNumThreads, C::SMEM_BYTES, st>>>(tmA, tmB, ep);
   NAWSOD_LAUNCH_OK();
   return NAWSOD_OK;

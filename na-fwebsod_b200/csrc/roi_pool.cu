@@ -97,6 +97,14 @@ struct ScanF32 {   // fp32 map, VEC = 4
       else m[k] = fmaxf(m[k], x[k]);
     }
   }
+  // fold a later scan segment in: it wins only where strictly greater, so ties keep the earlier cell
+  __device__ __forceinline__ void merge(const ScanF32& o) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (kArgmax) { if (o.m[k] > m[k]) { m[k] = o.m[k]; i[k] = o.i[k]; } }
+      else m[k] = fmaxf(m[k], o.m[k]);
+    }
+  }
   __device__ __forceinline__ void result(bool, float (&v)[4], int (&a)[4]) const {
 #pragma unroll
     for (int k = 0; k < 4; ++k) { v[k] = m[k]; a[k] = i[k]; }
@@ -110,9 +118,24 @@ struct ScanF32 {   // fp32 map, VEC = 4
 template <bool kArgmax>
 struct ScanBF16 {
   uint32_t m[4]; uint32_t i[4];
-  __device__ __forceinline__ void init(bool) {
+  __device__ __forceinline__ void init(bool empty) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) { m[k] = 0xFF80FF80u; i[k] = 0xFFFFFFFFu; }
+    for (int k = 0; k < 4; ++k) { m[k] = empty ? 0u : 0xFF80FF80u; i[k] = 0xFFFFFFFFu; }
+  }
+  __device__ __forceinline__ void merge(const ScanBF16& o) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const __nv_bfloat162 xv = *reinterpret_cast<const __nv_bfloat162*>(&o.m[k]);
+      const __nv_bfloat162 mv = *reinterpret_cast<const __nv_bfloat162*>(&m[k]);
+      if (kArgmax) {
+        const uint32_t gt = __hgt2_mask(xv, mv);
+        m[k] = (o.m[k] & gt) | (m[k] & ~gt);
+        i[k] = (o.i[k] & gt) | (i[k] & ~gt);
+      } else {
+        const __nv_bfloat162 r = __hmax2(xv, mv);
+        m[k] = *reinterpret_cast<const uint32_t*>(&r);
+      }
+    }
   }
   __device__ __forceinline__ void visit(const uint4& q, int idx) {
     const uint32_t x[4] = {q.x, q.y, q.z, q.w};
@@ -131,11 +154,11 @@ struct ScanBF16 {
       }
     }
   }
-  __device__ __forceinline__ void result(bool empty, float (&v)[8], int (&a)[8]) const {
+  __device__ __forceinline__ void result(bool, float (&v)[8], int (&a)[8]) const {
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      v[2 * k] = empty ? 0.f : __uint_as_float(m[k] << 16);
-      v[2 * k + 1] = empty ? 0.f : __uint_as_float(m[k] & 0xffff0000u);
+      v[2 * k] = __uint_as_float(m[k] << 16);            // an empty bin was initialised to +0
+      v[2 * k + 1] = __uint_as_float(m[k] & 0xffff0000u);
       const uint32_t lo = i[k] & 0xFFFFu, hi = i[k] >> 16;
       a[2 * k] = (lo == 0xFFFFu) ? -1 : static_cast<int>(lo);
       a[2 * k + 1] = (hi == 0xFFFFu) ? -1 : static_cast<int>(hi);
@@ -254,6 +277,129 @@ __global__ void __launch_bounds__(1024, 1) roi_pool_fwd_kernel(const PoolParams 
         store_vals<VEC>(yrow + o, maxv);
         if (kArgmax) store_idx<VEC>(arow + o, maxi);
       }
+    }
+  }
+}
+
+// Forward, bin-row variant (the default whenever one warp can hold a whole row of bins, PW <= 32 / vpr).
+// Same CTA / slab / dynamic-RoI structure as above, but the per-bin index arithmetic is hoisted out of
+// the bin loops, which the first kernel spent ~2/3 of its issue slots on (ncu: 79-83 % issue-active):
+//   * RoI geometry is computed lane-parallel ONCE per RoI: lane l rounds coordinate l of the RoI, lanes
+//     0..PH-1 evaluate the h-bounds of bin row l and lanes 8.. the w-bounds of bin column l-8 (one fp32
+//     division each), and every lane then pulls what it needs with shuffles;
+//   * a lane keeps ONE bin column for the whole RoI (w-range, shared-memory column offset and output
+//     pointer are per-RoI constants); the warp walks the PH bin rows together, so the h-loop is uniform;
+//   * the w-loop is unrolled by two with a clamped second load (a duplicate visit never wins a strict '>').
+// The scan order per bin is still (h, w) row-major with strict '>', so values and argmax stay bit-exact.
+template <typename TIn, typename TOut, bool kSmem, bool kArgmax>
+__global__ void __launch_bounds__(1024, 1) roi_pool_fwd_rows_kernel(const PoolParams p) {
+  constexpr int VEC = Vec<TIn>::N;
+  using Scan = typename std::conditional<sizeof(TIn) == 4, ScanF32<kArgmax>, ScanBF16<kArgmax>>::type;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ int next_roi;
+  const int slab = blockIdx.x, chunk = blockIdx.y, n = blockIdx.z;
+  const int HW = p.H * p.W;
+  const int vpr = p.SC / VEC;          // lanes per bin column (power of two, 32 / vpr >= PW)
+  const int vshift = __ffs(vpr) - 1;
+  const TIn* gbase = static_cast<const TIn*>(p.X) + (size_t)n * HW * p.C + (size_t)slab * p.SC;
+  const int r0 = chunk * p.rois_per_chunk;
+  const int r1 = min(p.R, r0 + p.rois_per_chunk);
+  if (threadIdx.x == 0) next_roi = r0;
+
+  const unsigned char* src;
+  int cell_bytes;
+  if (kSmem) {
+    const int total = HW * vpr;                 // 16-byte vectors in the slab
+    const unsigned char* g = reinterpret_cast<const unsigned char*>(gbase);
+    const size_t gcell = (size_t)p.C * sizeof(TIn);
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+      const int cell = i >> vshift, v = i & (vpr - 1);
+      cp_async16(smem_raw + (size_t)i * 16, g + (size_t)cell * gcell + v * 16);
+    }
+    asm volatile("cp.async.commit_group;\n" ::);
+    asm volatile("cp.async.wait_group 0;\n" ::);
+    src = smem_raw;
+    cell_bytes = p.SC * (int)sizeof(TIn);
+  } else {
+    src = reinterpret_cast<const unsigned char*>(gbase);
+    cell_bytes = p.C * (int)sizeof(TIn);
+  }
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31;
+  const int v = lane & (vpr - 1), sw = lane >> vshift;   // sw = this lane's bin column (idle when >= PW)
+  const int W = p.W, H = p.H, PH = p.PH, PW = p.PW;
+  const bool col_ok = sw < PW;
+  const int row_bytes = W * cell_bytes;
+  const unsigned char* lane_src = src + v * 16;
+  // lane-parallel bound evaluation: lanes [0, 8) -> bin row `lane` (h), lanes [8, 32) -> bin column `lane - 8` (w)
+  const bool is_h = lane < 8;
+  const int pidx = is_h ? lane : lane - 8;
+  const float fdiv = static_cast<float>(is_h ? PH : PW);
+  const int lim = is_h ? H : W;
+  const size_t bin_stride = (size_t)PW * p.C;    // elements between consecutive bin rows of Y
+
+  while (true) {
+    int r = 0;
+    if (lane == 0) r = atomicAdd(&next_roi, 1);
+    r = __shfl_sync(0xffffffffu, r, 0);
+    if (r >= r1) break;
+    // lane l (1..4) owns coordinate l of the RoI; detectron/ops/roi_loop_pool_op.cu:42-45
+    const float coord = __ldg(p.rois + (size_t)r * 5 + min(lane, 4));
+    if (static_cast<int>(__shfl_sync(0xffffffffu, coord, 0)) != n) continue;
+    const int rounded = static_cast<int>(roundf(coord * p.scale));
+    const int roi_start_w = __shfl_sync(0xffffffffu, rounded, 1);
+    const int roi_start_h = __shfl_sync(0xffffffffu, rounded, 2);
+    const int roi_end_w = __shfl_sync(0xffffffffu, rounded, 3);
+    const int roi_end_h = __shfl_sync(0xffffffffu, rounded, 4);
+    // roi_loop_pool_op.cu:54-68, one (row or column) bound pair per lane
+    const int extent = is_h ? max(roi_end_h - roi_start_h + 1, 1) : max(roi_end_w - roi_start_w + 1, 1);
+    const int offs = is_h ? roi_start_h : roi_start_w;
+    const float bin_size = __fdiv_rn(static_cast<float>(extent), fdiv);
+    int bstart = static_cast<int>(floorf(__fmul_rn(static_cast<float>(pidx), bin_size)));
+    int bend = static_cast<int>(ceilf(__fmul_rn(static_cast<float>(pidx + 1), bin_size)));
+    bstart = min(max(bstart + offs, 0), lim);
+    bend = min(max(bend + offs, 0), lim);
+    const int wstart = __shfl_sync(0xffffffffu, bstart, 8 + min(sw, 23));
+    const int wend = __shfl_sync(0xffffffffu, bend, 8 + min(sw, 23));
+    const int ncols = wend - wstart;               // cells per row of this lane's bins (<= 0: empty column)
+    const float s = p.boost ? __ldg(p.boost + r) : 1.0f;
+    const unsigned char* col_src = lane_src + (size_t)wstart * cell_bytes;
+    const size_t out_off = ((size_t)r * PH * PW + sw) * p.C + (size_t)slab * p.SC + v * VEC;
+    TOut* yout = static_cast<TOut*>(p.Y) + out_off;
+    int32_t* aout = kArgmax ? p.argmax + out_off : nullptr;
+
+#pragma unroll 1
+    for (int ph = 0; ph < PH; ++ph, yout += bin_stride, aout += (kArgmax ? bin_stride : 0)) {
+      const int hstart = __shfl_sync(0xffffffffu, bstart, ph);
+      const int hend = __shfl_sync(0xffffffffu, bend, ph);
+      if (!col_ok) continue;                       // idle lanes only take part in the shuffles
+      const bool is_empty = (hend <= hstart) || (ncols <= 0);
+      Scan sc;
+      sc.init(is_empty);
+      if (!is_empty) {
+        const unsigned char* rowp = col_src + (size_t)hstart * row_bytes;
+        int idx0 = hstart * W + wstart;
+#pragma unroll 1
+        for (int h = hstart; h < hend; ++h, rowp += row_bytes, idx0 += W) {
+          const unsigned char* cp = rowp;
+          int idx = idx0;
+#pragma unroll 1
+          for (int j = 0; j < ncols; j += 2, cp += 2 * cell_bytes, idx += 2) {
+            sc.visit(*reinterpret_cast<const uint4*>(cp), idx);
+            if (j + 1 < ncols) sc.visit(*reinterpret_cast<const uint4*>(cp + cell_bytes), idx + 1);
+          }
+        }
+      }
+      float maxv[VEC];
+      int maxi[VEC];
+      sc.result(is_empty, maxv, maxi);
+      if (p.boost) {
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) maxv[k] = __fmul_rn(maxv[k], s);
+      }
+      store_vals<VEC>(yout, maxv);
+      if (kArgmax) store_idx<VEC>(aout, maxi);
     }
   }
 }
@@ -377,6 +523,15 @@ int launch_pool_fwd3(const PoolParams& p, size_t smem_bytes, dim3 grid, int thre
 
 template <typename TIn, typename TOut, bool kSmem, bool kArgmax>
 int launch_pool_fwd2(const PoolParams& p, size_t smem_bytes, dim3 grid, int threads, cudaStream_t st) {
+  // bin-row kernel: one warp holds a whole row of bins (h-bounds on lanes 0..7, w-bounds on lanes 8..31)
+  const int slots = 32 / (p.SC / Vec<TIn>::N);
+  if (p.PH <= 8 && p.PW <= slots && slots <= 8 && get_tuning("pool_generic", 0) == 0) {
+    auto k = roi_pool_fwd_rows_kernel<TIn, TOut, kSmem, kArgmax>;
+    if (kSmem) NAWSOD_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    k<<<grid, threads, smem_bytes, st>>>(p);
+    NAWSOD_LAUNCH_OK();
+    return NAWSOD_OK;
+  }
   if (p.PH == 7 && p.PW == 7) return launch_pool_fwd3<TIn, TOut, kSmem, kArgmax, true>(p, smem_bytes, grid, threads, st);
   return launch_pool_fwd3<TIn, TOut, kSmem, kArgmax, false>(p, smem_bytes, grid, threads, st);
 }

@@ -36,8 +36,8 @@ extern "C" {
 const char* nawsod_last_error(void) { return nawsod::g_err; }
 int nawsod_version(void) { return 100; }
 int nawsod_set_tuning(const char* key, int64_t value) {
-  static const char* known[] = {"pool_slab_bytes", "pool_chunks", "pool_force_global", "pool_threads",
-                                "gemm_force_1cta", "mil_ctas", nullptr};
+  static const char* known[] = {"pool_slab_bytes", "pool_chunks", "pool_force_global", "pool_threads", "pool_generic",
+                                "gemm_force_1cta", "gemm_max_ctas", "mil_ctas", nullptr};
   if (!key) { nawsod::set_error("nawsod_set_tuning: null key"); return NAWSOD_ERR_ARG; }
   for (int i = 0; known[i]; ++i)
     if (std::strcmp(known[i], key) == 0) {

@@ -248,10 +248,11 @@ class WeblyHeadModel:
         detectron/utils/train_wsl.py:59, that lies between conv5 and the parameter gradients).
         Gradients land in ``self.g`` / ``self.flat_grad``; returns the blob dict.
 
-        Data-parallel hooks (dp.py): the dominant fc6 weight gradient is produced LAST in the
-        backward pass, so it is computed in ``fc6_panels`` row panels and ``on_fc6_panel(r0, r1)``
-        fires after each one (its all-reduce then overlaps the next panel's GEMM);
-        ``on_small_grads()`` fires once the fc7 / fc8 weight gradients are complete."""
+        Data-parallel hooks (dp.py): the dominant fc6 weight gradient is computed right after the
+        activation-gradient chain in ``fc6_panels`` row panels and ``on_fc6_panel(r0, r1)`` fires
+        after each one (its exchange then overlaps the next panel's GEMM and the fc7 / fc8
+        weight-gradient GEMMs); ``on_small_grads()`` fires once those are enqueued.  The bias
+        gradients of fc6 are complete with the last panel, all others with ``on_small_grads``."""
         if not self.train:
             raise RuntimeError("RunTrainStep on a test-mode model")
         bl, H, C, C2 = self.blobs, self.H, self.C, 2 * self.C
@@ -279,18 +280,17 @@ class WeblyHeadModel:
             dl = self._scratch("dlogits_lp", (self.S, R, ld), torch.float32)
             ops.round_to_tf32(dlog.view(self.S * R, ld), out=dl.view(self.S * R, ld))
         d6 = self._scratch("d_fc6", (R, self.S * H), self.dtype)
-        d7 = self._scratch("d_fc7", (R, H), self.dtype)
+        d7 = self._scratch("d_fc7", (R, self.S * H), self.dtype)
+        # activation-gradient chain first (fc8 dX -> fc7 dX): it is the critical path to the fc6 weight
+        # gradient, which carries 86 % of the gradient bytes and so must start its exchange earliest
         for s in range(self.S):
             dls = dl[s][:, :C2]
             a7 = drop7[:, s * H:(s + 1) * H]
             a6 = drop6[:, s * H:(s + 1) * H]
-            ops.FCGradientW(dls, a7, dW=self.g["W8_%d" % s], db=self.g["b8_%d" % s])
-            ops.FCGradientX(dls, self.w["W8_%d" % s], act_below=a7, dropout=self._dropped, out=d7, round_tf32=self.tf32)
-            ops.FCGradientW(d7, a6, dW=self.g["W7_%d" % s], db=self.g["b7_%d" % s])
-            ops.FCGradientX(d7, self.w["W7_%d" % s], act_below=a6, dropout=self._dropped, out=d6[:, s * H:(s + 1) * H],
+            d7s = d7[:, s * H:(s + 1) * H]
+            ops.FCGradientX(dls, self.w["W8_%d" % s], act_below=a7, dropout=self._dropped, out=d7s, round_tf32=self.tf32)
+            ops.FCGradientX(d7s, self.w["W7_%d" % s], act_below=a6, dropout=self._dropped, out=d6[:, s * H:(s + 1) * H],
                             round_tf32=self.tf32)
-        if on_small_grads is not None:
-            on_small_grads()
         rows = self.S * H
         step = _round_up((rows + fc6_panels - 1) // fc6_panels, 256)
         for r0 in range(0, rows, step):
@@ -299,6 +299,12 @@ class WeblyHeadModel:
                                                              db=self.g["b6"][r0:r1]))
             if on_fc6_panel is not None:
                 on_fc6_panel(r0, r1)
+        for s in range(self.S):
+            ops.FCGradientW(dl[s][:, :C2], drop7[:, s * H:(s + 1) * H], dW=self.g["W8_%d" % s], db=self.g["b8_%d" % s])
+            ops.FCGradientW(d7[:, s * H:(s + 1) * H], drop6[:, s * H:(s + 1) * H], dW=self.g["W7_%d" % s],
+                            db=self.g["b7_%d" % s])
+        if on_small_grads is not None:
+            on_small_grads()
         if need_dX:
             if bl["_argmax_roi_feat"] is None:
                 raise RuntimeError("need_dX requires freeze_conv_body=False (argmax is not kept otherwise)")

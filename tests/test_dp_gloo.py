@@ -1,0 +1,137 @@
+"""world_size-2 gloo tests (CPU) of the data-parallel host logic: image sharding, the bucket plan,
+and both gradient-exchange schedules of na-fwebsod_b200/dp.py.  The sharded schedule
+(reduce-scatter -> SGD on the rank's slice -> all-gather of the GEMM operands) must produce the
+parameters the reference's schedule produces (all-reduce, then the full
+ACMWeightDecayMomentumSGDUpdate on every rank; detectron/modeling/optimizer_wsl.py:52-137), with
+the update arithmetic taken from the oracle's restatement of the reference op."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import nawsod_oracle as O
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+# a miniature of the flat layout [W6 | other weights | biases] (heads.WeblyHeadModel._alloc_params)
+W6_ROWS, W6_COLS = 16, 24
+N_W6 = W6_ROWS * W6_COLS
+N_WEIGHTS = N_W6 + 128
+N_TOTAL = N_WEIGHTS + 64
+LR, MOM, WD = 1e-2, 0.9, 5e-4
+
+
+def _grads(rank, step):
+    rng = np.random.default_rng(100 * step + rank)
+    return rng.standard_normal(N_TOTAL).astype(np.float32)
+
+
+def _reference(world, steps):
+    """all-reduce + the full SGD op, in one process."""
+    rng = np.random.default_rng(7)
+    p = rng.standard_normal(N_TOTAL).astype(np.float32)
+    m = np.zeros(N_TOTAL, np.float32)
+    for it in range(steps):
+        g = np.zeros(N_TOTAL, np.float32)
+        for r in range(world):                       # gloo sums in rank order
+            g = (g + _grads(r, it)).astype(np.float32)
+        for lo, hi, wd, mult in ((0, N_WEIGHTS, WD, 1.0), (N_WEIGHTS, N_TOTAL, 0.0, 2.0)):
+            m[lo:hi], p[lo:hi], _, _ = O.acm_sgd_update(g[lo:hi], m[lo:hi], LR, p[lo:hi], np.zeros(hi - lo, np.float32),
+                                                        momentum=MOM, weight_decay=wd, lr_mult=mult, gpu_num=world, iter_count=it)
+    return p, m
+
+
+def _worker(rank, world, port, sync, panels, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from nafwebsod_b200 import dp
+        rng = np.random.default_rng(7)
+        p = torch.from_numpy(rng.standard_normal(N_TOTAL).astype(np.float32))
+        m = torch.zeros(N_TOTAL)
+        g = torch.zeros(N_TOTAL)
+        shadow = p.clone()                            # stands for the bf16 / TF32 GEMM-operand copy
+        plan = dp.bucket_plan(N_W6, W6_ROWS, W6_COLS, N_WEIGHTS, N_TOTAL, panels, align_rows=4)
+        assert sum(n for _, n, _ in plan) == N_TOTAL and plan[-1][2] == "biases"
+        state = {"it": 0}
+
+        def update(off, length, tag, so, sn):
+            bias = tag == "biases"
+            mm, pp, _, _ = O.acm_sgd_update(g[so:so + sn].numpy(), m[so:so + sn].numpy(), LR, p[so:so + sn].numpy(),
+                                            np.zeros(sn, np.float32), momentum=MOM, weight_decay=0.0 if bias else WD,
+                                            lr_mult=2.0 if bias else 1.0, gpu_num=world, iter_count=state["it"])
+            m[so:so + sn] = torch.from_numpy(mm)
+            p[so:so + sn] = torch.from_numpy(pp)
+            shadow[so:so + sn] = p[so:so + sn]
+
+        ex = dp.GradientExchange(g, shadow, sharded=(sync == "sharded"), update_fn=update)
+        for it in range(3):
+            state["it"] = it
+            g.copy_(torch.from_numpy(_grads(rank, it)))
+            for off, n, tag in plan:                  # the order the backward pass completes the buckets
+                ex.launch(off, n, tag)
+            ex.finish()
+            if sync == "allreduce":
+                update(0, N_WEIGHTS, "weights", 0, N_WEIGHTS)
+                update(N_WEIGHTS, N_TOTAL - N_WEIGHTS, "biases", N_WEIGHTS, N_TOTAL - N_WEIGHTS)
+        if sync == "sharded":
+            # operands are complete everywhere; masters only on their owner until gathered
+            for off, n, _ in plan:
+                so, sn = dp.rank_slice(off, n, world, rank)
+                for flat in (p, m):
+                    dist.all_gather_into_tensor(flat[off:off + n], flat[so:so + sn])
+        out[rank] = (p.numpy().copy(), m.numpy().copy(), shadow.numpy().copy())
+    finally:
+        dist.destroy_process_group()
+
+
+def _run(sync, panels, world=2):
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), sync, panels, out), nprocs=world, join=True)
+    return [out[r] for r in range(world)]
+
+
+@pytest.mark.parametrize("sync,panels", [("sharded", 4), ("sharded", 1), ("allreduce", 2)])
+def test_exchange_matches_reference_schedule(sync, panels):
+    res = _run(sync, panels)
+    p_ref, m_ref = _reference(2, 3)
+    for p, m, shadow in res:
+        # the same fp32 operations in the same order: bit-exact
+        assert np.array_equal(p, p_ref)
+        assert np.array_equal(m, m_ref)
+        assert np.array_equal(shadow, p_ref)
+    assert np.array_equal(res[0][0], res[1][0])
+
+
+def test_shard_images_and_plan():
+    from nafwebsod_b200 import dp
+    assert dp.shard_images(16, 8, 3) == [6, 7]
+    with pytest.raises(RuntimeError):
+        dp.shard_images(5, 2, 0)
+    # the real layout: NA head, 20 classes
+    n_w6 = 8192 * 25088
+    n_weights = n_w6 + 2 * 4096 * 4096 + 2 * 40 * 4096
+    n_total = n_weights + 8192 + 2 * 4096 + 2 * 64
+    plan = dp.bucket_plan(n_w6, 8192, 25088, n_weights, n_total, 4)
+    covered = 0
+    for off, n, tag in plan:
+        assert off == covered, "buckets must tile the flat buffer in order"
+        covered += n
+        for world in (2, 4, 8):
+            so, sn = dp.rank_slice(off, n, world, world - 1)
+            assert so + sn == off + n and sn % 4 == 0      # 16-byte aligned slices for the float4 SGD kernel
+    assert covered == n_total
+    with pytest.raises(RuntimeError):
+        dp.rank_slice(0, 10, 4, 0)
