@@ -353,7 +353,9 @@ def gpu_arm(args):
                                "RoIPoolF 7x7 @1/16 + boost, %s fc6/fc7 4096, seeded dropout" % (
                                    IMAGES_PER_GPU, ROIS_PER_IMAGE, NUM_CLASSES - 1, C5, H5, W5, "two-stack (clean + noisy)" if noise else "single-stack"),
                    "global_rois_per_step": world * R, "parallelism": "dp%d (images sharded by rank; gradient exchange per step: %s)" % (
-                       world, "none" if world == 1 else ("reduce-scatter fp32 grads + sharded SGD + all-gather bf16 operands" if args.dp_sync == "sharded" else "all-reduce fp32 grads + full SGD")),
+                       world, "none" if world == 1 else {"sharded": "NCCL reduce-scatter fp32 grads + sharded SGD + all-gather bf16 operands",
+                              "p2p": "copy-engine scatter of fp32 grads into peer-mapped staging + fused reduce/SGD on the owner + copy-engine gather of bf16 operands",
+                              "allreduce": "NCCL all-reduce fp32 grads + full SGD"}[dp.sync]),
                    "l2": "working set per step (weights 0.5 GB bf16 + 0.96 GB fp32 grads + activations) >> 126 MB L2; no flush needed",
                    "fc6_panels": dp.fc6_panels},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": d2h_bytes,
@@ -381,8 +383,8 @@ def main():
     ap.add_argument("--head", default="na", choices=["na", "wsddn"])
     ap.add_argument("--fc6-panels", type=int, default=4)
     ap.add_argument("--comm-sms", type=int, default=0, help="N>1: SMs the GEMMs leave to NCCL during the exchange (0 = no reservation)")
-    ap.add_argument("--dp-sync", default="sharded", choices=["sharded", "allreduce"],
-                    help="N>1: reduce-scatter + sharded SGD + all-gather (default) or the reference's all-reduce + full SGD")
+    ap.add_argument("--dp-sync", default="auto", choices=["auto", "sharded", "p2p", "allreduce"],
+                    help="N>1 gradient exchange: auto = p2p when the ranks can map each other's memory, else NCCL sharded; allreduce = the reference's schedule")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

@@ -191,6 +191,38 @@ int nawsod_sgd_update(const float* g, float* m, const float* lr, float* p, float
                       int iter_size, int gpu_num, int64_t iter_count, void* p_shadow,
                       int shadow_dtype, void* stream);
 
+/* a10 + a11 on the owner rank of a parameter slice: the gradient is the sum, in the order given, of
+ *   n_grads contributions (the rank's own slice and the copies its peers deposited), followed by the
+ *   same update as nawsod_sgd_update with iter_size 1 (the reference all-reduces, then updates:
+ *   modeling/optimizer_wsl.py:52-72, 96-137). */
+int nawsod_sgd_update_reduce(const float* const* grads, int n_grads, float* m, const float* lr,
+                             float* p, int64_t n, float momentum, float weight_decay,
+                             float lr_mult, int gpu_num, int64_t iter_count, void* p_shadow,
+                             int shadow_dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * a11: peer-to-peer plumbing of the gradient exchange (replaces the NCCLAllreduce ops of
+ *   modeling/optimizer_wsl.py:52-72 when the ranks of one NVSwitch box map each other's buffers).
+ *   nawsod_p2p_copy: cudaMemcpyAsync (copy engine) between local / peer-mapped device buffers.
+ *   nawsod_p2p_signal: store `value` (system-scope release) into each of n flag words, in stream
+ *   order after the copies that precede it.  nawsod_p2p_wait: block the stream until all n flag
+ *   words (device uint32, contiguous) have reached `value` (wrap-safe); after timeout_ms the
+ *   wait gives up and sets *status (device uint32, may be NULL) to 1 instead of hanging.
+ *   nawsod_p2p_enable_peer_access: let kernels and copies of the current device address memory of
+ *   `peer_device` (cudaDeviceEnablePeerAccess; idempotent).
+ * ------------------------------------------------------------------------------------- */
+int nawsod_p2p_enable_peer_access(int peer_device);
+/* export: the cudaIpcMemHandle_t (64 bytes) of the allocation holding `ptr` and ptr's offset inside it */
+int nawsod_p2p_get_mem_handle(const void* ptr, void* handle_out, int64_t handle_bytes,
+                              int64_t* offset_out);
+/* map a peer process's allocation (its cudaIpcMemHandle_t, 64 bytes) into the current device's context */
+int nawsod_p2p_open_mem_handle(const void* handle, int64_t handle_bytes, void** base);
+int nawsod_p2p_close_mem_handle(void* base);
+int nawsod_p2p_copy(void* dst, const void* src, int64_t bytes, void* stream);
+int nawsod_p2p_signal(void* const* flag_ptrs, int n, uint32_t value, void* stream);
+int nawsod_p2p_wait(const void* flags, int n, uint32_t value, int64_t timeout_ms, void* status,
+                    void* stream);
+
 #ifdef __cplusplus
 }
 #endif

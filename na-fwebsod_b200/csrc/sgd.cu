@@ -10,7 +10,11 @@
 namespace nawsod {
 namespace {
 
+constexpr int kMaxGradSources = 16;
+
 struct SgdArgs {
+  const float* extra[kMaxGradSources - 1];   // further gradient contributions, summed onto g in order (data-parallel owner)
+  int n_extra;
   const float* g; float* m; const float* lr; float* p; float* acc; __nv_bfloat16* p_bf16; float* p_tf32;
   int64_t n;
   float momentum, weight_decay, lr_mult, inv_norm;
@@ -50,7 +54,11 @@ __global__ void __launch_bounds__(256) sgd_kernel(const SgdArgs a) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   for (int64_t i = t0; i < n4; i += stride) {
-    const float4 g = reinterpret_cast<const float4*>(a.g)[i];
+    float4 g = reinterpret_cast<const float4*>(a.g)[i];
+    for (int e = 0; e < a.n_extra; ++e) {      // fixed (rank) order: the sum is deterministic
+      const float4 x = __ldcs(reinterpret_cast<const float4*>(a.extra[e]) + i);
+      g.x = __fadd_rn(g.x, x.x); g.y = __fadd_rn(g.y, x.y); g.z = __fadd_rn(g.z, x.z); g.w = __fadd_rn(g.w, x.w);
+    }
     float4 m = a.first_call ? make_float4(0.f, 0.f, 0.f, 0.f) : reinterpret_cast<const float4*>(a.m)[i];
     float4 p = reinterpret_cast<const float4*>(a.p)[i];
     float4 c = (a.first_call || !a.use_acc) ? make_float4(0.f, 0.f, 0.f, 0.f)
@@ -76,7 +84,9 @@ __global__ void __launch_bounds__(256) sgd_kernel(const SgdArgs a) {
     float m = a.first_call ? 0.f : a.m[i];
     float p = a.p[i];
     float c = (a.first_call || !a.use_acc) ? 0.f : a.acc[i];
-    sgd_elem(a.g[i], m, p, c, a, LR);
+    float g = a.g[i];
+    for (int e = 0; e < a.n_extra; ++e) g = __fadd_rn(g, a.extra[e][i]);
+    sgd_elem(g, m, p, c, a, LR);
     if (a.do_update || a.first_call) a.m[i] = m;
     if (a.do_update) {
       a.p[i] = p;
@@ -92,9 +102,10 @@ __global__ void __launch_bounds__(256) sgd_kernel(const SgdArgs a) {
 
 using namespace nawsod;
 
-extern "C" int nawsod_sgd_update(const float* g, float* m, const float* lr, float* p, float* acc, int64_t n,
-                                 float momentum, float weight_decay, float lr_mult, int iter_size, int gpu_num,
-                                 int64_t iter_count, void* p_shadow, int shadow_dtype, void* stream) {
+static int sgd_launch(const float* const* grads, int n_grads, float* m, const float* lr, float* p, float* acc, int64_t n,
+                      float momentum, float weight_decay, float lr_mult, int iter_size, int gpu_num,
+                      int64_t iter_count, void* p_shadow, int shadow_dtype, void* stream) {
+  const float* g = grads[0];
   NAWSOD_REQUIRE(n >= 0, NAWSOD_ERR_SHAPE, "sgd_update: negative n");
   NAWSOD_REQUIRE(iter_size >= 1 && gpu_num >= 1 && iter_count >= 0, NAWSOD_ERR_ARG,
                  "sgd_update: need iter_size >= 1, gpu_num >= 1, iter_count >= 0");
@@ -108,6 +119,11 @@ extern "C" int nawsod_sgd_update(const float* g, float* m, const float* lr, floa
   NAWSOD_REQUIRE(!p_shadow || shadow_dtype == NAWSOD_BF16 || shadow_dtype == NAWSOD_F32, NAWSOD_ERR_ARG,
                  "sgd_update: shadow_dtype must be NAWSOD_BF16 or NAWSOD_F32 (TF32-rounded)");
   a.g = g; a.m = m; a.lr = lr; a.p = p; a.acc = acc;
+  a.n_extra = n_grads - 1;
+  for (int e = 1; e < n_grads; ++e) {
+    NAWSOD_REQUIRE(grads[e] && aligned16(grads[e]), NAWSOD_ERR_ALIGN, "sgd_update: gradient source %d is null or not 16-byte aligned", e);
+    a.extra[e - 1] = grads[e];
+  }
   a.p_bf16 = (p_shadow && shadow_dtype == NAWSOD_BF16) ? static_cast<__nv_bfloat16*>(p_shadow) : nullptr;
   a.p_tf32 = (p_shadow && shadow_dtype == NAWSOD_F32) ? static_cast<float*>(p_shadow) : nullptr;
   a.n = n; a.momentum = momentum; a.weight_decay = weight_decay; a.lr_mult = lr_mult;
@@ -120,4 +136,22 @@ extern "C" int nawsod_sgd_update(const float* g, float* m, const float* lr, floa
   sgd_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
   NAWSOD_LAUNCH_OK();
   return NAWSOD_OK;
+}
+
+extern "C" int nawsod_sgd_update(const float* g, float* m, const float* lr, float* p, float* acc, int64_t n,
+                                 float momentum, float weight_decay, float lr_mult, int iter_size, int gpu_num,
+                                 int64_t iter_count, void* p_shadow, int shadow_dtype, void* stream) {
+  const float* grads[1] = {g};
+  return sgd_launch(grads, 1, m, lr, p, acc, n, momentum, weight_decay, lr_mult, iter_size, gpu_num, iter_count,
+                    p_shadow, shadow_dtype, stream);
+}
+
+extern "C" int nawsod_sgd_update_reduce(const float* const* grads, int n_grads, float* m, const float* lr, float* p,
+                                        int64_t n, float momentum, float weight_decay, float lr_mult, int gpu_num,
+                                        int64_t iter_count, void* p_shadow, int shadow_dtype, void* stream) {
+  NAWSOD_REQUIRE(grads && n_grads >= 1 && n_grads <= kMaxGradSources, NAWSOD_ERR_ARG,
+                 "sgd_update_reduce: need 1..%d gradient sources", kMaxGradSources);
+  NAWSOD_REQUIRE(n == 0 || grads[0], NAWSOD_ERR_ARG, "sgd_update_reduce: null gradient source");
+  return sgd_launch(grads, n_grads, m, lr, p, nullptr, n, momentum, weight_decay, lr_mult, 1, gpu_num, iter_count,
+                    p_shadow, shadow_dtype, stream);
 }

@@ -24,6 +24,13 @@ transfer may be in flight the persistent GEMMs leave ``comm_sms`` SMs to the NCC
 (``gemm_max_ctas`` tuning) -- a persistent CTA-per-SM grid would otherwise serialise behind them.
 The compute stream joins the side stream only at the start of the next step (or ``flush()``).
 
+``sync="p2p"`` is the same pipeline with the collectives replaced by the box's own hardware paths:
+every rank maps its peers' staging / flag / operand buffers (CUDA IPC over NVSwitch), the bulk data
+moves with the COPY ENGINES (so no SM is taken from the GEMMs and nothing has to be reserved), the
+owner's reduction is folded into its SGD kernel (``nawsod_sgd_update_reduce`` sums the W contributions
+in rank order -- deterministic -- while it updates), and cross-GPU ordering is a sequence number per
+(bucket, rank) published / awaited by one-warp kernels (``nawsod_p2p_signal`` / ``nawsod_p2p_wait``).
+
 ``sync="allreduce"`` keeps the reference's schedule (bucketed all-reduce, full SGD on every rank)
 for comparison.  torch.distributed (NCCL on the GPU box, gloo in the CPU tests) is the plumbing;
 the path has no other collective.  Inference shards by image with no collective (replicas only).
@@ -131,6 +138,143 @@ class GradientExchange:
         self.in_flight = False
 
 
+_OPENED = {}     # cudaIpcMemHandle bytes -> base address mapped in this process (a handle may be opened once)
+
+
+def _share_with_peers(t: torch.Tensor, group):
+    """Map every rank's copy of ``t`` into this process's device context (CUDA IPC; one node).
+    Returns (device addresses indexed by rank, error or None).  Every rank takes part in the one
+    collective whatever fails locally, so a failure never desynchronises the group; the caller
+    agrees on the outcome with an all-reduce."""
+    import ctypes
+    from . import _lib
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    infos, ptrs, err = [None] * world, [], None
+    with torch.cuda.device(t.device):
+        mine = None
+        try:
+            hbuf, off = ctypes.create_string_buffer(64), ctypes.c_int64()
+            _lib.call("nawsod_p2p_get_mem_handle", ctypes.c_void_p(t.data_ptr()), hbuf, 64, ctypes.byref(off))
+            mine = (hbuf.raw, int(off.value))
+        except RuntimeError as e:
+            err = e
+        dist.all_gather_object(infos, mine, group=group)
+        for k, info in enumerate(infos):
+            if k == rank:
+                ptrs.append(t.data_ptr())
+                continue
+            try:
+                if info is None:
+                    raise RuntimeError("rank %d could not export its buffer" % k)
+                h, off = info
+                if h not in _OPENED:
+                    base = ctypes.c_void_p()
+                    _lib.call("nawsod_p2p_open_mem_handle", h, len(h), ctypes.byref(base))
+                    _OPENED[h] = base.value
+                ptrs.append(_OPENED[h] + off)
+            except RuntimeError as e:
+                err = err or e
+                ptrs.append(0)
+    return ptrs, err
+
+
+class P2PExchange:
+    """The sharded bucket pipeline over peer-mapped memory: copy-engine transfers + flag kernels + a fused
+    reduce-and-update on the owner (CUDA only, one NVLink / NVSwitch box).
+
+    Per bucket b (length L, slice n = L / W; rank k owns slice k):
+      1. copy my part of slice k into rank k's staging area, slot [b][my rank]        (W-1 peer copies)
+      2. publish seq into flag RS[b][my rank] on every rank                             (one signal kernel)
+      3. wait until RS[b][*] == seq here, then update my slice from the W contributions (wait + fused SGD kernel)
+      4. copy my updated GEMM-operand slice into every peer's operand buffer            (W-1 peer copies)
+      5. publish seq into flag AG[b][my rank] on every rank
+    finish(): wait until AG[*][*] == seq, i.e. all operands of the step have landed here; since an owner signals
+    AG only after it consumed its staging area, that wait also licenses the next step's writes into it."""
+
+    RS, AG = 0, 1
+
+    def __init__(self, flat_grad, flat_out, plan, group=None, update_fn=None, timeout_ms=20000):
+        if not flat_grad.is_cuda:
+            raise RuntimeError("the p2p exchange needs CUDA buffers (use sync='sharded' with gloo on CPU)")
+        self.flat, self.out, self.group = flat_grad, flat_out, group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.plan = [(o, n, t) for o, n, t in plan if n > 0]
+        for o, n, _ in self.plan:
+            if n % self.world or (n // self.world) % 8:
+                raise RuntimeError("bucket of %d elements does not split into %d 32-byte aligned slices" % (n, self.world))
+        self.index = {o: i for i, (o, _, _) in enumerate(self.plan)}
+        self.update_fn = update_fn
+        self.timeout_ms = timeout_ms
+        dev = flat_grad.device
+        nb, W = len(self.plan), self.world
+        self.stage = torch.empty(flat_grad.numel(), dtype=torch.float32, device=dev)
+        self.flags = torch.zeros(2 * nb * W, dtype=torch.int32, device=dev)
+        self.status = torch.zeros(1, dtype=torch.int32, device=dev)
+        torch.cuda.synchronize(dev)
+        self.peer_stage, e1 = _share_with_peers(self.stage, group)
+        self.peer_flags, e2 = _share_with_peers(self.flags, group)
+        self.peer_out, e3 = _share_with_peers(self.out, group)
+        torch.cuda.synchronize(dev)
+        ok = torch.tensor([0 if (e1 or e2 or e3) else 1], dtype=torch.int32, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)          # also the setup barrier
+        if int(ok.item()) == 0:
+            raise RuntimeError("peer mapping failed on at least one rank: %s" % (e1 or e2 or e3 or "on a peer"))
+        self.stream = torch.cuda.Stream(device=dev, priority=-1)
+        self.seq = 0
+        self.in_flight = False
+        self.bytes_out = 0
+
+    def _flag_ptrs(self, kind, b):
+        W, nb = self.world, len(self.plan)
+        off = 4 * ((kind * nb + b) * W + self.rank)
+        return [self.peer_flags[k] + off for k in range(W)]
+
+    def begin_step(self):
+        self.seq += 1
+
+    def launch(self, offset: int, length: int, tag: str):
+        from . import ops
+        if length <= 0:
+            return
+        b = self.index[offset]
+        W, rank, n = self.world, self.rank, length // self.world
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.flat.device))
+        self.stream.wait_event(ev)
+        self.in_flight = True
+        es_out = self.out.element_size()
+        with torch.cuda.stream(self.stream):
+            for i in range(1, W):                     # staggered targets: no two ranks hit the same peer at once
+                k = (rank + i) % W
+                ops.p2p_copy(self.peer_stage[k] + 4 * (offset + rank * n), self.flat.data_ptr() + 4 * (offset + k * n), 4 * n)
+            self.bytes_out += 4 * n * (W - 1)
+            ops.p2p_signal(self._flag_ptrs(self.RS, b), self.seq)
+            fb = (self.RS * len(self.plan) + b) * W
+            ops.p2p_wait(self.flags[fb: fb + W], self.seq, self.timeout_ms, self.status)
+            so = offset + rank * n
+            grads = [self.flat[so: so + n] if r == rank else self.stage[offset + r * n: offset + (r + 1) * n] for r in range(W)]
+            self.update_fn(offset, length, tag, so, n, grads)
+            for i in range(1, W):
+                k = (rank + i) % W
+                ops.p2p_copy(self.peer_out[k] + es_out * so, self.out.data_ptr() + es_out * so, es_out * n)
+            ops.p2p_signal(self._flag_ptrs(self.AG, b), self.seq)
+
+    def finish(self):
+        from . import ops
+        if not self.in_flight:
+            return
+        nb, W = len(self.plan), self.world
+        with torch.cuda.stream(self.stream):
+            ops.p2p_wait(self.flags[nb * W: 2 * nb * W], self.seq, self.timeout_ms, self.status)
+        torch.cuda.current_stream(self.flat.device).wait_stream(self.stream)
+        self.in_flight = False
+
+    def check(self):
+        """Host-side check of the watchdog word (synchronises)."""
+        if int(self.status.item()) != 0:
+            raise RuntimeError("p2p exchange: a peer did not deliver within %d ms" % self.timeout_ms)
+
+
 class _Null:
     def __enter__(self):
         return self
@@ -143,8 +287,8 @@ class DataParallelHead:
     """model: heads.WeblyHeadModel of this rank.  step() = fwd + bwd + gradient exchange + SGD."""
 
     def __init__(self, model, group=None, fc6_panels: int = 4, sync: str = "sharded", comm_sms: int | None = None):
-        if sync not in ("sharded", "allreduce"):
-            raise RuntimeError("sync must be 'sharded' or 'allreduce'")
+        if sync not in ("auto", "sharded", "p2p", "allreduce"):
+            raise RuntimeError("sync must be 'auto', 'sharded', 'p2p' or 'allreduce'")
         self.model = model
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -158,7 +302,21 @@ class DataParallelHead:
         self.master_sharded = False
         self.comm_sms = int(os.environ.get("NAWSOD_COMM_SMS", "0")) if comm_sms is None else comm_sms
         self._hyper = dict(momentum=0.9, weight_decay=5e-4)
-        if self.world > 1:
+        if self.world > 1 and sync in ("p2p", "auto") and model.flat_grad.is_cuda:
+            # "auto": the peer-mapped path when every rank can set it up (one NVLink / NVSwitch box), else NCCL
+            try:                                     # raises on every rank or on none (see P2PExchange.__init__)
+                self.exchange = P2PExchange(model.flat_grad, model.flat_lp, self.plan, group, update_fn=self._update_slice)
+                sync = "p2p"
+                self.comm_sms = 0                    # copy engines move the data: nothing to reserve
+            except RuntimeError:
+                if sync == "p2p":
+                    raise
+                self.exchange = None
+                sync = "sharded"
+        elif sync == "auto":
+            sync = "sharded"
+        self.sync = sync
+        if self.world > 1 and self.exchange is None:
             self.exchange = GradientExchange(model.flat_grad, model.flat_lp, group, sharded=(sync == "sharded"),
                                              update_fn=self._update_slice)
 
@@ -185,17 +343,21 @@ class DataParallelHead:
         self.master_sharded = False
 
     # ------------------------------------------------------------------ the step
-    def _update_slice(self, off, length, tag, so, sn):
+    def _update_slice(self, off, length, tag, so, sn, grads=None):
         """ACMWeightDecayMomentumSGDUpdate on [so, so+sn) (runs on the exchange stream, right behind the
-        bucket's reduce-scatter).  Weights: wd, lr_mult 1; biases: no decay, lr_mult 2 (optimizer_wsl.py:106-123)."""
+        bucket's reduce-scatter; with ``grads`` the W contributions are summed inside the update kernel).
+        Weights: wd, lr_mult 1; biases: no decay, lr_mult 2 (optimizer_wsl.py:106-123)."""
         from . import ops
         m = self.model
         bias = tag == "biases"
-        ops.ACMWeightDecayMomentumSGDUpdate(
-            m.flat_grad[so: so + sn], m.flat_mom[so: so + sn], m.lr, m.flat_param[so: so + sn], None,
-            momentum=self._hyper["momentum"], gpu_num=self.world, lr_mult=2.0 if bias else 1.0,
-            weight_decay=0.0 if bias else self._hyper["weight_decay"], iter_count=m.iter_count,
-            p_shadow=m.flat_lp[so: so + sn])
+        kw = dict(momentum=self._hyper["momentum"], gpu_num=self.world, lr_mult=2.0 if bias else 1.0,
+                  weight_decay=0.0 if bias else self._hyper["weight_decay"], iter_count=m.iter_count,
+                  p_shadow=m.flat_lp[so: so + sn])
+        if grads is None:
+            ops.ACMWeightDecayMomentumSGDUpdate(m.flat_grad[so: so + sn], m.flat_mom[so: so + sn], m.lr,
+                                                m.flat_param[so: so + sn], None, **kw)
+        else:
+            ops.ACMWeightDecayMomentumSGDUpdateReduce(grads, m.flat_mom[so: so + sn], m.lr, m.flat_param[so: so + sn], **kw)
 
     def _limit_gemm_grid(self, on: bool):
         if self.model.flat_grad.is_cuda and self.comm_sms > 0:
@@ -212,6 +374,8 @@ class DataParallelHead:
         self._hyper = dict(momentum=momentum, weight_decay=weight_decay)
         ex.finish()                                  # the previous step's updated operands must have landed
         self._limit_gemm_grid(False)
+        if self.sync == "p2p":
+            ex.begin_step()
         small, biases = self.plan[-2], self.plan[-1]
 
         def on_panel(r0, r1):

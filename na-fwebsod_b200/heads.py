@@ -291,6 +291,15 @@ class WeblyHeadModel:
             ops.FCGradientX(dls, self.w["W8_%d" % s], act_below=a7, dropout=self._dropped, out=d7s, round_tf32=self.tf32)
             ops.FCGradientX(d7s, self.w["W7_%d" % s], act_below=a6, dropout=self._dropped, out=d6[:, s * H:(s + 1) * H],
                             round_tf32=self.tf32)
+        if need_dX:
+            # before the fc6 panels: a data-parallel exchange may refresh the W6 operands right behind them
+            if bl["_argmax_roi_feat"] is None:
+                raise RuntimeError("need_dX requires freeze_conv_body=False (argmax is not kept otherwise)")
+            d_feat = ops.FCGradientX(d6, self.w["W6"], out_dtype=self.dtype)
+            N, Hh, Ww, Cc = bl["conv5"].shape
+            bl["d_conv5"] = ops.RoIPoolFGradient(bl["conv5"], bl["rois"], bl["_argmax_roi_feat"],
+                                                 d_feat.view(R, self.roi_size, self.roi_size, Cc),
+                                                 boost=bl["obn_scores"], layout="NHWC")
         rows = self.S * H
         step = _round_up((rows + fc6_panels - 1) // fc6_panels, 256)
         for r0 in range(0, rows, step):
@@ -305,14 +314,6 @@ class WeblyHeadModel:
                             db=self.g["b7_%d" % s])
         if on_small_grads is not None:
             on_small_grads()
-        if need_dX:
-            if bl["_argmax_roi_feat"] is None:
-                raise RuntimeError("need_dX requires freeze_conv_body=False (argmax is not kept otherwise)")
-            d_feat = ops.FCGradientX(d6, self.w["W6"], out_dtype=self.dtype)
-            N, Hh, Ww, Cc = bl["conv5"].shape
-            bl["d_conv5"] = ops.RoIPoolFGradient(bl["conv5"], bl["rois"], bl["_argmax_roi_feat"],
-                                                 d_feat.view(R, self.roi_size, self.roi_size, Cc),
-                                                 boost=bl["obn_scores"], layout="NHWC")
         return bl
 
     def RunTestNet(self):

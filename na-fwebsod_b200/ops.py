@@ -318,6 +318,51 @@ def ACMWeightDecayMomentumSGDUpdate(g, m, lr, p, acc, *, momentum=0.9, iter_size
     return g, m, p, acc
 
 
+def ACMWeightDecayMomentumSGDUpdateReduce(grads, m, lr, p, *, momentum=0.9, gpu_num=1, lr_mult=1.0, weight_decay=0.0,
+                                          iter_count=0, p_shadow=None):
+    """Data-parallel owner's update: ``g = grads[0] + grads[1] + ...`` (in that order: the ranks'
+    contributions to this parameter slice), then ``ACMWeightDecayMomentumSGDUpdate`` with
+    iter_size 1 -- i.e. the reference's NCCLAllreduce + update pair (modeling/optimizer_wsl.py:52-72,
+    96-137) restricted to the slice this rank owns, in one pass over HBM."""
+    n = m.numel()
+    for t, nme in ((m, "m"), (p, "p")):
+        _req(t, nme, torch.float32)
+    _req(lr, "lr", torch.float32)
+    if not grads or p.numel() != n:
+        raise RuntimeError("need at least one gradient source and matching m / p sizes")
+    for i, g in enumerate(grads):
+        _req(g, "grads[%d]" % i, torch.float32)
+        if g.numel() != n:
+            raise RuntimeError("grads[%d] has %d elements, expected %d" % (i, g.numel(), n))
+    if p_shadow is not None:
+        _req(p_shadow, "p_shadow", (torch.bfloat16, torch.float32))
+    table = (ctypes.c_void_p * len(grads))(*[g.data_ptr() for g in grads])
+    _lib.call("nawsod_sgd_update_reduce", table, len(grads), _ptr(m), _ptr(lr), _ptr(p), n, float(momentum),
+              float(weight_decay), float(lr_mult), int(gpu_num), int(iter_count), _ptr(p_shadow),
+              _DT[p_shadow.dtype] if p_shadow is not None else F32, _stream())
+    return m, p
+
+
+# --------------------------------------------------------------------------------------------
+# peer-to-peer plumbing of the gradient exchange (raw device addresses; see csrc/p2p.cu)
+# --------------------------------------------------------------------------------------------
+def p2p_copy(dst_ptr: int, src_ptr: int, nbytes: int):
+    """Copy-engine transfer between local / peer-mapped device buffers on the current stream."""
+    _lib.call("nawsod_p2p_copy", ctypes.c_void_p(dst_ptr), ctypes.c_void_p(src_ptr), int(nbytes), _stream())
+
+
+def p2p_signal(flag_ptrs, value: int):
+    """Publish ``value`` into every flag word (system-scope release), in stream order."""
+    table = (ctypes.c_void_p * len(flag_ptrs))(*flag_ptrs)
+    _lib.call("nawsod_p2p_signal", table, len(flag_ptrs), int(value) & 0xFFFFFFFF, _stream())
+
+
+def p2p_wait(flags, value: int, timeout_ms: int = 20000, status=None):
+    """Block the current stream until every word of ``flags`` (int32 CUDA tensor) reached ``value``."""
+    _req(flags, "flags", torch.int32)
+    _lib.call("nawsod_p2p_wait", _ptr(flags), flags.numel(), int(value) & 0xFFFFFFFF, int(timeout_ms), _ptr(status), _stream())
+
+
 # --------------------------------------------------------------------------------------------
 # FC / FCGradient on the tcgen05 tensor cores (+ fused Relu / Dropout and their gradients)
 # --------------------------------------------------------------------------------------------

@@ -2,8 +2,8 @@
 
 Both exchange schedules of na-fwebsod_b200/dp.py run the same two training steps from the same
 initial state on rank-specific images: the sharded schedule (reduce-scatter -> SGD on the rank's
-slice -> all-gather of the bf16 operands, overlapped with the fc6 weight-gradient panels) must
-leave the parameters, momenta and GEMM operands the reference schedule leaves (bucketed
+slice -> all-gather of the bf16 operands, overlapped with the fc6 weight-gradient panels), over NCCL
+and over the peer-mapped copy-engine path (sync="p2p"), must leave the parameters, momenta and GEMM operands the reference schedule leaves (bucketed
 all-reduce + full ACMWeightDecayMomentumSGDUpdate on every rank,
 detectron/modeling/optimizer_wsl.py:52-137).  Tolerance: the two collectives may add the ranks'
 fp32 gradients in a different order and the bias-gradient column sums use atomics (run-to-run
@@ -38,7 +38,7 @@ def _worker(rank, world, port, out):
         from nafwebsod_b200.dp import DataParallelHead
         from oracle import nawsod_oracle as O
         res = {}
-        for sync in ("allreduce", "sharded"):
+        for sync in ("allreduce", "sharded", "p2p"):
             m = WeblyHeadModel(7, 64, 7, 256, noise=True, dtype=torch.bfloat16, device=dev)
             g = torch.Generator(device=dev).manual_seed(5)
             m.flat_param[:m.n_weights].normal_(0.0, 0.02, generator=g)
@@ -57,6 +57,8 @@ def _worker(rank, world, port, out):
                 dp.step(dropout_seed=it + 1)
             dp.gather_master_state()
             torch.cuda.synchronize()
+            if sync == "p2p":
+                dp.exchange.check()
             res[sync] = (m.flat_param.cpu().numpy().copy(), m.flat_mom.cpu().numpy().copy(),
                          m.flat_lp.float().cpu().numpy().copy(), m.blobs["loss"].cpu().numpy().copy())
         out[rank] = res
