@@ -217,6 +217,9 @@ def gpu_arm(args):
             os.environ.setdefault("NCCL_MAX_CTAS", str(args.comm_sms))
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
+    for kv in filter(None, os.environ.get("NAWSOD_TUNING", "").split(",")):      # e.g. NAWSOD_TUNING=sgd_max_ctas=148
+        k, v = kv.split("=")
+        pkg.set_tuning(k, int(v))
     dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
     noise = args.head == "na"
 
@@ -296,6 +299,20 @@ def gpu_arm(args):
     e2e_value = world * R * args.steps / (ms_e2e * 1e-3)
     d2h_bytes = int(losses[-1].numel() * losses[-1].element_size())
     assert all(bool(torch.isfinite(l).all()) for l in losses), "non-finite loss in the benchmark"
+
+    if os.environ.get("NAWSOD_P2P_PROFILE") and getattr(dp.exchange, "profile", 0) is None:
+        # one instrumented step: when did each bucket become ready / leave / arrive / get updated / get published
+        dp.flush(); sync_all()
+        dp.exchange.profile = []
+        base = torch.cuda.Event(enable_timing=True); base.record()
+        dp.step(dropout_seed=99); dp.flush()
+        end = torch.cuda.Event(enable_timing=True); end.record()
+        torch.cuda.synchronize()
+        if rank == 0:
+            tl = sorted((base.elapsed_time(e), lab, b) for lab, b, e in dp.exchange.profile)
+            sys.stderr.write("p2p timeline (ms from step start; step %.3f ms): %s\n" % (
+                base.elapsed_time(end), "  ".join("%.2f:%s[%d]" % t for t in tl)))
+        dp.exchange.profile = None
 
     if rank != 0:
         if world > 1:

@@ -125,6 +125,25 @@ int nawsod_fc_bwd_w(const void* dY, int64_t lddy, const void* A, int64_t lda, in
                     int K, int ab_dtype, float* dW, int64_t lddw, float* db, int flags,
                     void* stream);
 
+/* The same three GEMMs over S independent problems of one shape in ONE launch (the head's clean and
+ * noisy stacks, webly_heads.py:490-498: twice the tiles per launch, half the launches).  Stack s uses
+ * operand + s * stride (strides in elements of the operand's type; bias / db in floats; masks in
+ * bytes) and draws seeded dropout bits from dropout_seed + s.  S = 1 ignores the strides. */
+int nawsod_fc_fwd_stacks(const void* A, int64_t lda, int64_t sA, const void* W, int64_t ldw,
+                         int64_t sW, const float* bias, int64_t sbias, const uint8_t* mask,
+                         int64_t ldmask, int64_t smask, uint64_t dropout_seed, int S, int M, int N,
+                         int K, int ab_dtype, void* Y, int64_t ldy, int64_t sY, int y_dtype,
+                         int flags, void* stream);
+int nawsod_fc_bwd_x_stacks(const void* dY, int64_t lddy, int64_t sdY, const void* W, int64_t ldw,
+                           int64_t sW, const void* act_below, int64_t ldact, int64_t sact,
+                           int act_dtype, const uint8_t* mask_below, int64_t ldmask, int64_t smask,
+                           int S, int M, int N, int K, int ab_dtype, void* dA, int64_t ldda,
+                           int64_t sdA, int da_dtype, int flags, void* stream);
+int nawsod_fc_bwd_w_stacks(const void* dY, int64_t lddy, int64_t sdY, const void* A, int64_t lda,
+                           int64_t sA, int S, int M, int N, int K, int ab_dtype, float* dW,
+                           int64_t lddw, int64_t sdW, float* db, int64_t sdb, int flags,
+                           void* stream);
+
 /* Operand staging for the GEMMs above: float -> bf16, and float -> nearest-TF32 (kept in a
  * float container; dst may alias src) of a [rows, cols] matrix. */
 int nawsod_convert_f32_to_bf16(const float* src, int64_t ld_src, int64_t rows, int64_t cols,
@@ -220,6 +239,13 @@ int nawsod_p2p_open_mem_handle(const void* handle, int64_t handle_bytes, void** 
 int nawsod_p2p_close_mem_handle(void* base);
 int nawsod_p2p_copy(void* dst, const void* src, int64_t bytes, void* stream);
 int nawsod_p2p_signal(void* const* flag_ptrs, int n, uint32_t value, void* stream);
+/* SM-driven scatter (srcs differ) / broadcast (srcs equal): one launch copies `bytes` from srcs[i] to
+ * dsts[i] (local or peer-mapped) for each of npeers destinations with 16-byte posted stores, then
+ * stores `value` (system-scope release) into the nflags flag words.  No shared memory: its CTAs
+ * co-reside with the persistent GEMMs.  `slot` in [0,128) names the completion counter (distinct
+ * for launches that may overlap in time). */
+int nawsod_p2p_scatter(const void* const* srcs, void* const* dsts, int npeers, int64_t bytes,
+                       void* const* flag_ptrs, int nflags, uint32_t value, int slot, void* stream);
 int nawsod_p2p_wait(const void* flags, int n, uint32_t value, int64_t timeout_ms, void* status,
                     void* stream);
 

@@ -38,6 +38,11 @@ struct EpiParams {
   int flags;
   unsigned long long seed;   // counter-based dropout (fwd) when mask == nullptr and seed != 0
   int M, N, K;          // GEMM dims: out is [M, N], reduction over K
+  // independent problems of one shape in one launch (the head's clean / noisy stacks): problem b uses
+  // out + b*so, bias + b*sbias, mask + b*smask, act + b*sact (elements) and seed + b; the operand strides
+  // live in the 3-D tensor maps
+  int nbatch;
+  long long so, sbias, smask, sact;
 };
 
 // ------------------------------------------------------------------------------------------
@@ -64,10 +69,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "=r"(done) : "r"(bar), "r"(parity) : "memory");
   } while (!done);
 }
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
@@ -153,8 +158,9 @@ template <int BN, int ES> struct Cfg {
 
 template <int BN, bool A_MN, bool B_MN, int ES>
 __global__ void __launch_bounds__(kNumThreads, 1)
-gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const EpiParams ep) {
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const EpiParams ep_) {
   using C = Cfg<BN, ES>;
+  const EpiParams& ep = ep_;
   constexpr int BK = C::BK;
   constexpr int ATOM = 128 / ES;                 // MN elements per 128-byte panel
   extern __shared__ uint8_t smem_raw[];
@@ -172,7 +178,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_m = (ep.M + BLOCK_M - 1) / BLOCK_M;
   const int num_n = (ep.N + BN - 1) / BN;
-  const int num_tiles = num_m * num_n;
+  const int tiles_pb = num_m * num_n;
+  const int num_tiles = tiles_pb * ep.nbatch;
   const int num_kb = (ep.K + BK - 1) / BK;
 
   if (warp == 0 && lane == 0) {
@@ -196,21 +203,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile % num_m) * BLOCK_M, n0 = (tile / num_m) * BN;
+        const int bi = tile / tiles_pb, tb = tile - bi * tiles_pb;
+        const int m0 = (tb % num_m) * BLOCK_M, n0 = (tb / num_m) * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t sa = smem_base + stage * C::STAGE_BYTES, sb = sa + C::A_BYTES;
           mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
           const int k0 = kb * BK;
-          if (!A_MN) tma_load_2d(sa, &tmA, full_bar(stage), k0, m0);
+          if (!A_MN) tma_load_3d(sa, &tmA, full_bar(stage), k0, m0, bi);
           else {
 #pragma unroll
-            for (int a = 0; a < BLOCK_M / ATOM; ++a) tma_load_2d(sa + a * BK * 128, &tmA, full_bar(stage), m0 + a * ATOM, k0);
+            for (int a = 0; a < BLOCK_M / ATOM; ++a) tma_load_3d(sa + a * BK * 128, &tmA, full_bar(stage), m0 + a * ATOM, k0, bi);
           }
-          if (!B_MN) tma_load_2d(sb, &tmB, full_bar(stage), k0, n0);
+          if (!B_MN) tma_load_3d(sb, &tmB, full_bar(stage), k0, n0, bi);
           else {
 #pragma unroll
-            for (int a = 0; a < BN / ATOM; ++a) tma_load_2d(sb + a * BK * 128, &tmB, full_bar(stage), n0 + a * ATOM, k0);
+            for (int a = 0; a < BN / ATOM; ++a) tma_load_3d(sb + a * BK * 128, &tmB, full_bar(stage), n0 + a * ATOM, k0, bi);
           }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
@@ -259,7 +267,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const bool act_vec = ep.act && (reinterpret_cast<uintptr_t>(ep.act) & 15u) == 0 && (ep.ldact * 2) % 16 == 0;
     const bool mask_vec = ep.mask && (reinterpret_cast<uintptr_t>(ep.mask) & 15u) == 0 && ep.ldmask % 16 == 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile % num_m) * BLOCK_M, n0 = (tile / num_m) * BN;
+      const int bi = tile / tiles_pb, tb = tile - bi * tiles_pb;
+      const int m0 = (tb % num_m) * BLOCK_M, n0 = (tb / num_m) * BN;
+      EpiParams ep = ep_;                        // this problem's view of the epilogue operands
+      if (bi) {
+        const size_t oes = ep.out_dtype == NAWSOD_F32 ? 4 : 2, aes = ep.act_dtype == NAWSOD_BF16 ? 2 : 4;
+        ep.out = static_cast<char*>(ep.out) + (size_t)bi * ep.so * oes;
+        if (ep.bias) ep.bias += (size_t)bi * ep.sbias;
+        if (ep.mask) ep.mask += (size_t)bi * ep.smask;
+        if (ep.act) ep.act = static_cast<const char*>(ep.act) + (size_t)bi * ep.sact * aes;
+        if (ep.seed) ep.seed += bi;              // seed 0 means "no counter-based dropout" for every stack
+      }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const int m = m0 + q * 32 + lane;
@@ -458,19 +476,23 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// Row-major matrix [rows, cols] with leading dimension ld; box = [box_rows, box_cols] (cols innermost, 128 bytes).
+// nbatch row-major matrices [rows, cols] with leading dimension ld, `bstride` elements apart;
+// box = [1, box_rows, box_cols] (cols innermost, 128 bytes).
 int make_tmap(CUtensorMap* map, const void* ptr, int es, long long rows, long long cols, long long ld, int box_rows,
-              int box_cols, bool atom32) {
+              int box_cols, bool atom32, int nbatch, long long bstride) {
   EncodeTiledFn fn = get_encode_fn();
   NAWSOD_REQUIRE(fn != nullptr, NAWSOD_ERR_CUDA, "cuTensorMapEncodeTiled is not available (no CUDA driver?)");
   NAWSOD_REQUIRE(aligned16(ptr), NAWSOD_ERR_ALIGN, "fc: operand pointer must be 16-byte aligned");
   NAWSOD_REQUIRE((ld * es) % 16 == 0 && ld >= cols, NAWSOD_ERR_ALIGN,
                  "fc: leading dimension %lld (x%d bytes) must be >= cols and a multiple of 16 bytes", ld, es);
-  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t gstride[1] = {(cuuint64_t)ld * es};
-  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, es == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr),
+  if (nbatch <= 1) bstride = rows * ld;
+  NAWSOD_REQUIRE(bstride > 0 && (bstride * es) % 16 == 0, NAWSOD_ERR_ALIGN,
+                 "fc: stack stride %lld (x%d bytes) must be a positive multiple of 16 bytes", bstride, es);
+  cuuint64_t gdim[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)std::max(nbatch, 1)};
+  cuuint64_t gstride[2] = {(cuuint64_t)ld * es, (cuuint64_t)bstride * es};
+  cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, es == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(ptr),
                   gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -478,18 +500,20 @@ int make_tmap(CUtensorMap* map, const void* ptr, int es, long long rows, long lo
   return NAWSOD_OK;
 }
 
+struct Operands { const void* A; long long lda, sA; const void* B; long long ldb, sB; };
+
 template <int BN, bool A_MN, bool B_MN, int ES>
-int launch_gemm(const void* A, long long lda, const void* B, long long ldb, const EpiParams& ep, cudaStream_t st) {
+int launch_gemm(const Operands& o, const EpiParams& ep, cudaStream_t st) {
   using C = Cfg<BN, ES>;
   constexpr int ATOM = 128 / ES;
   CUtensorMap tmA, tmB;
   int rc;
   // K-major operand: stored [MN, K]; box [BLOCK rows, BK].  MN-major operand: stored [K, MN]; box [BK rows, ATOM].
-  if (!A_MN) rc = make_tmap(&tmA, A, ES, ep.M, ep.K, lda, BLOCK_M, C::BK, false);
-  else rc = make_tmap(&tmA, A, ES, ep.K, ep.M, lda, C::BK, ATOM, ES == 4);
+  if (!A_MN) rc = make_tmap(&tmA, o.A, ES, ep.M, ep.K, o.lda, BLOCK_M, C::BK, false, ep.nbatch, o.sA);
+  else rc = make_tmap(&tmA, o.A, ES, ep.K, ep.M, o.lda, C::BK, ATOM, ES == 4, ep.nbatch, o.sA);
   if (rc) return rc;
-  if (!B_MN) rc = make_tmap(&tmB, B, ES, ep.N, ep.K, ldb, BN, C::BK, false);
-  else rc = make_tmap(&tmB, B, ES, ep.K, ep.N, ldb, C::BK, ATOM, ES == 4);
+  if (!B_MN) rc = make_tmap(&tmB, o.B, ES, ep.N, ep.K, o.ldb, BN, C::BK, false, ep.nbatch, o.sB);
+  else rc = make_tmap(&tmB, o.B, ES, ep.K, ep.N, o.ldb, C::BK, ATOM, ES == 4, ep.nbatch, o.sB);
   if (rc) return rc;
   auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, ES>;
   static bool attr_set = false;
@@ -497,7 +521,7 @@ int launch_gemm(const void* A, long long lda, const void* B, long long ldb, cons
     NAWSOD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
-  const int num_tiles = ((ep.M + BLOCK_M - 1) / BLOCK_M) * ((ep.N + BN - 1) / BN);
+  const int num_tiles = ((ep.M + BLOCK_M - 1) / BLOCK_M) * ((ep.N + BN - 1) / BN) * ep.nbatch;
   // gemm_max_ctas: leave SMs to concurrently running collectives (a persistent one-CTA-per-SM grid
   // would otherwise wait behind them, or they behind it)
   const int cap = (int)get_tuning("gemm_max_ctas", 0);
@@ -508,17 +532,25 @@ int launch_gemm(const void* A, long long lda, const void* B, long long ldb, cons
 }
 
 template <bool A_MN, bool B_MN>
-int dispatch_gemm(const void* A, long long lda, const void* B, long long ldb, const EpiParams& ep, int ab_dtype, cudaStream_t st) {
+int dispatch_gemm(const Operands& o, EpiParams ep, int ab_dtype, cudaStream_t st) {
+  if (ep.nbatch < 1) ep.nbatch = 1;
+  if (ep.nbatch > 1) {
+    // the vectorised epilogue paths are chosen once per launch: every stack must keep problem 0's alignment
+    const long long oes = ep.out_dtype == NAWSOD_F32 ? 4 : 2, aes = ep.act_dtype == NAWSOD_BF16 ? 2 : 4;
+    NAWSOD_REQUIRE(ep.so > 0 && (ep.so * oes) % 16 == 0 && (!ep.bias || (ep.sbias * 4) % 16 == 0) &&
+                       (!ep.mask || ep.smask % 16 == 0) && (!ep.act || (ep.sact * aes) % 16 == 0),
+                   NAWSOD_ERR_ALIGN, "fc: stack strides of the output / bias / mask / activation must be multiples of 16 bytes");
+  }
   // BN = 256 for wide outputs; narrower tiles only when N itself is narrow (fc8: N = 2C)
   const int bn = ep.N > 128 ? 256 : (ep.N > 64 ? 128 : 64);
   if (ab_dtype == NAWSOD_BF16) {
-    if (bn == 256) return launch_gemm<256, A_MN, B_MN, 2>(A, lda, B, ldb, ep, st);
-    if (bn == 128) return launch_gemm<128, A_MN, B_MN, 2>(A, lda, B, ldb, ep, st);
-    return launch_gemm<64, A_MN, B_MN, 2>(A, lda, B, ldb, ep, st);
+    if (bn == 256) return launch_gemm<256, A_MN, B_MN, 2>(o, ep, st);
+    if (bn == 128) return launch_gemm<128, A_MN, B_MN, 2>(o, ep, st);
+    return launch_gemm<64, A_MN, B_MN, 2>(o, ep, st);
   }
-  if (bn == 256) return launch_gemm<256, A_MN, B_MN, 4>(A, lda, B, ldb, ep, st);
-  if (bn == 128) return launch_gemm<128, A_MN, B_MN, 4>(A, lda, B, ldb, ep, st);
-  return launch_gemm<64, A_MN, B_MN, 4>(A, lda, B, ldb, ep, st);
+  if (bn == 256) return launch_gemm<256, A_MN, B_MN, 4>(o, ep, st);
+  if (bn == 128) return launch_gemm<128, A_MN, B_MN, 4>(o, ep, st);
+  return launch_gemm<64, A_MN, B_MN, 4>(o, ep, st);
 }
 
 int check_common(const char* who, int M, int N, int K, int ab_dtype) {
@@ -532,10 +564,12 @@ int check_common(const char* who, int M, int N, int K, int ab_dtype) {
 
 using namespace nawsod;
 
-extern "C" int nawsod_fc_fwd(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, const uint8_t* mask,
-                             int64_t ldmask, uint64_t dropout_seed, int M, int N, int K, int ab_dtype, void* Y, int64_t ldy,
-                             int y_dtype, int flags, void* stream) {
+extern "C" int nawsod_fc_fwd_stacks(const void* A, int64_t lda, int64_t sA, const void* W, int64_t ldw, int64_t sW,
+                                    const float* bias, int64_t sbias, const uint8_t* mask, int64_t ldmask, int64_t smask,
+                                    uint64_t dropout_seed, int S, int M, int N, int K, int ab_dtype, void* Y, int64_t ldy,
+                                    int64_t sY, int y_dtype, int flags, void* stream) {
   if (int rc = check_common("fc_fwd", M, N, K, ab_dtype)) return rc;
+  NAWSOD_REQUIRE(S >= 1, NAWSOD_ERR_SHAPE, "fc_fwd: need at least one stack");
   NAWSOD_REQUIRE(A && W && Y, NAWSOD_ERR_ARG, "fc_fwd: null pointer");
   NAWSOD_REQUIRE(y_dtype == NAWSOD_F32 || y_dtype == NAWSOD_BF16, NAWSOD_ERR_ARG, "fc_fwd: bad y_dtype");
   NAWSOD_REQUIRE(!(flags & NAWSOD_FC_ACCUMULATE), NAWSOD_ERR_ARG, "fc_fwd: ACCUMULATE is a bwd_w flag");
@@ -544,13 +578,24 @@ extern "C" int nawsod_fc_fwd(const void* A, int64_t lda, const void* W, int64_t 
   EpiParams ep{};
   ep.out = Y; ep.ldo = ldy; ep.out_dtype = y_dtype; ep.bias = bias; ep.mask = (flags & NAWSOD_FC_DROPOUT) ? mask : nullptr;
   ep.ldmask = ldmask; ep.act = nullptr; ep.flags = flags; ep.seed = dropout_seed; ep.M = M; ep.N = N; ep.K = K;
-  return dispatch_gemm<false, false>(A, lda, W, ldw, ep, ab_dtype, static_cast<cudaStream_t>(stream));
+  ep.nbatch = S; ep.so = sY; ep.sbias = sbias; ep.smask = smask; ep.sact = 0;
+  const Operands o{A, lda, sA, W, ldw, sW};
+  return dispatch_gemm<false, false>(o, ep, ab_dtype, static_cast<cudaStream_t>(stream));
 }
 
-extern "C" int nawsod_fc_bwd_x(const void* dY, int64_t lddy, const void* W, int64_t ldw, const void* act_below, int64_t ldact,
-                               int act_dtype, const uint8_t* mask_below, int64_t ldmask, int M, int N, int K, int ab_dtype,
-                               void* dA, int64_t ldda, int da_dtype, int flags, void* stream) {
+extern "C" int nawsod_fc_fwd(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, const uint8_t* mask,
+                             int64_t ldmask, uint64_t dropout_seed, int M, int N, int K, int ab_dtype, void* Y, int64_t ldy,
+                             int y_dtype, int flags, void* stream) {
+  return nawsod_fc_fwd_stacks(A, lda, 0, W, ldw, 0, bias, 0, mask, ldmask, 0, dropout_seed, 1, M, N, K, ab_dtype, Y, ldy, 0,
+                              y_dtype, flags, stream);
+}
+
+extern "C" int nawsod_fc_bwd_x_stacks(const void* dY, int64_t lddy, int64_t sdY, const void* W, int64_t ldw, int64_t sW,
+                                      const void* act_below, int64_t ldact, int64_t sact, int act_dtype,
+                                      const uint8_t* mask_below, int64_t ldmask, int64_t smask, int S, int M, int N, int K,
+                                      int ab_dtype, void* dA, int64_t ldda, int64_t sdA, int da_dtype, int flags, void* stream) {
   if (int rc = check_common("fc_bwd_x", M, N, K, ab_dtype)) return rc;
+  NAWSOD_REQUIRE(S >= 1, NAWSOD_ERR_SHAPE, "fc_bwd_x: need at least one stack");
   NAWSOD_REQUIRE(dY && W && dA, NAWSOD_ERR_ARG, "fc_bwd_x: null pointer");
   NAWSOD_REQUIRE(da_dtype == NAWSOD_F32 || da_dtype == NAWSOD_BF16, NAWSOD_ERR_ARG, "fc_bwd_x: bad da_dtype");
   NAWSOD_REQUIRE(!(flags & NAWSOD_FC_RELU) || act_below, NAWSOD_ERR_ARG, "fc_bwd_x: RELU needs act_below");
@@ -562,12 +607,23 @@ extern "C" int nawsod_fc_bwd_x(const void* dY, int64_t lddy, const void* W, int6
   ep.mask = (flags & NAWSOD_FC_DROPOUT) ? mask_below : nullptr; ep.ldmask = ldmask;
   ep.act = (flags & NAWSOD_FC_RELU) ? act_below : nullptr; ep.ldact = ldact; ep.act_dtype = act_dtype;
   ep.flags = flags; ep.M = M; ep.N = K; ep.K = N;
-  return dispatch_gemm<false, true>(dY, lddy, W, ldw, ep, ab_dtype, static_cast<cudaStream_t>(stream));
+  ep.nbatch = S; ep.so = sdA; ep.sbias = 0; ep.smask = smask; ep.sact = sact;
+  const Operands o{dY, lddy, sdY, W, ldw, sW};
+  return dispatch_gemm<false, true>(o, ep, ab_dtype, static_cast<cudaStream_t>(stream));
 }
 
-extern "C" int nawsod_fc_bwd_w(const void* dY, int64_t lddy, const void* A, int64_t lda, int M, int N, int K, int ab_dtype,
-                               float* dW, int64_t lddw, float* db, int flags, void* stream) {
+extern "C" int nawsod_fc_bwd_x(const void* dY, int64_t lddy, const void* W, int64_t ldw, const void* act_below, int64_t ldact,
+                               int act_dtype, const uint8_t* mask_below, int64_t ldmask, int M, int N, int K, int ab_dtype,
+                               void* dA, int64_t ldda, int da_dtype, int flags, void* stream) {
+  return nawsod_fc_bwd_x_stacks(dY, lddy, 0, W, ldw, 0, act_below, ldact, 0, act_dtype, mask_below, ldmask, 0, 1, M, N, K,
+                                ab_dtype, dA, ldda, 0, da_dtype, flags, stream);
+}
+
+extern "C" int nawsod_fc_bwd_w_stacks(const void* dY, int64_t lddy, int64_t sdY, const void* A, int64_t lda, int64_t sA, int S,
+                                      int M, int N, int K, int ab_dtype, float* dW, int64_t lddw, int64_t sdW, float* db,
+                                      int64_t sdb, int flags, void* stream) {
   if (int rc = check_common("fc_bwd_w", M, N, K, ab_dtype)) return rc;
+  NAWSOD_REQUIRE(S >= 1, NAWSOD_ERR_SHAPE, "fc_bwd_w: need at least one stack");
   NAWSOD_REQUIRE(dY && A && dW, NAWSOD_ERR_ARG, "fc_bwd_w: null pointer");
   NAWSOD_REQUIRE(lddw >= K, NAWSOD_ERR_SHAPE, "fc_bwd_w: lddw smaller than K");
   NAWSOD_REQUIRE(!(flags & (NAWSOD_FC_RELU | NAWSOD_FC_DROPOUT | NAWSOD_FC_ROUND_TF32)), NAWSOD_ERR_ARG,
@@ -576,19 +632,31 @@ extern "C" int nawsod_fc_bwd_w(const void* dY, int64_t lddy, const void* A, int6
   EpiParams ep{};
   // GEMM view: out [N, K] = dY^T [N, M] . A [M, K] -> reduction over M
   ep.out = dW; ep.ldo = lddw; ep.out_dtype = NAWSOD_F32; ep.flags = flags; ep.M = N; ep.N = K; ep.K = M;
-  if (int rc = dispatch_gemm<true, true>(dY, lddy, A, lda, ep, ab_dtype, st)) return rc;
+  ep.nbatch = S; ep.so = sdW;
+  const Operands o{dY, lddy, sdY, A, lda, sA};
+  if (int rc = dispatch_gemm<true, true>(o, ep, ab_dtype, st)) return rc;
   if (db) {
-    if (!(flags & NAWSOD_FC_ACCUMULATE)) NAWSOD_CUDA_OK(cudaMemsetAsync(db, 0, (size_t)N * sizeof(float), st));
-    const int row_blocks = std::max(1, std::min(64, M / 64));
-    const int rpb = (M + row_blocks - 1) / row_blocks;
-    dim3 grid((N + 31) / 32, row_blocks);
-    if (ab_dtype == NAWSOD_BF16)
-      colsum_kernel<uint16_t><<<grid, 256, 0, st>>>(static_cast<const uint16_t*>(dY), lddy, M, N, rpb, db);
-    else
-      colsum_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(dY), lddy, M, N, rpb, db);
-    NAWSOD_LAUNCH_OK();
+    const int es = ab_dtype == NAWSOD_BF16 ? 2 : 4;
+    for (int s = 0; s < S; ++s) {
+      float* dbs = db + (size_t)s * sdb;
+      const char* dys = static_cast<const char*>(dY) + (size_t)s * sdY * es;
+      if (!(flags & NAWSOD_FC_ACCUMULATE)) NAWSOD_CUDA_OK(cudaMemsetAsync(dbs, 0, (size_t)N * sizeof(float), st));
+      const int row_blocks = std::max(1, std::min(64, M / 64));
+      const int rpb = (M + row_blocks - 1) / row_blocks;
+      dim3 grid((N + 31) / 32, row_blocks);
+      if (ab_dtype == NAWSOD_BF16)
+        colsum_kernel<uint16_t><<<grid, 256, 0, st>>>(reinterpret_cast<const uint16_t*>(dys), lddy, M, N, rpb, dbs);
+      else
+        colsum_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(dys), lddy, M, N, rpb, dbs);
+      NAWSOD_LAUNCH_OK();
+    }
   }
   return NAWSOD_OK;
+}
+
+extern "C" int nawsod_fc_bwd_w(const void* dY, int64_t lddy, const void* A, int64_t lda, int M, int N, int K, int ab_dtype,
+                               float* dW, int64_t lddw, float* db, int flags, void* stream) {
+  return nawsod_fc_bwd_w_stacks(dY, lddy, 0, A, lda, 0, 1, M, N, K, ab_dtype, dW, lddw, 0, db, 0, flags, stream);
 }
 
 extern "C" int nawsod_convert_f32_to_bf16(const float* src, int64_t ld_src, int64_t rows, int64_t cols, void* dst, int64_t ld_dst,

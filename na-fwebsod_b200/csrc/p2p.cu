@@ -9,6 +9,7 @@
 //           number, with a system-scope acquire load; a watchdog bounds the spin so that a lost peer
 //           surfaces as an error code instead of a hung GPU.
 #include <cuda.h>
+#include <algorithm>
 #include <cstring>
 #include "common.cuh"
 
@@ -46,10 +47,90 @@ __global__ void p2p_wait_kernel(const uint32_t* __restrict__ flags, int n, uint3
   __threadfence_system();
 }
 
+// SM-driven scatter / broadcast over NVLink: ONE launch moves `bytes` from src[i] to dst[i] for every peer i
+// (the reduce-scatter leg sends a different gradient slice to each owner, the all-gather leg the same operand
+// slice to everyone) and then publishes the sequence number, so a bucket costs one kernel instead of W-1 copies
+// + a signal.  The kernel needs no shared memory and few registers, so its CTAs run on the SMs the persistent
+// tcgen05 GEMMs already occupy -- the transfer genuinely overlaps the math (an NCCL kernel has to wait for
+// those SMs, and the copy engines reach only ~400 GB/s of egress when eight ranks scatter at once).  Work is
+// cut into 32 KB pieces dealt round-robin over the peers, so all links carry traffic all the time; each thread
+// keeps four independent 16-byte loads in flight; remote stores are posted.
+constexpr int kMaxPeers = 15;
+constexpr int kScatterThreads = 512;
+constexpr int kScatterUnroll = 4;
+struct ScatterArgs {
+  const char* src[kMaxPeers]; char* dst[kMaxPeers];
+  int npeers; long long bytes;
+  uint32_t* flag[kMaxPeers + 1]; int nflags; uint32_t value;
+  int slot;
+};
+__device__ unsigned int g_scatter_done[128];
+
+__global__ void __launch_bounds__(kScatterThreads) p2p_scatter_kernel(const ScatterArgs a) {
+  constexpr long long kPiece = (long long)kScatterThreads * 16 * kScatterUnroll;
+  const long long pieces_pp = (a.bytes + kPiece - 1) / kPiece;
+  const long long total = pieces_pp * a.npeers;
+  for (long long c = blockIdx.x; c < total; c += gridDim.x) {
+    const int peer = static_cast<int>(c % a.npeers);
+    const long long base = (c / a.npeers) * kPiece + (long long)threadIdx.x * 16;
+    const char* s = a.src[peer];
+    char* d = a.dst[peer];
+    uint4 v[kScatterUnroll];
+#pragma unroll
+    for (int u = 0; u < kScatterUnroll; ++u) {
+      const long long o = base + (long long)u * kScatterThreads * 16;
+      if (o < a.bytes) asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                                    : "=r"(v[u].x), "=r"(v[u].y), "=r"(v[u].z), "=r"(v[u].w) : "l"(s + o));
+    }
+#pragma unroll
+    for (int u = 0; u < kScatterUnroll; ++u) {
+      const long long o = base + (long long)u * kScatterThreads * 16;
+      if (o < a.bytes) asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(d + o), "r"(v[u].x), "r"(v[u].y), "r"(v[u].z), "r"(v[u].w) : "memory");
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned prev = atomicAdd(&g_scatter_done[a.slot], 1u);
+    if (prev == gridDim.x - 1) {                 // last CTA: every piece of every CTA is out -> publish
+      g_scatter_done[a.slot] = 0;
+      __threadfence_system();
+      for (int i = 0; i < a.nflags; ++i)
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.flag[i]), "r"(a.value) : "memory");
+    }
+  }
+}
+
 }  // namespace
 }  // namespace nawsod
 
 using namespace nawsod;
+
+extern "C" int nawsod_p2p_scatter(const void* const* srcs, void* const* dsts, int npeers, int64_t bytes,
+                                  void* const* flag_ptrs, int nflags, uint32_t value, int slot, void* stream) {
+  NAWSOD_REQUIRE(npeers >= 0 && npeers <= kMaxPeers && nflags >= 0 && nflags <= kMaxPeers + 1 && slot >= 0 && slot < 128,
+                 NAWSOD_ERR_ARG, "p2p_scatter: at most %d peers, %d flags, slot in [0, 128)", kMaxPeers, kMaxPeers + 1);
+  NAWSOD_REQUIRE(bytes >= 0 && bytes % 16 == 0, NAWSOD_ERR_ALIGN, "p2p_scatter: byte count must be a multiple of 16");
+  ScatterArgs a;
+  a.npeers = (bytes == 0) ? 0 : npeers; a.bytes = bytes; a.nflags = nflags; a.value = value; a.slot = slot;
+  for (int i = 0; i < npeers; ++i) {
+    NAWSOD_REQUIRE(srcs && dsts && srcs[i] && dsts[i] && aligned16(srcs[i]) && aligned16(dsts[i]), NAWSOD_ERR_ALIGN,
+                   "p2p_scatter: source / destination %d is null or not 16-byte aligned", i);
+    a.src[i] = static_cast<const char*>(srcs[i]); a.dst[i] = static_cast<char*>(dsts[i]);
+  }
+  for (int i = 0; i < nflags; ++i) {
+    NAWSOD_REQUIRE(flag_ptrs && flag_ptrs[i], NAWSOD_ERR_ARG, "p2p_scatter: null flag pointer %d", i);
+    a.flag[i] = static_cast<uint32_t*>(flag_ptrs[i]);
+  }
+  if (a.npeers == 0 && nflags == 0) return NAWSOD_OK;
+  const long long piece = (long long)kScatterThreads * 16 * kScatterUnroll;
+  const long long total = std::max<long long>(1, ((bytes + piece - 1) / piece) * std::max(a.npeers, 0));
+  const long long want = get_tuning("p2p_ctas", 0) > 0 ? get_tuning("p2p_ctas", 0) : 2LL * sm_count();
+  const int grid = (int)std::max<long long>(1, std::min<long long>(total, want));
+  p2p_scatter_kernel<<<grid, kScatterThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  NAWSOD_LAUNCH_OK();
+  return NAWSOD_OK;
+}
 
 extern "C" int nawsod_p2p_enable_peer_access(int peer_device) {
   int dev = 0, can = 0;

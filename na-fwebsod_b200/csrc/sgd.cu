@@ -54,22 +54,22 @@ __global__ void __launch_bounds__(256) sgd_kernel(const SgdArgs a) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   for (int64_t i = t0; i < n4; i += stride) {
-    float4 g = reinterpret_cast<const float4*>(a.g)[i];
+    float4 g = __ldcs(reinterpret_cast<const float4*>(a.g) + i);
     for (int e = 0; e < a.n_extra; ++e) {      // fixed (rank) order: the sum is deterministic
       const float4 x = __ldcs(reinterpret_cast<const float4*>(a.extra[e]) + i);
       g.x = __fadd_rn(g.x, x.x); g.y = __fadd_rn(g.y, x.y); g.z = __fadd_rn(g.z, x.z); g.w = __fadd_rn(g.w, x.w);
     }
-    float4 m = a.first_call ? make_float4(0.f, 0.f, 0.f, 0.f) : reinterpret_cast<const float4*>(a.m)[i];
-    float4 p = reinterpret_cast<const float4*>(a.p)[i];
+    float4 m = a.first_call ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldcs(reinterpret_cast<const float4*>(a.m) + i);
+    float4 p = __ldcs(reinterpret_cast<const float4*>(a.p) + i);
     float4 c = (a.first_call || !a.use_acc) ? make_float4(0.f, 0.f, 0.f, 0.f)
                                             : reinterpret_cast<const float4*>(a.acc)[i];
     sgd_elem(g.x, m.x, p.x, c.x, a, LR);
     sgd_elem(g.y, m.y, p.y, c.y, a, LR);
     sgd_elem(g.z, m.z, p.z, c.z, a, LR);
     sgd_elem(g.w, m.w, p.w, c.w, a, LR);
-    if (a.do_update || a.first_call) reinterpret_cast<float4*>(a.m)[i] = m;
+    if (a.do_update || a.first_call) __stcs(reinterpret_cast<float4*>(a.m) + i, m);
     if (a.do_update) {
-      reinterpret_cast<float4*>(a.p)[i] = p;
+      __stcs(reinterpret_cast<float4*>(a.p) + i, p);
       if (a.p_bf16) {
         __nv_bfloat162 lo = __floats2bfloat162_rn(p.x, p.y), hi = __floats2bfloat162_rn(p.z, p.w);
         reinterpret_cast<uint2*>(a.p_bf16)[i] =
@@ -132,7 +132,10 @@ static int sgd_launch(const float* const* grads, int n_grads, float* m, const fl
   a.do_update = ((iter_count + 1) % iter_size) == 0;
   a.use_acc = acc != nullptr;
   const int64_t work = std::max<int64_t>(n / 4, 1);
-  const int blocks = (int)std::min<int64_t>((work + 255) / 256, (int64_t)sm_count() * 16);
+  // sgd_max_ctas: when the update runs beside the tensor-core GEMMs it only has to keep up with them;
+  // a narrower grid leaves the memory system's queues to the GEMM epilogues
+  const int64_t cap = get_tuning("sgd_max_ctas", 0);
+  const int blocks = (int)std::min<int64_t>((work + 255) / 256, cap > 0 ? cap : (int64_t)sm_count() * 16);
   sgd_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
   NAWSOD_LAUNCH_OK();
   return NAWSOD_OK;

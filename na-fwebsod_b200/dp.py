@@ -23,6 +23,8 @@ panel p overlaps the tensor-core GEMM of panel p+1 and the fc7/fc8 weight-gradie
 transfer may be in flight the persistent GEMMs leave ``comm_sms`` SMs to the NCCL kernels
 (``gemm_max_ctas`` tuning) -- a persistent CTA-per-SM grid would otherwise serialise behind them.
 The compute stream joins the side stream only at the start of the next step (or ``flush()``).
+On ONE GPU the same pipeline runs without a collective: each bucket's SGD update (HBM-bound) goes to
+the side stream behind its producer GEMM and overlaps the remaining tensor-bound weight-gradient GEMMs.
 
 ``sync="p2p"`` is the same pipeline with the collectives replaced by the box's own hardware paths:
 every rank maps its peers' staging / flag / operand buffers (CUDA IPC over NVSwitch), the bulk data
@@ -89,8 +91,9 @@ class GradientExchange:
     def __init__(self, flat_grad: torch.Tensor, flat_out, group=None, sharded: bool = True, update_fn=None):
         self.flat, self.out = flat_grad, flat_out
         self.group = group
-        self.world = dist.get_world_size(group)
-        self.rank = dist.get_rank(group)
+        self.local = not dist.is_initialized()       # one GPU: no collective, the pipeline still hides the update
+        self.world = 1 if self.local else dist.get_world_size(group)
+        self.rank = 0 if self.local else dist.get_rank(group)
         self.sharded = sharded
         self.update_fn = update_fn
         self.cuda = flat_grad.is_cuda
@@ -118,6 +121,9 @@ class GradientExchange:
             ctx = _Null()
         self.in_flight = True
         with ctx:
+            if self.local:
+                self.update_fn(offset, length, tag, offset, length)
+                return
             if not self.sharded:
                 dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group)
                 return
@@ -220,9 +226,20 @@ class P2PExchange:
         if int(ok.item()) == 0:
             raise RuntimeError("peer mapping failed on at least one rank: %s" % (e1 or e2 or e3 or "on a peer"))
         self.stream = torch.cuda.Stream(device=dev, priority=-1)
+        self.send_stream = torch.cuda.Stream(device=dev, priority=-1)
+        # "sm": one co-resident scatter kernel per bucket and leg (default); "ce": copy-engine transfers
+        self.engine = os.environ.get("NAWSOD_P2P_ENGINE", "sm")
+        if self.engine not in ("sm", "ce"):
+            raise RuntimeError("NAWSOD_P2P_ENGINE must be 'sm' or 'ce'")
+        if len(self.plan) > 64:
+            raise RuntimeError("at most 64 exchange buckets")
+        nfan = int(os.environ.get("NAWSOD_P2P_COPY_STREAMS", "3"))
+        self.rs_streams = [torch.cuda.Stream(device=dev, priority=-1) for _ in range(nfan)]
+        self.ag_streams = [torch.cuda.Stream(device=dev, priority=-1) for _ in range(nfan)]
         self.seq = 0
         self.in_flight = False
         self.bytes_out = 0
+        self.profile = None      # list of (label, bucket, event) while a caller instruments one step
 
     def _flag_ptrs(self, kind, b):
         W, nb = self.world, len(self.plan)
@@ -240,24 +257,73 @@ class P2PExchange:
         W, rank, n = self.world, self.rank, length // self.world
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(self.flat.device))
-        self.stream.wait_event(ev)
         self.in_flight = True
         es_out = self.out.element_size()
+        prof = self.profile
+        # scatter side: never blocked by a peer, so the contributions leave as soon as their GEMM has finished
+        if prof is not None:
+            self.send_stream.wait_event(ev)
+            with torch.cuda.stream(self.send_stream):
+                prof.append(("ready", b, self._mark()))
+        peers = [(rank + i) % W for i in range(1, W)]             # staggered targets
+        rs_copies = [(self.peer_stage[k] + 4 * (offset + rank * n), self.flat.data_ptr() + 4 * (offset + k * n), 4 * n) for k in peers]
+        self.bytes_out += 4 * n * (W - 1)
+        if self.engine == "sm":
+            self.send_stream.wait_event(ev)
+            with torch.cuda.stream(self.send_stream):
+                ops.p2p_scatter([c[1] for c in rs_copies], [c[0] for c in rs_copies], 4 * n, self._flag_ptrs(self.RS, b), self.seq, b)
+                if prof is not None:
+                    prof.append(("sent", b, self._mark()))
+        else:
+            self._fan_out(self.rs_streams, ev, self.send_stream, rs_copies)
+            with torch.cuda.stream(self.send_stream):
+                ops.p2p_signal(self._flag_ptrs(self.RS, b), self.seq)
+                if prof is not None:
+                    prof.append(("sent", b, self._mark()))
+        # update side: wait for the W contributions, reduce + SGD on the owned slice, publish the operands
+        self.stream.wait_event(ev)
+        so = offset + rank * n
         with torch.cuda.stream(self.stream):
-            for i in range(1, W):                     # staggered targets: no two ranks hit the same peer at once
-                k = (rank + i) % W
-                ops.p2p_copy(self.peer_stage[k] + 4 * (offset + rank * n), self.flat.data_ptr() + 4 * (offset + k * n), 4 * n)
-            self.bytes_out += 4 * n * (W - 1)
-            ops.p2p_signal(self._flag_ptrs(self.RS, b), self.seq)
             fb = (self.RS * len(self.plan) + b) * W
             ops.p2p_wait(self.flags[fb: fb + W], self.seq, self.timeout_ms, self.status)
-            so = offset + rank * n
+            if prof is not None:
+                prof.append(("arrived", b, self._mark()))
             grads = [self.flat[so: so + n] if r == rank else self.stage[offset + r * n: offset + (r + 1) * n] for r in range(W)]
             self.update_fn(offset, length, tag, so, n, grads)
-            for i in range(1, W):
-                k = (rank + i) % W
-                ops.p2p_copy(self.peer_out[k] + es_out * so, self.out.data_ptr() + es_out * so, es_out * n)
-            ops.p2p_signal(self._flag_ptrs(self.AG, b), self.seq)
+            if prof is not None:
+                prof.append(("updated", b, self._mark()))
+            ag_copies = [(self.peer_out[k] + es_out * so, self.out.data_ptr() + es_out * so, es_out * n) for k in peers]
+            if self.engine == "sm":
+                ops.p2p_scatter([c[1] for c in ag_copies], [c[0] for c in ag_copies], es_out * n, self._flag_ptrs(self.AG, b), self.seq, 64 + b)
+            upd = torch.cuda.Event()
+            upd.record()
+        if self.engine != "sm":
+            self._fan_out(self.ag_streams, upd, self.stream, ag_copies)
+            with torch.cuda.stream(self.stream):
+                ops.p2p_signal(self._flag_ptrs(self.AG, b), self.seq)
+        if prof is not None:
+            with torch.cuda.stream(self.stream):
+                prof.append(("published", b, self._mark()))
+
+    def _fan_out(self, streams, after, join, copies):
+        """Issue the peer copies round-robin over a few streams (their per-copy set-up latencies overlap, the
+        link stays busy), each gated on event ``after``; stream ``join`` continues once all have completed."""
+        from . import ops
+        used = streams[:max(1, min(len(streams), len(copies)))]
+        for st in used:
+            st.wait_event(after)
+        for i, (dst, src, nbytes) in enumerate(copies):
+            with torch.cuda.stream(used[i % len(used)]):
+                ops.p2p_copy(dst, src, nbytes)
+        for st in used:
+            e = torch.cuda.Event()
+            e.record(st)
+            join.wait_event(e)
+
+    def _mark(self):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
 
     def finish(self):
         from . import ops
@@ -266,7 +332,11 @@ class P2PExchange:
         nb, W = len(self.plan), self.world
         with torch.cuda.stream(self.stream):
             ops.p2p_wait(self.flags[nb * W: 2 * nb * W], self.seq, self.timeout_ms, self.status)
-        torch.cuda.current_stream(self.flat.device).wait_stream(self.stream)
+            if self.profile is not None:
+                self.profile.append(("all operands here", -1, self._mark()))
+        cur = torch.cuda.current_stream(self.flat.device)
+        cur.wait_stream(self.stream)
+        cur.wait_stream(self.send_stream)
         self.in_flight = False
 
     def check(self):
@@ -294,7 +364,7 @@ class DataParallelHead:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.sync = sync
-        self.fc6_panels = fc6_panels if self.world > 1 else 1
+        self.fc6_panels = fc6_panels
         off, n, shp = model._slices["W6"]
         assert off == 0
         self.plan = bucket_plan(n, shp[0], shp[1], model.n_weights, model.n_total, self.fc6_panels)
@@ -316,8 +386,12 @@ class DataParallelHead:
         elif sync == "auto":
             sync = "sharded"
         self.sync = sync
-        if self.world > 1 and self.exchange is None:
-            self.exchange = GradientExchange(model.flat_grad, model.flat_lp, group, sharded=(sync == "sharded"),
+        if self.world == 1:
+            self.sync = sync = "local"
+            if not model.flat_grad.is_cuda or os.environ.get("NAWSOD_LOCAL_PIPELINE", "1") == "0":
+                self.fc6_panels = 1                  # plain schedule: backward, then two SGD launches
+        if self.exchange is None and (self.world > 1 or self.fc6_panels > 1):
+            self.exchange = GradientExchange(model.flat_grad, model.flat_lp, group, sharded=(sync != "allreduce"),
                                              update_fn=self._update_slice)
 
     # ------------------------------------------------------------------ parameters
@@ -366,24 +440,26 @@ class DataParallelHead:
 
     def step(self, dropout_seed=0, dropout_masks=None, momentum=0.9, weight_decay=5e-4):
         m = self.model
-        if self.world == 1:
+        if self.exchange is None:
             bl = m.RunTrainStep(dropout_masks=dropout_masks, dropout_seed=dropout_seed)
             m.param_update(momentum=momentum, weight_decay=weight_decay, gpu_num=1)
             return bl
         ex, cols = self.exchange, m._slices["W6"][2][1]
         self._hyper = dict(momentum=momentum, weight_decay=weight_decay)
-        ex.finish()                                  # the previous step's updated operands must have landed
-        self._limit_gemm_grid(False)
-        if self.sync == "p2p":
-            ex.begin_step()
         small, biases = self.plan[-2], self.plan[-1]
+
+        def before_params():                         # RoI pooling needs no parameters: join the previous exchange after it
+            ex.finish()
+            self._limit_gemm_grid(False)
+            if self.sync == "p2p":
+                ex.begin_step()
 
         def on_panel(r0, r1):
             self._limit_gemm_grid(True)              # GEMMs launched from here on share the GPU with NCCL
             ex.launch(r0 * cols, (r1 - r0) * cols, "fc6_panel")
 
         bl = m.RunTrainStep(dropout_masks=dropout_masks, dropout_seed=dropout_seed, fc6_panels=self.fc6_panels,
-                            on_fc6_panel=on_panel,
+                            on_fc6_panel=on_panel, on_before_params=before_params,
                             on_small_grads=lambda: ex.launch(small[0], small[1], "small_weights"))
         ex.launch(biases[0], biases[1], "biases")
         if self.sync == "allreduce":
@@ -391,7 +467,7 @@ class DataParallelHead:
             self._limit_gemm_grid(False)
             m.param_update(momentum=momentum, weight_decay=weight_decay, gpu_num=self.world)
         else:
-            self.master_sharded = True
+            self.master_sharded = self.world > 1
             m.iter_count += 1
         return bl
 

@@ -65,9 +65,10 @@ class WeblyHeadModel:
     # ------------------------------------------------------------------ parameters
     def _alloc_params(self):
         S, H, D, C2 = self.S, self.H, self.D, 2 * self.C
-        shapes_w = [("W6", (S * H, D))] + [("W7_%d" % s, (H, H)) for s in range(S)] + \
-                   [("W8_%d" % s, (C2, H)) for s in range(S)]
-        shapes_b = [("b6", (S * H,))] + [("b7_%d" % s, (H,)) for s in range(S)] + [("b8_%d" % s, (C2,)) for s in range(S)]
+        C2p = _round_up(C2, 8)     # per-stack pitch of the fc8 biases (keeps every stack 16-byte aligned)
+        # the stacks' fc7 / fc8 parameters are [S, ., .] blocks: one stacked GEMM launch serves all stacks
+        shapes_w = [("W6", (S * H, D)), ("W7", (S, H, H)), ("W8", (S, C2, H))]
+        shapes_b = [("b6", (S * H,)), ("b7", (S, H)), ("b8", (S, C2p))]
         off, self._slices = 0, {}
         for name, shp in shapes_w:
             n = int(np.prod(shp))
@@ -85,9 +86,16 @@ class WeblyHeadModel:
         self.flat_lp = z(self.dtype)
         self.lr = torch.zeros(1, dtype=torch.float32, device=self.device)   # the reference's `lr` blob
         view = lambda flat, k: flat[self._slices[k][0]: self._slices[k][0] + self._slices[k][1]].view(self._slices[k][2])
-        self.p = {k: view(self.flat_param, k) for k in self._slices}       # fp32 masters
-        self.g = {k: view(self.flat_grad, k) for k in self._slices}
-        self.w = {k: view(self.flat_lp, k) for k in self._slices}          # GEMM operands (bf16 shadow or the master)
+        def views(flat):
+            d = {k: view(flat, k) for k in self._slices}
+            d["b8"] = d["b8"][:, :C2]
+            for s in range(S):                                             # per-stack aliases
+                d["W7_%d" % s], d["W8_%d" % s] = d["W7"][s], d["W8"][s]
+                d["b7_%d" % s], d["b8_%d" % s] = d["b7"][s], d["b8"][s]
+            return d
+        self.p = views(self.flat_param)       # fp32 masters
+        self.g = views(self.flat_grad)
+        self.w = views(self.flat_lp)          # GEMM operands (bf16 shadow or the master)
 
     def _ref_names(self, s):
         """Reference blob-name prefixes of stack s (detectron/modeling/webly_heads.py:490-498, 36-55)."""
@@ -191,7 +199,7 @@ class WeblyHeadModel:
             self.blobs["labels_oh"] = labels_oh
 
     # ------------------------------------------------------------------ forward pieces
-    def _fc_stack(self, dropout_masks=None, dropout_seed=0, stacks=None):
+    def _fc_stack(self, dropout_masks=None, dropout_seed=0, stacks=None, on_before_params=None):
         """RoIFeatureTransform -> RoIFeatureBoost -> (fc6 -> Relu -> Dropout -> fc7 -> Relu -> Dropout) per stack."""
         bl, H = self.blobs, self.H
         stacks = list(range(self.S)) if stacks is None else stacks
@@ -204,6 +212,8 @@ class WeblyHeadModel:
         if self.tf32:
             ops.round_to_tf32(feat, out=feat)     # GEMM operand: nearest-TF32 (the stand-alone RoIPoolF op stays exact)
         bl["roi_feat"], bl["_argmax_roi_feat"] = feat, argmax
+        if on_before_params is not None:
+            on_before_params()            # first parameter read of the step follows (fc6)
         nS = len(stacks)
         drop6 = self._scratch("drop6", (R, nS * H), self.dtype)
         drop7 = self._scratch("drop7", (R, nS * H), self.dtype)
@@ -221,13 +231,25 @@ class WeblyHeadModel:
             feat, self.w["W6"][s0 * H:s1 * H], self.p["b6"][s0 * H:s1 * H], relu=True, dropout=use_drop,
             dropout_mask=m6, dropout_seed=(dropout_seed * 4 + 1) if (use_drop and m6 is None) else 0, out=drop6,
             round_tf32=self.tf32))
-        for i, s in enumerate(stacks):
-            ops.FC(drop6[:, i * H:(i + 1) * H], self.w["W7_%d" % s], self.p["b7_%d" % s], relu=True, dropout=use_drop,
-                   dropout_mask=None if m7 is None else m7[i],
-                   dropout_seed=(dropout_seed * 4 + 2 + s) if (use_drop and m7 is None) else 0,
-                   out=drop7[:, i * H:(i + 1) * H], round_tf32=self.tf32)
+        if nS == self.S:      # all stacks: one launch ([S, R, H] views of the column blocks; nothing is copied)
+            ops.FC(self._stacked(drop6, nS), self.w["W7"], self.p["b7"], relu=True, dropout=use_drop,
+                   dropout_mask=None if m7 is None else torch.stack(m7),
+                   dropout_seed=(dropout_seed * 4 + 2) if (use_drop and m7 is None) else 0,
+                   out=self._stacked(drop7, nS), round_tf32=self.tf32)
+        else:
+            for i, s in enumerate(stacks):
+                ops.FC(drop6[:, i * H:(i + 1) * H], self.w["W7_%d" % s], self.p["b7_%d" % s], relu=True, dropout=use_drop,
+                       dropout_mask=None if m7 is None else m7[i],
+                       dropout_seed=(dropout_seed * 4 + 2 + s) if (use_drop and m7 is None) else 0,
+                       out=drop7[:, i * H:(i + 1) * H], round_tf32=self.tf32)
         bl["drop6_cat"], bl["drop7_cat"] = drop6, drop7
         return drop6, drop7
+
+    @staticmethod
+    def _stacked(buf, nS):
+        """[R, nS*H] activation buffer -> [nS, R, H] strided view of its per-stack column blocks."""
+        R = buf.shape[0]
+        return buf.view(R, nS, buf.shape[1] // nS).permute(1, 0, 2)
 
     def _fc8(self, drop7, stacks=None):
         """fc8c | fc8d of every stack: one [R, 2C] GEMM per stack (fp32 logits)."""
@@ -236,14 +258,17 @@ class WeblyHeadModel:
         R = drop7.shape[0]
         ld = _round_up(C2, 8)
         logits = self._scratch("logits", (len(stacks), R, ld), torch.float32)
-        for i, s in enumerate(stacks):
-            ops.FC(drop7[:, i * H:(i + 1) * H], self.w["W8_%d" % s], self.p["b8_%d" % s], out=logits[i][:, :C2])
+        if len(stacks) == self.S:
+            ops.FC(self._stacked(drop7, self.S), self.w["W8"], self.p["b8"], out=logits[:, :, :C2])
+        else:
+            for i, s in enumerate(stacks):
+                ops.FC(drop7[:, i * H:(i + 1) * H], self.w["W8_%d" % s], self.p["b8_%d" % s], out=logits[i][:, :C2])
         self.blobs["fc8_logits"] = logits
         return logits
 
     # ------------------------------------------------------------------ the reference's builder names
     def RunTrainStep(self, dropout_masks=None, dropout_seed=0, need_dX=False, fc6_panels=1, on_small_grads=None,
-                     on_fc6_panel=None):
+                     on_fc6_panel=None, on_before_params=None):
         """One fwd+bwd pass of the head on the fed blobs (the slice of ``workspace.RunNet(net)``,
         detectron/utils/train_wsl.py:59, that lies between conv5 and the parameter gradients).
         Gradients land in ``self.g`` / ``self.flat_grad``; returns the blob dict.
@@ -252,11 +277,13 @@ class WeblyHeadModel:
         activation-gradient chain in ``fc6_panels`` row panels and ``on_fc6_panel(r0, r1)`` fires
         after each one (its exchange then overlaps the next panel's GEMM and the fc7 / fc8
         weight-gradient GEMMs); ``on_small_grads()`` fires once those are enqueued.  The bias
-        gradients of fc6 are complete with the last panel, all others with ``on_small_grads``."""
+        gradients of fc6 are complete with the last panel, all others with ``on_small_grads``.
+        ``on_before_params()`` fires after RoI pooling, right before the first parameter read (fc6):
+        the place to join a parameter update that is still in flight from the previous step."""
         if not self.train:
             raise RuntimeError("RunTrainStep on a test-mode model")
         bl, H, C, C2 = self.blobs, self.H, self.C, 2 * self.C
-        drop6, drop7 = self._fc_stack(dropout_masks, dropout_seed)
+        drop6, drop7 = self._fc_stack(dropout_masks, dropout_seed, on_before_params=on_before_params)
         logits = self._fc8(drop7)
         R = drop7.shape[0]
         ld = logits.shape[2]
@@ -283,14 +310,11 @@ class WeblyHeadModel:
         d7 = self._scratch("d_fc7", (R, self.S * H), self.dtype)
         # activation-gradient chain first (fc8 dX -> fc7 dX): it is the critical path to the fc6 weight
         # gradient, which carries 86 % of the gradient bytes and so must start its exchange earliest
-        for s in range(self.S):
-            dls = dl[s][:, :C2]
-            a7 = drop7[:, s * H:(s + 1) * H]
-            a6 = drop6[:, s * H:(s + 1) * H]
-            d7s = d7[:, s * H:(s + 1) * H]
-            ops.FCGradientX(dls, self.w["W8_%d" % s], act_below=a7, dropout=self._dropped, out=d7s, round_tf32=self.tf32)
-            ops.FCGradientX(d7s, self.w["W7_%d" % s], act_below=a6, dropout=self._dropped, out=d6[:, s * H:(s + 1) * H],
-                            round_tf32=self.tf32)
+        S = self.S
+        dl3, a7, a6 = dl[:, :, :C2], self._stacked(drop7, S), self._stacked(drop6, S)
+        d73, d63 = self._stacked(d7, S), self._stacked(d6, S)
+        ops.FCGradientX(dl3, self.w["W8"], act_below=a7, dropout=self._dropped, out=d73, round_tf32=self.tf32)
+        ops.FCGradientX(d73, self.w["W7"], act_below=a6, dropout=self._dropped, out=d63, round_tf32=self.tf32)
         if need_dX:
             # before the fc6 panels: a data-parallel exchange may refresh the W6 operands right behind them
             if bl["_argmax_roi_feat"] is None:
@@ -308,10 +332,8 @@ class WeblyHeadModel:
                                                              db=self.g["b6"][r0:r1]))
             if on_fc6_panel is not None:
                 on_fc6_panel(r0, r1)
-        for s in range(self.S):
-            ops.FCGradientW(dl[s][:, :C2], drop7[:, s * H:(s + 1) * H], dW=self.g["W8_%d" % s], db=self.g["b8_%d" % s])
-            ops.FCGradientW(d7[:, s * H:(s + 1) * H], drop6[:, s * H:(s + 1) * H], dW=self.g["W7_%d" % s],
-                            db=self.g["b7_%d" % s])
+        ops.FCGradientW(dl3, a7, dW=self.g["W8"], db=self.g["b8"])
+        ops.FCGradientW(d73, a6, dW=self.g["W7"], db=self.g["b7"])
         if on_small_grads is not None:
             on_small_grads()
         return bl

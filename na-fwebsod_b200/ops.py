@@ -357,6 +357,15 @@ def p2p_signal(flag_ptrs, value: int):
     _lib.call("nawsod_p2p_signal", table, len(flag_ptrs), int(value) & 0xFFFFFFFF, _stream())
 
 
+def p2p_scatter(srcs, dsts, nbytes: int, flag_ptrs, value: int, slot: int):
+    """One SM-driven launch: copy ``nbytes`` from srcs[i] to dsts[i] (raw addresses, local or peer-mapped) for every
+    peer, then publish ``value`` into the flag words."""
+    ts = (ctypes.c_void_p * max(len(srcs), 1))(*srcs)
+    td = (ctypes.c_void_p * max(len(dsts), 1))(*dsts)
+    tf = (ctypes.c_void_p * max(len(flag_ptrs), 1))(*flag_ptrs)
+    _lib.call("nawsod_p2p_scatter", ts, td, len(srcs), int(nbytes), tf, len(flag_ptrs), int(value) & 0xFFFFFFFF, int(slot), _stream())
+
+
 def p2p_wait(flags, value: int, timeout_ms: int = 20000, status=None):
     """Block the current stream until every word of ``flags`` (int32 CUDA tensor) reached ``value``."""
     _req(flags, "flags", torch.int32)
@@ -381,77 +390,115 @@ def _ab(dtype):
     return _DT[dtype]
 
 
+def _mat3(t, name):
+    """Stack of equally shaped row-major matrices: (S, rows, cols, leading dimension, stack stride), all in
+    elements.  A 2-d matrix is a stack of one.  Stacks are strided views (e.g. the per-stack column blocks
+    of an [R, S*H] activation buffer, ``buf.view(R, S, H).permute(1, 0, 2)``) -- nothing is copied."""
+    if isinstance(t, torch.Tensor) and t.dim() == 2:
+        r, c, ld = _mat(t, name)
+        return 1, r, c, ld, 0
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError("%s must be a CUDA tensor (libnawsod has no CPU path)" % name)
+    if t.dim() != 3 or t.stride(2) != 1:
+        raise RuntimeError("%s must be a 2-d matrix or a 3-d stack of row-major matrices" % name)
+    ld = t.stride(1) if t.shape[1] > 1 else max(t.stride(1), t.shape[2])
+    return t.shape[0], t.shape[1], t.shape[2], ld, (t.stride(0) if t.shape[0] > 1 else 0)
+
+
+def _same_stacks(who, *ss):
+    S = max(ss)
+    if any(x not in (S,) for x in ss):
+        raise RuntimeError("%s: operands disagree on the number of stacks %s" % (who, ss))
+    return S
+
+
 def FC(X, W, b=None, *, relu=False, dropout_mask=None, dropout=False, dropout_seed=0, out=None, out_dtype=None,
        round_tf32=False):
     """``FC([X, W, b] -> Y)`` with W [out, in] (Caffe2 layout), optionally fused with the
     ``Relu`` and ``Dropout(ratio=0.5, is_test=0)`` that follow it in the head
-    (modeling/wsl_heads.py:674-679).  X may be a column slice of a wider matrix."""
-    M, K, lda = _mat(X, "X")
-    N, K2, ldw = _mat(W, "W")
+    (modeling/wsl_heads.py:674-679).  X may be a column slice of a wider matrix.  3-d operands
+    ([S, ., .] strided views, b [S, N]) run the S stacks of the head as ONE launch; stack s draws its
+    seeded dropout bits from ``dropout_seed + s``."""
+    S, M, K, lda, sA = _mat3(X, "X")
+    S2, N, K2, ldw, sW = _mat3(W, "W")
     if K != K2 or X.dtype != W.dtype:
         raise RuntimeError("FC: X [%d,%d] %s and W [%d,%d] %s do not match" % (M, K, X.dtype, N, K2, W.dtype))
+    sb = 0
     if b is not None:
-        _req(b, "b", torch.float32)
-        if b.numel() != N:
-            raise RuntimeError("FC: bias must have %d elements" % N)
+        _req(b, "b", torch.float32) if b.dim() == 1 else None
+        if b.dtype != torch.float32 or not b.is_cuda or b.shape[-1] != N or b.stride(-1) != 1 or b.numel() != S * N:
+            raise RuntimeError("FC: bias must be float32 with %d elements per stack" % N)
+        sb = b.stride(0) if b.dim() == 2 and S > 1 else 0
     out_dtype = out_dtype or (out.dtype if out is not None else X.dtype)
-    Y = torch.empty((M, N), dtype=out_dtype, device=X.device) if out is None else out
-    _, N2, ldy = _mat(Y, "Y")
-    if N2 != N or Y.shape[0] != M:
+    Y = torch.empty((M, N) if X.dim() == 2 else (S, M, N), dtype=out_dtype, device=X.device) if out is None else out
+    S3, M3, N2, ldy, sY = _mat3(Y, "Y")
+    _same_stacks("FC", S, S2, S3)
+    if N2 != N or M3 != M:
         raise RuntimeError("FC: out has the wrong shape")
     flags = (_lib.FC_RELU if relu else 0) | \
             (_lib.FC_DROPOUT if (dropout or dropout_mask is not None or dropout_seed) else 0) | \
             (_lib.FC_ROUND_TF32 if round_tf32 else 0)
-    ldm = 0
+    ldm = sm = 0
     if dropout_mask is not None:
         if dropout_mask.dtype != torch.uint8:
             raise RuntimeError("dropout_mask must be uint8 (0/1)")
-        _, _, ldm = _mat(dropout_mask, "dropout_mask")
-    _lib.call("nawsod_fc_fwd", _ptr(X), lda, _ptr(W), ldw, _ptr(b), _ptr(dropout_mask), ldm, int(dropout_seed), M, N, K, _ab(X.dtype),
-              _ptr(Y), ldy, _DT[Y.dtype], flags, _stream())
+        S4, _, _, ldm, sm = _mat3(dropout_mask, "dropout_mask")
+        _same_stacks("FC", S, S4)
+    _lib.call("nawsod_fc_fwd_stacks", _ptr(X), lda, sA, _ptr(W), ldw, sW, _ptr(b), sb, _ptr(dropout_mask), ldm, sm,
+              int(dropout_seed), S, M, N, K, _ab(X.dtype), _ptr(Y), ldy, sY, _DT[Y.dtype], flags, _stream())
     return Y
 
 
 def FCGradientX(dY, W, *, act_below=None, mask_below=None, dropout=False, out=None, out_dtype=None, round_tf32=False):
     """dX of ``FCGradient([X, W, dY] -> [dW, db, dX])`` fused with the ``DropoutGradient`` and
-    ``ReluGradient`` of the layer below: dX = (dY . W) * 2[dropout] * (act_below > 0)."""
-    M, N, lddy = _mat(dY, "dY")
-    N2, K, ldw = _mat(W, "W")
+    ``ReluGradient`` of the layer below: dX = (dY . W) * 2[dropout] * (act_below > 0).  3-d operands = stacks."""
+    S, M, N, lddy, sdY = _mat3(dY, "dY")
+    S2, N2, K, ldw, sW = _mat3(W, "W")
     if N != N2 or dY.dtype != W.dtype:
         raise RuntimeError("FCGradientX: dY and W do not match")
     out_dtype = out_dtype or (out.dtype if out is not None else dY.dtype)
-    dX = torch.empty((M, K), dtype=out_dtype, device=dY.device) if out is None else out
-    _, K2, ldda = _mat(dX, "dX")
-    if K2 != K or dX.shape[0] != M:
+    dX = torch.empty((M, K) if dY.dim() == 2 else (S, M, K), dtype=out_dtype, device=dY.device) if out is None else out
+    S3, M3, K2, ldda, sdA = _mat3(dX, "dX")
+    _same_stacks("FCGradientX", S, S2, S3)
+    if K2 != K or M3 != M:
         raise RuntimeError("FCGradientX: out has the wrong shape")
     flags = (_lib.FC_RELU if act_below is not None else 0) | (_lib.FC_DROPOUT if (dropout or mask_below is not None) else 0) | \
             (_lib.FC_ROUND_TF32 if round_tf32 else 0)
-    ldact, act_dt, ldm = 0, F32, 0
+    ldact, sact, act_dt, ldm, sm = 0, 0, F32, 0, 0
     if act_below is not None:
-        _, _, ldact = _mat(act_below, "act_below")
+        S4, _, _, ldact, sact = _mat3(act_below, "act_below")
+        _same_stacks("FCGradientX", S, S4)
         act_dt = _DT[act_below.dtype]
     if mask_below is not None:
-        _, _, ldm = _mat(mask_below, "mask_below")
-    _lib.call("nawsod_fc_bwd_x", _ptr(dY), lddy, _ptr(W), ldw, _ptr(act_below), ldact, act_dt, _ptr(mask_below), ldm,
-              M, N, K, _ab(dY.dtype), _ptr(dX), ldda, _DT[dX.dtype], flags, _stream())
+        S5, _, _, ldm, sm = _mat3(mask_below, "mask_below")
+        _same_stacks("FCGradientX", S, S5)
+    _lib.call("nawsod_fc_bwd_x_stacks", _ptr(dY), lddy, sdY, _ptr(W), ldw, sW, _ptr(act_below), ldact, sact, act_dt,
+              _ptr(mask_below), ldm, sm, S, M, N, K, _ab(dY.dtype), _ptr(dX), ldda, sdA, _DT[dX.dtype], flags, _stream())
     return dX
 
 
 def FCGradientW(dY, X, *, dW=None, db=None, want_db=True, accumulate=False):
-    """dW, db of ``FCGradient``: dW [N,K] = dY^T . X (float32), db [N] = column sums of dY."""
-    M, N, lddy = _mat(dY, "dY")
-    M2, K, lda = _mat(X, "X")
+    """dW, db of ``FCGradient``: dW [N,K] = dY^T . X (float32), db [N] = column sums of dY.  3-d operands = stacks
+    (dW [S,N,K], db [S,N])."""
+    S, M, N, lddy, sdY = _mat3(dY, "dY")
+    S2, M2, K, lda, sA = _mat3(X, "X")
     if M != M2 or dY.dtype != X.dtype:
         raise RuntimeError("FCGradientW: dY and X do not match")
     if dW is None:
-        dW = torch.empty((N, K), dtype=torch.float32, device=dY.device)
-    _, _, lddw = _mat(dW, "dW")
-    if dW.dtype != torch.float32 or tuple(dW.shape) != (N, K):
-        raise RuntimeError("FCGradientW: dW must be float32 [%d,%d]" % (N, K))
+        dW = torch.empty((N, K) if dY.dim() == 2 else (S, N, K), dtype=torch.float32, device=dY.device)
+    S3, N3, K3, lddw, sdW = _mat3(dW, "dW")
+    _same_stacks("FCGradientW", S, S2, S3)
+    if dW.dtype != torch.float32 or (N3, K3) != (N, K):
+        raise RuntimeError("FCGradientW: dW must be float32 [%d,%d] per stack" % (N, K))
     if db is None and want_db:
-        db = torch.empty((N,), dtype=torch.float32, device=dY.device)
-    _lib.call("nawsod_fc_bwd_w", _ptr(dY), lddy, _ptr(X), lda, M, N, K, _ab(dY.dtype), _ptr(dW), lddw, _ptr(db),
-              _lib.FC_ACCUMULATE if accumulate else 0, _stream(), extra_kernels=1 if db is not None else 0)
+        db = torch.empty((N,) if dY.dim() == 2 else (S, N), dtype=torch.float32, device=dY.device)
+    sdb = 0
+    if db is not None:
+        if db.dtype != torch.float32 or db.shape[-1] != N or db.stride(-1) != 1 or db.numel() != S * N:
+            raise RuntimeError("FCGradientW: db must be float32 with %d elements per stack" % N)
+        sdb = db.stride(0) if db.dim() == 2 and S > 1 else 0
+    _lib.call("nawsod_fc_bwd_w_stacks", _ptr(dY), lddy, sdY, _ptr(X), lda, sA, S, M, N, K, _ab(dY.dtype), _ptr(dW), lddw, sdW,
+              _ptr(db), sdb, _lib.FC_ACCUMULATE if accumulate else 0, _stream(), extra_kernels=S if db is not None else 0)
     return dW, db
 
 

@@ -226,3 +226,40 @@ def test_sgd_step_matches_oracle():
                                          np.zeros_like(p0[k].cpu().numpy()), weight_decay=0.0 if bias else 5e-4,
                                          lr_mult=2.0 if bias else 1.0, gpu_num=4, iter_count=0)
         assert np.array_equal(p1[k].cpu().numpy(), want), k
+
+
+def test_pipelined_update_matches_plain_schedule():
+    """One GPU: the pipelined schedule of dp.DataParallelHead (per-bucket SGD on a side stream behind the
+    producer GEMMs, fc6 weight gradient in row panels) must leave exactly the parameters, momenta and GEMM
+    operands of the plain schedule (whole backward, then the two ACMWeightDecayMomentumSGDUpdate launches).
+    Weight gradients are deterministic -> bit-exact; bias gradients are atomically accumulated column sums
+    -> equal up to fp32 summation order."""
+    from nafwebsod_b200.dp import DataParallelHead
+    prob = _problem(2, 64, 20, 25, 192, 7, 256, seed=21)
+    X, rois, obn, L, params, masks, offs = prob
+    res = []
+    for pipelined in (False, True):
+        from nafwebsod_b200.heads import WeblyHeadModel
+        m = WeblyHeadModel(L.shape[1] + 1, 64, 7, 256, noise=True, dtype=torch.bfloat16)
+        m.load_reference_params(params)
+        m.UpdateWorkspaceLr(1e-2)
+        m.FeedBlobs(t(X), t(rois), t(obn), t(L), torch.tensor(offs, dtype=torch.int32, device="cuda"), x_layout="NCHW")
+        if pipelined:
+            dp = DataParallelHead(m, fc6_panels=2)
+            assert dp.sync == "local" and dp.exchange is not None
+            for it in range(2):
+                dp.step(dropout_seed=it + 1)
+            dp.flush()
+        else:
+            for it in range(2):
+                m.RunTrainStep(dropout_seed=it + 1)
+                m.param_update()
+        torch.cuda.synchronize()
+        res.append((m.flat_param.cpu().numpy().copy(), m.flat_mom.cpu().numpy().copy(), m.flat_lp.float().cpu().numpy().copy(),
+                    m.n_weights))
+    (pa, ma, la, nw), (pb, mb, lb, _) = res
+    upd = np.abs(ma).max()
+    assert upd > 0
+    assert np.abs(pa - pb).max() <= 1e-3 * upd and np.abs(ma - mb).max() <= 1e-3 * upd
+    # first-step weight updates do not depend on the (atomically summed) bias gradients at all
+    assert np.abs(la - lb).max() <= 2e-2 * np.abs(la).max()
