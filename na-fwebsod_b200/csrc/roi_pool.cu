@@ -291,7 +291,14 @@ __global__ void __launch_bounds__(1024, 1) roi_pool_fwd_kernel(const PoolParams 
 //     pointer are per-RoI constants); the warp walks the PH bin rows together, so the h-loop is uniform;
 //   * the w-loop is unrolled by two with a clamped second load (a duplicate visit never wins a strict '>').
 // The scan order per bin is still (h, w) row-major with strict '>', so values and argmax stay bit-exact.
-template <typename TIn, typename TOut, bool kSmem, bool kArgmax>
+//   * (kRowCache) consecutive bin rows overlap by one map row whenever (ph+1)*bin_size_h is not an integer
+//     (hend(ph) = ceil, hstart(ph+1) = floor), and bins of RoIs shorter than PH cells repeat the same row: the
+//     lane keeps the scan result of the last map row it walked (its own w-range of that row: first maximum and
+//     its cell index) and folds it into the next bin instead of re-reading the row.  Folding whole rows in
+//     increasing h with strict '>' selects the same (first) cell as the reference's flat (h, w) scan, so values
+//     and argmax are unchanged; shared-memory reads and issue slots drop by the overlap factor (~1.7x for the
+//     10 x 20-cell windows of the 38 x 50 map).
+template <typename TIn, typename TOut, bool kSmem, bool kArgmax, bool kRowCache>
 __global__ void __launch_bounds__(1024, 1) roi_pool_fwd_rows_kernel(const PoolParams p) {
   constexpr int VEC = Vec<TIn>::N;
   using Scan = typename std::conditional<sizeof(TIn) == 4, ScanF32<kArgmax>, ScanBF16<kArgmax>>::type;
@@ -369,6 +376,9 @@ __global__ void __launch_bounds__(1024, 1) roi_pool_fwd_rows_kernel(const PoolPa
     TOut* yout = static_cast<TOut*>(p.Y) + out_off;
     int32_t* aout = kArgmax ? p.argmax + out_off : nullptr;
 
+    int cached_h = -1;                             // map row whose scan `cached` holds (kRowCache)
+    Scan cached;
+    cached.init(false);
 #pragma unroll 1
     for (int ph = 0; ph < PH; ++ph, yout += bin_stride, aout += (kArgmax ? bin_stride : 0)) {
       const int hstart = __shfl_sync(0xffffffffu, bstart, ph);
@@ -382,12 +392,29 @@ __global__ void __launch_bounds__(1024, 1) roi_pool_fwd_rows_kernel(const PoolPa
         int idx0 = hstart * W + wstart;
 #pragma unroll 1
         for (int h = hstart; h < hend; ++h, rowp += row_bytes, idx0 += W) {
-          const unsigned char* cp = rowp;
-          int idx = idx0;
+          if (kRowCache) {
+            if (h != cached_h) {                   // uniform over the lanes that scan (h-ranges are per warp)
+              cached.init(false);
+              const unsigned char* cp = rowp;
+              int idx = idx0;
 #pragma unroll 1
-          for (int j = 0; j < ncols; j += 2, cp += 2 * cell_bytes, idx += 2) {
-            sc.visit(*reinterpret_cast<const uint4*>(cp), idx);
-            if (j + 1 < ncols) sc.visit(*reinterpret_cast<const uint4*>(cp + cell_bytes), idx + 1);
+              for (int j = 0; j < ncols; j += 2, cp += 2 * cell_bytes, idx += 2) {
+                cached.visit(*reinterpret_cast<const uint4*>(cp), idx);
+                const int more = (j + 1 < ncols) ? 1 : 0;      // clamped second cell: re-visiting a cell never wins '>'
+                cached.visit(*reinterpret_cast<const uint4*>(cp + (more ? cell_bytes : 0)), idx + more);
+              }
+              cached_h = h;
+            }
+            sc.merge(cached);
+          } else {
+            const unsigned char* cp = rowp;
+            int idx = idx0;
+#pragma unroll 1
+            for (int j = 0; j < ncols; j += 2, cp += 2 * cell_bytes, idx += 2) {
+              sc.visit(*reinterpret_cast<const uint4*>(cp), idx);
+              const int more = (j + 1 < ncols) ? 1 : 0;
+              sc.visit(*reinterpret_cast<const uint4*>(cp + (more ? cell_bytes : 0)), idx + more);
+            }
           }
         }
       }
@@ -526,9 +553,15 @@ int launch_pool_fwd2(const PoolParams& p, size_t smem_bytes, dim3 grid, int thre
   // bin-row kernel: one warp holds a whole row of bins (h-bounds on lanes 0..7, w-bounds on lanes 8..31)
   const int slots = 32 / (p.SC / Vec<TIn>::N);
   if (p.PH <= 8 && p.PW <= slots && slots <= 8 && get_tuning("pool_generic", 0) == 0) {
-    auto k = roi_pool_fwd_rows_kernel<TIn, TOut, kSmem, kArgmax>;
-    if (kSmem) NAWSOD_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-    k<<<grid, threads, smem_bytes, st>>>(p);
+    if (get_tuning("pool_rowcache", 1) != 0) {
+      auto k = roi_pool_fwd_rows_kernel<TIn, TOut, kSmem, kArgmax, true>;
+      if (kSmem) NAWSOD_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+      k<<<grid, threads, smem_bytes, st>>>(p);
+    } else {
+      auto k = roi_pool_fwd_rows_kernel<TIn, TOut, kSmem, kArgmax, false>;
+      if (kSmem) NAWSOD_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+      k<<<grid, threads, smem_bytes, st>>>(p);
+    }
     NAWSOD_LAUNCH_OK();
     return NAWSOD_OK;
   }

@@ -83,6 +83,71 @@ def test_roi_pool_bf16_path():
     assert np.array_equal(A.cpu().numpy(), Ao.transpose(0, 2, 3, 1))
 
 
+def _mixed_rois(R, img_h, img_w, batch, seed):
+    """RoI mixture of BASELINE config 3: MCG-like boxes, boxes smaller than one cell / one bin row
+    (bins repeat a map row), full-image boxes, boxes hanging over the border or fully outside,
+    inverted boxes, and half-integer coordinates that exercise roundf()."""
+    rng = np.random.default_rng(seed)
+    base = O.synth_rois(R, img_h, img_w, batch, seed=seed)
+    kind = rng.integers(0, 8, size=R)
+    out = base.copy()
+    for i in range(R):
+        k = kind[i]
+        if k == 0:      # tiny: 1..40 px on a side (less than 7 cells at 1/16 and often at 1/8)
+            x1, y1 = rng.integers(0, img_w - 41), rng.integers(0, img_h - 41)
+            out[i, 1:] = (x1, y1, x1 + rng.integers(0, 40), y1 + rng.integers(0, 40))
+        elif k == 1:    # full image
+            out[i, 1:] = (0, 0, img_w - 1, img_h - 1)
+        elif k == 2:    # overhanging the border
+            out[i, 1:] = (-60, -35, rng.integers(20, img_w // 2), rng.integers(20, img_h // 2))
+        elif k == 3:    # overhanging bottom / right, or completely outside
+            out[i, 1:] = (img_w - rng.integers(1, 90), img_h - rng.integers(1, 90), img_w + 100, img_h + 70)
+            if rng.random() < 0.3:
+                out[i, 1:] += (img_w, img_h, img_w, img_h)
+        elif k == 4:    # inverted (x2 < x1): width clamps to 1
+            out[i, 1:] = (out[i, 3], out[i, 4], out[i, 1], out[i, 2])
+        elif k == 5:    # half-way coordinates: x*scale lands on .5 exactly
+            out[i, 1:] = np.floor(out[i, 1:] / 16) * 16 + 8
+    return out.astype(np.float32)
+
+
+@pytest.mark.parametrize("knobs", [{}, {"pool_rowcache": 0}, {"pool_generic": 1}, {"pool_force_global": 1},
+                                   {"pool_slab_bytes": 32 * 1024}])
+@pytest.mark.parametrize("cfg", [(2, 512, 38, 50, 1 / 16, 16), (1, 128, 75, 125, 1 / 16, 16), (1, 64, 60, 80, 1 / 8, 8)])
+def test_roi_pool_mixed_rois_all_variants(cfg, knobs):
+    """Every forward variant (bin-row kernel with / without the row cache, generic kernel, direct
+    global reads, small slabs) on the config-3 RoI mixture, fp32 and bf16 maps, with and without
+    argmax: bit-exact values and argmax against the C oracle."""
+    ops = _ops()
+    import nafwebsod_b200 as pkg
+    N, C, H, W, scale, stride = cfg
+    R = 700
+    X = O.synth_conv5(N, C, H, W, seed=11)
+    X[:, ::3] -= 0.25                    # negative planes: the running maximum must start below zero
+    rois = np.concatenate([_mixed_rois(R // N, H * stride, W * stride, b, seed=20 + b) for b in range(N)])
+    Xb = dev(X).to(torch.bfloat16)
+    Yo, Ao = CO.roi_pool_f(X, rois, scale)
+    Yob, Aob = CO.roi_pool_f(Xb.float().cpu().numpy(), rois, scale)
+    for k, v in knobs.items():
+        pkg.set_tuning(k, v)
+    try:
+        Xcl = ops.to_channels_last(dev(X))
+        Y, A = ops.RoIPoolF(Xcl, dev(rois), spatial_scale=scale, x_layout="NHWC", y_layout="NHWC")
+        assert np.array_equal(Y.cpu().numpy(), Yo.transpose(0, 2, 3, 1))
+        assert np.array_equal(A.cpu().numpy(), Ao.transpose(0, 2, 3, 1))
+        Yt, _ = ops.RoIPoolF(Xcl, dev(rois), spatial_scale=scale, is_test=True, x_layout="NHWC", y_layout="NHWC")
+        assert np.array_equal(Yt.cpu().numpy(), Yo.transpose(0, 2, 3, 1))
+        Xbcl = Xb.permute(0, 2, 3, 1).contiguous()
+        Y2, A2 = ops.RoIPoolF(Xbcl, dev(rois), spatial_scale=scale, x_layout="NHWC", y_layout="NHWC")
+        assert np.array_equal(Y2.float().cpu().numpy(), Yob.transpose(0, 2, 3, 1))
+        assert np.array_equal(A2.cpu().numpy(), Aob.transpose(0, 2, 3, 1))
+        Y3, _ = ops.RoIPoolF(Xbcl, dev(rois), spatial_scale=scale, is_test=True, x_layout="NHWC", y_layout="NHWC")
+        assert np.array_equal(Y3.float().cpu().numpy(), Yob.transpose(0, 2, 3, 1))
+    finally:
+        for k in knobs:
+            pkg.set_tuning(k, {"pool_rowcache": 1, "pool_slab_bytes": 200 * 1024}.get(k, 0))
+
+
 def test_roi_pool_empty_and_errors():
     ops = _ops()
     X = dev(O.synth_conv5(1, 8, 6, 6))
