@@ -249,6 +249,54 @@ int nawsod_p2p_scatter(const void* const* srcs, void* const* dsts, int npeers, i
 int nawsod_p2p_wait(const void* flags, int n, uint32_t value, int64_t timeout_ms, void* status,
                     void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * SURVEY.md 8f "next" rows: the test-time wrapper around the head.
+ *
+ * N1  core/test_wsl.py:100-178 (im_detect_bbox), :181-281 (im_detect_bbox_aug), :998-1059.
+ *   nawsod_project_rois   rois[R,5] = [batch_idx, (float)((double)box * im_scale)]; flip_width >= 0
+ *                         first flips the boxes horizontally (utils/boxes.py:246-251:
+ *                         x1' = W - x2 - 1, x2' = W - x1 - 1); flip_width < 0: no flip.  obn_out = obn_scores + 1
+ *                         (core/test_wsl.py:1058) when both are given.
+ *   nawsod_dedup_rois     hashes = round(rois * DEDUP_BOXES) . [1,1e3,1e6,1e9,1e12];
+ *                         np.unique(hashes, return_index, return_inverse) (core/test_wsl.py:125-133):
+ *                         index[u] = first row with the u-th smallest hash (entries u >= num_unique
+ *                         repeat index[0]), inv_index[r] = rank of row r's hash, num_unique[0].
+ *                         R <= 8192.  All outputs are device arrays; roi_offsets (or NULL) receives
+ *                         {0, num_unique}, the row range nawsod_mil_head_fwd_bwd takes for one image, so the
+ *                         head can run on the unique set without a host round trip.
+ *   nawsod_gather_rows    dst[i,:] = src[index[i],:]   (rois / obn_scores / boxes of the unique set)
+ *   nawsod_scatter_scores cls_prob[r,:] (=|+=) concat(rois_pred[u,:1], rois_pred[u,:]), u = inv_index[r]
+ *                         (modeling/wsl_heads.py:57-67 + core/test_wsl.py:173-176); inv_index NULL = identity;
+ *                         accumulate != 0 adds in float32 (np.mean(scores_ts, axis=0) sums the passes
+ *                         in order, core/test_wsl.py:262-263) and nawsod_scores_finalize divides by T.
+ * ------------------------------------------------------------------------------------- */
+int nawsod_project_rois(const float* boxes, int R, double im_scale, double flip_width, int batch_idx,
+                        float* rois, const float* obn_scores, float* obn_out, void* stream);
+int nawsod_dedup_rois(const float* rois, int R, float dedup_scale, int32_t* index, int32_t* inv_index,
+                      int32_t* num_unique, int32_t* roi_offsets, void* stream);
+int nawsod_gather_rows(const float* src, const int32_t* index, int n, int cols, float* dst, void* stream);
+int nawsod_scatter_scores(const float* rois_pred, int64_t ld, const int32_t* inv_index, int R, int C,
+                          int accumulate, float* cls_prob, void* stream);
+int nawsod_scores_finalize(float* acc, int64_t n, int count, void* stream);
+
+/* N2  box_results_with_nms_and_limit (core/test_wsl.py:803-863) with the greedy NMS of
+ *   utils/cython_nms.pyx:38-93 (float32 arithmetic, suppress when ovr >= nms_thresh), classes
+ *   1..num_classes-1; scores [R,num_classes], boxes [R,4] (COORD_HEUR 'ID': one box per proposal).
+ *   keep [num_classes,R] uint8, num_keep [num_classes] int32, image_thresh [1] float or NULL
+ *   (-FLT_MAX when the detections_per_im limit did not bite).  Equal scores are visited higher row
+ *   first.  R <= 16384. */
+int nawsod_nms_and_limit(const float* scores, const float* boxes, int R, int num_classes,
+                         float score_thresh, float nms_thresh, int detections_per_im, uint8_t* keep,
+                         int32_t* num_keep, float* image_thresh, void* stream);
+
+/* N4  MinEntropyLoss([X, L] -> Y) / MinEntropyLossGradient([X, L, dY] -> dX)
+ *   (ops/min_entropy_loss_op.cu:34-66,70-152): X [N,C] probabilities, L [1,C] labels (B must be 1),
+ *   Y scalar = sum_{L[c]>=0.5} -p log p / (1 + count); norm / norm_ws: one float of scratch. */
+int nawsod_min_entropy_loss_fwd(const float* X, const float* L, int N, int C, int B, float* Y,
+                                float* norm, void* stream);
+int nawsod_min_entropy_loss_bwd(const float* X, const float* L, const float* dY, int N, int C, int B,
+                                float* dX, float* norm_ws, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

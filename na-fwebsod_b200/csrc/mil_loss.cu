@@ -177,8 +177,11 @@ __global__ void __launch_bounds__(kThreads, 1) mil_head_kernel(const MilParams p
   while (b + 1 < B && g >= first_cta_s[b + 1]) ++b;
   const int cta0 = first_cta_s[b], Gb = first_cta_s[b + 1] - cta0, k = g - cta0;
   const int img_row0 = p.roi_offsets[b], img_rows = p.roi_offsets[b + 1] - img_row0;
-  const int row0 = img_row0 + (int)(((long long)img_rows * k) / Gb);
-  const int row1 = img_row0 + (int)(((long long)img_rows * (k + 1)) / Gb);
+  // CTAs past the last image's group own no rows (roi_offsets[B] may be smaller than R when the caller
+  // pads the row count, e.g. de-duplicated test-time RoIs); they only take part in the grid barriers
+  const bool idle_cta = k >= Gb;
+  const int row0 = idle_cta ? img_row0 + img_rows : img_row0 + (int)(((long long)img_rows * k) / Gb);
+  const int row1 = idle_cta ? img_row0 + img_rows : img_row0 + (int)(((long long)img_rows * (k + 1)) / Gb);
 
   // ---- P1: partial column statistics of the RoI-axis softmax -----------------------------------
   {

@@ -338,9 +338,11 @@ class WeblyHeadModel:
             on_small_grads()
         return bl
 
-    def RunTestNet(self):
+    def RunTestNet(self, want_cls_prob=True):
         """Test-time forward (detectron/core/test_wsl.py:142 ``RunNet``): clean stack only, no dropout;
-        ``cls_prob`` [R, C+1] with column 0 duplicated (detectron/modeling/wsl_heads.py:57-67)."""
+        ``cls_prob`` [R, C+1] with column 0 duplicated (detectron/modeling/wsl_heads.py:57-67).
+        ``want_cls_prob=False`` stops at ``rois_pred`` (test_time.im_detect_bbox builds cls_prob while it
+        maps the scores back to the original boxes)."""
         bl, C, C2 = self.blobs, self.C, 2 * self.C
         was_train, self.train = self.train, False
         try:
@@ -351,13 +353,15 @@ class WeblyHeadModel:
         R = drop7.shape[0]
         B = bl["roi_offsets"].numel() - 1
         labels = bl.get("labels_oh")
-        if labels is None:
+        if labels is None or labels.shape[0] != B:          # labels do not enter the test-time outputs
             labels = torch.zeros((B, C), dtype=torch.float32, device=self.device)
         out = ops.mil_head(logits[0][:, :C], logits[0][:, C:C2], bl["rois"], bl["roi_offsets"], labels,
                            entropy=False, is_mean=self.mean_loss, backward=False)
         rp = out["rois_pred"]
         bl["rois_pred"] = rp
-        bl["cls_prob"] = torch.cat([rp[:, :1], rp], dim=1)      # Split/Concat of the reference: a copy, no arithmetic
+        if not want_cls_prob:
+            return rp
+        bl["cls_prob"] = ops.scatter_scores(rp)                 # Split/Concat of the reference: a copy, no arithmetic
         return bl["cls_prob"]
 
     # ------------------------------------------------------------------ optimizer (single GPU; dp.py adds the all-reduce)

@@ -522,3 +522,125 @@ def round_to_tf32(src, out=None):
     _, _, ldd = _mat(dst, "dst")
     _lib.call("nawsod_round_to_tf32", _ptr(src), lds, rows, cols, _ptr(dst), ldd, _stream())
     return dst
+
+
+# --------------------------------------------------------------------------------------------
+# Test-time wrapper and MinEntropyLoss (N4); see csrc/post.cu
+# --------------------------------------------------------------------------------------------
+def project_rois(boxes, im_scale, *, flip_width=None, batch_idx=0, obn_scores=None):
+    """``_get_rois_blob(im_rois, im_scale)`` (core/test_wsl.py:998-1027), optionally on the horizontally
+    flipped boxes (utils/boxes.py:246-251), plus ``obn_scores + 1`` (core/test_wsl.py:1058).
+    Returns rois [R,5] (and the boosted obn_scores [R] when given)."""
+    _req(boxes, "boxes", torch.float32, 2)
+    if boxes.shape[1] != 4:
+        raise RuntimeError("boxes must be [R,4]")
+    R = boxes.shape[0]
+    rois = torch.empty((R, 5), dtype=torch.float32, device=boxes.device)
+    obn_out = None
+    if obn_scores is not None:
+        _req(obn_scores, "obn_scores", torch.float32)
+        if obn_scores.numel() != R:
+            raise RuntimeError("obn_scores must have one entry per box")
+        obn_out = torch.empty(R, dtype=torch.float32, device=boxes.device)
+    _lib.call("nawsod_project_rois", _ptr(boxes), R, float(im_scale), -1.0 if flip_width is None else float(flip_width),
+              int(batch_idx), _ptr(rois), _ptr(obn_scores), _ptr(obn_out), _stream())
+    return rois if obn_scores is None else (rois, obn_out)
+
+
+def dedup_rois(rois, dedup_boxes=1.0 / 16):
+    """The dedup block of ``im_detect_bbox`` (core/test_wsl.py:125-133).  Returns device tensors
+    (index [R], inv_index [R], num_unique [1], roi_offsets [2] = {0, num_unique})."""
+    _req(rois, "rois", torch.float32, 2)
+    if rois.shape[1] != 5:
+        raise RuntimeError("rois must be [R,5]")
+    R = rois.shape[0]
+    new = lambda n: torch.empty(n, dtype=torch.int32, device=rois.device)
+    index, inv, nu, offs = new(R), new(R), new(1), new(2)
+    _lib.call("nawsod_dedup_rois", _ptr(rois), R, float(dedup_boxes), _ptr(index), _ptr(inv), _ptr(nu), _ptr(offs), _stream())
+    return index, inv, nu, offs
+
+
+def gather_rows(src, index, n=None):
+    """dst[i, :] = src[index[i], :] for i < n (``rois[index, :]``, core/test_wsl.py:131-133)."""
+    _req(src, "src", torch.float32)
+    _req(index, "index", torch.int32, 1)
+    n = index.numel() if n is None else int(n)
+    cols = src.numel() // max(src.shape[0], 1)
+    dst = torch.empty((n,) + tuple(src.shape[1:]), dtype=torch.float32, device=src.device)
+    _lib.call("nawsod_gather_rows", _ptr(src), _ptr(index), n, cols, _ptr(dst), _stream())
+    return dst
+
+
+def scatter_scores(rois_pred, inv_index=None, *, R=None, out=None, accumulate=False):
+    """``cls_prob = concat(rois_pred[:, :1], rois_pred)`` (modeling/wsl_heads.py:57-67) mapped back to the
+    original boxes, ``scores[inv_index, :]`` (core/test_wsl.py:173-176); ``accumulate`` adds into ``out``
+    (the running sum of the 'AVG' score heuristic, core/test_wsl.py:262-263)."""
+    Ru, C, ld = _mat(rois_pred, "rois_pred")
+    if rois_pred.dtype != torch.float32:
+        raise RuntimeError("rois_pred must be float32")
+    if inv_index is not None:
+        _req(inv_index, "inv_index", torch.int32, 1)
+        R = inv_index.numel()
+    elif R is None:
+        R = Ru
+    if out is None:
+        if accumulate:
+            raise RuntimeError("scatter_scores: accumulate needs an existing out tensor")
+        out = torch.empty((R, C + 1), dtype=torch.float32, device=rois_pred.device)
+    _req(out, "out", torch.float32, 2)
+    if tuple(out.shape) != (R, C + 1):
+        raise RuntimeError("scatter_scores: out must be [R, C+1]")
+    _lib.call("nawsod_scatter_scores", _ptr(rois_pred), ld, _ptr(inv_index), R, C, int(bool(accumulate)), _ptr(out), _stream())
+    return out
+
+
+def scores_finalize(acc, count):
+    """Divide the accumulated scores by the number of passes (np.mean's final step)."""
+    _req(acc, "acc", torch.float32)
+    _lib.call("nawsod_scores_finalize", _ptr(acc), acc.numel(), int(count), _stream())
+    return acc
+
+
+def nms_and_limit(scores, boxes, *, score_thresh=0.05, nms_thresh=0.3, detections_per_im=100):
+    """Device part of ``box_results_with_nms_and_limit`` (core/test_wsl.py:803-863): per-class threshold,
+    greedy NMS (utils/cython_nms.pyx:38-93) and the detections-per-image limit.  scores [R, num_classes],
+    boxes [R, 4].  Returns (keep [num_classes, R] uint8, num_keep [num_classes] int32, image_thresh [1])."""
+    _req(scores, "scores", torch.float32, 2)
+    _req(boxes, "boxes", torch.float32, 2)
+    R, K1 = scores.shape
+    if tuple(boxes.shape) != (R, 4):
+        raise RuntimeError("boxes must be [R,4] (COORD_HEUR 'ID': one box per proposal)")
+    keep = torch.empty((K1, R), dtype=torch.uint8, device=scores.device)
+    num_keep = torch.empty(K1, dtype=torch.int32, device=scores.device)
+    thr = torch.empty(1, dtype=torch.float32, device=scores.device)
+    _lib.call("nawsod_nms_and_limit", _ptr(scores), _ptr(boxes), R, K1, float(score_thresh), float(nms_thresh),
+              int(detections_per_im), _ptr(keep), _ptr(num_keep), _ptr(thr), _stream())
+    return keep, num_keep, thr
+
+
+def MinEntropyLoss(X, L):
+    """``MinEntropyLoss([X, L] -> Y)`` (ops/min_entropy_loss_op.cu:70-104)."""
+    _req(X, "X", torch.float32, 2)                    # CAFFE_ENFORCE_EQ(X.dim(), 2)
+    _req(L, "L", torch.float32, 2)                    # CAFFE_ENFORCE_EQ(L.dim(), 2)
+    if X.shape[1] != L.shape[1]:                      # CAFFE_ENFORCE_EQ(X.dim32(1), L.dim32(1))
+        raise RuntimeError("MinEntropyLoss: X and L disagree on the number of classes")
+    Y = torch.empty((), dtype=torch.float32, device=X.device)
+    norm = torch.empty(1, dtype=torch.float32, device=X.device)
+    _lib.call("nawsod_min_entropy_loss_fwd", _ptr(X), _ptr(L), X.shape[0], X.shape[1], L.shape[0], _ptr(Y), _ptr(norm), _stream())
+    return Y
+
+
+def MinEntropyLossGradient(X, L, dY):
+    """``MinEntropyLossGradient([X, L, dY] -> dX)`` (ops/min_entropy_loss_op.cu:106-152)."""
+    _req(X, "X", torch.float32, 2)
+    _req(L, "L", torch.float32, 2)
+    _req(dY, "dY", torch.float32)
+    if X.shape[1] != L.shape[1]:
+        raise RuntimeError("MinEntropyLoss: X and L disagree on the number of classes")
+    if dY.numel() != 1:                               # CAFFE_ENFORCE_EQ(dY.numel(), 1)
+        raise RuntimeError("dY must have one element")
+    dX = torch.empty_like(X)
+    norm = torch.empty(1, dtype=torch.float32, device=X.device)
+    _lib.call("nawsod_min_entropy_loss_bwd", _ptr(X), _ptr(L), _ptr(dY), X.shape[0], X.shape[1], L.shape[0], _ptr(dX),
+              _ptr(norm), _stream())
+    return dX

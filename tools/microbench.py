@@ -120,6 +120,42 @@ def bench_gemm():
     run("fwd tf32", 4000, 4096, 4096, lambda: ops.FC(Xf, Wf, None, out=Yf))
 
 
+def bench_testtime():
+    """BASELINE config 5: test-time-augmented inference (5 scales x {orig, hflip} = 10 passes per image, forward only,
+    bf16) with a proposal-count sweep, through test_time.im_detect_bbox_aug; then threshold + NMS + limit on the GPU next
+    to the CPU oracle (the reference's Cython NMS restated in C)."""
+    import time
+    from nafwebsod_b200.heads import WeblyHeadModel
+    from nafwebsod_b200 import test_time
+    from oracle import test_time_oracle as T
+    m = WeblyHeadModel(21, 512, 7, 4096, dtype=torch.bfloat16, train=False)
+    g = torch.Generator(device="cuda").manual_seed(2)
+    m.flat_param[:m.n_weights].normal_(0.0, 0.01, generator=g)
+    m.sync_shadow()
+    img_h, img_w = 375, 500                                   # a VOC-sized image
+    scales = [688, 480, 576, 864, 1200]                       # TEST.SCALE, then TEST.BBOX_AUG.SCALES (yaml:40,52)
+    maps = {}
+    for s in scales:
+        sc = s / float(min(img_h, img_w))
+        h, w = int(np.ceil(img_h * sc / 16)), int(np.ceil(img_w * sc / 16))
+        maps[s] = (torch.from_numpy(O.synth_conv5(1, 512, h, w, seed=s)).cuda().permute(0, 2, 3, 1).contiguous().to(torch.bfloat16), sc)
+    order = [(688, True)] + [(s, f) for s in scales[1:] for f in (False, True)] + [(688, False)]
+    passes = [(maps[s][0], maps[s][1], img_w if f else None) for s, f in order]
+    for R in (500, 1000, 2000, 4000, 8000):
+        boxes = torch.from_numpy(O.synth_rois(R, img_h, img_w, 0, seed=R)[:, 1:].copy()).cuda()
+        obn = torch.rand(R, device="cuda")
+        for sync in (True, False):
+            med, best = timeit(lambda: test_time.im_detect_bbox_aug(m, passes, boxes, obn, sync=sync), iters=5, warmup=2, flush=False)
+            print("tta R=%d sync=%d: %d passes med %.2f ms  %.2f M RoI-passes/s" % (R, sync, len(passes), med, R * len(passes) / med / 1e3), flush=True)
+        scores = test_time.im_detect_bbox_aug(m, passes, boxes, obn)
+        med, best = timeit(lambda: ops.nms_and_limit(scores, boxes, score_thresh=1e-9, nms_thresh=0.5, detections_per_im=100), iters=10, flush=False)
+        sc_h, bx_h = scores.cpu().numpy(), boxes.cpu().numpy()
+        t0 = time.perf_counter()
+        T.box_results_with_nms_and_limit(sc_h, bx_h, 21, 1e-9, 0.5, 100)
+        cpu_ms = (time.perf_counter() - t0) * 1e3
+        print("nms+limit R=%d K=20: GPU med %.3f ms, CPU oracle (1 core) %.1f ms" % (R, med, cpu_ms), flush=True)
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["pool", "poolbwd", "mil", "sgd"]
     for w in which:
