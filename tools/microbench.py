@@ -58,6 +58,28 @@ def bench_pool():
                 PEAKS["hbm_gbs"], R / med / 1e3), flush=True)
 
 
+def bench_pool2():
+    """The bench.py shapes only, bin-row kernel with and without the row cache."""
+    for (N, R, H, W, dt, train) in [(2, 4000, 38, 50, torch.bfloat16, False), (2, 4000, 38, 50, torch.bfloat16, True),
+                                    (1, 2000, 38, 50, torch.float32, True), (2, 4000, 38, 50, torch.float32, False),
+                                    (1, 4000, 43, 57, torch.bfloat16, False)]:
+        C = 512
+        X = torch.from_numpy(O.synth_conv5(N, C, H, W)).cuda()
+        Xcl = ops.to_channels_last(X, dt)
+        rois = torch.from_numpy(np.concatenate([O.synth_rois(R // N, H * 16, W * 16, b, seed=1 + b) for b in range(N)])).cuda()
+        boost = torch.rand(R, device="cuda") + 1
+        es = 4 if dt == torch.float32 else 2
+        alg = R * (C * 49 * es + (C * 49 * 4 if train else 0) + 20) + N * C * H * W * es
+        for knobs in [dict(), dict(pool_rowcache=0), dict(pool_chunks=5), dict(pool_chunks=9), dict(pool_chunks=14), dict(pool_threads=512)]:
+            for k, v in knobs.items():
+                pkg.set_tuning(k, v)
+            med, best = timeit(lambda: ops.RoIPoolF(Xcl, rois, boost=boost, is_test=not train, x_layout="NHWC", y_layout="NHWC"))
+            pkg.set_tuning("pool_rowcache", 1); pkg.set_tuning("pool_threads", 0); pkg.set_tuning("pool_chunks", 0)
+            print("pool N=%d R=%d %dx%d %s train=%d %s: med %.1f us best %.1f us  %.0f GB/s (%.1f%% of %.0f)  %.2f M RoIs/s" % (
+                N, R, H, W, str(dt)[6:], train, knobs, med * 1e3, best * 1e3, alg / med / 1e6, 100 * alg / med / 1e6 / PEAKS["hbm_gbs"],
+                PEAKS["hbm_gbs"], R / med / 1e3), flush=True)
+
+
 def bench_poolbwd():
     N, R, H, W, C = 2, 4000, 38, 50, 512
     X = torch.from_numpy(O.synth_conv5(N, C, H, W)).cuda()
