@@ -150,7 +150,7 @@ def reference_arm(args):
 class ClockSampler:
     """nvidia-smi sampled DURING the timed region (B200_PROFILING.md 'clocks line')."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,timestamp")
 
     def __init__(self, gpu_index):
         self.idx, self.proc, self.path = gpu_index, None, "/tmp/nawsod_clocks_%d.csv" % os.getpid()
@@ -163,7 +163,11 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
-    def stop(self):
+    def stop(self, t_start=None, t_end=None, legs=None):
+        """Samples taken between the wall-clock marks t_start / t_end (the timed regions) are the ones reported;
+        nvidia-smi itself is started earlier (its start-up takes longer than a short timed region).
+        legs: {name: (t0, t1)} adds the median SM clock of each timed leg (a short first leg may still run at
+        boost clocks while a later one is already power-capped)."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -172,16 +176,29 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         self.f.close()
-        sm, smax, reasons, power = [], None, set(), []
+        import datetime
+        rows, smax = [], None
         for ln in open(self.path):
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
             try:
-                sm.append(float(f[1])); smax = float(f[2]); power.append(float(f[3]))
+                row = [float(f[1]), float(f[3]), f[5:9], None]
+                smax = float(f[2])
             except ValueError:
                 continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+            if len(f) > 9:
+                try:
+                    row[3] = datetime.datetime.strptime(f[9], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                except ValueError:
+                    pass
+            rows.append(row)
+        inside = [r for r in rows if r[3] is not None and t_start is not None and t_start - 0.05 <= r[3] <= t_end + 0.05]
+        window = "timed regions" if inside else "whole run (no sample fell inside the timed regions)"
+        sm, power, reasons = [], [], set()
+        for c, p, flags, _ in (inside or rows):
+            sm.append(c); power.append(p)
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), flags):
                 if val.lower().startswith("active"):
                     reasons.add(name)
         try:
@@ -191,8 +208,12 @@ class ClockSampler:
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": smax, "reasons": ["no samples"]}
         busy = [c for c, p in zip(sm, power) if p > 0.5 * max(power)] or sm
-        return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm),
-                "power_w_max": max(power)}
+        out = {"sm_mhz": float(np.median(busy)), "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm),
+               "power_w_max": max(power), "window": window}
+        for name, (a, b) in (legs or {}).items():
+            leg = [r[0] for r in rows if r[3] is not None and a <= r[3] <= b]
+            out["sm_mhz_" + name] = float(np.median(leg)) if leg else None
+        return out
 
 
 def gpu_arm(args):
@@ -252,7 +273,7 @@ def gpu_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, steps, tail=None):
         sync_all()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
@@ -260,6 +281,8 @@ def gpu_arm(args):
             fn(i)
         dp.flush()                      # the last step's parameter exchange belongs to the timed region
         b.record()
+        if tail is not None:
+            tail()                      # e.g. the last device->host reads (enqueued before b was recorded)
         sync_all()
         ms = torch.tensor([a.elapsed_time(b)], device=dev)
         if world > 1:
@@ -269,33 +292,51 @@ def gpu_arm(args):
     # ---- resident-input leg (value) ----
     feed_from_host()                      # inputs now live in HBM (channels-last bf16 map etc.)
     step_resident = lambda i: dp.step(dropout_seed=i + 1)
-    for i in range(args.warmup):
-        step_resident(i)
     sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.start()               # before the warm-up: nvidia-smi needs a moment to deliver its first sample
+    for i in range(args.warmup):
+        step_resident(i)
+    t_mark0 = time.time()
     model.profile = {}
     launches0 = _lib.launch_count
     ms_total = timed(step_resident, args.steps)
+    t_mark1 = time.time()
     launches = _lib.launch_count - launches0
     prof, model.profile = model.profile, None
     ms_step = ms_total / args.steps
     value = world * R * args.steps / (ms_total * 1e-3)
 
     # ---- end-to-end leg: host buffers in, loss out, every step ----
-    losses = []
+    # The public feed path is the device-side blobs queue of nafwebsod_b200/loader.py (the reference's RoIDataLoader /
+    # BlobsQueue, loader_wsl.py:215-238): step i's inputs are copied from pinned host memory on a copy stream while
+    # step i-1 computes, and its loss is copied back to pinned host memory behind the step; the host blocks on the
+    # loss of the previous step only.  Every step's H2D and D2H copies are issued and completed inside the timed region.
+    from nafwebsod_b200.loader import BlobsQueue, LossFetcher
 
-    def step_e2e(i):
-        feed_from_host()
-        bl = dp.step(dropout_seed=i + 1)
-        losses.append(bl["loss"].to("cpu", non_blocking=False))      # D2H read of the step's result
+    def run_e2e(steps, seed0=0):
+        queue, fetch = BlobsQueue(model, capacity=2, x_layout="NCHW"), LossFetcher(lag=1)
 
-    for i in range(max(1, args.warmup // 2)):
-        step_e2e(i)
-    ms_e2e = timed(step_e2e, args.steps)
+        def step(i):
+            if i == 0:
+                queue.enqueue_blobs(hX, hrois, hobn, hL, hoffs)
+            queue.dequeue_blobs()
+            if i + 1 < steps:
+                queue.enqueue_blobs(hX, hrois, hobn, hL, hoffs)      # prefetch: overlaps this step's kernels
+            bl = dp.step(dropout_seed=seed0 + i + 1)
+            fetch.push(bl["loss"])                                    # D2H read of the step's result
+        ms = timed(step, steps, tail=fetch.wait_all)
+        assert queue.h2d_bytes == steps * h2d_bytes
+        return ms, fetch
+
+    run_e2e(max(2, args.warmup // 2))
+    t_mark2 = time.time()
+    ms_e2e, fetch = run_e2e(args.steps)
+    losses = fetch.values
     # clocks are sampled across BOTH timed regions (resident + end-to-end) so that short runs still
     # collect samples under load
-    clocks = sampler.stop() if rank == 0 else None
+    t_mark3 = time.time()
+    clocks = sampler.stop(t_mark0, t_mark3, legs={"value_leg": (t_mark0, t_mark1), "e2e_leg": (t_mark2, t_mark3)}) if rank == 0 else None
     e2e_value = world * R * args.steps / (ms_e2e * 1e-3)
     d2h_bytes = int(losses[-1].numel() * losses[-1].element_size())
     assert all(bool(torch.isfinite(l).all()) for l in losses), "non-finite loss in the benchmark"
