@@ -297,6 +297,32 @@ int nawsod_min_entropy_loss_fwd(const float* X, const float* L, int N, int C, in
 int nawsod_min_entropy_loss_bwd(const float* X, const float* L, const float* dY, int N, int C, int B,
                                 float* dX, float* norm_ws, void* stream);
 
+/* N3  the training-input contract: proposals -> the `rois` / `obn_scores` / `labels_oh` blobs, crop offsets,
+ *   bagging-mixup (roi_data/wsl.py:87-225, roi_data/loader_wsl.py:149-168, tools/convert_mcg.py:37-49).
+ *   nawsod_sample_rois   _sample_rois + _project_im_rois (roi_data/wsl.py:101-111,212-225) for ONE image: boxes
+ *                        [R,4] float (the first min(BATCH_SIZE_PER_IM, n) rows of roidb['boxes'], original image
+ *                        pixels) are clipped to the crop window (x1,y1,x2,y2; minibatch_wsl.py:63-64), shifted by
+ *                        its origin and scaled in double; rois[R,5] = (batch_idx, x1, y1, x2, y2) float;
+ *                        obn_out = obn_scores + 1 (both or neither).  rois may point into a larger [sum R,5] blob
+ *                        (add_wsl_blobs concatenates per-image blobs, roi_data/wsl.py:59-85).
+ *   nawsod_image_labels  labels_oh[num_classes-1] one-hot union of the rows with gt_classes > 0; labels_int32[1] =
+ *                        class - 1 of the LAST such row (roi_data/wsl.py:139-155), -1 if there is none
+ *                        (the reference asserts); labels_int32 may be NULL.
+ *   nawsod_bagging_mixup out = lam0 * x0 + lam1 * x1 in float32, each product and sum rounded separately
+ *                        (loader_wsl.py:158-164, `data` and `labels_oh` blobs); out may alias x0 or x1.
+ *   nawsod_set_column    a[:, col] = value for a [rows, ld] float matrix (`blobs['rois'][:, 0] = 0`, :165).
+ *   nawsod_convert_mcg_boxes  1-indexed (y1,x1,y2,x2) double -> 0-indexed (x1,y1,x2,y2) uint16 with the script's
+ *                        uint16 arithmetic (tools/convert_mcg.py:45-49). */
+int nawsod_sample_rois(const float* boxes, int R, double im_scale, int crop_x1, int crop_y1, int crop_x2,
+                       int crop_y2, int batch_idx, float* rois, const float* obn_scores, float* obn_out,
+                       void* stream);
+int nawsod_image_labels(const int32_t* gt_classes, int n, int num_classes, float* labels_oh,
+                        int32_t* labels_int32, void* stream);
+int nawsod_bagging_mixup(const float* x0, const float* x1, int64_t n, float lam0, float lam1, float* out,
+                         void* stream);
+int nawsod_set_column(float* a, int rows, int64_t ld, int col, float value, void* stream);
+int nawsod_convert_mcg_boxes(const double* bboxes, int R, uint16_t* boxes_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

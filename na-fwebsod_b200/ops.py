@@ -644,3 +644,86 @@ def MinEntropyLossGradient(X, L, dY):
     _lib.call("nawsod_min_entropy_loss_bwd", _ptr(X), _ptr(L), _ptr(dY), X.shape[0], X.shape[1], L.shape[0], _ptr(dX),
               _ptr(norm), _stream())
     return dX
+
+
+# ---------------------------------------------------------------------------------------------
+# the training-input contract (roi_data/wsl.py, roi_data/loader_wsl.py, tools/convert_mcg.py)
+# ---------------------------------------------------------------------------------------------
+def sample_rois(boxes, im_scale, im_crop, batch_idx=0, *, obn_scores=None, out_rois=None, out_obn=None):
+    """``_sample_rois`` + ``_project_im_rois`` for one image (roi_data/wsl.py:101-111, 212-225): boxes [R,4]
+    float32 in original-image pixels, ``im_crop`` = (x1, y1, x2, y2) integers (minibatch_wsl.py:63-64).
+    Returns rois [R,5] (and obn_scores + 1 as [R,1] when given).  ``out_rois`` / ``out_obn``: row slices of the
+    minibatch blobs to fill in place (add_wsl_blobs concatenates the images, roi_data/wsl.py:59-85)."""
+    _req(boxes, "boxes", torch.float32, 2)
+    if boxes.shape[1] != 4:
+        raise RuntimeError("boxes must be [R,4]")
+    R = boxes.shape[0]
+    crop = [int(v) for v in im_crop]
+    if len(crop) != 4:
+        raise RuntimeError("im_crop must be (x1, y1, x2, y2)")
+    rois = out_rois if out_rois is not None else torch.empty((R, 5), dtype=torch.float32, device=boxes.device)
+    _req(rois, "rois", torch.float32, 2)
+    if tuple(rois.shape) != (R, 5):
+        raise RuntimeError("rois must be [R,5]")
+    obn_out = None
+    if obn_scores is not None:
+        _req(obn_scores, "obn_scores", torch.float32)
+        if obn_scores.numel() != R:
+            raise RuntimeError("obn_scores must have one entry per box")
+        obn_out = out_obn if out_obn is not None else torch.empty((R, 1), dtype=torch.float32, device=boxes.device)
+        _req(obn_out, "obn_out", torch.float32)
+        if obn_out.numel() != R:
+            raise RuntimeError("obn_out must have one entry per box")
+    _lib.call("nawsod_sample_rois", _ptr(boxes), R, float(im_scale), crop[0], crop[1], crop[2], crop[3], int(batch_idx),
+              _ptr(rois), _ptr(obn_scores), _ptr(obn_out), _stream())
+    return rois if obn_scores is None else (rois, obn_out)
+
+
+def image_labels(gt_classes, num_classes, *, out_oh=None, out_int=None):
+    """The label half of ``_sample_rois`` (roi_data/wsl.py:139-155): gt_classes [n] int32 (0 = proposal row).
+    Returns (labels_oh [1, num_classes-1] float32, labels_int32 [1] int32: -1 if no ground-truth row)."""
+    _req(gt_classes, "gt_classes", torch.int32, 1)
+    dev = gt_classes.device
+    oh = out_oh if out_oh is not None else torch.empty((1, num_classes - 1), dtype=torch.float32, device=dev)
+    li = out_int if out_int is not None else torch.empty(1, dtype=torch.int32, device=dev)
+    _req(oh, "labels_oh", torch.float32)
+    _req(li, "labels_int32", torch.int32)
+    if oh.numel() != num_classes - 1 or li.numel() != 1:
+        raise RuntimeError("labels_oh must hold num_classes-1 entries and labels_int32 one")
+    _lib.call("nawsod_image_labels", _ptr(gt_classes), gt_classes.numel(), int(num_classes), _ptr(oh), _ptr(li), _stream())
+    return oh, li
+
+
+def bagging_mixup(x, lam, out=None):
+    """``out[0] = lam * x[0] + (1 - lam) * x[1]`` in float32 (roi_data/loader_wsl.py:152-164) for a blob whose
+    leading dimension holds the two images (``data`` [2,3,H,W], ``labels_oh`` [2,C])."""
+    _req(x, "x", torch.float32)
+    if x.dim() < 1 or x.shape[0] != 2:
+        raise RuntimeError("bagging_mixup mixes exactly two images (leading dimension 2)")
+    out = out if out is not None else torch.empty((1,) + tuple(x.shape[1:]), dtype=torch.float32, device=x.device)
+    _req(out, "out", torch.float32)
+    n = x[0].numel()
+    if out.numel() != n:
+        raise RuntimeError("out must have the shape of one image")
+    import numpy as np
+    l0, l1 = float(np.float32(lam)), float(np.float32(1.0 - float(lam)))     # the scalar takes the array's type (NumPy 1.x casting)
+    _lib.call("nawsod_bagging_mixup", _ptr(x[0]), _ptr(x[1]), n, l0, l1, _ptr(out), _stream())
+    return out
+
+
+def set_column(a, col, value):
+    """``a[:, col] = value`` in place (``blobs['rois'][:, 0] = 0``, roi_data/loader_wsl.py:165)."""
+    _req(a, "a", torch.float32, 2)
+    _lib.call("nawsod_set_column", _ptr(a), a.shape[0], a.shape[1], int(col), float(value), _stream())
+    return a
+
+
+def convert_mcg_boxes(bboxes):
+    """tools/convert_mcg.py:45-49: 1-indexed (y1,x1,y2,x2) float64 .mat boxes -> 0-indexed (x1,y1,x2,y2).
+    Returns an int16 tensor holding the uint16 bit patterns (``.view(torch.uint16)`` / NumPy ``view('uint16')``)."""
+    _req(bboxes, "bboxes", torch.float64, 2)
+    if bboxes.shape[1] != 4:
+        raise RuntimeError("bboxes must be [R,4]")
+    out = torch.empty((bboxes.shape[0], 4), dtype=torch.int16, device=bboxes.device)
+    _lib.call("nawsod_convert_mcg_boxes", _ptr(bboxes), bboxes.shape[0], _ptr(out), _stream())
+    return out
