@@ -355,6 +355,35 @@ def gpu_arm(args):
                 base.elapsed_time(end), "  ".join("%.2f:%s[%d]" % t for t in tl)))
         dp.exchange.profile = None
 
+    # ---- isolated legs (rank 0, after the timed regions): RoIPoolF launched back to back with nothing else on the GPU.
+    # In the step the pool overlaps the tail of the previous step's pipelined SGD (HBM-bound), so its in-step duration
+    # understates the kernel; each launch writes 196-401 MB (> 126 MB L2), so back-to-back launches stay HBM-to-HBM.
+    iso = {}
+    if rank == 0 and not args.no_isolated:
+        from nafwebsod_b200 import ops
+        dp.flush(); torch.cuda.synchronize()
+
+        def isolated_ms(fn, iters=20):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(iters):
+                fn()
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / iters
+        bl = model.blobs
+        iso["step_config"] = isolated_ms(lambda: ops.RoIPoolF(
+            bl["conv5"], bl["rois"], spatial_scale=1.0 / 16, is_test=True, boost=bl["obn_scores"], x_layout="NHWC", y_layout="NHWC",
+            out_dtype=dtype))
+        x32 = ops.to_channels_last(hX.to(dev), torch.float32)
+        iso["fp32_train"] = isolated_ms(lambda: ops.RoIPoolF(
+            x32, bl["rois"], spatial_scale=1.0 / 16, is_test=False, boost=bl["obn_scores"], x_layout="NHWC", y_layout="NHWC",
+            out_dtype=torch.float32))
+        del x32
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -394,6 +423,18 @@ def gpu_arm(args):
         "step_tensor_frac": _flops_per_roi(noise) * R / (ms_step * 1e-3) / 1e12 / tensor_peak,
     }
 
+    if iso:
+        # algorithmic bytes: Y + (argmax when the conv body trains) + rois + the map read once
+        b_step = pool_bytes
+        b_f32 = R * (C5 * 49 * 4 * 2 + 20) + IMAGES_PER_GPU * C5 * H5 * W5 * 4
+        kernels["roi_pool_f_isolated"] = {
+            "note": "RoIPoolF alone, back-to-back launches (burst HBM peak applies); in the step it shares HBM with the pipelined SGD",
+            "step_config": {"ms": iso["step_config"], "gbs": b_step / (iso["step_config"] * 1e-3) / 1e9,
+                            "frac_hbm": b_step / (iso["step_config"] * 1e-3) / 1e9 / peaks["hbm"], "algorithmic_bytes": b_step},
+            "fp32_train_argmax": {"ms": iso["fp32_train"], "gbs": b_f32 / (iso["fp32_train"] * 1e-3) / 1e9,
+                                  "frac_hbm": b_f32 / (iso["fp32_train"] * 1e-3) / 1e9 / peaks["hbm"], "algorithmic_bytes": b_f32},
+        }
+
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
@@ -412,7 +453,7 @@ def gpu_arm(args):
                                    IMAGES_PER_GPU, ROIS_PER_IMAGE, NUM_CLASSES - 1, C5, H5, W5, "two-stack (clean + noisy)" if noise else "single-stack"),
                    "global_rois_per_step": world * R, "parallelism": "dp%d (images sharded by rank; gradient exchange per step: %s)" % (
                        world, "none" if world == 1 else {"sharded": "NCCL reduce-scatter fp32 grads + sharded SGD + all-gather bf16 operands",
-                              "p2p": "copy-engine scatter of fp32 grads into peer-mapped staging + fused reduce/SGD on the owner + copy-engine gather of bf16 operands",
+                              "p2p": "peer-mapped (CUDA IPC over NVSwitch) scatter of fp32 grads into the owner's staging + fused reduce/SGD on the owner + scatter of the bf16 operands back, ordered by flag kernels",
                               "allreduce": "NCCL all-reduce fp32 grads + full SGD"}[dp.sync]),
                    "l2": "working set per step (weights 0.5 GB bf16 + 0.96 GB fp32 grads + activations) >> 126 MB L2; no flush needed",
                    "fc6_panels": dp.fc6_panels},
@@ -444,6 +485,7 @@ def main():
     ap.add_argument("--dp-sync", default="auto", choices=["auto", "sharded", "p2p", "allreduce"],
                     help="N>1 gradient exchange: auto = p2p when the ranks can map each other's memory, else NCCL sharded; allreduce = the reference's schedule")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-isolated", action="store_true", help="skip the isolated RoIPoolF timing after the timed regions")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
