@@ -407,7 +407,8 @@ def gpu_arm(args):
         traffic = json.load(open(tpath)).get("fc6_bwd_w_dram_bytes_per_launch")
     tensor_peak = peaks["tf_sustained"] * (1.0 if dtype == torch.bfloat16 else 0.5)
     roofline = {
-        "kernel": "gemm_tcgen05_kernel<256,MN,MN> (fc6 weight gradient, dY^T.X, both stacks fused)",
+        "kernel": "gemm_tcgen05_kernel<256,MN,MN> (fc6 weight gradient, dY^T.X, both stacks fused%s)" % (
+            "; ACMWeightDecayMomentumSGDUpdate of fc6_w in its epilogue" if dp.fused_fc6 else ""),
         "bound": "tensor", "achieved": fc6_flops / (t_bww_total * 1e-3) / 1e12 if t_bww_total else None, "peak": tensor_peak,
         "unit": "TFLOP/s", "traffic": traffic, "peak_source": peaks["source"] + ("; sustained bf16" if dtype == torch.bfloat16 else "; TF32 = bf16/2"),
     }
@@ -456,7 +457,9 @@ def gpu_arm(args):
                               "p2p": "peer-mapped (CUDA IPC over NVSwitch) scatter of fp32 grads into the owner's staging + fused reduce/SGD on the owner + scatter of the bf16 operands back, ordered by flag kernels",
                               "allreduce": "NCCL all-reduce fp32 grads + full SGD"}[dp.sync]),
                    "l2": "working set per step (weights 0.5 GB bf16 + 0.96 GB fp32 grads + activations) >> 126 MB L2; no flush needed",
-                   "fc6_panels": dp.fc6_panels},
+                   "fc6_panels": dp.fc6_panels,
+                   "fc6_update": ("inside the fc6 weight-gradient GEMM's epilogue (NAWSOD_LOCAL_FUSED_SGD=1)" if dp.fused_fc6 else
+                                  "stand-alone SGD kernel per row panel on a side stream" if world == 1 else "on the owner rank of each slice")},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": d2h_bytes,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
