@@ -32,6 +32,25 @@ IMAGES_PER_GPU, ROIS_PER_IMAGE, NUM_CLASSES = 2, 2000, 21
 C5, H5, W5 = 512, 38, 50
 
 
+_JSON_OUT = None
+
+
+def _protect_stdout():
+    """Keep stdout for the ONE JSON line: libraries that print to fd 1 (NCCL's version banner under torchrun) are
+    sent to stderr instead."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def _peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -140,7 +159,7 @@ def reference_arm(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    _emit(line)
     return 0
 
 
@@ -407,8 +426,7 @@ def gpu_arm(args):
         traffic = json.load(open(tpath)).get("fc6_bwd_w_dram_bytes_per_launch")
     tensor_peak = peaks["tf_sustained"] * (1.0 if dtype == torch.bfloat16 else 0.5)
     roofline = {
-        "kernel": "gemm_tcgen05_kernel<256,MN,MN> (fc6 weight gradient, dY^T.X, both stacks fused%s)" % (
-            "; ACMWeightDecayMomentumSGDUpdate of fc6_w in its epilogue" if dp.fused_fc6 else ""),
+        "kernel": "gemm_tcgen05_kernel<256,MN,MN> (fc6 weight gradient, dY^T.X, both stacks in one GEMM)",
         "bound": "tensor", "achieved": fc6_flops / (t_bww_total * 1e-3) / 1e12 if t_bww_total else None, "peak": tensor_peak,
         "unit": "TFLOP/s", "traffic": traffic, "peak_source": peaks["source"] + ("; sustained bf16" if dtype == torch.bfloat16 else "; TF32 = bf16/2"),
     }
@@ -458,8 +476,7 @@ def gpu_arm(args):
                               "allreduce": "NCCL all-reduce fp32 grads + full SGD"}[dp.sync]),
                    "l2": "working set per step (weights 0.5 GB bf16 + 0.96 GB fp32 grads + activations) >> 126 MB L2; no flush needed",
                    "fc6_panels": dp.fc6_panels,
-                   "fc6_update": ("inside the fc6 weight-gradient GEMM's epilogue (NAWSOD_LOCAL_FUSED_SGD=1)" if dp.fused_fc6 else
-                                  "stand-alone SGD kernel per row panel on a side stream" if world == 1 else "on the owner rank of each slice")},
+                   "fc6_update": "stand-alone SGD kernel per row panel on a side stream" if world == 1 else "on the owner rank of each slice"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": d2h_bytes,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
@@ -469,7 +486,7 @@ def gpu_arm(args):
         "cpu_baseline": cpu,
         "loss": [float(x) for x in losses[-1].flatten().tolist()],
     }
-    print(json.dumps(line))
+    _emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -491,9 +508,11 @@ def main():
     ap.add_argument("--no-isolated", action="store_true", help="skip the isolated RoIPoolF timing after the timed regions")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not (args.impl == "ours" and world == 1 and args.gpus > 1):      # the torchrun re-launch keeps the parent's stdout
+        _protect_stdout()
     if args.impl == "reference":
         return reference_arm(args)
-    world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.gpus != world:
         if world == 1 and args.gpus > 1:
             # convenience: re-launch under torchrun on one node

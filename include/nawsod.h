@@ -125,20 +125,6 @@ int nawsod_fc_bwd_w(const void* dY, int64_t lddy, const void* A, int64_t lda, in
                     int K, int ab_dtype, float* dW, int64_t lddw, float* db, int flags,
                     void* stream);
 
-/* a4 + a10 fused (one GPU, iter_size 1): FCGradient's dW immediately consumed by
- *   ACMWeightDecayMomentumSGDUpdate in the GEMM epilogue (modeling/optimizer_wsl.py:96-137 applied to
- *   the blob modeling/wsl_heads.py:674 creates), so the 0.8 GB fc6 weight gradient is neither written
- *   to nor re-read from HBM: per weight the epilogue reads m, p and writes m, p and the GEMM-operand
- *   shadow (18-20 B instead of 26-30 B for GEMM + separate update).  m, p [N, ldw] float and
- *   p_shadow (bf16 / TF32-rounded float, or NULL) share dW's geometry; dW may be NULL (gradient
- *   not kept) unless NAWSOD_FC_ACCUMULATE is set; `lr` is a 1-element DEVICE float; the update is
- *   bit-identical to nawsod_sgd_update(iter_size = 1) applied to the same gradient.  db as in
- *   nawsod_fc_bwd_w (the bias takes the stand-alone update). */
-int nawsod_fc_bwd_w_sgd(const void* dY, int64_t lddy, const void* A, int64_t lda, int M, int N, int K,
-                        int ab_dtype, float* dW, int64_t ldw, float* db, int flags, float* m, float* p,
-                        void* p_shadow, int shadow_dtype, const float* lr, float momentum,
-                        float weight_decay, float lr_mult, int gpu_num, int64_t iter_count, void* stream);
-
 /* The same three GEMMs over S independent problems of one shape in ONE launch (the head's clean and
  * noisy stacks, webly_heads.py:490-498: twice the tiles per launch, half the launches).  Stack s uses
  * operand + s * stride (strides in elements of the operand's type; bias / db in floats; masks in

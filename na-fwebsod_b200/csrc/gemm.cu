@@ -43,25 +43,7 @@ struct EpiParams {
   // live in the 3-D tensor maps
   int nbatch;
   long long so, sbias, smask, sact;
-  // bwd_w fused with ACMWeightDecayMomentumSGDUpdate (kernel template SGD = true): momentum, master parameter and GEMM-operand
-  // shadow share out's [M, N] / ldo geometry (the flat parameter buffers have one layout); out may be null when the gradient
-  // itself is not wanted.
-  float* sgd_m; float* sgd_p; void* sgd_shadow; int sgd_shadow_dtype;
-  const float* sgd_lr;
-  float sgd_momentum, sgd_wd, sgd_lr_mult, sgd_inv_norm;
-  int sgd_first_call, sgd_write_grad;
 };
-
-// One element of ACMWeightDecayMomentumSGDUpdate with iter_size == 1, in the reference's operation order
-// (acm_weightdecay_momentum_sgd_op.h:72-109; the same sequence as sgd.cu's sgd_elem with a zero accumulator).
-__device__ __forceinline__ void acm_sgd_step(float g, float& m, float& p, float inv_norm, float wd, float LR, float mom) {
-  float ac = __fadd_rn(g, 0.f);
-  ac = __fmul_rn(ac, inv_norm);
-  ac = __fadd_rn(ac, __fmul_rn(wd, p));
-  const float v = __fadd_rn(__fmul_rn(LR, ac), __fmul_rn(mom, m));
-  m = v;
-  p = __fsub_rn(p, v);
-}
 
 // ------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -174,7 +156,7 @@ template <int BN, int ES> struct Cfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
-template <int BN, bool A_MN, bool B_MN, int ES, bool SGD = false>
+template <int BN, bool A_MN, bool B_MN, int ES>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const EpiParams ep_) {
   using C = Cfg<BN, ES>;
@@ -284,9 +266,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const bool bias_vec = ep.bias && (reinterpret_cast<uintptr_t>(ep.bias) & 15u) == 0;
     const bool act_vec = ep.act && (reinterpret_cast<uintptr_t>(ep.act) & 15u) == 0 && (ep.ldact * 2) % 16 == 0;
     const bool mask_vec = ep.mask && (reinterpret_cast<uintptr_t>(ep.mask) & 15u) == 0 && ep.ldmask % 16 == 0;
-    // fused update: 16-byte accesses to m / p / shadow need their bases aligned and ldo a multiple of 8 elements (bf16 shadow)
-    const bool sgd_vec = SGD && ((reinterpret_cast<uintptr_t>(ep.sgd_m) | reinterpret_cast<uintptr_t>(ep.sgd_p) |
-                                  reinterpret_cast<uintptr_t>(ep.sgd_shadow)) & 15u) == 0 && ep.ldo % 8 == 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int bi = tile / tiles_pb, tb = tile - bi * tiles_pb;
       const int m0 = (tb % num_m) * BLOCK_M, n0 = (tb / num_m) * BN;
@@ -393,65 +372,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
               for (int i = 0; i < 32; ++i) v[i] = round_tf32(v[i]);
             }
-            bool store_out = true;
-            if constexpr (SGD) {
-              // v = this row's 32 weight gradients: update momentum and master parameter in place and emit the operand shadow
-              const size_t off = (size_t)m * ep.ldo + n;
-              float* mo = ep.sgd_m + off;
-              float* po = ep.sgd_p + off;
-              const float LR = __fmul_rn(__ldg(ep.sgd_lr), ep.sgd_lr_mult);
-              const bool first = ep.sgd_first_call != 0;
-              float pn[32];
-              if (full && vec_ok && sgd_vec) {
-#pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                  float4 m4 = first ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldcs(reinterpret_cast<const float4*>(mo + i));
-                  float4 p4 = __ldcs(reinterpret_cast<const float4*>(po + i));
-                  acm_sgd_step(v[i], m4.x, p4.x, ep.sgd_inv_norm, ep.sgd_wd, LR, ep.sgd_momentum);
-                  acm_sgd_step(v[i + 1], m4.y, p4.y, ep.sgd_inv_norm, ep.sgd_wd, LR, ep.sgd_momentum);
-                  acm_sgd_step(v[i + 2], m4.z, p4.z, ep.sgd_inv_norm, ep.sgd_wd, LR, ep.sgd_momentum);
-                  acm_sgd_step(v[i + 3], m4.w, p4.w, ep.sgd_inv_norm, ep.sgd_wd, LR, ep.sgd_momentum);
-                  __stcs(reinterpret_cast<float4*>(mo + i), m4);
-                  __stcs(reinterpret_cast<float4*>(po + i), p4);
-                  pn[i] = p4.x; pn[i + 1] = p4.y; pn[i + 2] = p4.z; pn[i + 3] = p4.w;
-                }
-                if (ep.sgd_shadow) {
-                  if (ep.sgd_shadow_dtype == NAWSOD_BF16) {
-                    __nv_bfloat16* so = static_cast<__nv_bfloat16*>(ep.sgd_shadow) + off;
-#pragma unroll
-                    for (int i = 0; i < 32; i += 8) {
-                      __nv_bfloat162 h0 = __floats2bfloat162_rn(pn[i], pn[i + 1]), h1 = __floats2bfloat162_rn(pn[i + 2], pn[i + 3]);
-                      __nv_bfloat162 h2 = __floats2bfloat162_rn(pn[i + 4], pn[i + 5]), h3 = __floats2bfloat162_rn(pn[i + 6], pn[i + 7]);
-                      *reinterpret_cast<uint4*>(so + i) = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
-                                                                     *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
-                    }
-                  } else {
-                    float* so = static_cast<float*>(ep.sgd_shadow) + off;
-#pragma unroll
-                    for (int i = 0; i < 32; i += 4)
-                      *reinterpret_cast<float4*>(so + i) = make_float4(round_tf32(pn[i]), round_tf32(pn[i + 1]), round_tf32(pn[i + 2]), round_tf32(pn[i + 3]));
-                  }
-                }
-              } else {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                  if (i < ncols) {
-                    float mm = first ? 0.f : mo[i];
-                    float pp = po[i];
-                    acm_sgd_step(v[i], mm, pp, ep.sgd_inv_norm, ep.sgd_wd, LR, ep.sgd_momentum);
-                    mo[i] = mm;
-                    po[i] = pp;
-                    if (ep.sgd_shadow) {
-                      if (ep.sgd_shadow_dtype == NAWSOD_BF16) static_cast<__nv_bfloat16*>(ep.sgd_shadow)[off + i] = __float2bfloat16_rn(pp);
-                      else static_cast<float*>(ep.sgd_shadow)[off + i] = round_tf32(pp);
-                    }
-                  }
-                }
-              }
-              store_out = ep.sgd_write_grad != 0;
-            }
-            if (!store_out) {
-            } else if (vec_ok && full) {
+            if (vec_ok && full) {
 #pragma unroll
               for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
             } else {
@@ -581,7 +502,7 @@ int make_tmap(CUtensorMap* map, const void* ptr, int es, long long rows, long lo
 
 struct Operands { const void* A; long long lda, sA; const void* B; long long ldb, sB; };
 
-template <int BN, bool A_MN, bool B_MN, int ES, bool SGD = false>
+template <int BN, bool A_MN, bool B_MN, int ES>
 int launch_gemm(const Operands& o, const EpiParams& ep, cudaStream_t st) {
   using C = Cfg<BN, ES>;
   constexpr int ATOM = 128 / ES;
@@ -594,7 +515,7 @@ int launch_gemm(const Operands& o, const EpiParams& ep, cudaStream_t st) {
   if (!B_MN) rc = make_tmap(&tmB, o.B, ES, ep.N, ep.K, o.ldb, BN, C::BK, false, ep.nbatch, o.sB);
   else rc = make_tmap(&tmB, o.B, ES, ep.K, ep.N, o.ldb, C::BK, ATOM, ES == 4, ep.nbatch, o.sB);
   if (rc) return rc;
-  auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, ES, SGD>;
+  auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, ES>;
   static bool attr_set = false;
   if (!attr_set) {
     NAWSOD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
@@ -610,7 +531,7 @@ int launch_gemm(const Operands& o, const EpiParams& ep, cudaStream_t st) {
   return NAWSOD_OK;
 }
 
-template <bool A_MN, bool B_MN, bool SGD = false>
+template <bool A_MN, bool B_MN>
 int dispatch_gemm(const Operands& o, EpiParams ep, int ab_dtype, cudaStream_t st) {
   if (ep.nbatch < 1) ep.nbatch = 1;
   if (ep.nbatch > 1) {
@@ -623,13 +544,13 @@ int dispatch_gemm(const Operands& o, EpiParams ep, int ab_dtype, cudaStream_t st
   // BN = 256 for wide outputs; narrower tiles only when N itself is narrow (fc8: N = 2C)
   const int bn = ep.N > 128 ? 256 : (ep.N > 64 ? 128 : 64);
   if (ab_dtype == NAWSOD_BF16) {
-    if (bn == 256) return launch_gemm<256, A_MN, B_MN, 2, SGD>(o, ep, st);
-    if (bn == 128) return launch_gemm<128, A_MN, B_MN, 2, SGD>(o, ep, st);
-    return launch_gemm<64, A_MN, B_MN, 2, SGD>(o, ep, st);
+    if (bn == 256) return launch_gemm<256, A_MN, B_MN, 2>(o, ep, st);
+    if (bn == 128) return launch_gemm<128, A_MN, B_MN, 2>(o, ep, st);
+    return launch_gemm<64, A_MN, B_MN, 2>(o, ep, st);
   }
-  if (bn == 256) return launch_gemm<256, A_MN, B_MN, 4, SGD>(o, ep, st);
-  if (bn == 128) return launch_gemm<128, A_MN, B_MN, 4, SGD>(o, ep, st);
-  return launch_gemm<64, A_MN, B_MN, 4, SGD>(o, ep, st);
+  if (bn == 256) return launch_gemm<256, A_MN, B_MN, 4>(o, ep, st);
+  if (bn == 128) return launch_gemm<128, A_MN, B_MN, 4>(o, ep, st);
+  return launch_gemm<64, A_MN, B_MN, 4>(o, ep, st);
 }
 
 int check_common(const char* who, int M, int N, int K, int ab_dtype) {
@@ -698,10 +619,6 @@ extern "C" int nawsod_fc_bwd_x(const void* dY, int64_t lddy, const void* W, int6
                                 ab_dtype, dA, ldda, 0, da_dtype, flags, stream);
 }
 
-// bias gradient db[s] = column sums of dY[s] (shared by the plain and the SGD-fused weight-gradient entry points)
-static int fc_bias_grad(const void* dY, int64_t lddy, int64_t sdY, int S, int M, int N, int ab_dtype, float* db, int64_t sdb,
-                        int flags, cudaStream_t st);
-
 extern "C" int nawsod_fc_bwd_w_stacks(const void* dY, int64_t lddy, int64_t sdY, const void* A, int64_t lda, int64_t sA, int S,
                                       int M, int N, int K, int ab_dtype, float* dW, int64_t lddw, int64_t sdW, float* db,
                                       int64_t sdb, int flags, void* stream) {
@@ -718,40 +635,6 @@ extern "C" int nawsod_fc_bwd_w_stacks(const void* dY, int64_t lddy, int64_t sdY,
   ep.nbatch = S; ep.so = sdW;
   const Operands o{dY, lddy, sdY, A, lda, sA};
   if (int rc = dispatch_gemm<true, true>(o, ep, ab_dtype, st)) return rc;
-  return fc_bias_grad(dY, lddy, sdY, S, M, N, ab_dtype, db, sdb, flags, st);
-}
-
-extern "C" int nawsod_fc_bwd_w_sgd(const void* dY, int64_t lddy, const void* A, int64_t lda, int M, int N, int K, int ab_dtype,
-                                   float* dW, int64_t ldw, float* db, int flags, float* m, float* p, void* p_shadow,
-                                   int shadow_dtype, const float* lr, float momentum, float weight_decay, float lr_mult,
-                                   int gpu_num, int64_t iter_count, void* stream) {
-  if (int rc = check_common("fc_bwd_w_sgd", M, N, K, ab_dtype)) return rc;
-  NAWSOD_REQUIRE(dY && A && m && p && lr, NAWSOD_ERR_ARG, "fc_bwd_w_sgd: null pointer");
-  NAWSOD_REQUIRE(ldw >= K, NAWSOD_ERR_SHAPE, "fc_bwd_w_sgd: ldw smaller than K");
-  NAWSOD_REQUIRE(!(flags & (NAWSOD_FC_RELU | NAWSOD_FC_DROPOUT | NAWSOD_FC_ROUND_TF32)), NAWSOD_ERR_ARG,
-                 "fc_bwd_w_sgd: only ACCUMULATE is valid");
-  NAWSOD_REQUIRE(dW || !(flags & NAWSOD_FC_ACCUMULATE), NAWSOD_ERR_ARG, "fc_bwd_w_sgd: ACCUMULATE needs the gradient buffer dW");
-  NAWSOD_REQUIRE(gpu_num >= 1 && iter_count >= 0, NAWSOD_ERR_ARG, "fc_bwd_w_sgd: need gpu_num >= 1 and iter_count >= 0");
-  NAWSOD_REQUIRE(!p_shadow || shadow_dtype == NAWSOD_BF16 || shadow_dtype == NAWSOD_F32, NAWSOD_ERR_ARG,
-                 "fc_bwd_w_sgd: shadow_dtype must be NAWSOD_BF16 or NAWSOD_F32 (TF32-rounded)");
-  NAWSOD_REQUIRE((reinterpret_cast<uintptr_t>(m) & 3u) == 0 && (reinterpret_cast<uintptr_t>(p) & 3u) == 0, NAWSOD_ERR_ALIGN,
-                 "fc_bwd_w_sgd: m / p must be float aligned");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  EpiParams ep{};
-  ep.out = dW; ep.ldo = ldw; ep.out_dtype = NAWSOD_F32; ep.flags = flags; ep.M = N; ep.N = K; ep.K = M;
-  ep.nbatch = 1; ep.so = 0;
-  ep.sgd_m = m; ep.sgd_p = p; ep.sgd_shadow = p_shadow; ep.sgd_shadow_dtype = shadow_dtype; ep.sgd_lr = lr;
-  ep.sgd_momentum = momentum; ep.sgd_wd = weight_decay; ep.sgd_lr_mult = lr_mult;
-  ep.sgd_inv_norm = static_cast<float>(1.0 / static_cast<double>(gpu_num));      // T(1.0 / (iter_size_ * gpu_num_)), iter_size 1
-  ep.sgd_first_call = iter_count == 0;
-  ep.sgd_write_grad = dW != nullptr;
-  const Operands o{dY, lddy, 0, A, lda, 0};
-  if (int rc = dispatch_gemm<true, true, true>(o, ep, ab_dtype, st)) return rc;
-  return fc_bias_grad(dY, lddy, 0, 1, M, N, ab_dtype, db, 0, flags, st);
-}
-
-static int fc_bias_grad(const void* dY, int64_t lddy, int64_t sdY, int S, int M, int N, int ab_dtype, float* db, int64_t sdb,
-                        int flags, cudaStream_t st) {
   if (db) {
     const int es = ab_dtype == NAWSOD_BF16 ? 2 : 4;
     for (int s = 0; s < S; ++s) {

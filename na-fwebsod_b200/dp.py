@@ -45,10 +45,6 @@ import torch
 import torch.distributed as dist
 
 
-# default of NAWSOD_LOCAL_FUSED_SGD (one GPU: fc6 SGD update inside the weight-gradient GEMM's epilogue)
-_FUSED_SGD_DEFAULT = "0"
-
-
 def shard_images(num_images_total: int, world_size: int, rank: int):
     """Rank g gets images {g*B .. g*B+B-1} with all their RoIs; B must divide evenly."""
     if num_images_total % world_size:
@@ -376,7 +372,6 @@ class DataParallelHead:
         self.master_sharded = False
         self.comm_sms = int(os.environ.get("NAWSOD_COMM_SMS", "0")) if comm_sms is None else comm_sms
         self._hyper = dict(momentum=0.9, weight_decay=5e-4)
-        self.keep_fc6_grad = False                   # fused fc6 update: also write the gradient (export / debugging)
         if self.world > 1 and sync in ("p2p", "auto") and model.flat_grad.is_cuda:
             # "auto": the peer-mapped path when every rank can set it up (one NVLink / NVSwitch box), else NCCL
             try:                                     # raises on every rank or on none (see P2PExchange.__init__)
@@ -391,16 +386,11 @@ class DataParallelHead:
         elif sync == "auto":
             sync = "sharded"
         self.sync = sync
-        # one GPU: the fc6 weight update can live in the epilogue of its weight-gradient GEMM (no gradient round trip)
-        self.fused_fc6 = False
         if self.world == 1:
             self.sync = sync = "local"
             if not model.flat_grad.is_cuda or os.environ.get("NAWSOD_LOCAL_PIPELINE", "1") == "0":
                 self.fc6_panels = 1                  # plain schedule: backward, then two SGD launches
-            elif os.environ.get("NAWSOD_LOCAL_FUSED_SGD", _FUSED_SGD_DEFAULT) == "1":
-                self.fused_fc6 = True
-                self.fc6_panels = 1                  # nothing to pipeline behind the panels: one full-width GEMM
-        if self.exchange is None and (self.world > 1 or self.fc6_panels > 1 or self.fused_fc6):
+        if self.exchange is None and (self.world > 1 or self.fc6_panels > 1):
             self.exchange = GradientExchange(model.flat_grad, model.flat_lp, group, sharded=(sync != "allreduce"),
                                              update_fn=self._update_slice)
 
@@ -468,13 +458,9 @@ class DataParallelHead:
             self._limit_gemm_grid(True)              # GEMMs launched from here on share the GPU with NCCL
             ex.launch(r0 * cols, (r1 - r0) * cols, "fc6_panel")
 
-        fused = None
-        if self.fused_fc6:
-            fused = dict(momentum=momentum, weight_decay=weight_decay, gpu_num=1, keep_grad=self.keep_fc6_grad)
         bl = m.RunTrainStep(dropout_masks=dropout_masks, dropout_seed=dropout_seed, fc6_panels=self.fc6_panels,
-                            on_fc6_panel=None if self.fused_fc6 else on_panel, on_before_params=before_params,
-                            on_small_grads=lambda: ex.launch(small[0], small[1], "small_weights"),
-                            fused_fc6_update=fused)
+                            on_fc6_panel=on_panel, on_before_params=before_params,
+                            on_small_grads=lambda: ex.launch(small[0], small[1], "small_weights"))
         ex.launch(biases[0], biases[1], "biases")
         if self.sync == "allreduce":
             ex.finish()

@@ -268,7 +268,7 @@ class WeblyHeadModel:
 
     # ------------------------------------------------------------------ the reference's builder names
     def RunTrainStep(self, dropout_masks=None, dropout_seed=0, need_dX=False, fc6_panels=1, on_small_grads=None,
-                     on_fc6_panel=None, on_before_params=None, fused_fc6_update=None):
+                     on_fc6_panel=None, on_before_params=None):
         """One fwd+bwd pass of the head on the fed blobs (the slice of ``workspace.RunNet(net)``,
         detectron/utils/train_wsl.py:59, that lies between conv5 and the parameter gradients).
         Gradients land in ``self.g`` / ``self.flat_grad``; returns the blob dict.
@@ -279,11 +279,7 @@ class WeblyHeadModel:
         weight-gradient GEMMs); ``on_small_grads()`` fires once those are enqueued.  The bias
         gradients of fc6 are complete with the last panel, all others with ``on_small_grads``.
         ``on_before_params()`` fires after RoI pooling, right before the first parameter read (fc6):
-        the place to join a parameter update that is still in flight from the previous step.
-        ``fused_fc6_update`` (one GPU, iter_size 1): dict(momentum, weight_decay, gpu_num, keep_grad) -- the fc6
-        weight gradient (86 % of the parameters) is consumed by the SGD update inside its GEMM's epilogue
-        (ops.FCGradientW_SGDUpdate) instead of being written to ``self.g['W6']`` and updated by a second kernel;
-        all other parameters keep the stand-alone update."""
+        the place to join a parameter update that is still in flight from the previous step."""
         if not self.train:
             raise RuntimeError("RunTrainStep on a test-mode model")
         bl, H, C, C2 = self.blobs, self.H, self.C, 2 * self.C
@@ -330,23 +326,10 @@ class WeblyHeadModel:
                                                  boost=bl["obn_scores"], layout="NHWC")
         rows = self.S * H
         step = _round_up((rows + fc6_panels - 1) // fc6_panels, 256)
-        if fused_fc6_update is not None:
-            if need_dX:
-                raise RuntimeError("fused_fc6_update rewrites W6 inside the step: not with need_dX")
-            off6, n6, shp6 = self._slices["W6"]
-            mom6 = self.flat_mom[off6: off6 + n6].view(shp6)
-            fu = fused_fc6_update
         for r0 in range(0, rows, step):
             r1 = min(rows, r0 + step)
-            if fused_fc6_update is not None:
-                self._timed("fc6_bwd_w", lambda: ops.FCGradientW_SGDUpdate(
-                    d6[:, r0:r1], bl["roi_feat"], mom6[r0:r1], self.lr, self.p["W6"][r0:r1],
-                    dW=self.g["W6"][r0:r1] if fu.get("keep_grad") else None, db=self.g["b6"][r0:r1],
-                    momentum=fu["momentum"], weight_decay=fu["weight_decay"], gpu_num=fu.get("gpu_num", 1), lr_mult=1.0,
-                    iter_count=self.iter_count, p_shadow=self.w["W6"][r0:r1]))
-            else:
-                self._timed("fc6_bwd_w", lambda: ops.FCGradientW(d6[:, r0:r1], bl["roi_feat"], dW=self.g["W6"][r0:r1],
-                                                                 db=self.g["b6"][r0:r1]))
+            self._timed("fc6_bwd_w", lambda: ops.FCGradientW(d6[:, r0:r1], bl["roi_feat"], dW=self.g["W6"][r0:r1],
+                                                             db=self.g["b6"][r0:r1]))
             if on_fc6_panel is not None:
                 on_fc6_panel(r0, r1)
         ops.FCGradientW(dl3, a7, dW=self.g["W8"], db=self.g["b8"])

@@ -502,43 +502,6 @@ def FCGradientW(dY, X, *, dW=None, db=None, want_db=True, accumulate=False):
     return dW, db
 
 
-def FCGradientW_SGDUpdate(dY, X, m, lr, p, *, dW=None, db=None, accumulate=False, momentum=0.9, gpu_num=1, lr_mult=1.0,
-                          weight_decay=0.0, iter_count=0, p_shadow=None):
-    """``FCGradient``'s dW consumed in the GEMM epilogue by ``ACMWeightDecayMomentumSGDUpdate([g, m, lr, p, acc])``
-    with iter_size 1 (modeling/optimizer_wsl.py:96-137): m, p [N,K] float32 are updated in place, ``p_shadow``
-    (bf16 or TF32-rounded float32, same shape) receives the new GEMM operand.  The gradient itself is written only
-    if ``dW`` is given.  Bit-identical to ``FCGradientW`` followed by ``ACMWeightDecayMomentumSGDUpdate``."""
-    S, M, N, lddy, _ = _mat3(dY, "dY")
-    S2, M2, K, lda, _ = _mat3(X, "X")
-    if S != 1 or S2 != 1:
-        raise RuntimeError("FCGradientW_SGDUpdate: one problem per call (no stacks)")
-    if M != M2 or dY.dtype != X.dtype:
-        raise RuntimeError("FCGradientW_SGDUpdate: dY and X do not match")
-    _req(lr, "lr", torch.float32)
-    if lr.numel() != 1:
-        raise RuntimeError("lr must have one element")
-    lds = []
-    for t, nme, dts in ((m, "m", torch.float32), (p, "p", torch.float32), (dW, "dW", torch.float32),
-                        (p_shadow, "p_shadow", (torch.bfloat16, torch.float32))):
-        if t is None:
-            continue
-        r, c, ld = _mat(t, nme)
-        if (r, c) != (N, K) or t.dtype not in (dts if isinstance(dts, tuple) else (dts,)):
-            raise RuntimeError("FCGradientW_SGDUpdate: %s must be [%d,%d] of %s" % (nme, N, K, dts))
-        lds.append(ld)
-    if len(set(lds)) != 1:
-        raise RuntimeError("FCGradientW_SGDUpdate: m, p, dW and p_shadow must share one leading dimension")
-    if accumulate and dW is None:
-        raise RuntimeError("FCGradientW_SGDUpdate: accumulate needs dW")
-    if db is not None and (db.dtype != torch.float32 or db.numel() != N or not db.is_contiguous()):
-        raise RuntimeError("FCGradientW_SGDUpdate: db must be float32 [%d]" % N)
-    _lib.call("nawsod_fc_bwd_w_sgd", _ptr(dY), lddy, _ptr(X), lda, M, N, K, _ab(dY.dtype), _ptr(dW), lds[0], _ptr(db),
-              _lib.FC_ACCUMULATE if accumulate else 0, _ptr(m), _ptr(p), _ptr(p_shadow),
-              _DT[p_shadow.dtype] if p_shadow is not None else F32, _ptr(lr), float(momentum), float(weight_decay),
-              float(lr_mult), int(gpu_num), int(iter_count), _stream(), extra_kernels=1 if db is not None else 0)
-    return dW, db
-
-
 def to_bf16(src, out=None):
     """float32 [rows, cols] (may be a column slice) -> bfloat16, by the library's conversion kernel."""
     rows, cols, lds = _mat(src, "src")

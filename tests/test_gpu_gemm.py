@@ -119,58 +119,44 @@ def test_to_bf16_and_errors():
         ops.FC(torch.zeros(8, 12, device="cuda", dtype=torch.bfloat16), torch.zeros(8, 12, device="cuda", dtype=torch.bfloat16))
 
 
+def _stacked(buf, S):
+    """[R, S*H] buffer -> [S, R, H] strided view of its column blocks (heads.WeblyHeadModel._stacked)."""
+    R = buf.shape[0]
+    return buf.view(R, S, buf.shape[1] // S).permute(1, 0, 2)
+
+
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
-@pytest.mark.parametrize("shape,iter_count,keep", [((256, 512, 256), 0, True), ((300, 520, 200), 3, True), ((1000, 768, 1568), 2, False),
-                                                   ((777, 40, 4096), 1, True), ((2000, 1024, 3136), 5, False)])
-def test_fc_backward_w_fused_sgd_is_bit_exact(shape, iter_count, keep, dtype):
-    """FCGradient's dW consumed by ACMWeightDecayMomentumSGDUpdate inside the GEMM epilogue == the weight-gradient
-    GEMM followed by the stand-alone update kernel: the same fp32 operations in the same order on the same
-    gradient, so momentum, master parameter and GEMM-operand shadow agree bit for bit (also on the scalar edge
-    tiles of shapes that are not multiples of the tile, and on the first call, which ignores the momentum buffer)."""
+@pytest.mark.parametrize("shape", [(96, 128, 128), (96, 128, 12), (300, 256, 40), (2000, 1024, 512)])
+def test_fc_stacked_launch_equals_per_stack_launches(shape, dtype):
+    """The head's clean / noisy stacks run as ONE launch over 3-d tensor maps (nawsod_fc_*_stacks): every stacked
+    op must be bit-identical to the same op launched once per stack on the 2-d column blocks -- forward (bias,
+    ReLU, injected dropout mask), dX (ReLU/dropout gradient of the layer below) and dW / db, operands given as
+    column-block views of [R, S*H] activation buffers exactly like heads.py passes them."""
     ops = _ops()
-    M, N, K = shape
-    X, W, b, mask = _data(M, N, K, dtype, seed=3)
-    g = torch.Generator(device="cuda").manual_seed(4)
-    dY = (torch.randn(M, N, device="cuda", generator=g) * 0.1).to(dtype)
-    p0 = W.float().contiguous()
-    m0 = torch.randn(N, K, device="cuda", generator=g) * 1e-3
-    lr = torch.tensor([3e-3], device="cuda")
-    hyper = dict(momentum=0.9, weight_decay=5e-4, lr_mult=1.0, gpu_num=1, iter_count=iter_count)
-    # reference schedule: GEMM -> gradient buffer -> update kernel
-    dW, db = ops.FCGradientW(dY, X)
-    p_ref, m_ref, s_ref = p0.clone(), m0.clone(), torch.empty(N, K, dtype=dtype, device="cuda")
-    ops.ACMWeightDecayMomentumSGDUpdate(dW.view(-1), m_ref.view(-1), lr, p_ref.view(-1), None, p_shadow=s_ref.view(-1), **hyper)
-    # fused
-    p, m, s = p0.clone(), m0.clone(), torch.empty(N, K, dtype=dtype, device="cuda")
-    dW2 = torch.full((N, K), float("nan"), device="cuda") if keep else None
-    db2 = torch.empty(N, device="cuda")
-    ops.FCGradientW_SGDUpdate(dY, X, m, lr, p, dW=dW2, db=db2, p_shadow=s, **hyper)
-    torch.cuda.synchronize()
-    assert torch.equal(p, p_ref) and torch.equal(m, m_ref)
-    assert torch.equal(s.view(torch.int16 if dtype == torch.bfloat16 else torch.int32),
-                       s_ref.view(torch.int16 if dtype == torch.bfloat16 else torch.int32))
-    assert not torch.equal(p, p0)
-    if keep:
-        assert torch.equal(dW2, dW)
-    assert _rel(db2, db) <= 1e-5
-    # row panels of a wider parameter block (how the head calls it): leading dimension > K is not needed, row slices are
-    if N >= 512:
-        p, m, s = p0.clone(), m0.clone(), torch.empty(N, K, dtype=dtype, device="cuda")
-        h = (N // 2) // 64 * 64                    # panel boundary: a TMA operand base must stay 16-byte aligned
-        for r0, r1 in ((0, h), (h, N)):
-            ops.FCGradientW_SGDUpdate(dY[:, r0:r1], X, m[r0:r1], lr, p[r0:r1], p_shadow=s[r0:r1], **hyper)
-        assert torch.equal(p, p_ref) and torch.equal(m, m_ref)
-
-
-def test_fc_backward_w_fused_sgd_errors():
-    ops = _ops()
-    X, W, b, mask = _data(128, 64, 128, torch.bfloat16)
-    dY = torch.zeros(128, 64, dtype=torch.bfloat16, device="cuda")
-    lr = torch.tensor([1e-3], device="cuda")
-    p, m = torch.zeros(64, 128, device="cuda"), torch.zeros(64, 128, device="cuda")
-    with pytest.raises(RuntimeError):
-        ops.FCGradientW_SGDUpdate(dY, X, m[:32], lr, p)                       # shape mismatch
-    with pytest.raises(RuntimeError):
-        ops.FCGradientW_SGDUpdate(dY, X, m, lr, p, accumulate=True)           # accumulate without a gradient buffer
-    with pytest.raises(RuntimeError):
-        ops.FCGradientW_SGDUpdate(dY, X, m, torch.zeros(2, device="cuda"), p)
+    R, H, N = shape
+    S = 2
+    g = torch.Generator(device="cuda").manual_seed(5)
+    Np = (N + 15) // 16 * 16          # padded row pitch of the narrow (fc8-like) operands
+    X = torch.randn(R, S * H, device="cuda", generator=g).to(dtype)
+    W = (torch.randn(S, N, H, device="cuda", generator=g) * 0.1).to(dtype)
+    b = torch.randn(S, Np, device="cuda", generator=g)[:, :N]
+    mask = (torch.rand(S, R, Np, device="cuda", generator=g) < 0.5).to(torch.uint8)[:, :, :N]
+    Y = torch.full((R, S * Np), float("nan"), device="cuda", dtype=dtype)
+    Ys = _stacked(Y, S)[:, :, :N]
+    ops.FC(_stacked(X, S), W, b, relu=True, dropout_mask=mask, out=Ys)
+    for s in range(S):
+        ref = ops.FC(X[:, s * H:(s + 1) * H], W[s], b[s].contiguous(), relu=True, dropout_mask=mask[s])
+        assert torch.equal(Ys[s], ref), ("fwd", s)
+    dY = torch.randn(S, R, Np, device="cuda", generator=g).to(dtype)[:, :, :N]
+    dX = torch.full((R, S * H), float("nan"), device="cuda", dtype=dtype)
+    ops.FCGradientX(dY, W, act_below=_stacked(X, S), out=_stacked(dX, S))
+    for s in range(S):
+        ref = ops.FCGradientX(dY[s], W[s], act_below=X[:, s * H:(s + 1) * H])
+        assert torch.equal(dX[:, s * H:(s + 1) * H], ref), ("bwd_x", s)
+    dW = torch.full((S, N, H), float("nan"), device="cuda")
+    db = torch.zeros(S, Np, device="cuda")[:, :N]
+    ops.FCGradientW(dY, _stacked(X, S), dW=dW, db=db)
+    for s in range(S):
+        rW, rb = ops.FCGradientW(dY[s], X[:, s * H:(s + 1) * H])
+        assert torch.equal(dW[s], rW), ("bwd_w", s)
+        assert torch.allclose(db[s], rb, rtol=1e-4, atol=1e-4), ("db", s)      # column sums use float atomics
