@@ -269,15 +269,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int bi = tile / tiles_pb, tb = tile - bi * tiles_pb;
       const int m0 = (tb % num_m) * BLOCK_M, n0 = (tb / num_m) * BN;
-      EpiParams ep = ep_;                        // this problem's view of the epilogue operands
-      if (bi) {
-        const size_t oes = ep.out_dtype == NAWSOD_F32 ? 4 : 2, aes = ep.act_dtype == NAWSOD_BF16 ? 2 : 4;
-        ep.out = static_cast<char*>(ep.out) + (size_t)bi * ep.so * oes;
-        if (ep.bias) ep.bias += (size_t)bi * ep.sbias;
-        if (ep.mask) ep.mask += (size_t)bi * ep.smask;
-        if (ep.act) ep.act = static_cast<const char*>(ep.act) + (size_t)bi * ep.sact * aes;
-        if (ep.seed) ep.seed += bi;              // seed 0 means "no counter-based dropout" for every stack
-      }
+      // this problem's view of the epilogue operands, as scalars (a per-tile mutable copy of the whole parameter
+      // struct proved fragile: one build kept reading the unshifted kernel parameters for stacks > 0)
+      const size_t oes = ep.out_dtype == NAWSOD_F32 ? 4 : 2, aes = ep.act_dtype == NAWSOD_BF16 ? 2 : 4;
+      char* const out_b = static_cast<char*>(ep.out) + (size_t)bi * ep.so * oes;
+      const float* const bias_b = ep.bias ? ep.bias + (size_t)bi * ep.sbias : nullptr;
+      const uint8_t* const mask_b = ep.mask ? ep.mask + (size_t)bi * ep.smask : nullptr;
+      const char* const act_b = ep.act ? static_cast<const char*>(ep.act) + (size_t)bi * ep.sact * aes : nullptr;
+      const unsigned long long seed_b = ep.seed ? ep.seed + bi : 0;   // seed 0 means "no counter-based dropout" for every stack
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const int m = m0 + q * 32 + lane;
@@ -296,22 +295,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
           const bool full = ncols == 32;
-          if (ep.bias) {
+          if (bias_b) {
             if (full && bias_vec) {
 #pragma unroll
               for (int i = 0; i < 32; i += 4) {
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + n + i));
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias_b + n + i));
                 v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
               }
             } else {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) if (i < ncols) v[i] += __ldg(ep.bias + n + i);
+              for (int i = 0; i < 32; ++i) if (i < ncols) v[i] += __ldg(bias_b + n + i);
             }
           }
           if (ep.flags & NAWSOD_FC_RELU) {
-            if (ep.act) {
+            if (act_b) {
               if (full && act_vec && ep.act_dtype == NAWSOD_BF16) {
-                const uint4* ap = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(ep.act) + (size_t)m * ep.ldact + n);
+                const uint4* ap = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(act_b) + (size_t)m * ep.ldact + n);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                   const uint4 a4 = ap[i];
@@ -326,7 +325,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               } else {
 #pragma unroll
                 for (int i = 0; i < 32; ++i)
-                  if (i < ncols) v[i] = ld_act(ep.act, ep.act_dtype, (size_t)m * ep.ldact + n + i) > 0.f ? v[i] : 0.f;
+                  if (i < ncols) v[i] = ld_act(act_b, ep.act_dtype, (size_t)m * ep.ldact + n + i) > 0.f ? v[i] : 0.f;
               }
             } else {
 #pragma unroll
@@ -334,9 +333,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
           }
           if (ep.flags & NAWSOD_FC_DROPOUT) {
-            if (ep.mask) {
+            if (mask_b) {
               if (full && mask_vec) {
-                const uint4* mp = reinterpret_cast<const uint4*>(ep.mask + (size_t)m * ep.ldmask + n);
+                const uint4* mp = reinterpret_cast<const uint4*>(mask_b + (size_t)m * ep.ldmask + n);
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
                   const uint4 m4 = mp[i];
@@ -347,11 +346,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 }
               } else {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) if (i < ncols) v[i] *= 2.0f * static_cast<float>(ep.mask[(size_t)m * ep.ldmask + n + i]);
+                for (int i = 0; i < 32; ++i) if (i < ncols) v[i] *= 2.0f * static_cast<float>(mask_b[(size_t)m * ep.ldmask + n + i]);
               }
-            } else if (ep.seed != 0) {
+            } else if (seed_b != 0) {
               // counter-based keep bits: one 64-bit mix per (row, 32-column chunk), one bit per column
-              unsigned long long h = ep.seed ^ (0x9E3779B97F4A7C15ull * (unsigned long long)(m + 1)) ^
+              unsigned long long h = seed_b ^ (0x9E3779B97F4A7C15ull * (unsigned long long)(m + 1)) ^
                                      (0xC2B2AE3D27D4EB4Full * (unsigned long long)(n / 32 + 1));
               h ^= h >> 33; h *= 0xFF51AFD7ED558CCDull; h ^= h >> 33; h *= 0xC4CEB9FE1A85EC53ull; h ^= h >> 33;
               const uint32_t bits = static_cast<uint32_t>(h);
@@ -363,7 +362,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
           }
           if (ep.out_dtype == NAWSOD_F32) {
-            float* o = static_cast<float*>(ep.out) + (size_t)m * ep.ldo + n;
+            float* o = reinterpret_cast<float*>(out_b) + (size_t)m * ep.ldo + n;
             if (ep.flags & NAWSOD_FC_ACCUMULATE) {
 #pragma unroll
               for (int i = 0; i < 32; ++i) if (i < ncols) v[i] += o[i];
@@ -380,7 +379,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               for (int i = 0; i < 32; ++i) if (i < ncols) o[i] = v[i];
             }
           } else {
-            __nv_bfloat16* o = static_cast<__nv_bfloat16*>(ep.out) + (size_t)m * ep.ldo + n;
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out_b) + (size_t)m * ep.ldo + n;
             if (vec_ok && full) {
 #pragma unroll
               for (int i = 0; i < 32; i += 8) {
