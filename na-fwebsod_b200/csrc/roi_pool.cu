@@ -21,6 +21,10 @@
 namespace nawsod {
 namespace {
 
+// default of the pool_rows2 tuning knob: 0 = roi_pool_fwd_rows_kernel, 1 = roi_pool_fwd_rows2_kernel for maps staged in shared
+// memory, 2 = also for maps read from L2 directly
+constexpr long long kPoolRows2Default = 1;
+
 struct PoolParams {
   const void* X;        // channels-last map [N, H, W, C]
   const float* rois;    // [R, 5]
@@ -89,6 +93,11 @@ struct ScanF32 {   // fp32 map, VEC = 4
 #pragma unroll
     for (int k = 0; k < 4; ++k) { m[k] = empty ? 0.f : -FLT_MAX; i[k] = -1; }
   }
+  // start of a bin: the cached row's scan when the bin shares that row, else the empty scan
+  __device__ __forceinline__ void select(bool share, const ScanF32& c) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { m[k] = share ? c.m[k] : -FLT_MAX; i[k] = share ? c.i[k] : -1; }
+  }
   __device__ __forceinline__ void visit(const uint4& q, int idx) {
     const float x[4] = {__uint_as_float(q.x), __uint_as_float(q.y), __uint_as_float(q.z), __uint_as_float(q.w)};
 #pragma unroll
@@ -121,6 +130,10 @@ struct ScanBF16 {
   __device__ __forceinline__ void init(bool empty) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) { m[k] = empty ? 0u : 0xFF80FF80u; i[k] = 0xFFFFFFFFu; }
+  }
+  __device__ __forceinline__ void select(bool share, const ScanBF16& c) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { m[k] = share ? c.m[k] : 0xFF80FF80u; i[k] = share ? c.i[k] : 0xFFFFFFFFu; }
   }
   __device__ __forceinline__ void merge(const ScanBF16& o) {
 #pragma unroll
@@ -431,6 +444,203 @@ __global__ void __launch_bounds__(1024, 1) roi_pool_fwd_rows_kernel(const PoolPa
   }
 }
 
+// Forward, bin-row variant 2 ("rows2"): the same mapping and scan order as roi_pool_fwd_rows_kernel (a warp owns one
+// RoI, a lane one bin column x one 16-byte channel vector, bin rows walked together, last map row cached), with the
+// control overhead that kernel spent ~85 % of its issue slots on (ncu: 81 % issue-active, 16 K warp instructions per
+// RoI of which ~2 K are loads and compares) removed:
+//   * four lanes per bin column, always (SC = 4 vectors), so lane -> (column, vector) is two bit operations;
+//   * the w-scan has NO per-lane loop: its trip count is the warp-uniform maximum NC of the column widths, the cells
+//     beyond a lane's own width are re-reads of its last cell (a re-visited cell never wins the strict '>' and
+//     never changes a maximum) at offsets computed once per RoI, and the whole bin loop is instantiated for
+//     NC = 1..4 (straight-line loads, then compares) with one generic instance for wider bins;
+//   * the map-row pointer runs on across bin rows: consecutive bins either share exactly one row (the cached one:
+//     hend(ph) = ceil, hstart(ph+1) = floor of the same product) or continue with the next row, so a bin costs no
+//     address arithmetic and the cached row is folded in by a register move before the row loop;
+//   * the idle lanes (columns >= PW) shadow the last column instead of branching around the scan, only their stores
+//     write the same values to the same addresses; RoIs with an empty bin (clipped by the map border) take a
+//     separate instance of the bin loop, chosen by one vote per RoI, so the common instance has no emptiness tests.
+// Scan order per bin is still (h, w) row-major with strict '>': values and argmax are bit-identical.
+template <typename Scan, int NC>
+__device__ __forceinline__ void rows2_scan_row(Scan& c, const unsigned char* rowp, int idx0, int o1, int o2, int o3,
+                                               int ncmax, int last, int cell_bytes) {
+  const uint4 q0 = *reinterpret_cast<const uint4*>(rowp);
+  uint4 q1 = q0, q2 = q0, q3 = q0;
+  if (NC == 0 || NC >= 2) q1 = *reinterpret_cast<const uint4*>(rowp + o1);
+  if (NC == 0 || NC >= 3) q2 = *reinterpret_cast<const uint4*>(rowp + o2);
+  if (NC == 0 || NC >= 4) q3 = *reinterpret_cast<const uint4*>(rowp + o3);
+  c.visit(q0, idx0);
+  if (NC == 0 || NC >= 2) c.visit(q1, idx0 + 1);
+  if (NC == 0 || NC >= 3) c.visit(q2, idx0 + 2);
+  if (NC == 0 || NC >= 4) c.visit(q3, idx0 + 3);
+  if (NC == 0) {
+#pragma unroll 1
+    for (int j = 4; j < ncmax; ++j)
+      c.visit(*reinterpret_cast<const uint4*>(rowp + min(j, last) * cell_bytes), idx0 + j);
+  }
+}
+
+struct Rows2Roi {            // per-RoI, per-lane constants of the bin loop
+  const unsigned char* col_src;   // first cell of the lane's w-range in map row 0 (clamped into the row)
+  int wstart, ncols, ncmax, last, o1, o2, o3, cell_bytes, row_bytes, W, PH;
+  int bstart, bend;               // lane l < 8: h-bounds of bin row l
+  unsigned share_mask;            // bit ph: bin row ph starts on the last map row of bin row ph - 1
+  float s;                        // boost factor (1 when there is none: x * 1 is exact)
+  size_t bin_stride;
+};
+
+// kEmpty = false: every bin of the RoI is non-empty (the common case, decided by one vote per RoI).  Then bin row
+// ph + 1 starts either on the last row of bin row ph (share_mask) or right below it, so the row pointer simply runs on.
+// kEmpty = true: RoIs clipped by the map border or degenerate; bins are tested one by one.
+template <typename TIn, typename TOut, bool kArgmax, int NC, bool kEmpty>
+__device__ __forceinline__ void rows2_bins(const Rows2Roi& g, TOut* yout, int32_t* aout) {
+  constexpr int VEC = Vec<TIn>::N;
+  using Scan = typename std::conditional<sizeof(TIn) == 4, ScanF32<kArgmax>, ScanBF16<kArgmax>>::type;
+  int next_h = kEmpty ? -8 : __shfl_sync(0xffffffffu, g.bstart, 0);   // map row `rowp` points at; `cached` = row next_h - 1
+  const unsigned char* rowp = g.col_src + (kEmpty ? (size_t)0 : (size_t)next_h * g.row_bytes);
+  int idx0 = kEmpty ? 0 : next_h * g.W + g.wstart;
+  Scan cached;
+  cached.init(false);
+#pragma unroll 1
+  for (int ph = 0; ph < g.PH; ++ph, yout += g.bin_stride, aout += (kArgmax ? g.bin_stride : 0)) {
+    const int hend = __shfl_sync(0xffffffffu, g.bend, ph);
+    Scan sc;
+    bool is_empty = false, row_empty = false;   // row_empty: warp-uniform (no map row in this bin row)
+    if (!kEmpty) {
+      sc.select((g.share_mask >> ph) & 1u, cached);
+    } else {
+      const int hstart = __shfl_sync(0xffffffffu, g.bstart, ph);
+      row_empty = hend <= hstart;
+      is_empty = row_empty || (g.ncols <= 0);
+      if (!row_empty) {                         // warp-uniform
+        sc.select(hstart == next_h - 1, cached);
+        if (hstart != next_h - 1 && hstart != next_h) {          // first non-empty bin of the RoI
+          next_h = hstart;
+          rowp = g.col_src + (size_t)hstart * g.row_bytes;
+          idx0 = hstart * g.W + g.wstart;
+        }
+      } else {
+        sc.init(true);
+      }
+    }
+    const int hstop = (kEmpty && row_empty) ? next_h : hend;
+#pragma unroll 1
+    for (; next_h < hstop; ++next_h, rowp += g.row_bytes, idx0 += g.W) {
+      cached.init(false);
+      rows2_scan_row<Scan, NC>(cached, rowp, idx0, g.o1, g.o2, g.o3, g.ncmax, g.last, g.cell_bytes);
+      sc.merge(cached);
+    }
+    if (kEmpty && is_empty) sc.init(true);
+    float maxv[VEC];
+    int maxi[VEC];
+    sc.result(is_empty, maxv, maxi);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) maxv[k] = __fmul_rn(maxv[k], g.s);
+    // lanes of the idle columns (>= PW) shadow the last column: they store the same values to the same addresses
+    store_vals<VEC>(yout, maxv);
+    if (kArgmax) store_idx<VEC>(aout, maxi);
+  }
+}
+
+template <typename TIn, typename TOut, bool kSmem, bool kArgmax>
+__global__ void __launch_bounds__(1024, 1) roi_pool_fwd_rows2_kernel(const PoolParams p) {
+  constexpr int VEC = Vec<TIn>::N;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ int next_roi;
+  const int slab = blockIdx.x, chunk = blockIdx.y, n = blockIdx.z;
+  const int HW = p.H * p.W;
+  const TIn* gbase = static_cast<const TIn*>(p.X) + (size_t)n * HW * p.C + (size_t)slab * (4 * VEC);
+  const int r0 = chunk * p.rois_per_chunk;
+  const int r1 = min(p.R, r0 + p.rois_per_chunk);
+  if (threadIdx.x == 0) next_roi = r0;
+
+  Rows2Roi g;
+  const unsigned char* src;
+  if (kSmem) {
+    const int total = HW * 4;                   // 16-byte vectors in the slab (64 bytes per cell)
+    const unsigned char* gsrc = reinterpret_cast<const unsigned char*>(gbase);
+    const size_t gcell = (size_t)p.C * sizeof(TIn);
+    for (int i = threadIdx.x; i < total; i += blockDim.x)
+      cp_async16(smem_raw + (size_t)i * 16, gsrc + (size_t)(i >> 2) * gcell + (i & 3) * 16);
+    asm volatile("cp.async.commit_group;\n" ::);
+    asm volatile("cp.async.wait_group 0;\n" ::);
+    src = smem_raw;
+    g.cell_bytes = 64;
+  } else {
+    src = reinterpret_cast<const unsigned char*>(gbase);
+    g.cell_bytes = p.C * (int)sizeof(TIn);
+  }
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31;
+  const int v = lane & 3;
+  const int W = p.W, H = p.H, PH = p.PH, PW = p.PW;
+  const int sw = min(lane >> 2, PW - 1);         // idle lanes shadow the last bin column
+  g.W = W; g.PH = PH;
+  g.row_bytes = W * g.cell_bytes;
+  g.bin_stride = (size_t)PW * p.C;               // elements between consecutive bin rows of Y
+  const unsigned char* lane_src = src + v * 16;
+  // lane-parallel bound evaluation: lanes [0, 8) -> bin row `lane` (h), lanes [8, 32) -> bin column `lane - 8` (w)
+  const bool is_h = lane < 8;
+  const int pidx = is_h ? lane : lane - 8;
+  const float fdiv = static_cast<float>(is_h ? PH : PW);
+  const int lim = is_h ? H : W;
+
+  while (true) {
+    int r = 0;
+    if (lane == 0) r = atomicAdd(&next_roi, 1);
+    r = __shfl_sync(0xffffffffu, r, 0);
+    if (r >= r1) break;
+    // lane l (1..4) owns coordinate l of the RoI; detectron/ops/roi_loop_pool_op.cu:42-45
+    const float coord = __ldg(p.rois + (size_t)r * 5 + min(lane, 4));
+    if (static_cast<int>(__shfl_sync(0xffffffffu, coord, 0)) != n) continue;
+    const int rounded = static_cast<int>(roundf(coord * p.scale));
+    const int roi_start_w = __shfl_sync(0xffffffffu, rounded, 1);
+    const int roi_start_h = __shfl_sync(0xffffffffu, rounded, 2);
+    const int roi_end_w = __shfl_sync(0xffffffffu, rounded, 3);
+    const int roi_end_h = __shfl_sync(0xffffffffu, rounded, 4);
+    // roi_loop_pool_op.cu:54-68, one (row or column) bound pair per lane
+    const int extent = is_h ? max(roi_end_h - roi_start_h + 1, 1) : max(roi_end_w - roi_start_w + 1, 1);
+    const int offs = is_h ? roi_start_h : roi_start_w;
+    const float bin_size = __fdiv_rn(static_cast<float>(extent), fdiv);
+    const int bstart = static_cast<int>(floorf(__fmul_rn(static_cast<float>(pidx), bin_size)));
+    const int bend = static_cast<int>(ceilf(__fmul_rn(static_cast<float>(pidx + 1), bin_size)));
+    g.bstart = min(max(bstart + offs, 0), lim);
+    g.bend = min(max(bend + offs, 0), lim);
+    g.wstart = __shfl_sync(0xffffffffu, g.bstart, 8 + sw);
+    const int wend = __shfl_sync(0xffffffffu, g.bend, 8 + sw);
+    g.ncols = wend - g.wstart;                     // cells per row of this lane's bins (<= 0: empty column)
+    g.ncmax = __reduce_max_sync(0xffffffffu, g.ncols);     // warp-uniform trip count of the w-scan
+    g.last = max(g.ncols - 1, 0);
+    // byte offsets of cells 1..3 of the lane's w-range, clamped to its last cell
+    g.o1 = min(1, g.last) * g.cell_bytes; g.o2 = min(2, g.last) * g.cell_bytes; g.o3 = min(3, g.last) * g.cell_bytes;
+    g.s = p.boost ? __ldg(p.boost + r) : 1.0f;
+    // an empty column may start at W: keep its (discarded) reads inside the row
+    g.col_src = lane_src + (size_t)min(g.wstart, W - 1) * g.cell_bytes;
+    const size_t out_off = ((size_t)r * PH * PW + sw) * p.C + (size_t)slab * (4 * VEC) + v * VEC;
+    TOut* yout = static_cast<TOut*>(p.Y) + out_off;
+    int32_t* aout = kArgmax ? p.argmax + out_off : nullptr;
+    // bin row ph starts on the last map row of bin row ph - 1 (lanes < 8 hold the h-bounds)
+    const int prev_end = __shfl_up_sync(0xffffffffu, g.bend, 1);
+    g.share_mask = __ballot_sync(0xffffffffu, lane > 0 && lane < PH && g.bstart == prev_end - 1);
+    const bool bound_empty = (is_h ? lane < PH : lane - 8 < PW) && g.bend <= g.bstart;
+    const bool any_empty = __any_sync(0xffffffffu, bound_empty);
+#define NAWSOD_ROWS2(NC_)                                                        \
+  do {                                                                           \
+    if (any_empty) rows2_bins<TIn, TOut, kArgmax, NC_, true>(g, yout, aout);     \
+    else rows2_bins<TIn, TOut, kArgmax, NC_, false>(g, yout, aout);              \
+  } while (0)
+    switch (g.ncmax) {                             // warp-uniform
+      case 2: NAWSOD_ROWS2(2); break;
+      case 3: NAWSOD_ROWS2(3); break;
+      case 4: NAWSOD_ROWS2(4); break;
+      default:
+        if (g.ncmax <= 1) NAWSOD_ROWS2(1);         // <= 0: every column empty, reads stay in bounds
+        else NAWSOD_ROWS2(0);
+    }
+#undef NAWSOD_ROWS2
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Backward.  NHWC: dX[b, argmax, c] += dY[r, bin, c] (lanes = channels: coalesced reads, one
 // red per element).  NCHW: lanes = consecutive (c, bin): neighbouring bins often share their
@@ -552,6 +762,13 @@ template <typename TIn, typename TOut, bool kSmem, bool kArgmax>
 int launch_pool_fwd2(const PoolParams& p, size_t smem_bytes, dim3 grid, int threads, cudaStream_t st) {
   // bin-row kernel: one warp holds a whole row of bins (h-bounds on lanes 0..7, w-bounds on lanes 8..31)
   const int slots = 32 / (p.SC / Vec<TIn>::N);
+  if (p.PH <= 8 && p.PW <= 8 && slots == 8 && get_tuning("pool_generic", 0) == 0 && get_tuning("pool_rows2", kPoolRows2Default) != 0) {
+    auto k = roi_pool_fwd_rows2_kernel<TIn, TOut, kSmem, kArgmax>;
+    if (kSmem) NAWSOD_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    k<<<grid, threads, smem_bytes, st>>>(p);
+    NAWSOD_LAUNCH_OK();
+    return NAWSOD_OK;
+  }
   if (p.PH <= 8 && p.PW <= slots && slots <= 8 && get_tuning("pool_generic", 0) == 0) {
     if (get_tuning("pool_rowcache", 1) != 0) {
       auto k = roi_pool_fwd_rows_kernel<TIn, TOut, kSmem, kArgmax, true>;
@@ -619,16 +836,20 @@ static int pool_fwd_nhwc(const void* X, int x_dtype, const float* rois, const fl
   // whole warp of channel vectors per bin.
   const int64_t budget = std::min<int64_t>(get_tuning("pool_slab_bytes", 200 * 1024), 200 * 1024);
   const bool force_global = get_tuning("pool_force_global", 0) != 0;
+  // the rows2 kernel maps exactly four lanes to a bin column: prefer the 4-vector slab wherever it applies, also for
+  // small maps whose wider slabs would fit (those fall back to the slower generic kernel)
+  // (pool_rows2 = 2 also takes it for maps that are read from L2 directly)
+  const int rows2 = (get_tuning("pool_generic", 0) == 0 && PH <= 8 && PW <= 8) ? (int)get_tuning("pool_rows2", kPoolRows2Default) : 0;
   int SC = 0;
   if (!force_global)
-    for (int lanes = 32; lanes >= 1; lanes >>= 1) {
+    for (int lanes = rows2 ? 4 : 32; lanes >= 1; lanes >>= 1) {
       const int cand = lanes * VEC;
       if (cand > C || C % cand) continue;
       if ((int64_t)H * W * cand * esize <= budget) { SC = cand; break; }
     }
   const bool use_smem = SC > 0;
   if (!use_smem)
-    for (int lanes = 32; lanes >= 1; lanes >>= 1)
+    for (int lanes = rows2 == 2 ? 4 : 32; lanes >= 1; lanes >>= 1)
       if (lanes * VEC <= C && C % (lanes * VEC) == 0) { SC = lanes * VEC; break; }
   NAWSOD_REQUIRE(SC > 0, NAWSOD_ERR_SHAPE, "roi_pool_f: C=%d has no power-of-two multiple of %d as a divisor", C, VEC);
   const size_t smem_bytes = use_smem ? (size_t)H * W * SC * esize : 0;
@@ -642,7 +863,11 @@ static int pool_fwd_nhwc(const void* X, int x_dtype, const float* rois, const fl
     // ~2 CTAs per SM slot overall; never fewer than one RoI per warp
     // fill whole waves: choose the chunk count (2..8 waves' worth) whose CTA total wastes the least
     // of its last wave; never fewer than ~4 RoIs per warp
-    const int64_t base = (int64_t)slabs * N;
+    // RoIs arrive grouped by image (roi_data/wsl.py:59-85 concatenates per-image blobs), so a chunk holds the RoIs of
+    // ONE image: of the N CTAs that share a (slab, chunk) only one finds work, the others return after staging.  The
+    // waves that matter are therefore counted over slabs x chunks (measured, 2 x 2000 RoIs bf16: 18 chunks 80.8 us,
+    // 9 chunks 96.3 us; profiles/r1j_microbench_pool.log).
+    const int64_t base = (int64_t)slabs;
     const int64_t slots = (int64_t)sm_count() * (use_smem ? 1 : (2048 / threads));
     const int64_t max_chunks = std::max<int64_t>(1, (int64_t)R / ((use_smem ? 4 : 1) * warps));
     double best_eff = -1.0;

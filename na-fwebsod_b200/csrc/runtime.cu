@@ -36,13 +36,14 @@ extern "C" {
 const char* nawsod_last_error(void) { return nawsod::g_err; }
 int nawsod_version(void) { return 100; }
 int nawsod_set_tuning(const char* key, int64_t value) {
-  static const char* known[] = {"pool_slab_bytes", "pool_chunks", "pool_force_global", "pool_threads", "pool_generic", "pool_rowcache",
+  static const char* known[] = {"pool_slab_bytes", "pool_chunks", "pool_force_global", "pool_threads", "pool_generic", "pool_rowcache", "pool_rows2",
                                 "gemm_force_1cta", "gemm_max_ctas", "mil_ctas", "sgd_max_ctas", "p2p_ctas", nullptr};
   if (!key) { nawsod::set_error("nawsod_set_tuning: null key"); return NAWSOD_ERR_ARG; }
   for (int i = 0; known[i]; ++i)
     if (std::strcmp(known[i], key) == 0) {
       std::lock_guard<std::mutex> l(nawsod::g_mu);
-      nawsod::tuning()[key] = value;
+      if (value < 0 && std::strcmp(key, "pool_rows2") == 0) nawsod::tuning().erase(key);   // back to the built-in default
+      else nawsod::tuning()[key] = value;
       return NAWSOD_OK;
     }
   nawsod::set_error("nawsod_set_tuning: unknown key '%s'", key);

@@ -111,11 +111,12 @@ def _mixed_rois(R, img_h, img_w, batch, seed):
     return out.astype(np.float32)
 
 
-@pytest.mark.parametrize("knobs", [{}, {"pool_rowcache": 0}, {"pool_generic": 1}, {"pool_force_global": 1},
-                                   {"pool_slab_bytes": 32 * 1024}])
+@pytest.mark.parametrize("knobs", [{}, {"pool_rows2": 0}, {"pool_rows2": 0, "pool_rowcache": 0}, {"pool_generic": 1},
+                                   {"pool_force_global": 1}, {"pool_slab_bytes": 32 * 1024}, {"pool_rows2": 1}, {"pool_rows2": 2},
+                                   {"pool_rows2": 2, "pool_force_global": 1}, {"pool_chunks": 3}])
 @pytest.mark.parametrize("cfg", [(2, 512, 38, 50, 1 / 16, 16), (1, 128, 75, 125, 1 / 16, 16), (1, 64, 60, 80, 1 / 8, 8)])
 def test_roi_pool_mixed_rois_all_variants(cfg, knobs):
-    """Every forward variant (bin-row kernel with / without the row cache, generic kernel, direct
+    """Every forward variant (both bin-row kernels, with / without the row cache, generic kernel, direct
     global reads, small slabs) on the config-3 RoI mixture, fp32 and bf16 maps, with and without
     argmax: bit-exact values and argmax against the C oracle."""
     ops = _ops()
@@ -145,7 +146,7 @@ def test_roi_pool_mixed_rois_all_variants(cfg, knobs):
         assert np.array_equal(Y3.float().cpu().numpy(), Yob.transpose(0, 2, 3, 1))
     finally:
         for k in knobs:
-            pkg.set_tuning(k, {"pool_rowcache": 1, "pool_slab_bytes": 200 * 1024}.get(k, 0))
+            pkg.set_tuning(k, {"pool_rowcache": 1, "pool_slab_bytes": 200 * 1024, "pool_rows2": -1}.get(k, 0))
 
 
 def test_roi_pool_empty_and_errors():

@@ -4,6 +4,9 @@ import numpy as np, torch
 import nafwebsod_b200 as pkg
 from nafwebsod_b200 import ops
 import bench
+for kv in filter(None, os.environ.get("NAWSOD_TUNING", "").split(",")):      # e.g. NAWSOD_TUNING=pool_rows2=1
+    k, v = kv.split("=")
+    pkg.set_tuning(k, int(v))
 X, rois, obn, L, offs = bench.synth_inputs(1, 2000, 0)
 Xd = torch.from_numpy(X).cuda(); r = torch.from_numpy(rois).cuda(); b = torch.from_numpy(obn).cuda()
 for dt, train in ((torch.float32, True), (torch.bfloat16, False)):
