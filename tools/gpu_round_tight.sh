@@ -21,7 +21,10 @@ tail -n 5 $OUT/${TAG}_bench_n1.err
 el "smoke"
 timeout 90 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/${TAG}_smoke.log 2>&1; echo "smoke exit $?" | tee -a $OUT/${TAG}_smoke.log
 tail -n 3 $OUT/${TAG}_smoke.log
+el "microbench pool2"
+timeout 40 python tools/microbench.py pool2 > $OUT/${TAG}_microbench_pool.log 2>&1; echo "microbench exit $?"
+grep -v "pool_chunks\|pool_rows2" $OUT/${TAG}_microbench_pool.log | cut -c1-160
 el "ncu launch list (bench command)"
-timeout 120 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/${TAG}_ncu_launches_bench.csv \
+timeout 70 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/${TAG}_ncu_launches_bench.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-isolated > $OUT/${TAG}_ncu_launches_bench.log 2>&1
 el "done"
