@@ -30,6 +30,7 @@ METRIC = "RoIs/sec (fwd+bwd, WSDDN head)"
 UNIT = "RoIs/s"
 IMAGES_PER_GPU, ROIS_PER_IMAGE, NUM_CLASSES = 2, 2000, 21
 C5, H5, W5 = 512, 38, 50
+CPU_SAMPLE_ROIS = 1000        # CPU legs: one image x 1000 of its 2000 RoIs per step (about 2 s per step on 16 cores)
 
 
 _JSON_OUT = None
@@ -145,7 +146,7 @@ def reference_arm(args):
     if rank != 0:
         return 0
     cores = os.cpu_count() or 1
-    sample = 250
+    sample = CPU_SAMPLE_ROIS
     steps, warmup = max(1, min(args.steps, 10)), max(1, min(args.warmup, 2))
     value, per = run_cpu(steps, warmup, sample)
     desc = ("1 image x %d RoIs per step (of the 2 x 2000 workload), 512x38x50 map, 20 classes, two-stack head, fwd+bwd, fp32; "
@@ -457,10 +458,10 @@ def gpu_arm(args):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        sample = 250
-        v, per = run_cpu(3, 1, sample)
+        sample = CPU_SAMPLE_ROIS
+        v, per = run_cpu(5, 1, sample)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": "3 steps of 1 image x %d RoIs (bounded sample of the 2 x 2000 workload), fp32 oracle port: C/OpenMP RoIPoolF + NumPy/BLAS "
+               "sample": "5 steps of 1 image x %d RoIs (bounded sample of the 2 x 2000 workload), fp32 oracle port: C/OpenMP RoIPoolF + NumPy/BLAS "
                          "FC stack + MIL/loss restatement, %.2f s per step" % (sample, per)}
 
     line = {
