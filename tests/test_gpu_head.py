@@ -112,9 +112,10 @@ def _oracle(prob, noise=True, entropy=True, use_masks=True, image=None, dtype=to
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("cfg", [dict(N=1, soft=False), dict(N=2, soft=True)])
+@pytest.mark.parametrize("cfg", [dict(N=1, soft=False), dict(N=2, soft=True), dict(N=1, soft=True, ncls=81)])
 def test_head_small_vs_oracle(dtype, cfg):
-    prob = _problem(cfg["N"], 32, 14, 18, 96, 6, 128, seed=3, soft=cfg["soft"], wscale=1.0)
+    # ncls=81: the flickr_coco head (80 classes, BASELINE config 3) -- 2.5 warps of classes per RoI in the MIL kernel
+    prob = _problem(cfg["N"], 32, 14, 18, 96, cfg.get("ncls", 6), 128, seed=3, soft=cfg["soft"], wscale=1.0)
     m, bl = _run(dtype, prob)
     tol = TOL[dtype]
     offs = prob[6]

@@ -114,7 +114,8 @@ def _mixed_rois(R, img_h, img_w, batch, seed):
 @pytest.mark.parametrize("knobs", [{}, {"pool_rows2": 0}, {"pool_rows2": 0, "pool_rowcache": 0}, {"pool_generic": 1},
                                    {"pool_force_global": 1}, {"pool_slab_bytes": 32 * 1024}, {"pool_rows2": 1}, {"pool_rows2": 2},
                                    {"pool_rows2": 2, "pool_force_global": 1}, {"pool_chunks": 3}])
-@pytest.mark.parametrize("cfg", [(2, 512, 38, 50, 1 / 16, 16), (1, 128, 75, 125, 1 / 16, 16), (1, 64, 60, 80, 1 / 8, 8)])
+@pytest.mark.parametrize("cfg", [(2, 512, 38, 50, 1 / 16, 16), (1, 128, 75, 125, 1 / 16, 16), (1, 64, 60, 80, 1 / 8, 8),
+                                 (1, 32, 150, 250, 1 / 8, 8)])      # the largest config-3 map: short side 1200, max side 2000 at 1/8
 def test_roi_pool_mixed_rois_all_variants(cfg, knobs):
     """Every forward variant (both bin-row kernels, with / without the row cache, generic kernel, direct
     global reads, small slabs) on the config-3 RoI mixture, fp32 and bf16 maps, with and without
