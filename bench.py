@@ -357,6 +357,8 @@ def gpu_arm(args):
     # collect samples under load
     t_mark3 = time.time()
     clocks = sampler.stop(t_mark0, t_mark3, legs={"value_leg": (t_mark0, t_mark1), "e2e_leg": (t_mark2, t_mark3)}) if rank == 0 else None
+    if hasattr(dp.exchange, "check"):
+        dp.exchange.check()           # peer exchange: a watchdog time-out in any wait kernel invalidates the run -- fail loudly
     e2e_value = world * R * args.steps / (ms_e2e * 1e-3)
     d2h_bytes = int(losses[-1].numel() * losses[-1].element_size())
     assert all(bool(torch.isfinite(l).all()) for l in losses), "non-finite loss in the benchmark"

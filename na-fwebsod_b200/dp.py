@@ -81,6 +81,14 @@ def rank_slice(offset: int, length: int, world: int, rank: int):
     return offset + rank * n, n
 
 
+def slices_aligned(length: int, world: int) -> bool:
+    """A bucket is exchanged in per-rank slices only if it splits evenly into slices of a multiple of 8 elements:
+    the update kernel moves 16-byte vectors of the fp32 buffers AND of the bf16 operand shadow, so every slice must
+    start on a 16-byte boundary in both (2 x 4096 + 8192 + 80 bias floats over 4 or 8 ranks do not).  Other buckets
+    take the whole-bucket all-reduce with a redundant update on every rank."""
+    return length % world == 0 and (length // world) % 8 == 0
+
+
 class GradientExchange:
     """Bucket pipeline on a side stream (CUDA) or inline (CPU tensors / gloo).
 
@@ -104,7 +112,7 @@ class GradientExchange:
         self.bytes_out = 0      # gradient bytes handed to the collective (per step accounting by the caller)
 
     def _divisible(self, length):
-        return length % self.world == 0
+        return slices_aligned(length, self.world)
 
     def launch(self, offset: int, length: int, tag: str):
         """Call once the kernels producing flat[offset:offset+length] are enqueued on the current stream."""
@@ -130,7 +138,7 @@ class GradientExchange:
             if self._divisible(length):
                 so, sn = rank_slice(offset, length, self.world, self.rank)
                 dist.reduce_scatter_tensor(self.flat[so: so + sn], view, op=dist.ReduceOp.SUM, group=self.group)
-            else:                      # odd world sizes: whole-bucket all-reduce, every rank updates its share redundantly
+            else:                      # uneven or misaligned slices: whole-bucket all-reduce, every rank updates the bucket redundantly
                 dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group)
                 so, sn = offset, length
             self.update_fn(offset, length, tag, so, sn)
@@ -206,7 +214,7 @@ class P2PExchange:
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         self.plan = [(o, n, t) for o, n, t in plan if n > 0]
         for o, n, _ in self.plan:
-            if n % self.world or (n // self.world) % 8:
+            if not slices_aligned(n, self.world):
                 raise RuntimeError("bucket of %d elements does not split into %d 32-byte aligned slices" % (n, self.world))
         self.index = {o: i for i, (o, _, _) in enumerate(self.plan)}
         self.update_fn = update_fn

@@ -150,6 +150,12 @@ def test_shard_images_and_plan():
         for world in (2, 4, 8):
             so, sn = dp.rank_slice(off, n, world, world - 1)
             assert so + sn == off + n and sn % 4 == 0      # 16-byte aligned slices for the float4 SGD kernel
+            # ... and for the bf16 operand shadow (8 elements): every bucket of the real layout is exchanged in slices
+            assert dp.slices_aligned(n, world)
     assert covered == n_total
     with pytest.raises(RuntimeError):
         dp.rank_slice(0, 10, 4, 0)
+    # an unpadded bias block (8192 + 8192 + 80 floats) splits evenly over 4 and 8 ranks but into slices that do not
+    # start on 16-byte boundaries of the bf16 shadow: such a bucket takes the whole-bucket all-reduce path
+    assert dp.slices_aligned(16464, 2) and not dp.slices_aligned(16464, 4) and not dp.slices_aligned(16464, 8)
+    assert not dp.slices_aligned(10, 4)
