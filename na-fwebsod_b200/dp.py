@@ -417,8 +417,8 @@ class DataParallelHead:
         if self.world == 1 or not self.master_sharded:
             return
         for off, length, _ in self.plan:
-            if length <= 0 or length % self.world:
-                continue
+            if length <= 0 or not slices_aligned(length, self.world):
+                continue          # updated redundantly on every rank: already complete everywhere
             so, sn = rank_slice(off, length, self.world, self.rank)
             for flat in (self.model.flat_param, self.model.flat_mom):
                 dist.all_gather_into_tensor(flat[off: off + length], flat[so: so + sn], group=self.group)
