@@ -61,6 +61,13 @@ def _peaks():
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback (B200_PROFILING.md)")
 
 
+def _workload(noise=True):
+    """The workload both arms are quoted on (BASELINE.json configs[1], per GPU)."""
+    return ("NA-fWebSOD head fwd+bwd+gradient exchange+SGD, BASELINE config 2 per GPU: %d images x %d RoIs, %d classes, conv5 %dx%dx%d, "
+            "RoIPoolF 7x7 @1/16 + boost, %s fc6/fc7 4096, seeded dropout" % (
+                IMAGES_PER_GPU, ROIS_PER_IMAGE, NUM_CLASSES - 1, C5, H5, W5, "two-stack (clean + noisy)" if noise else "single-stack"))
+
+
 def _flops_per_roi(noise=True, C=NUM_CLASSES - 1, D=C5 * 49, H=4096):
     """fwd 2*(D*H + H*H + 2*H*C), bwd as the reference runs it (no fc6 dX)."""
     fwd = 2 * (D * H + H * H + 2 * H * C)
@@ -154,7 +161,8 @@ def reference_arm(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
         "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "NA-fWebSOD head fwd+bwd, BASELINE config 2 shapes (2 img x 2000 RoIs, 20 classes, conv5 512x38x50), CPU sample",
+        "config": {"workload": _workload(True), "global_rois_per_step": args.gpus * IMAGES_PER_GPU * ROIS_PER_IMAGE,
+                   "parallelism": "host cores of rank 0 (the reference's CPU path does not shard)",
                    "sample": desc},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -470,9 +478,7 @@ def gpu_arm(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16" if dtype == torch.bfloat16 else "tf32", "data": "synthetic",
-        "config": {"workload": "NA-fWebSOD head fwd+bwd+gradient exchange+SGD, BASELINE config 2 per GPU: %d images x %d RoIs, %d classes, conv5 %dx%dx%d, "
-                               "RoIPoolF 7x7 @1/16 + boost, %s fc6/fc7 4096, seeded dropout" % (
-                                   IMAGES_PER_GPU, ROIS_PER_IMAGE, NUM_CLASSES - 1, C5, H5, W5, "two-stack (clean + noisy)" if noise else "single-stack"),
+        "config": {"workload": _workload(noise),
                    "global_rois_per_step": world * R, "parallelism": "dp%d (images sharded by rank; gradient exchange per step: %s)" % (
                        world, "none" if world == 1 else {"sharded": "NCCL reduce-scatter fp32 grads + sharded SGD + all-gather bf16 operands",
                               "p2p": "peer-mapped (CUDA IPC over NVSwitch) scatter of fp32 grads into the owner's staging + fused reduce/SGD on the owner + scatter of the bf16 operands back, ordered by flag kernels",
