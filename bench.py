@@ -485,6 +485,7 @@ def gpu_arm(args):
                               "allreduce": "NCCL all-reduce fp32 grads + full SGD"}[dp.sync]),
                    "l2": "working set per step (weights 0.5 GB bf16 + 0.96 GB fp32 grads + activations) >> 126 MB L2; no flush needed",
                    "fc6_panels": dp.fc6_panels,
+                   "p2p_selftest": dp.p2p_selftest,
                    "fc6_update": "stand-alone SGD kernel per row panel on a side stream" if world == 1 else "on the owner rank of each slice"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": d2h_bytes,
                 "ms_per_step": ms_e2e / args.steps},

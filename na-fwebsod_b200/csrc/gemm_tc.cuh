@@ -1,0 +1,178 @@
+// tcgen05 / TMEM / TMA building blocks shared by the FC GEMM kernels (gemm.cu, gemm_fused.cu): PTX wrappers, UMMA
+// descriptors, the tile configuration and the host-side tensor-map encoder.  Everything lives in an anonymous
+// namespace: each translation unit gets its own inlined copy.
+#pragma once
+#include <cuda.h>
+#include <algorithm>
+#include <mutex>
+#include "common.cuh"
+
+namespace nawsod {
+
+// defined in gemm.cu
+int fc_bias_grad(const void* dY, int64_t lddy, int64_t sdY, int S, int M, int N, int ab_dtype, float* db, int64_t sdb, int flags,
+                 cudaStream_t st);
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int kNumThreads = 192;
+constexpr int kSmemBudget = 220 * 1024;
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+template <int ES>
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  if (ES == 2) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+  } else {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+  }
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor bit layout): start>>4 [0,14),
+// LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout SWIZZLE_128B=2 [61,64).
+// layout: 2 = SWIZZLE_128B (16-byte atoms), 1 = SWIZZLE_128B_BASE32B (32-byte atoms; the layout
+// an MN-major operand of 4-byte elements must use: Swizzle<2,5,2>, 4-row k-groups).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= 1ull << 46;
+  d |= static_cast<uint64_t>(layout) << 61;
+  return d;
+}
+
+// Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32=1 [4,6), a/b format
+// (BF16=1, TF32=2) [7,10)/[10,13), a_major bit 15, b_major bit 16 (1 = MN-major),
+// N>>3 [17,23), M>>4 [24,29).
+__host__ __device__ constexpr uint32_t make_idesc(int es, bool a_mn, bool b_mn, int m, int n) {
+  return (1u << 4) | ((es == 2 ? 1u : 2u) << 7) | ((es == 2 ? 1u : 2u) << 10) | ((a_mn ? 1u : 0u) << 15) |
+         ((b_mn ? 1u : 0u) << 16) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
+
+// Round-to-nearest TF32 (10-bit mantissa) kept in an fp32 container.  kind::tf32 reads only the
+// upper 19 bits of each operand, i.e. it truncates; feeding it pre-rounded operands removes the
+// systematic under-estimate (~7e-4 per layer) that truncation would add.
+__device__ __forceinline__ float round_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+__device__ __forceinline__ float ld_act(const void* act, int act_dtype, size_t i) {
+  return act_dtype == NAWSOD_BF16 ? __bfloat162float(static_cast<const __nv_bfloat16*>(act)[i])
+                                  : static_cast<const float*>(act)[i];
+}
+
+template <int BN, int ES> struct Cfg {
+  static constexpr int BK = 128 / ES;                        // elements per k-block (one 128-byte swizzle atom)
+  static constexpr int UMMA_K = 32 / ES;
+  static constexpr int A_BYTES = BLOCK_M * 128;
+  static constexpr int B_BYTES = BN * 128;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (kSmemBudget / STAGE_BYTES) > 8 ? 8 : (kSmemBudget / STAGE_BYTES);
+  static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+// ------------------------------------------------------------------------------------------
+// host side: tensor maps
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// nbatch row-major matrices [rows, cols] with leading dimension ld, `bstride` elements apart;
+// box = [1, box_rows, box_cols] (cols innermost, 128 bytes).
+int make_tmap(CUtensorMap* map, const void* ptr, int es, long long rows, long long cols, long long ld, int box_rows,
+              int box_cols, bool atom32, int nbatch, long long bstride) {
+  EncodeTiledFn fn = get_encode_fn();
+  NAWSOD_REQUIRE(fn != nullptr, NAWSOD_ERR_CUDA, "cuTensorMapEncodeTiled is not available (no CUDA driver?)");
+  NAWSOD_REQUIRE(aligned16(ptr), NAWSOD_ERR_ALIGN, "fc: operand pointer must be 16-byte aligned");
+  NAWSOD_REQUIRE((ld * es) % 16 == 0 && ld >= cols, NAWSOD_ERR_ALIGN,
+                 "fc: leading dimension %lld (x%d bytes) must be >= cols and a multiple of 16 bytes", ld, es);
+  if (nbatch <= 1) bstride = rows * ld;
+  NAWSOD_REQUIRE(bstride > 0 && (bstride * es) % 16 == 0, NAWSOD_ERR_ALIGN,
+                 "fc: stack stride %lld (x%d bytes) must be a positive multiple of 16 bytes", bstride, es);
+  cuuint64_t gdim[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)std::max(nbatch, 1)};
+  cuuint64_t gstride[2] = {(cuuint64_t)ld * es, (cuuint64_t)bstride * es};
+  cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, es == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(ptr),
+                  gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  NAWSOD_REQUIRE(r == CUDA_SUCCESS, NAWSOD_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d", (int)r);
+  return NAWSOD_OK;
+}
+
+}  // namespace
+}  // namespace nawsod

@@ -152,6 +152,8 @@ class GradientExchange:
         self.in_flight = False
 
 
+P2P_VERIFIED_WORLD = 2   # largest world size the peer-mapped exchange has run on (profiles/r1e_*); larger ones self-test
+
 _OPENED = {}     # cudaIpcMemHandle bytes -> base address mapped in this process (a handle may be opened once)
 
 
@@ -347,6 +349,56 @@ class P2PExchange:
         cur.wait_stream(self.send_stream)
         self.in_flight = False
 
+    def self_test(self, timeout_ms=3000):
+        """One dry run of the whole bucket pipeline on recognisable data, so that a world size this box has not run
+        before fails HERE (and the caller falls back to NCCL) instead of inside a training step.  Rank r contributes
+        the constant r + 1 as every gradient; the owner checks the W contributions it received for its slice of every
+        bucket and publishes r + 1 as the slice's operands; after finish() every rank checks the operand slices it
+        received.  Overwrites flat_grad and the operand shadow (the caller restores the shadow from the masters).
+        Returns (ok, message) -- the same on every rank (agreed with an all-reduce); never raises for a failed check."""
+        W, rank, dev = self.world, self.rank, self.flat.device
+        bad = torch.zeros(1, dtype=torch.int32, device=dev)        # number of failed checks on this rank
+        saved_fn, saved_to, msg = self.update_fn, self.timeout_ms, ""
+        sync = (lambda: torch.cuda.synchronize(dev)) if self.flat.is_cuda else (lambda: None)
+
+        def expect(t, value):
+            lo, hi = torch.aminmax(t.float())
+            bad.add_(((lo != value) | (hi != value)).to(torch.int32))
+
+        def check_and_publish(off, length, tag, so, n, grads):
+            for r, g in enumerate(grads):
+                expect(g, float(r + 1))
+            self.out[so: so + n].fill_(float(rank + 1))
+
+        try:
+            self.update_fn, self.timeout_ms = check_and_publish, timeout_ms
+            self.flat.fill_(float(rank + 1))
+            sync()
+            dist.barrier(group=self.group)
+            self.begin_step()
+            for off, length, tag in self.plan:
+                self.launch(off, length, tag)
+            self.finish()
+            for off, length, _ in self.plan:
+                n = length // W
+                for r in range(W):
+                    expect(self.out[off + r * n: off + (r + 1) * n], float(r + 1))
+            sync()
+            if int(self.status.item()) != 0:
+                msg = "a wait kernel timed out after %d ms" % timeout_ms
+            elif int(bad.item()) != 0:
+                msg = "%d data checks failed on rank %d" % (int(bad.item()), rank)
+        except Exception as e:               # noqa: BLE001 -- any local failure must still reach the agreement below
+            msg = "%s: %s" % (type(e).__name__, e)
+        finally:
+            self.update_fn, self.timeout_ms = saved_fn, saved_to
+        ok = torch.tensor([0 if msg else 1], dtype=torch.int32, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+        self.flat.zero_()
+        if int(ok.item()) == 1:
+            return True, "ok"
+        return False, msg or "failed on a peer"
+
     def check(self):
         """Host-side check of the watchdog word (synchronises)."""
         if int(self.status.item()) != 0:
@@ -380,17 +432,33 @@ class DataParallelHead:
         self.master_sharded = False
         self.comm_sms = int(os.environ.get("NAWSOD_COMM_SMS", "0")) if comm_sms is None else comm_sms
         self._hyper = dict(momentum=0.9, weight_decay=5e-4)
+        self.p2p_selftest = None                     # outcome of P2PExchange.self_test() when it ran ("ok" or the reason)
         if self.world > 1 and sync in ("p2p", "auto") and model.flat_grad.is_cuda:
             # "auto": the peer-mapped path when every rank can set it up (one NVLink / NVSwitch box), else NCCL
+            requested = sync
             try:                                     # raises on every rank or on none (see P2PExchange.__init__)
                 self.exchange = P2PExchange(model.flat_grad, model.flat_lp, self.plan, group, update_fn=self._update_slice)
                 sync = "p2p"
                 self.comm_sms = 0                    # copy engines move the data: nothing to reserve
-            except RuntimeError:
+            except RuntimeError as e:
                 if sync == "p2p":
                     raise
                 self.exchange = None
                 sync = "sharded"
+                self.p2p_selftest = "not set up: %s" % e
+            # "auto" on a world size the peer path was not verified on (verified on B200: 2) proves itself first
+            want_test = os.environ.get("NAWSOD_P2P_SELFTEST", "auto")
+            if self.exchange is not None and (want_test == "1" or (want_test == "auto" and requested == "auto" and
+                                                                   self.world > P2P_VERIFIED_WORLD)):
+                ok, why = self.exchange.self_test()
+                self.p2p_selftest = why
+                model.sync_shadow()                  # the dry run used the operand shadow as its payload
+                if not ok:
+                    if requested == "p2p":
+                        raise RuntimeError("p2p exchange self-test failed: %s" % why)
+                    self.exchange = None
+                    sync = "sharded"
+                    self.comm_sms = int(os.environ.get("NAWSOD_COMM_SMS", "0")) if comm_sms is None else comm_sms
         elif sync == "auto":
             sync = "sharded"
         self.sync = sync

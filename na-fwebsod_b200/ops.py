@@ -502,6 +502,65 @@ def FCGradientW(dY, X, *, dW=None, db=None, want_db=True, accumulate=False):
     return dW, db
 
 
+def _dw_operands(who, dY, X):
+    M, N, lddy = _mat(dY, "dY")
+    M2, K, lda = _mat(X, "X")
+    if M != M2 or dY.dtype != X.dtype:
+        raise RuntimeError("%s: dY and X do not match" % who)
+    return M, N, K, lddy, lda
+
+
+def _dw_bias(who, db, N):
+    if db is not None and (db.dtype != torch.float32 or not db.is_cuda or db.numel() != N or not db.is_contiguous()):
+        raise RuntimeError("%s: db must be a contiguous float32 CUDA tensor with %d elements" % (who, N))
+
+
+def FCGradientWSGD(dY, X, m, lr, p, p_shadow, *, dW=None, db=None, accumulate=False, momentum=0.9, gpu_num=1, lr_mult=1.0,
+                   weight_decay=0.0, iter_count=0):
+    """EXPERIMENTAL.  ``FCGradient`` (dW, db) fused with ``ACMWeightDecayMomentumSGDUpdate([dW, m, lr, p] -> [m, p])`` of
+    the weight (iter_size 1; modeling/optimizer_wsl.py:127-136): the update runs in the GEMM epilogue on the tile it just
+    accumulated, so the gradient is never re-read (and with ``dW=None`` never written).  ``m``, ``p`` [N,K] float32 and
+    ``p_shadow`` (the GEMM-operand copy of ``p``, in the operands' dtype) are updated in place; bit-identical to
+    ``FCGradientW`` followed by the stand-alone update.  ``db`` is only computed, its update stays with the caller."""
+    M, N, K, lddy, lda = _dw_operands("FCGradientWSGD", dY, X)
+    ld = None
+    for t, nme, dt in ((m, "m", torch.float32), (p, "p", torch.float32), (p_shadow, "p_shadow", dY.dtype), (dW, "dW", torch.float32)):
+        if t is None and nme == "dW":
+            continue
+        r, c, l = _mat(t, nme)
+        if t.dtype != dt or (r, c) != (N, K):
+            raise RuntimeError("FCGradientWSGD: %s must be %s [%d,%d]" % (nme, dt, N, K))
+        if ld is not None and l != ld:
+            raise RuntimeError("FCGradientWSGD: m, p, p_shadow and dW must share one row pitch")
+        ld = l
+    _req(lr, "lr", torch.float32)
+    if lr.numel() != 1:
+        raise RuntimeError("lr must have one element")
+    if accumulate and dW is None:
+        raise RuntimeError("FCGradientWSGD: accumulate needs the gradient buffer dW")
+    _dw_bias("FCGradientWSGD", db, N)
+    _lib.call("nawsod_fc_bwd_w_sgd", _ptr(dY), lddy, _ptr(X), lda, M, N, K, _ab(dY.dtype), _ptr(dW), ld, _ptr(db),
+              _lib.FC_ACCUMULATE if accumulate else 0, _ptr(m), _ptr(p), _ptr(p_shadow), _DT[p_shadow.dtype], _ptr(lr),
+              float(momentum), float(weight_decay), float(lr_mult), int(gpu_num), int(iter_count), _stream(),
+              extra_kernels=1 if db is not None else 0)
+    return dW, db
+
+
+def FCGradientWScatter(dY, X, owner_ptrs, rows_per_owner, ldw, *, db=None):
+    """EXPERIMENTAL.  ``FCGradient`` (dW, db) whose epilogue stores rows ``[k*rows_per_owner, (k+1)*rows_per_owner)`` of
+    dW straight to ``owner_ptrs[k]`` (device addresses: this rank's own gradient slice, or a peer's staging memory mapped
+    with ``nawsod_p2p_open_mem_handle``) -- the GEMM and the send leg of the reduce-scatter that replaces the reference's
+    ``NCCLAllreduce`` (modeling/optimizer_wsl.py:52-72) as one kernel.  The caller signals the owners afterwards."""
+    M, N, K, lddy, lda = _dw_operands("FCGradientWScatter", dY, X)
+    if not owner_ptrs or any(int(a) == 0 for a in owner_ptrs):
+        raise RuntimeError("FCGradientWScatter: need one non-null destination per owner")
+    _dw_bias("FCGradientWScatter", db, N)
+    table = (ctypes.c_void_p * len(owner_ptrs))(*[int(a) for a in owner_ptrs])
+    _lib.call("nawsod_fc_bwd_w_scatter", _ptr(dY), lddy, _ptr(X), lda, M, N, K, _ab(dY.dtype), table, len(owner_ptrs),
+              int(rows_per_owner), int(ldw), _ptr(db), _stream(), extra_kernels=1 if db is not None else 0)
+    return db
+
+
 def to_bf16(src, out=None):
     """float32 [rows, cols] (may be a column slice) -> bfloat16, by the library's conversion kernel."""
     rows, cols, lds = _mat(src, "src")

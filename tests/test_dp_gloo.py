@@ -159,3 +159,72 @@ def test_shard_images_and_plan():
     # start on 16-byte boundaries of the bf16 shadow: such a bucket takes the whole-bucket all-reduce path
     assert dp.slices_aligned(16464, 2) and not dp.slices_aligned(16464, 4) and not dp.slices_aligned(16464, 8)
     assert not dp.slices_aligned(10, 4)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# P2PExchange.self_test(): the dry run that lets sync="auto" fall back to NCCL on a world size the peer path was
+# never run on.  The transport (peer-mapped memory + flag kernels) needs CUDA; here it is replaced by gloo
+# collectives with the same contract (launch: the owner's update_fn sees the W contributions for its slice in rank
+# order and its operand slice is published to every rank; finish: everything has landed), so that the CHECK logic
+# and the cross-rank agreement are what is tested.
+# ---------------------------------------------------------------------------------------------------------------
+def _selftest_worker(rank, world, port, corrupt_rank, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from nafwebsod_b200 import dp
+
+        class GlooTransport(dp.P2PExchange):
+            def __init__(self, flat, outbuf, plan):
+                self.flat, self.out, self.group = flat, outbuf, None
+                self.world, self.rank = world, rank
+                self.plan = list(plan)
+                self.update_fn, self.timeout_ms = None, 20000
+                self.status = torch.zeros(1, dtype=torch.int32)
+                self.seq = 0
+
+            def launch(self, offset, length, tag):
+                n = length // world
+                mine = [self.flat[offset + k * n: offset + (k + 1) * n].clone() for k in range(world)]
+                if rank == corrupt_rank and tag == "small_weights":
+                    mine[(rank + 1) % world][3] += 1.0                     # one wrong element sent to one owner
+                got = None
+                for k in range(world):                                     # scatter leg: owner k receives every rank's part
+                    parts = [torch.empty(n) for _ in range(world)] if rank == k else None
+                    dist.gather(mine[k], parts, dst=k)
+                    if rank == k:
+                        got = parts
+                so = offset + rank * n
+                self.update_fn(offset, length, tag, so, n, got)
+                outs = [torch.empty(n, dtype=self.out.dtype) for _ in range(world)]
+                dist.all_gather(outs, self.out[so: so + n].clone())        # operand leg
+                for k in range(world):
+                    self.out[offset + k * n: offset + (k + 1) * n] = outs[k]
+
+            def finish(self):
+                pass
+
+        n_total = 3 * 64 * world
+        plan = [(0, 64 * world, "fc6_panel"), (64 * world, 64 * world, "small_weights"), (128 * world, 64 * world, "biases")]
+        ex = GlooTransport(torch.zeros(n_total), torch.zeros(n_total, dtype=torch.bfloat16), plan)
+        marker = lambda *a: None
+        ex.update_fn = marker
+        ok, why = ex.self_test(timeout_ms=1000)
+        assert ex.update_fn is marker and ex.timeout_ms == 20000            # restored
+        assert float(ex.flat.abs().sum()) == 0.0                            # the scratch gradients are cleared again
+        out[rank] = (ok, why)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,corrupt_rank", [(2, -1), (3, -1), (3, 1)])
+def test_p2p_self_test_agrees_across_ranks(world, corrupt_rank):
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_selftest_worker, args=(world, _free_port(), corrupt_rank, out), nprocs=world, join=True)
+        res = [out[r] for r in range(world)]
+    if corrupt_rank < 0:
+        assert all(ok and why == "ok" for ok, why in res), res
+    else:
+        assert not any(ok for ok, _ in res), res                            # every rank falls back, not only the one that saw it
+        assert any("data checks failed" in why for _, why in res), res
