@@ -486,7 +486,11 @@ def gpu_arm(args):
                    "l2": "working set per step (weights 0.5 GB bf16 + 0.96 GB fp32 grads + activations) >> 126 MB L2; no flush needed",
                    "fc6_panels": dp.fc6_panels,
                    "p2p_selftest": dp.p2p_selftest,
-                   "fc6_update": "stand-alone SGD kernel per row panel on a side stream" if world == 1 else "on the owner rank of each slice"},
+                   "fc6_update": {"sgd": "EXPERIMENTAL: fused into the fc6 weight-gradient GEMM epilogue (NAWSOD_FUSED_SGD=1)",
+                                  "scatter": "on the owner rank of each slice; EXPERIMENTAL: the GEMM epilogue stores its tiles into the "
+                                             "owners' peer-mapped staging (NAWSOD_P2P_FUSED_SCATTER=1)"}.get(
+                       dp._fused_mode(), "stand-alone SGD kernel per row panel on a side stream" if world == 1
+                       else "on the owner rank of each slice")},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": d2h_bytes,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),

@@ -259,7 +259,16 @@ class P2PExchange:
     def begin_step(self):
         self.seq += 1
 
-    def launch(self, offset: int, length: int, tag: str):
+    def owner_ptrs(self, offset: int, length: int):
+        """Where this rank's contribution to slice k of the bucket belongs, for k = 0..W-1 (device addresses): its own
+        gradient buffer for the slice it owns, slot [bucket][my rank] of the owner's staging area otherwise.  A GEMM whose
+        epilogue stores there (ops.FCGradientWScatter) has done the scatter leg; launch(..., prescattered=True) then
+        only publishes the sequence number."""
+        n = length // self.world
+        return [self.flat.data_ptr() + 4 * (offset + k * n) if k == self.rank else self.peer_stage[k] + 4 * (offset + self.rank * n)
+                for k in range(self.world)]
+
+    def launch(self, offset: int, length: int, tag: str, prescattered: bool = False):
         from . import ops
         if length <= 0:
             return
@@ -278,7 +287,14 @@ class P2PExchange:
         peers = [(rank + i) % W for i in range(1, W)]             # staggered targets
         rs_copies = [(self.peer_stage[k] + 4 * (offset + rank * n), self.flat.data_ptr() + 4 * (offset + k * n), 4 * n) for k in peers]
         self.bytes_out += 4 * n * (W - 1)
-        if self.engine == "sm":
+        if prescattered:
+            # the producer GEMM stored its tiles at owner_ptrs(): all that is left of the scatter leg is the signal
+            self.send_stream.wait_event(ev)
+            with torch.cuda.stream(self.send_stream):
+                ops.p2p_signal(self._flag_ptrs(self.RS, b), self.seq)
+                if prof is not None:
+                    prof.append(("sent", b, self._mark()))
+        elif self.engine == "sm":
             self.send_stream.wait_event(ev)
             with torch.cuda.stream(self.send_stream):
                 ops.p2p_scatter([c[1] for c in rs_copies], [c[0] for c in rs_copies], 4 * n, self._flag_ptrs(self.RS, b), self.seq, b)
@@ -433,6 +449,11 @@ class DataParallelHead:
         self.comm_sms = int(os.environ.get("NAWSOD_COMM_SMS", "0")) if comm_sms is None else comm_sms
         self._hyper = dict(momentum=0.9, weight_decay=5e-4)
         self.p2p_selftest = None                     # outcome of P2PExchange.self_test() when it ran ("ok" or the reason)
+        # EXPERIMENTAL (gemm_fused.cu), off until measured: fc6 weight gradient fused with the SGD update (one GPU) or with
+        # the scatter to the owner ranks (p2p); NAWSOD_FUSED_KEEP_GRAD=1 also stores the fc6 gradient (parity runs)
+        self.fused_sgd = os.environ.get("NAWSOD_FUSED_SGD", "0") == "1"
+        self.fused_scatter = os.environ.get("NAWSOD_P2P_FUSED_SCATTER", "0") == "1"
+        self.fused_keep_grad = os.environ.get("NAWSOD_FUSED_KEEP_GRAD", "0") == "1"
         if self.world > 1 and sync in ("p2p", "auto") and model.flat_grad.is_cuda:
             # "auto": the peer-mapped path when every rank can set it up (one NVLink / NVSwitch box), else NCCL
             requested = sync
@@ -520,6 +541,7 @@ class DataParallelHead:
             bl = m.RunTrainStep(dropout_masks=dropout_masks, dropout_seed=dropout_seed)
             m.param_update(momentum=momentum, weight_decay=weight_decay, gpu_num=1)
             return bl
+        from . import ops
         ex, cols = self.exchange, m._slices["W6"][2][1]
         self._hyper = dict(momentum=momentum, weight_decay=weight_decay)
         small, biases = self.plan[-2], self.plan[-1]
@@ -530,12 +552,26 @@ class DataParallelHead:
             if self.sync == "p2p":
                 ex.begin_step()
 
+        fused = self._fused_mode()
+
         def on_panel(r0, r1):
             self._limit_gemm_grid(True)              # GEMMs launched from here on share the GPU with NCCL
-            ex.launch(r0 * cols, (r1 - r0) * cols, "fc6_panel")
+            if fused == "sgd":
+                return                               # the panel's GEMM already updated its rows of W6
+            ex.launch(r0 * cols, (r1 - r0) * cols, "fc6_panel", **({"prescattered": True} if fused == "scatter" else {}))
+
+        def fc6_dw(r0, r1, dY, feat):
+            rows, lo, hi = r1 - r0, r0 * cols, r1 * cols
+            if fused == "sgd":
+                ops.FCGradientWSGD(dY, feat, m.flat_mom[lo:hi].view(rows, cols), m.lr, m.flat_param[lo:hi].view(rows, cols),
+                                   m.flat_lp[lo:hi].view(rows, cols), dW=m.g["W6"][r0:r1] if self.fused_keep_grad else None,
+                                   db=m.g["b6"][r0:r1], momentum=momentum, gpu_num=1, lr_mult=1.0, weight_decay=weight_decay,
+                                   iter_count=m.iter_count)
+            else:
+                ops.FCGradientWScatter(dY, feat, ex.owner_ptrs(lo, hi - lo), rows // self.world, cols, db=m.g["b6"][r0:r1])
 
         bl = m.RunTrainStep(dropout_masks=dropout_masks, dropout_seed=dropout_seed, fc6_panels=self.fc6_panels,
-                            on_fc6_panel=on_panel, on_before_params=before_params,
+                            on_fc6_panel=on_panel, on_before_params=before_params, fc6_dw=fc6_dw if fused else None,
                             on_small_grads=lambda: ex.launch(small[0], small[1], "small_weights"))
         ex.launch(biases[0], biases[1], "biases")
         if self.sync == "allreduce":
@@ -546,6 +582,21 @@ class DataParallelHead:
             self.master_sharded = self.world > 1
             m.iter_count += 1
         return bl
+
+    def _fused_mode(self):
+        """Which experimental fused fc6 weight-gradient kernel this step uses: "sgd" (one GPU: GEMM + update), "scatter"
+        (p2p: GEMM + scatter to the owners; every panel must split into whole 128-row tiles per owner) or None."""
+        if not self.model.flat_grad.is_cuda:
+            return None
+        if self.sync == "local" and self.fused_sgd and self.exchange is not None:
+            return "sgd"
+        if self.sync == "p2p" and self.fused_scatter:
+            rows_total = self.model._slices["W6"][2][0]
+            step = ((rows_total + self.fc6_panels - 1) // self.fc6_panels + 255) // 256 * 256
+            panels = [min(rows_total, r0 + step) - r0 for r0 in range(0, rows_total, step)]
+            if all(r % (128 * self.world) == 0 for r in panels):
+                return "scatter"
+        return None
 
     def flush(self):
         """Join the exchange stream (end of a timed region, before reading parameters)."""

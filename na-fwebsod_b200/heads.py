@@ -268,7 +268,7 @@ class WeblyHeadModel:
 
     # ------------------------------------------------------------------ the reference's builder names
     def RunTrainStep(self, dropout_masks=None, dropout_seed=0, need_dX=False, fc6_panels=1, on_small_grads=None,
-                     on_fc6_panel=None, on_before_params=None):
+                     on_fc6_panel=None, on_before_params=None, fc6_dw=None):
         """One fwd+bwd pass of the head on the fed blobs (the slice of ``workspace.RunNet(net)``,
         detectron/utils/train_wsl.py:59, that lies between conv5 and the parameter gradients).
         Gradients land in ``self.g`` / ``self.flat_grad``; returns the blob dict.
@@ -279,7 +279,10 @@ class WeblyHeadModel:
         weight-gradient GEMMs); ``on_small_grads()`` fires once those are enqueued.  The bias
         gradients of fc6 are complete with the last panel, all others with ``on_small_grads``.
         ``on_before_params()`` fires after RoI pooling, right before the first parameter read (fc6):
-        the place to join a parameter update that is still in flight from the previous step."""
+        the place to join a parameter update that is still in flight from the previous step.
+        ``fc6_dw(r0, r1, dY_panel, roi_feat)`` (experimental) replaces the plain ``FCGradientW`` of an fc6 row panel,
+        e.g. by the GEMM fused with the SGD update or with the scatter to the rows' owner ranks (dp.py); it must
+        also produce ``self.g["b6"][r0:r1]``."""
         if not self.train:
             raise RuntimeError("RunTrainStep on a test-mode model")
         bl, H, C, C2 = self.blobs, self.H, self.C, 2 * self.C
@@ -328,8 +331,11 @@ class WeblyHeadModel:
         step = _round_up((rows + fc6_panels - 1) // fc6_panels, 256)
         for r0 in range(0, rows, step):
             r1 = min(rows, r0 + step)
-            self._timed("fc6_bwd_w", lambda: ops.FCGradientW(d6[:, r0:r1], bl["roi_feat"], dW=self.g["W6"][r0:r1],
-                                                             db=self.g["b6"][r0:r1]))
+            if fc6_dw is not None:
+                self._timed("fc6_bwd_w", lambda: fc6_dw(r0, r1, d6[:, r0:r1], bl["roi_feat"]))
+            else:
+                self._timed("fc6_bwd_w", lambda: ops.FCGradientW(d6[:, r0:r1], bl["roi_feat"], dW=self.g["W6"][r0:r1],
+                                                                 db=self.g["b6"][r0:r1]))
             if on_fc6_panel is not None:
                 on_fc6_panel(r0, r1)
         ops.FCGradientW(dl3, a7, dW=self.g["W8"], db=self.g["b8"])

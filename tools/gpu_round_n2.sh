@@ -1,5 +1,5 @@
 #!/usr/bin/env bash
-# Multi-GPU gpurun call (N = $2 GPUs, default 2): the 2-GPU parity test of the gradient exchange and bench.py under
+# Multi-GPU gpurun call (N = $2 GPUs, default 2; NAWSOD_EXPERIMENTAL=1 adds the GEMM-fused scatter variant): the 2-GPU parity test of the gradient exchange and bench.py under
 # torchrun for each exchange schedule.    gpurun --gpus 2 --timeout 300 -- 'bash tools/gpu_round_n2.sh r1e 2'
 set -u
 TAG="${1:-r1}"; N="${2:-2}"
