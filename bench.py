@@ -434,12 +434,21 @@ def gpu_arm(args):
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get("fc6_bwd_w_dram_bytes_per_launch")
+        tj = json.load(open(tpath))
+        # per LAUNCH, like `achieved`: the capture of a row-panel launch when the step runs the captured panel count, the
+        # capture of the whole-matrix launch when it runs unpanelled, else unknown
+        if n_panels == tj.get("fc6_bwd_w_panels"):
+            traffic = tj.get("fc6_bwd_w_panel_dram_bytes_per_launch")
+        elif n_panels == 1:
+            traffic = tj.get("fc6_bwd_w_dram_bytes_per_launch")
     tensor_peak = peaks["tf_sustained"] * (1.0 if dtype == torch.bfloat16 else 0.5)
     roofline = {
         "kernel": "gemm_tcgen05_kernel<256,MN,MN> (fc6 weight gradient, dY^T.X, both stacks in one GEMM)",
         "bound": "tensor", "achieved": fc6_flops / (t_bww_total * 1e-3) / 1e12 if t_bww_total else None, "peak": tensor_peak,
-        "unit": "TFLOP/s", "traffic": traffic, "peak_source": peaks["source"] + ("; sustained bf16" if dtype == torch.bfloat16 else "; TF32 = bf16/2"),
+        "unit": "TFLOP/s", "traffic": traffic, "launches_per_step": n_panels,
+        # a panel launch reads its columns of dY and all pooled features and writes its rows of dW (fp32)
+        "algorithmic_bytes_per_launch": (R * (S * 4096) * es + R * (C5 * 49) * es * n_panels + (S * 4096) * (C5 * 49) * 4) / n_panels,
+        "peak_source": peaks["source"] + ("; sustained bf16" if dtype == torch.bfloat16 else "; TF32 = bf16/2"),
     }
     roofline["frac"] = roofline["achieved"] / tensor_peak if roofline["achieved"] else None
     kernels = {
