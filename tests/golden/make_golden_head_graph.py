@@ -1,0 +1,341 @@
+"""Generate tests/golden/head_graph.npz: the forward blobs of the head AS THE REFERENCE'S OWN GRAPH BUILDERS WIRE THEM
+(SURVEY.md section 8 rows a3-a8).  Run in the BUILD container (needs /root/reference and oracle/_ref):
+
+    python tests/golden/make_golden_head_graph.py
+
+The reference describes the head as a Caffe2 graph: `add_VGG16_roi_2fc_noise_head` (modeling/webly_heads.py:463-502) over
+`add_VGG16_roi_2fc_head` (modeling/wsl_heads.py:654-681) and `DetectionModelHelper.RoIFeatureTransform`
+(modeling/detector.py:268-331), `add_webly_outputs` (webly_heads.py:32-74) over `add_wsl_outputs` (wsl_heads.py:23-56),
+`add_webly_losses` (webly_heads.py:123-197) with `add_cls_pred` (wsl_heads.py:213-227), `add_spatial_entropy_weight`
+(webly_heads.py:265-391) and `add_cross_entropy_loss` (wsl_heads.py:292-302).  Caffe2 itself cannot be installed here, so
+those functions are imported UNMODIFIED and run against an EAGER model helper: every `model.net.<Op>(inputs, outputs, **args)`
+they emit is executed at once on a NumPy workspace.  Which operator runs on which blobs, in which order, with which axes /
+flags / broadcast arguments -- everything a re-reading of the builders could get wrong -- therefore comes from the
+reference's code.  What the interpreter supplies is the arithmetic of each operator:
+  * the operators that live in the reference tree run the reference's own code: RoIFeatureBoost and
+    [Weighted]CrossEntropyWithLogits are the unmodified CPU operators of oracle/_ref/libnawsod_ref.so, RoIIoU is the
+    unmodified CUDA kernel run on the host (oracle/_ref/libnawsod_ref_kernels.so), RoIPoolF is the C restatement that is
+    pinned bit for bit to the in-tree pooling kernel (tests/test_ref_kernels.py);
+  * the Caffe2 built-ins (FC, Relu, Dropout, Softmax, Transpose, Add, Sub, Mul, Div, ReduceSum, Log, Scale, ReplaceNaN,
+    MatMul, LeakyRelu, Shape, Cast, Clip, ConstantFill, StopGradient, AveragedLoss, Split, Concat) are float32 NumPy with
+    the documented pytorch v1.3.0 defaults (LeakyRelu alpha 0.01, ReplaceNaN value 0, Dropout scale 1/(1-ratio),
+    max-subtracted Softmax, NumPy-style broadcasting) -- the one part that stays a restatement.
+The operator trace (type + blob names, in emission order) is stored next to the blobs, so the test can also show that the
+oracle covers every operator the builders emit.
+"""
+import importlib.util
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+F32 = np.float32
+
+
+def _load_roi_data_maker():
+    spec = importlib.util.spec_from_file_location("make_golden_roi_data", os.path.join(HERE, "make_golden_roi_data.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+class EagerNet:
+    """`model.net` / `model.param_init_net`: attribute access yields an operator that executes immediately."""
+
+    def __init__(self, model):
+        self._m = model
+
+    def __getattr__(self, op_type):
+        if op_type.startswith("_"):
+            raise AttributeError(op_type)
+        return lambda inputs, outputs=None, **args: self._m.run_op(op_type, inputs, outputs, **args)
+
+    def Proto(self):
+        raise RuntimeError("the eager net has no NetDef")
+
+
+class EagerModel:
+    """Stands for detectron.modeling.detector.DetectionModelHelper (a caffe2 CNNModelHelper): the builder-facing surface
+    the head uses, executing on `self.ws` (blob name -> float32 / int array)."""
+
+    def __init__(self, num_classes, train, ws, dropout_masks=None):
+        from oracle import c_oracle, ref_kernels, ref_ops
+        self.num_classes, self.train, self.ws = num_classes, train, ws
+        self.net = EagerNet(self)
+        self.param_init_net = self.net
+        self.trace = []
+        self.losses, self.metrics = [], []
+        self.masks = dropout_masks or {}
+        self._co, self._rk, self._ro = c_oracle, ref_kernels, ref_ops
+
+    # ---- CNNModelHelper / DetectionModelHelper helpers the builders call (thin forwards to net ops, as in caffe2's brew) ----
+    def FC(self, blob_in, blob_out, dim_in, dim_out, **kw):
+        W, b = self.ws[blob_out + "_w"], self.ws[blob_out + "_b"]
+        assert W.shape == (dim_out, dim_in) and b.shape == (dim_out,), (blob_out, W.shape, dim_out, dim_in)
+        return self.run_op("FC", [blob_in, blob_out + "_w", blob_out + "_b"], blob_out)
+
+    def Relu(self, i, o, **kw):
+        return self.run_op("Relu", i, o, **kw)
+
+    def Dropout(self, i, o, **kw):
+        return self.run_op("Dropout", i, [o, "_" + str(o) + "_mask"], **kw)[0]       # brew.dropout returns the data output
+
+    def Softmax(self, i, o, **kw):
+        return self.run_op("Softmax", i, o, **kw)
+
+    def Transpose(self, i, o, **kw):
+        return self.run_op("Transpose", i, o, **kw)
+
+    def StopGradient(self, i, o):
+        return self.run_op("StopGradient", i, o)
+
+    def Accuracy(self, i, o, **kw):
+        return self.run_op("Accuracy", i, o, **kw)
+
+    def AddLosses(self, losses):
+        self.losses += [losses] if isinstance(losses, str) else list(losses)
+
+    def AddMetrics(self, metrics):
+        self.metrics += [metrics] if isinstance(metrics, str) else list(metrics)
+
+    # ---- the interpreter ----
+    def run_op(self, op_type, inputs, outputs=None, **args):
+        ins = [inputs] if isinstance(inputs, str) else [str(i) for i in inputs]
+        if outputs is None:
+            raise RuntimeError("%s: the builders always name their outputs" % op_type)
+        outs = [outputs] if isinstance(outputs, str) else [str(o) for o in outputs]
+        self.trace.append("%s(%s)->(%s)%s" % (op_type, ",".join(ins), ",".join(outs),
+                                               "" if not args else " " + repr(sorted((k, str(v)) for k, v in args.items()))))
+        x = [self.ws[i] for i in ins if i in self.ws] if op_type == "Accuracy" else [self.ws[i] for i in ins]
+        res = getattr(self, "op_" + op_type)(x, args, outs)
+        res = res if isinstance(res, (list, tuple)) else [res]
+        for name, val in zip(outs, res):
+            self.ws[name] = val
+        return outs[0] if len(outs) == 1 else tuple(outs)     # core.Net._CreateAndAddToSelf: one output -> one BlobReference
+
+    # reference-tree operators: the reference's own code
+    def op_RoIPoolF(self, x, a, outs):
+        assert a["pooled_w"] == a["pooled_h"] == 7
+        Y, A = self._co.roi_pool_f(x[0], x[1], float(a["spatial_scale"]))
+        return [Y, A]
+
+    def op_RoIFeatureBoost(self, x, a, outs):
+        return self._ro.RefOp("RoIFeatureBoost").run([x[0], x[1]], 1)[0].reshape(x[0].shape)
+
+    def op_RoIIoU(self, x, a, outs):
+        return self._rk.roi_iou(x[0])
+
+    def op_WeightedCrossEntropyWithLogits(self, x, a, outs):
+        return self._ro.RefOp("WeightedCrossEntropyWithLogits", is_mean=float(bool(a.get("is_mean", False)))).run(x, 1, out_cap=4)[0]
+
+    def op_CrossEntropyWithLogits(self, x, a, outs):
+        return self._ro.RefOp("CrossEntropyWithLogits", is_mean=float(bool(a.get("is_mean", False)))).run(x, 1, out_cap=4)[0]
+
+    # Caffe2 built-ins (pytorch v1.3.0 caffe2/operators/*), float32 NumPy
+    def op_FC(self, x, a, outs):
+        return (x[0].reshape(x[0].shape[0], -1) @ x[1].T + x[2]).astype(F32)
+
+    def op_Relu(self, x, a, outs):
+        return np.maximum(x[0], F32(0))
+
+    def op_Dropout(self, x, a, outs):
+        assert not a.get("is_test", False)
+        ratio = F32(a["ratio"])
+        mask = self.masks[outs[0]].astype(F32)
+        return [(x[0] * mask * (F32(1) / (F32(1) - ratio))).astype(F32), mask]
+
+    def op_Softmax(self, x, a, outs):
+        assert a.get("axis", 1) == 1 and x[0].ndim == 2
+        e = np.exp(x[0] - x[0].max(axis=1, keepdims=True), dtype=F32)
+        return (e / e.sum(axis=1, keepdims=True, dtype=F32)).astype(F32)
+
+    def op_Transpose(self, x, a, outs):
+        return np.ascontiguousarray(np.transpose(x[0], a["axes"]))
+
+    def op_Add(self, x, a, outs):
+        return (x[0] + x[1]).astype(F32)
+
+    def op_Sub(self, x, a, outs):
+        return (x[0] - x[1]).astype(F32)
+
+    def op_Mul(self, x, a, outs):
+        return (x[0] * x[1]).astype(F32)
+
+    def op_Div(self, x, a, outs):
+        with np.errstate(divide="ignore", invalid="ignore"):
+            return (x[0] / x[1]).astype(F32)
+
+    def op_ReduceSum(self, x, a, outs):
+        return x[0].sum(axis=tuple(a["axes"]), keepdims=bool(a.get("keepdims", True)), dtype=F32)
+
+    def op_Log(self, x, a, outs):
+        with np.errstate(divide="ignore", invalid="ignore"):
+            return np.log(x[0]).astype(F32)
+
+    def op_Scale(self, x, a, outs):
+        return (x[0] * F32(a.get("scale", 1.0))).astype(F32)
+
+    def op_ReplaceNaN(self, x, a, outs):
+        return np.where(np.isnan(x[0]), F32(a.get("value", 0.0)), x[0]).astype(F32)
+
+    def op_MatMul(self, x, a, outs):
+        assert not a.get("trans_a") and not a.get("trans_b")
+        return (x[0] @ x[1]).astype(F32)
+
+    def op_LeakyRelu(self, x, a, outs):
+        return np.where(x[0] > 0, x[0], x[0] * F32(a.get("alpha", 0.01))).astype(F32)
+
+    def op_Shape(self, x, a, outs):
+        shp = np.array(x[0].shape, np.int64)
+        return shp[list(a["axes"])] if "axes" in a else shp
+
+    def op_Cast(self, x, a, outs):
+        assert a["to"] == 1                              # caffe2_pb2.TensorProto.FLOAT
+        return x[0].astype(F32)
+
+    def op_Clip(self, x, a, outs):
+        return np.clip(x[0], F32(a["min"]), F32(a["max"])).astype(F32)
+
+    def op_ConstantFill(self, x, a, outs):
+        return np.full(x[0].shape, F32(a.get("value", 0.0)), F32)      # shape of the input blob (no `shape` argument given)
+
+    def op_StopGradient(self, x, a, outs):
+        return x[0]
+
+    def op_AveragedLoss(self, x, a, outs):
+        return np.asarray(x[0], F32).mean(dtype=F32).reshape(())
+
+    def op_Accuracy(self, x, a, outs):
+        return np.zeros((), F32)                         # metric only; needs labels_int32, which the head's parity does not feed
+
+    def op_Stat(self, x, a, outs):
+        return [np.zeros((), F32) for _ in outs]         # logging only (detectron/ops/stat_op.*): prints running means every `display` calls
+
+    def op_Split(self, x, a, outs):
+        assert a["axis"] == 1
+        return np.split(x[0], np.cumsum(a["split"])[:-1], axis=1)
+
+    def op_Concat(self, x, a, outs):
+        assert a["axis"] == 1
+        return [np.concatenate(x, axis=1), np.array([t.shape[1] for t in x], np.int32)]
+
+
+def reference_roi_feature_transform():
+    """detector.DetectionModelHelper.RoIFeatureTransform as a plain function (the class itself derives from a caffe2
+    class that does not exist here; only this one method is needed and it only touches `self.net`)."""
+    import ast
+    import inspect
+    import textwrap
+    src = open("/root/reference/detectron/modeling/detector.py").read()
+    tree = ast.parse(src)
+    for node in ast.walk(tree):
+        if isinstance(node, ast.FunctionDef) and node.name == "RoIFeatureTransform":
+            lines = src.split("\n")[node.lineno - 1: node.end_lineno]
+            code = textwrap.dedent("\n".join(lines))
+            from detectron.core.config import cfg
+            ns = {"cfg": cfg}
+            exec(compile(code, "/root/reference/detectron/modeling/detector.py::RoIFeatureTransform", "exec"), ns)
+            assert "self.net.__getattr__(method)" in code and inspect.isfunction(ns["RoIFeatureTransform"])
+            return ns["RoIFeatureTransform"]
+    raise RuntimeError("RoIFeatureTransform not found in the reference")
+
+
+def build_case(rng, mods, cfg, *, Cc, Hc, Wc, R, hidden, ncls, soft, train, seed):
+    """One head problem of reduced width (the builders hard-code 4096 hidden units; see `hidden` below), run through the
+    reference's builders.  Returns (inputs, outputs, trace)."""
+    from oracle import nawsod_oracle as O
+    webly, wsl_heads, xform = mods
+    C = ncls - 1
+    X = O.synth_conv5(1, Cc, Hc, Wc, seed=seed)
+    rois = O.synth_rois(R, Hc * 16, Wc * 16, seed=seed + 1)
+    obn = (rng.random((R, 1)) + 1).astype(F32)
+    labels = np.zeros((1, C), F32)
+    labels[0, rng.integers(0, C)] = 1
+    if soft:                                                    # bagging-mixup: (lam, 1 - lam) on two classes
+        lam = F32(rng.beta(1.5, 1.5))
+        a, b = rng.choice(C, 2, replace=False)
+        labels[:] = 0
+        labels[0, a], labels[0, b] = lam, F32(1) - lam
+    params = O.synth_params(C, Cc * 49, hidden, noise=True, seed=seed + 2)
+    for k in list(params):                                      # scale the narrow layers so activations stay O(1)
+        if k.endswith("fc6_w"):
+            params[k] = (params[k] * F32(np.sqrt(25088.0 / (Cc * 49)))).astype(F32)
+        if k.endswith("fc7_w"):
+            params[k] = (params[k] * F32(np.sqrt(4096.0 / hidden))).astype(F32)
+    ws = {"conv5_3": X, "rois": rois, "obn_scores": obn, "labels_oh": labels}
+    for k, v in params.items():                                 # the oracle's 'noisy_' prefix -> the reference's blob names
+        name = k
+        if k.startswith("noisy_fc6") or k.startswith("noisy_fc7"):
+            name = "_[noisy]_" + k[len("noisy_"):]
+        ws[name] = v
+    masks = {}
+    if train:
+        for nme in ("drop6", "drop7", "_[noisy]_drop6", "_[noisy]_drop7"):
+            masks[nme] = (rng.random((R, hidden)) < 0.5).astype(F32)
+    model = EagerModel(ncls, train, ws, masks)
+    model.RoIFeatureTransform = lambda *a, **k: xform(model, *a, **k)
+
+    # The builders hard-code 4096 hidden units (wsl_heads.py:674-678, webly_heads.py:490-498).  The golden case keeps
+    # the test small by running them at `hidden` units: FC() checks each weight against the dims it is GIVEN, so the
+    # literal 4096 is mapped onto the width of the weights that were fed -- the wiring is untouched.
+    real_fc = model.FC
+    model.FC = lambda bi, bo, di, do, **kw: real_fc(bi, bo, hidden if di == 4096 else di, hidden if do == 4096 else do, **kw)
+
+    blobs, dims = webly.add_VGG16_roi_2fc_noise_head(model, "conv5_3", Cc, 1.0 / 16)
+    assert dims == [4096, 4096]
+    webly.add_webly_outputs(model, blobs, dims)
+    if train:
+        webly.add_webly_losses(model)
+    inputs = dict(X=X, rois=rois, obn=obn, labels=labels)
+    inputs.update({"param_" + k: v for k, v in params.items()})
+    inputs.update({"mask_" + k: v for k, v in masks.items()})
+    keep = ["roi_feat", "fc6", "fc7", "_[noisy]_fc6", "_[noisy]_fc7", "fc8c", "fc8d", "noisy_fc8c", "noisy_fc8d", "rois_pred",
+            "rois_pred_noise", "cls_prob", "cls_prob_noise", "rois_J", "rois_pred_E", "rois_pred_D", "rois_pred_hatE_sum",
+            "rois_pred_hatE_sum_norm", "rois_class_weight", "rois_class_weight_noise", "cross_entropy", "cross_entropy_noise",
+            "loss_cls", "loss_cls_noise", "loss_cls_grad", "loss_cls_noise_grad", "drop7", "_[noisy]_drop7"]
+    outputs = {k: np.asarray(ws[k]) for k in keep if k in ws}
+    return inputs, outputs, model.trace, model.losses
+
+
+def main():
+    maker = _load_roi_data_maker()
+    sys.meta_path.insert(0, maker._Absent())
+    import future.utils
+    future.utils.iteritems = lambda d: iter(d.items())
+    sys.path.insert(0, "/root/reference")
+    from detectron.core.config import cfg, merge_cfg_from_file
+    import detectron.modeling.webly_heads as webly
+    import detectron.modeling.wsl_heads as wsl_heads
+    import yaml
+    import detectron.utils.env as envu
+    envu.yaml_load = lambda f: yaml.load(f, Loader=yaml.SafeLoader)     # PyYAML >= 6 needs the Loader the reference omits
+    merge_cfg_from_file("/root/reference/configs/flickr_voc/na_wsddn_V-16-C5_1x.yaml")      # the shipped NA-fWebSOD config
+    assert cfg.WEBLY.ENTROPY and cfg.WSL.MEAN_LOSS and cfg.FAST_RCNN.ROI_XFORM_METHOD == "RoIPoolF"
+    assert cfg.FAST_RCNN.ROI_XFORM_RESOLUTION == 7 and cfg.TRAIN.FREEZE_CONV_BODY and cfg.TRAIN.IMS_PER_BATCH == 1
+    mods = (webly, wsl_heads, reference_roi_feature_transform())
+    rng = np.random.default_rng(2024)
+    out = {}
+    cases = [dict(Cc=16, Hc=12, Wc=16, R=96, hidden=64, ncls=21, soft=False, train=True, seed=11),
+             dict(Cc=8, Hc=10, Wc=14, R=130, hidden=32, ncls=81, soft=True, train=True, seed=21),
+             dict(Cc=16, Hc=12, Wc=16, R=64, hidden=64, ncls=21, soft=False, train=False, seed=31)]
+    for i, c in enumerate(cases):
+        inputs, outputs, trace, losses = build_case(rng, mods, cfg, **c)
+        pre = "case%d_" % i
+        for k, v in inputs.items():
+            out[pre + "in_" + k] = v
+        for k, v in outputs.items():
+            out[pre + "out_" + k] = v
+        out[pre + "trace"] = np.array(trace)
+        out[pre + "losses"] = np.array(losses)
+        out[pre + "cfg"] = np.array([c["ncls"], c["hidden"], int(c["soft"]), int(c["train"])], np.int32)
+        print("case", i, c, "->", len(trace), "operators;", {k: v.shape for k, v in outputs.items() if k in ("rois_pred", "cls_prob", "loss_cls")})
+    out["cases"] = np.int32(len(cases))
+    np.savez_compressed(os.path.join(HERE, "head_graph.npz"), **out)
+    print("wrote head_graph.npz (%d arrays)" % len(out))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,108 @@
+"""The oracle's head against the reference's OWN graph builders (tests/golden/head_graph.npz, made by
+tests/golden/make_golden_head_graph.py): add_VGG16_roi_2fc_noise_head, add_webly_outputs, add_webly_losses,
+add_spatial_entropy_weight, add_cls_pred, add_cross_entropy_loss and RoIFeatureTransform were imported unmodified from
+/root/reference and executed operator by operator on an eager NumPy workspace, with the reference's own code for the
+operators that live in its tree.  This pins the WIRING of SURVEY.md section 8 rows a3-a8 (which operator, on which blobs,
+in which order, with which axes / flags) to the reference; the arithmetic of the Caffe2 built-ins stays a float32
+restatement of their documented defaults.  The GPU test of the same vectors is tests/test_gpu_head.py."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import nawsod_oracle as O
+
+
+@pytest.fixture(scope="module")
+def gold(golden_dir):
+    return np.load(os.path.join(golden_dir, "head_graph.npz"))
+
+
+def case_inputs(gold, i):
+    pre = "case%d_in_" % i
+    params = {k[len(pre) + 6:]: gold[k] for k in gold.files if k.startswith(pre + "param_")}
+    masks = {k[len(pre) + 5:].replace("_[noisy]_", "noisy_"): gold[k] for k in gold.files if k.startswith(pre + "mask_")}
+    ncls, hidden, soft, train = (int(v) for v in gold["case%d_cfg" % i])
+    return gold[pre + "X"], gold[pre + "rois"], gold[pre + "obn"], gold[pre + "labels"], params, (masks or None), train
+
+
+def out(gold, i, name):
+    return gold["case%d_out_%s" % (i, name)]
+
+
+def close(a, b, rtol=2e-5, atol=1e-7):
+    np.testing.assert_allclose(np.asarray(a, np.float64), np.asarray(b, np.float64), rtol=rtol, atol=atol)
+
+
+@pytest.mark.parametrize("i", [0, 1])
+def test_training_graph_blobs(gold, i):
+    X, rois, obn, L, params, masks, train = case_inputs(gold, i)
+    assert train
+    ref = O.head_forward_backward(X, rois, obn, L, params, masks=masks, noise=True, entropy=True, is_mean=True, backward=False)
+    # RoIPoolF -> RoIFeatureBoost -> StopGradient: the same code on both sides, exact
+    assert np.array_equal(ref["roi_feat"], out(gold, i, "roi_feat").reshape(ref["roi_feat"].shape))
+    # FC / Relu / Dropout x2 per stack, fc8c | fc8d per stack (float32 GEMMs: summation order only)
+    close(ref["acts"]["fc6"], out(gold, i, "fc6"))
+    close(ref["acts"]["drop7"], out(gold, i, "drop7"))
+    close(ref["noisy_acts"]["drop7"], out(gold, i, "_[noisy]_drop7"))
+    for mine, theirs in (("fc8c", "fc8c"), ("fc8d", "fc8d"), ("nfc8c", "noisy_fc8c"), ("nfc8d", "noisy_fc8d")):
+        close(ref[mine], out(gold, i, theirs), rtol=1e-4, atol=1e-6)
+    # the two-stream MIL outputs of both streams, the image scores
+    for k in ("rois_pred", "rois_pred_noise", "cls_prob", "cls_prob_noise"):
+        close(ref[k], out(gold, i, k), rtol=1e-4, atol=1e-9)
+    # the noise-aware class weights and both losses
+    close(ref["class_weight"], out(gold, i, "rois_class_weight"), rtol=1e-4, atol=1e-6)
+    close(ref["class_weight_noise"], out(gold, i, "rois_class_weight_noise"), rtol=1e-4, atol=1e-6)
+    close(ref["loss_cls"], out(gold, i, "loss_cls"), rtol=1e-4)
+    close(ref["loss_cls_noise"], out(gold, i, "loss_cls_noise"), rtol=1e-4)
+    # loss-gradient seeds are 1.0 per loss, no 1/NUM_GPUS (utils/blob.py:167-173)
+    assert float(out(gold, i, "loss_cls_grad")) == 1.0 and float(out(gold, i, "loss_cls_noise_grad")) == 1.0
+    assert list(gold["case%d_losses" % i]) == ["loss_cls", "loss_cls_noise"]
+
+
+@pytest.mark.parametrize("i", [0, 1])
+def test_entropy_weight_intermediates(gold, i):
+    """add_spatial_entropy_weight blob by blob: J, E = -P log P (NaN -> 0), D = LeakyRelu(J E), sum_r E^2 / D and its
+    normalisation by y (log R - log y), clipped to [0, 1]."""
+    P, y = out(gold, i, "rois_pred"), out(gold, i, "cls_prob")
+    rois, L = gold["case%d_in_rois" % i], gold["case%d_in_labels" % i]
+    assert np.array_equal(O.roi_iou(rois), out(gold, i, "rois_J"))
+    w_clean, w_noise, parts = O.spatial_entropy_weight(P, y, rois, L, return_parts=True)
+    close(parts["E"], out(gold, i, "rois_pred_E"), rtol=1e-6, atol=0)
+    close(parts["D"], out(gold, i, "rois_pred_D"), rtol=1e-4, atol=1e-9)
+    close(parts["hatE_sum"], out(gold, i, "rois_pred_hatE_sum"), rtol=1e-4)
+    close(parts["norm"], out(gold, i, "rois_pred_hatE_sum_norm"), rtol=1e-4, atol=1e-7)
+    close(w_noise, out(gold, i, "rois_class_weight_noise"), rtol=1e-4, atol=1e-7)
+    close(w_clean, out(gold, i, "rois_class_weight"), rtol=1e-4, atol=1e-7)
+
+
+def test_test_mode_graph(gold):
+    """model.train == False: no Dropout, no losses, cls_prob = Concat(Split(rois_pred)[0], rois_pred) [R, C+1]."""
+    X, rois, obn, L, params, masks, train = case_inputs(gold, 2)
+    assert not train and masks is None
+    ref = O.head_forward_backward(X, rois, obn, L, params, masks=None, noise=True, backward=False)
+    close(ref["rois_pred"], out(gold, 2, "rois_pred"), rtol=1e-4, atol=1e-9)
+    cp = O.test_cls_prob(ref["rois_pred"])
+    assert cp.shape == out(gold, 2, "cls_prob").shape == (rois.shape[0], L.shape[1] + 1)
+    close(cp, out(gold, 2, "cls_prob"), rtol=1e-4, atol=1e-9)
+    assert not any(t.startswith("Dropout") for t in gold["case2_trace"])
+
+
+def test_every_emitted_operator_is_accounted_for(gold):
+    """The builders' operator trace: nothing outside what the oracle restates (or deliberately ignores), the live branch of
+    the entropy normalisation, and the order FC -> Relu -> Dropout of both stacks."""
+    trace = [str(t) for t in gold["case0_trace"]]
+    kinds = [t.split("(")[0] for t in trace]
+    restated = {"RoIPoolF", "RoIFeatureBoost", "FC", "Relu", "Dropout", "Softmax", "Transpose", "Add", "Sub", "Mul", "Div",
+                "ReduceSum", "RoIIoU", "Log", "Scale", "ReplaceNaN", "MatMul", "LeakyRelu", "Shape", "Cast", "Clip",
+                "ConstantFill", "WeightedCrossEntropyWithLogits", "AveragedLoss"}
+    ignored = {"StopGradient", "Stat", "Accuracy"}          # identity in the forward pass / logging / metric
+    assert set(kinds) <= restated | ignored, set(kinds) - restated - ignored
+    assert "Tile" not in kinds                               # the `if True and False` branch (webly_heads.py:294-332) is dead
+    assert any(t.startswith("Div(rois_pred_hatE_sum,rois_pred_y_logN__logy)") for t in trace)
+    assert kinds[:9] == ["RoIPoolF", "RoIFeatureBoost", "StopGradient", "FC", "Relu", "Dropout", "FC", "Relu", "Dropout"]
+    assert kinds.count("FC") == 8 and kinds.count("WeightedCrossEntropyWithLogits") == 2 and kinds.count("RoIIoU") == 1
+    ce = [t for t in trace if t.startswith("WeightedCrossEntropyWithLogits")]
+    assert ce[0].startswith("WeightedCrossEntropyWithLogits(cls_prob,labels_oh,rois_class_weight)->(cross_entropy)")
+    assert ce[1].startswith("WeightedCrossEntropyWithLogits(cls_prob_noise,labels_oh,rois_class_weight_noise)->(cross_entropy_noise)")
+    assert all("('is_mean', 'True')" in t for t in ce)
