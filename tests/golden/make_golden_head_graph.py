@@ -69,6 +69,8 @@ class EagerModel:
         self.trace = []
         self.losses, self.metrics = [], []
         self.masks = dropout_masks or {}
+        self.update_ops, self._last_ins = [], []
+        self.biases, self.gn_params, self.param_to_grad, self.weights = [], [], {}, []
         self._co, self._rk, self._ro = c_oracle, ref_kernels, ref_ops
 
     # ---- CNNModelHelper / DetectionModelHelper helpers the builders call (thin forwards to net ops, as in caffe2's brew) ----
@@ -101,6 +103,9 @@ class EagerModel:
     def AddMetrics(self, metrics):
         self.metrics += [metrics] if isinstance(metrics, str) else list(metrics)
 
+    def TrainableParams(self, gpu_id=-1):
+        return list(self.weights) + list(self.biases)          # cnn.CNNModelHelper.TrainableParams: weights, then biases
+
     # ---- the interpreter ----
     def run_op(self, op_type, inputs, outputs=None, **args):
         ins = [inputs] if isinstance(inputs, str) else [str(i) for i in inputs]
@@ -110,6 +115,7 @@ class EagerModel:
         self.trace.append("%s(%s)->(%s)%s" % (op_type, ",".join(ins), ",".join(outs),
                                                "" if not args else " " + repr(sorted((k, str(v)) for k, v in args.items()))))
         x = [self.ws[i] for i in ins if i in self.ws] if op_type == "Accuracy" else [self.ws[i] for i in ins]
+        self._last_ins = ins
         res = getattr(self, "op_" + op_type)(x, args, outs)
         res = res if isinstance(res, (list, tuple)) else [res]
         for name, val in zip(outs, res):
@@ -200,7 +206,21 @@ class EagerModel:
         return np.clip(x[0], F32(a["min"]), F32(a["max"])).astype(F32)
 
     def op_ConstantFill(self, x, a, outs):
-        return np.full(x[0].shape, F32(a.get("value", 0.0)), F32)      # shape of the input blob (no `shape` argument given)
+        shape = tuple(a["shape"]) if not x else x[0].shape             # ConstantFill([], shape=...) or ConstantFill([like])
+        return np.full(shape, F32(a.get("value", 0.0)), F32)
+
+    def op_ACMWeightDecayMomentumSGDUpdate(self, x, a, outs):
+        """The reference's own CPU operator (one instance per emitted op, like a Caffe2 net: its hidden iter_count_ lives
+        across runs).  The instance and its blob names are kept so that `run_updates()` can run the update net again."""
+        op = self._ro.RefOp("ACMWeightDecayMomentumSGDUpdate", **{k: float(v) for k, v in a.items()})
+        self.update_ops.append((op, list(self._last_ins), list(outs), dict(a)))
+        return op.run(x, 4, out_alias=[0, 1, 3, 4])
+
+    def run_updates(self):
+        for op, ins, outs, _ in self.update_ops:
+            res = op.run([self.ws[i] for i in ins], 4, out_alias=[0, 1, 3, 4])
+            for name, val in zip(outs, res):
+                self.ws[name] = val
 
     def op_StopGradient(self, x, a, outs):
         return x[0]
@@ -300,6 +320,58 @@ def build_case(rng, mods, cfg, *, Cc, Hc, Wc, R, hidden, ncls, soft, train, seed
     return inputs, outputs, model.trace, model.losses
 
 
+def build_optimizer_case(rng, cfg):
+    """add_single_gpu_param_update_ops (modeling/optimizer_wsl.py:75-137) over the head's parameter blobs: which blob gets
+    which weight decay / lr multiplier / gpu_num / iter_size comes from the reference; the update itself is the reference's
+    CPU operator.  Three runs of the update net with fresh gradients (lr 1e-3, 1e-3, 1e-4)."""
+    import detectron.modeling.optimizer_wsl as opt
+    weights = ["fc6_w", "fc7_w", "_[noisy]_fc6_w", "_[noisy]_fc7_w", "fc8c_w", "fc8d_w", "noisy_fc8c_w", "noisy_fc8d_w"]
+    biases = [w[:-2] + "_b" for w in weights]
+    ws = {}
+    for k, name in enumerate(weights + biases):
+        ws[name] = rng.standard_normal(37 + 3 * k).astype(F32)
+    model = EagerModel(21, True, ws)
+    model.weights, model.biases = weights, biases
+    model.param_to_grad = {p: p + "_grad" for p in weights + biases}
+    steps, G = 3, {}
+    for p in weights + biases:
+        G[p] = rng.standard_normal((steps, ws[p].size)).astype(F32)
+        ws[p + "_grad"] = G[p][0].copy()
+    p0 = {p: ws[p].copy() for p in weights + biases}
+    P, M = {p: [] for p in p0}, {p: [] for p in p0}
+    lrs = [1e-3, 1e-3, 1e-4]
+    for s in range(steps):
+        if s == 0:
+            opt.add_single_gpu_param_update_ops(model, 0)        # builds AND (eagerly) runs the update net once, with lr = 0 ...
+            # ... so rewind: the dummy lr of the builder is "set properly at the start of training" (optimizer_wsl.py:81-85)
+            for p in p0:
+                ws[p] = p0[p].copy()
+            model.update_ops_args = [(o[1], o[2], o[3]) for o in model.update_ops]
+            # fresh operator instances (iter_count_ = 0) with exactly the blobs / arguments the builder emitted
+            model.update_ops = [(model._ro.RefOp("ACMWeightDecayMomentumSGDUpdate", **{k: float(v) for k, v in a.items()}), i, o, a)
+                                for (_, i, o, a) in model.update_ops]
+        for p in p0:
+            ws[p + "_grad"] = G[p][s].copy()
+        ws["lr"] = np.array([lrs[s]], F32)
+        model.run_updates()
+        for p in p0:
+            P[p].append(ws[p].copy()); M[p].append(ws[p + "_momentum"].copy())
+    out = {"opt_params": np.array(weights + biases), "opt_lrs": np.array(lrs, F32), "opt_trace": np.array(model.trace),
+           "opt_gpu_num": np.int32(cfg.NUM_GPUS), "opt_iter_size": np.int32(cfg.WSL.ITER_SIZE)}
+    for p in p0:
+        out["opt_p0_" + p], out["opt_G_" + p] = p0[p], G[p]
+        out["opt_P_" + p], out["opt_M_" + p] = np.stack(P[p]), np.stack(M[p])
+    args = {}
+    for ins, outs, a in model.update_ops_args:
+        args[ins[3]] = a                                         # keyed by the parameter blob
+        assert ins == [ins[3] + "_grad", ins[3] + "_momentum", "lr", ins[3], ins[3] + "_acmgrad"], ins
+        assert outs == [ins[0], ins[1], ins[3], ins[4]], outs
+    for p in p0:
+        out["opt_args_" + p] = np.array([args[p]["momentum"], args[p]["iter_size"], args[p]["gpu_num"], args[p]["lr_mult"],
+                                         args[p]["weight_decay"]], np.float64)
+    return out
+
+
 def main():
     maker = _load_roi_data_maker()
     sys.meta_path.insert(0, maker._Absent())
@@ -333,6 +405,7 @@ def main():
         out[pre + "cfg"] = np.array([c["ncls"], c["hidden"], int(c["soft"]), int(c["train"])], np.int32)
         print("case", i, c, "->", len(trace), "operators;", {k: v.shape for k, v in outputs.items() if k in ("rois_pred", "cls_prob", "loss_cls")})
     out["cases"] = np.int32(len(cases))
+    out.update(build_optimizer_case(rng, cfg))
     np.savez_compressed(os.path.join(HERE, "head_graph.npz"), **out)
     print("wrote head_graph.npz (%d arrays)" % len(out))
 

@@ -106,3 +106,47 @@ def test_every_emitted_operator_is_accounted_for(gold):
     assert ce[0].startswith("WeightedCrossEntropyWithLogits(cls_prob,labels_oh,rois_class_weight)->(cross_entropy)")
     assert ce[1].startswith("WeightedCrossEntropyWithLogits(cls_prob_noise,labels_oh,rois_class_weight_noise)->(cross_entropy_noise)")
     assert all("('is_mean', 'True')" in t for t in ce)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# row a10 wiring: add_single_gpu_param_update_ops (modeling/optimizer_wsl.py:75-137) run on the same eager helper
+# ---------------------------------------------------------------------------------------------------------------
+def test_optimizer_builder_arguments_and_trajectories(gold):
+    params = [str(p) for p in gold["opt_params"]]
+    assert int(gold["opt_gpu_num"]) == 4 and int(gold["opt_iter_size"]) == 1          # the shipped flickr_voc config
+    for p in params:
+        mom, isz, gn, lr_mult, wd = gold["opt_args_" + p]
+        bias = p.endswith("_b")
+        # biases: no weight decay, 2x learning rate; weights: SOLVER.WEIGHT_DECAY, 1x (optimizer_wsl.py:106-123)
+        assert (mom, isz, gn, lr_mult, wd) == (0.9, 1.0, 4.0, 2.0 if bias else 1.0, 0.0 if bias else 5e-4), (p, gold["opt_args_" + p])
+        # three runs of the update net == the oracle's restatement with those arguments, bit for bit
+        pv, mv = gold["opt_p0_" + p].copy(), np.zeros_like(gold["opt_p0_" + p])
+        for s, lr in enumerate(gold["opt_lrs"]):
+            mv, pv, _, _ = O.acm_sgd_update(gold["opt_G_" + p][s], mv, lr, pv, np.zeros_like(pv), momentum=0.9, weight_decay=wd,
+                                            lr_mult=lr_mult, gpu_num=int(gn), iter_count=s)
+            assert np.array_equal(pv, gold["opt_P_" + p][s]) and np.array_equal(mv, gold["opt_M_" + p][s]), (p, s)
+    kinds = [str(t).split("(")[0] for t in gold["opt_trace"]]
+    assert kinds.count("ACMWeightDecayMomentumSGDUpdate") == len(params) == 16
+    assert set(kinds) == {"ConstantFill", "ACMWeightDecayMomentumSGDUpdate"}
+
+
+def test_host_update_wiring_matches_the_reference_builder(gold, monkeypatch):
+    """dp.DataParallelHead._update_slice (the product's per-bucket update call): weights and biases get the arguments the
+    reference's builder gives them, gpu_num is the world size."""
+    import torch
+    from nafwebsod_b200 import dp, ops
+    seen = []
+    monkeypatch.setattr(ops, "ACMWeightDecayMomentumSGDUpdate", lambda g, m, lr, p, acc, **kw: seen.append(kw))
+
+    class M:
+        flat_grad = flat_mom = flat_param = flat_lp = torch.zeros(64)
+        lr, iter_count = torch.zeros(1), 5
+    head = dp.DataParallelHead.__new__(dp.DataParallelHead)
+    head.model, head.world, head._hyper = M(), 4, dict(momentum=0.9, weight_decay=5e-4)
+    for tag in ("fc6_panel", "small_weights", "biases"):
+        head._update_slice(0, 64, tag, 0, 64)
+    want_w = gold["opt_args_fc6_w"]
+    want_b = gold["opt_args_fc6_b"]
+    for kw, want in zip(seen, (want_w, want_w, want_b)):
+        assert (kw["momentum"], 1.0, float(kw["gpu_num"]), kw["lr_mult"], kw["weight_decay"]) == tuple(want)
+        assert kw["iter_count"] == 5
