@@ -106,6 +106,9 @@ def test_every_emitted_operator_is_accounted_for(gold):
     assert ce[0].startswith("WeightedCrossEntropyWithLogits(cls_prob,labels_oh,rois_class_weight)->(cross_entropy)")
     assert ce[1].startswith("WeightedCrossEntropyWithLogits(cls_prob_noise,labels_oh,rois_class_weight_noise)->(cross_entropy_noise)")
     assert all("('is_mean', 'True')" in t for t in ce)
+    # both class-weight vectors are constants for the backward pass (webly_heads.py:390-391); roi_feat too (FREEZE_CONV_BODY)
+    for blob in ("rois_class_weight", "rois_class_weight_noise", "roi_feat"):
+        assert "StopGradient(%s)->(%s)" % (blob, blob) in trace
 
 
 # ---------------------------------------------------------------------------------------------------------------
