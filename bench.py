@@ -244,6 +244,92 @@ class ClockSampler:
         return out
 
 
+def assemble_line(*, steps, warmup, world, R, S, bf16, noise, ms_total, ms_e2e, h2d_bytes, d2h_bytes, launches, clocks, kernel_ms,
+                  n_panels, iso, cpu, loss, dp_info):
+    """The ONE JSON line of the GPU arm from the run's raw measurements (pure: no CUDA, no torch -- tests/test_bench_contract.py
+    runs it on the CPU).  ms_total / ms_e2e: device time of the `steps` timed steps of the resident / end-to-end leg (max over
+    ranks); kernel_ms: mean CUDA-event duration per launch of fc6_fwd, fc6_bwd_w (one row panel), roi_pool_f, mil_head inside
+    the timed steps; iso: isolated RoIPoolF timings (rank 0) or {}; dp_info: sync / fc6_panels / p2p_selftest / fused."""
+    peaks = _peaks()
+    ms_step = ms_total / steps
+    value = world * R * steps / (ms_total * 1e-3)
+    e2e_value = world * R * steps / (ms_e2e * 1e-3)
+    es = 2 if bf16 else 4
+    fc6_flops = 2.0 * R * (S * 4096) * (C5 * 49)
+    t_fwd, t_bww, t_pool, t_mil = (kernel_ms.get(k) for k in ("fc6_fwd", "fc6_bwd_w", "roi_pool_f", "mil_head"))
+    t_bww_total = t_bww * n_panels if t_bww else None
+    pool_bytes = R * (C5 * 49 * es + 20) + IMAGES_PER_GPU * C5 * H5 * W5 * es     # no argmax: conv body frozen (StopGradient)
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        # per LAUNCH, like `achieved`: the capture of a row-panel launch when the step runs the captured panel count, the
+        # capture of the whole-matrix launch when it runs unpanelled, else unknown
+        if n_panels == tj.get("fc6_bwd_w_panels"):
+            traffic = tj.get("fc6_bwd_w_panel_dram_bytes_per_launch")
+        elif n_panels == 1:
+            traffic = tj.get("fc6_bwd_w_dram_bytes_per_launch")
+    tensor_peak = peaks["tf_sustained"] * (1.0 if bf16 else 0.5)
+    roofline = {
+        "kernel": "gemm_tcgen05_kernel<256,MN,MN> (fc6 weight gradient, dY^T.X, both stacks in one GEMM)",
+        "bound": "tensor", "achieved": fc6_flops / (t_bww_total * 1e-3) / 1e12 if t_bww_total else None, "peak": tensor_peak,
+        "unit": "TFLOP/s", "traffic": traffic, "launches_per_step": n_panels,
+        # a panel launch reads its columns of dY and all pooled features and writes its rows of dW (fp32)
+        "algorithmic_bytes_per_launch": (R * (S * 4096) * es + R * (C5 * 49) * es * n_panels + (S * 4096) * (C5 * 49) * 4) / n_panels,
+        "peak_source": peaks["source"] + ("; sustained bf16" if bf16 else "; TF32 = bf16/2"),
+    }
+    roofline["frac"] = roofline["achieved"] / tensor_peak if roofline["achieved"] else None
+    kernels = {
+        "fc6_fwd": {"ms": t_fwd, "tflops": fc6_flops / (t_fwd * 1e-3) / 1e12 if t_fwd else None,
+                    "frac_tensor": fc6_flops / (t_fwd * 1e-3) / 1e12 / tensor_peak if t_fwd else None},
+        "fc6_bwd_w": {"ms": t_bww_total, "panels": n_panels, "tflops": roofline["achieved"], "frac_tensor": roofline["frac"]},
+        "roi_pool_f": {"ms": t_pool, "gbs": pool_bytes / (t_pool * 1e-3) / 1e9 if t_pool else None,
+                       "frac_hbm": pool_bytes / (t_pool * 1e-3) / 1e9 / peaks["hbm"] if t_pool else None,
+                       "algorithmic_bytes": pool_bytes},
+        "mil_head": {"ms": t_mil},
+        "step_tensor_frac": _flops_per_roi(noise) * R / (ms_step * 1e-3) / 1e12 / tensor_peak,
+    }
+    if iso:
+        # algorithmic bytes (SURVEY.md 8d): Y + (argmax when the conv body trains) + rois + the map read once
+        b_step = pool_bytes
+        b_f32 = R * (C5 * 49 * 4 * 2 + 20) + IMAGES_PER_GPU * C5 * H5 * W5 * 4
+        kernels["roi_pool_f_isolated"] = {
+            "note": "RoIPoolF alone, back-to-back launches (burst HBM peak applies); in the step it shares HBM with the pipelined SGD",
+            "step_config": {"ms": iso["step_config"], "gbs": b_step / (iso["step_config"] * 1e-3) / 1e9,
+                            "frac_hbm": b_step / (iso["step_config"] * 1e-3) / 1e9 / peaks["hbm"], "algorithmic_bytes": b_step},
+            "fp32_train_argmax": {"ms": iso["fp32_train"], "gbs": b_f32 / (iso["fp32_train"] * 1e-3) / 1e9,
+                                  "frac_hbm": b_f32 / (iso["fp32_train"] * 1e-3) / 1e9 / peaks["hbm"], "algorithmic_bytes": b_f32},
+        }
+    exchange = {"sharded": "NCCL reduce-scatter fp32 grads + sharded SGD + all-gather bf16 operands",
+                "p2p": "peer-mapped (CUDA IPC over NVSwitch) scatter of fp32 grads into the owner's staging + fused reduce/SGD on the owner "
+                       "+ scatter of the bf16 operands back, ordered by flag kernels",
+                "allreduce": "NCCL all-reduce fp32 grads + full SGD"}
+    fc6_update = {"sgd": "EXPERIMENTAL: fused into the fc6 weight-gradient GEMM epilogue (NAWSOD_FUSED_SGD=1)",
+                  "scatter": "on the owner rank of each slice; EXPERIMENTAL: the GEMM epilogue stores its tiles into the owners' "
+                             "peer-mapped staging (NAWSOD_P2P_FUSED_SCATTER=1)"}
+    return {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16" if bf16 else "tf32", "data": "synthetic",
+        "config": {"workload": _workload(noise),
+                   "global_rois_per_step": world * R, "parallelism": "dp%d (images sharded by rank; gradient exchange per step: %s)" % (
+                       world, "none" if world == 1 else exchange.get(dp_info["sync"], dp_info["sync"])),
+                   "l2": "working set per step (weights 0.5 GB bf16 + 0.96 GB fp32 grads + activations) >> 126 MB L2; no flush needed",
+                   "fc6_panels": dp_info["fc6_panels"],
+                   "p2p_selftest": dp_info["p2p_selftest"],
+                   "fc6_update": fc6_update.get(dp_info["fused"], "stand-alone SGD kernel per row panel on a side stream" if world == 1
+                                                else "on the owner rank of each slice")},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),
+                "ms_per_step": ms_e2e / steps},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roofline,
+        "kernels": kernels,
+        "cpu_baseline": cpu,
+        "loss": loss,
+    }
+
+
 def gpu_arm(args):
     import torch
     import torch.distributed as dist
@@ -332,8 +418,6 @@ def gpu_arm(args):
     t_mark1 = time.time()
     launches = _lib.launch_count - launches0
     prof, model.profile = model.profile, None
-    ms_step = ms_total / args.steps
-    value = world * R * args.steps / (ms_total * 1e-3)
 
     # ---- end-to-end leg: host buffers in, loss out, every step ----
     # The public feed path is the device-side blobs queue of nafwebsod_b200/loader.py (the reference's RoIDataLoader /
@@ -367,7 +451,6 @@ def gpu_arm(args):
     clocks = sampler.stop(t_mark0, t_mark3, legs={"value_leg": (t_mark0, t_mark1), "e2e_leg": (t_mark2, t_mark3)}) if rank == 0 else None
     if hasattr(dp.exchange, "check"):
         dp.exchange.check()           # peer exchange: a watchdog time-out in any wait kernel invalidates the run -- fail loudly
-    e2e_value = world * R * args.steps / (ms_e2e * 1e-3)
     d2h_bytes = int(losses[-1].numel() * losses[-1].element_size())
     assert all(bool(torch.isfinite(l).all()) for l in losses), "non-finite loss in the benchmark"
 
@@ -420,60 +503,9 @@ def gpu_arm(args):
         return 0
 
     # ---- roofline of the dominant kernel + per-kernel breakdown from the in-run events ----
-    peaks = _peaks()
     def avg_ms(name):
         ev = prof.get(name, [])
         return sum(a.elapsed_time(b) for a, b in ev) / max(len(ev), 1) if ev else None
-    S = model.S
-    es = 2 if dtype == torch.bfloat16 else 4
-    fc6_flops = 2.0 * R * (S * 4096) * (C5 * 49)
-    t_fwd, t_bww, t_pool, t_mil = avg_ms("fc6_fwd"), avg_ms("fc6_bwd_w"), avg_ms("roi_pool_f"), avg_ms("mil_head")
-    n_panels = max(1, len(prof.get("fc6_bwd_w", [])) // max(args.steps, 1))
-    t_bww_total = t_bww * n_panels if t_bww else None
-    pool_bytes = R * (C5 * 49 * es + 20) + IMAGES_PER_GPU * C5 * H5 * W5 * es     # no argmax: conv body frozen (StopGradient)
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if os.path.exists(tpath):
-        tj = json.load(open(tpath))
-        # per LAUNCH, like `achieved`: the capture of a row-panel launch when the step runs the captured panel count, the
-        # capture of the whole-matrix launch when it runs unpanelled, else unknown
-        if n_panels == tj.get("fc6_bwd_w_panels"):
-            traffic = tj.get("fc6_bwd_w_panel_dram_bytes_per_launch")
-        elif n_panels == 1:
-            traffic = tj.get("fc6_bwd_w_dram_bytes_per_launch")
-    tensor_peak = peaks["tf_sustained"] * (1.0 if dtype == torch.bfloat16 else 0.5)
-    roofline = {
-        "kernel": "gemm_tcgen05_kernel<256,MN,MN> (fc6 weight gradient, dY^T.X, both stacks in one GEMM)",
-        "bound": "tensor", "achieved": fc6_flops / (t_bww_total * 1e-3) / 1e12 if t_bww_total else None, "peak": tensor_peak,
-        "unit": "TFLOP/s", "traffic": traffic, "launches_per_step": n_panels,
-        # a panel launch reads its columns of dY and all pooled features and writes its rows of dW (fp32)
-        "algorithmic_bytes_per_launch": (R * (S * 4096) * es + R * (C5 * 49) * es * n_panels + (S * 4096) * (C5 * 49) * 4) / n_panels,
-        "peak_source": peaks["source"] + ("; sustained bf16" if dtype == torch.bfloat16 else "; TF32 = bf16/2"),
-    }
-    roofline["frac"] = roofline["achieved"] / tensor_peak if roofline["achieved"] else None
-    kernels = {
-        "fc6_fwd": {"ms": t_fwd, "tflops": fc6_flops / (t_fwd * 1e-3) / 1e12 if t_fwd else None,
-                    "frac_tensor": fc6_flops / (t_fwd * 1e-3) / 1e12 / tensor_peak if t_fwd else None},
-        "fc6_bwd_w": {"ms": t_bww_total, "panels": n_panels, "tflops": roofline["achieved"], "frac_tensor": roofline["frac"]},
-        "roi_pool_f": {"ms": t_pool, "gbs": pool_bytes / (t_pool * 1e-3) / 1e9 if t_pool else None,
-                       "frac_hbm": pool_bytes / (t_pool * 1e-3) / 1e9 / peaks["hbm"] if t_pool else None,
-                       "algorithmic_bytes": pool_bytes},
-        "mil_head": {"ms": t_mil},
-        "step_tensor_frac": _flops_per_roi(noise) * R / (ms_step * 1e-3) / 1e12 / tensor_peak,
-    }
-
-    if iso:
-        # algorithmic bytes: Y + (argmax when the conv body trains) + rois + the map read once
-        b_step = pool_bytes
-        b_f32 = R * (C5 * 49 * 4 * 2 + 20) + IMAGES_PER_GPU * C5 * H5 * W5 * 4
-        kernels["roi_pool_f_isolated"] = {
-            "note": "RoIPoolF alone, back-to-back launches (burst HBM peak applies); in the step it shares HBM with the pipelined SGD",
-            "step_config": {"ms": iso["step_config"], "gbs": b_step / (iso["step_config"] * 1e-3) / 1e9,
-                            "frac_hbm": b_step / (iso["step_config"] * 1e-3) / 1e9 / peaks["hbm"], "algorithmic_bytes": b_step},
-            "fp32_train_argmax": {"ms": iso["fp32_train"], "gbs": b_f32 / (iso["fp32_train"] * 1e-3) / 1e9,
-                                  "frac_hbm": b_f32 / (iso["fp32_train"] * 1e-3) / 1e9 / peaks["hbm"], "algorithmic_bytes": b_f32},
-        }
-
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
@@ -482,33 +514,13 @@ def gpu_arm(args):
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": "5 steps of 1 image x %d RoIs (bounded sample of the 2 x 2000 workload), fp32 oracle port: C/OpenMP RoIPoolF + NumPy/BLAS "
                          "FC stack + MIL/loss restatement, %.2f s per step" % (sample, per)}
-
-    line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16" if dtype == torch.bfloat16 else "tf32", "data": "synthetic",
-        "config": {"workload": _workload(noise),
-                   "global_rois_per_step": world * R, "parallelism": "dp%d (images sharded by rank; gradient exchange per step: %s)" % (
-                       world, "none" if world == 1 else {"sharded": "NCCL reduce-scatter fp32 grads + sharded SGD + all-gather bf16 operands",
-                              "p2p": "peer-mapped (CUDA IPC over NVSwitch) scatter of fp32 grads into the owner's staging + fused reduce/SGD on the owner + scatter of the bf16 operands back, ordered by flag kernels",
-                              "allreduce": "NCCL all-reduce fp32 grads + full SGD"}[dp.sync]),
-                   "l2": "working set per step (weights 0.5 GB bf16 + 0.96 GB fp32 grads + activations) >> 126 MB L2; no flush needed",
-                   "fc6_panels": dp.fc6_panels,
-                   "p2p_selftest": dp.p2p_selftest,
-                   "fc6_update": {"sgd": "EXPERIMENTAL: fused into the fc6 weight-gradient GEMM epilogue (NAWSOD_FUSED_SGD=1)",
-                                  "scatter": "on the owner rank of each slice; EXPERIMENTAL: the GEMM epilogue stores its tiles into the "
-                                             "owners' peer-mapped staging (NAWSOD_P2P_FUSED_SCATTER=1)"}.get(
-                       dp._fused_mode(), "stand-alone SGD kernel per row panel on a side stream" if world == 1
-                       else "on the owner rank of each slice")},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": d2h_bytes,
-                "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": int(launches),
-        "clocks": clocks,
-        "roofline": roofline,
-        "kernels": kernels,
-        "cpu_baseline": cpu,
-        "loss": [float(x) for x in losses[-1].flatten().tolist()],
-    }
+    line = assemble_line(
+        steps=args.steps, warmup=args.warmup, world=world, R=R, S=model.S, bf16=dtype == torch.bfloat16, noise=noise,
+        ms_total=ms_total, ms_e2e=ms_e2e, h2d_bytes=h2d_bytes, d2h_bytes=d2h_bytes, launches=launches, clocks=clocks,
+        kernel_ms={k: avg_ms(k) for k in ("fc6_fwd", "fc6_bwd_w", "roi_pool_f", "mil_head")},
+        n_panels=max(1, len(prof.get("fc6_bwd_w", [])) // max(args.steps, 1)), iso=iso, cpu=cpu,
+        loss=[float(x) for x in losses[-1].flatten().tolist()],
+        dp_info={"sync": dp.sync, "fc6_panels": dp.fc6_panels, "p2p_selftest": dp.p2p_selftest, "fused": dp._fused_mode()})
     _emit(line)
     if world > 1:
         dist.destroy_process_group()
