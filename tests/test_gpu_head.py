@@ -264,34 +264,3 @@ def test_pipelined_update_matches_plain_schedule():
     assert np.abs(pa - pb).max() <= 1e-3 * upd and np.abs(ma - mb).max() <= 1e-3 * upd
     # first-step weight updates do not depend on the (atomically summed) bias gradients at all
     assert np.abs(la - lb).max() <= 2e-2 * np.abs(la).max()
-
-
-def test_head_forward_vs_reference_graph_builders(golden_dir):
-    """fp32/TF32 path against tests/golden/head_graph.npz -- the blobs the reference's OWN graph builders produce when they
-    are executed operator by operator (tests/golden/make_golden_head_graph.py; CPU counterpart tests/test_head_graph.py).
-    Forward quantities, tolerance of the fp32/TF32 path (rel <= 1e-3)."""
-    import os
-    from nafwebsod_b200.heads import WeblyHeadModel
-    g = np.load(os.path.join(golden_dir, "head_graph.npz"))
-    pre = "case0_in_"
-    params = {k[len(pre) + 6:]: g[k] for k in g.files if k.startswith(pre + "param_")}
-    masks = {k[len(pre) + 5:].replace("_[noisy]_", "noisy_"): g[k].astype(np.uint8) for k in g.files if k.startswith(pre + "mask_")}
-    ncls, hidden = int(g["case0_cfg"][0]), int(g["case0_cfg"][1])
-    X, rois, obn, L = g[pre + "X"], g[pre + "rois"], g[pre + "obn"], g[pre + "labels"]
-    m = WeblyHeadModel(ncls, X.shape[1], 7, hidden, noise=True, entropy=True, mean_loss=True, dtype=torch.float32)
-    m.load_reference_params(params)
-    m.FeedBlobs(t(X), t(rois), t(obn), t(L), x_layout="NCHW")
-    bl = m.RunTrainStep(dropout_masks={k: t(v) for k, v in masks.items()})
-    torch.cuda.synchronize()
-    tol = TOL[torch.float32]
-    want = lambda k: g["case0_out_" + k]
-    # the head keeps roi_feat as the fc6 GEMM operand, i.e. rounded to the nearest TF32 (2^-11 relative) and pooled-NHWC
-    assert rel_l2(bl["roi_feat"].cpu().numpy().reshape(rois.shape[0], 7, 7, -1).transpose(0, 3, 1, 2), want("roi_feat")) <= tol
-    assert rel_l2(bl["rois_pred"].cpu().numpy(), want("rois_pred")) <= tol
-    assert rel_l2(bl["rois_pred_noise"].cpu().numpy(), want("rois_pred_noise")) <= tol
-    assert rel_l2(bl["cls_prob"][0].cpu().numpy(), want("cls_prob")[0]) <= tol
-    assert rel_l2(bl["cls_prob_noise"][0].cpu().numpy(), want("cls_prob_noise")[0]) <= tol
-    assert rel_l2(bl["class_weight_noise"][0].cpu().numpy(), want("rois_class_weight_noise")[0]) <= 5 * tol
-    assert rel_l2(bl["class_weight"][0].cpu().numpy(), want("rois_class_weight")[0]) <= 5 * tol
-    assert abs(bl["loss_cls"][0].item() - float(want("loss_cls"))) <= tol * abs(float(want("loss_cls")))
-    assert abs(bl["loss_cls_noise"][0].item() - float(want("loss_cls_noise"))) <= tol * abs(float(want("loss_cls_noise")))

@@ -240,28 +240,6 @@ def test_sgd_matches_reference_golden(golden_dir):
                 assert torch.equal(shadow, p.to(torch.bfloat16))
 
 
-@pytest.mark.parametrize("n", [4096, 4099, 1 << 20])
-@pytest.mark.parametrize("shadow", [torch.bfloat16, torch.float32])
-def test_sgd_update_reduce_equals_sum_then_update(n, shadow):
-    """The data-parallel owner's kernel: contributions summed in list (rank) order inside the update == the
-    reference's NCCLAllreduce + ACMWeightDecayMomentumSGDUpdate on that sum (modeling/optimizer_wsl.py:52-72,
-    96-137), bit for bit, operand shadow included; n = 4099 exercises the scalar tail."""
-    ops = _ops()
-    g = torch.Generator(device="cuda").manual_seed(n)
-    pad = lambda k: torch.randn(k + 4, device="cuda", generator=g)[:k]            # 16-byte aligned views of any length
-    grads = [pad(n) for _ in range(3)]
-    lr = torch.tensor([1e-3], device="cuda")
-    kw = dict(momentum=0.9, gpu_num=3, lr_mult=1.0, weight_decay=5e-4)
-    p0, m0 = pad(n).clone(), pad(n).clone() * 0.01
-    for it in (0, 2):
-        pa, ma, sa = p0.clone(), m0.clone(), torch.zeros(n, device="cuda", dtype=shadow)
-        pb, mb, sb = p0.clone(), m0.clone(), torch.zeros(n, device="cuda", dtype=shadow)
-        total = (grads[0] + grads[1]) + grads[2]
-        ops.ACMWeightDecayMomentumSGDUpdate(total, ma, lr, pa, None, iter_count=it, p_shadow=sa, **kw)
-        ops.ACMWeightDecayMomentumSGDUpdateReduce(grads, mb, lr, pb, iter_count=it, p_shadow=sb, **kw)
-        assert torch.equal(pa, pb) and torch.equal(ma, mb)
-        assert torch.equal(sa.float(), sb.float())
-
 
 
 def test_sgd_large_no_acc():

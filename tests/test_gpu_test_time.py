@@ -246,86 +246,3 @@ def test_im_detect_bbox_and_aug_vs_oracle():
         wants.append(_oracle_detect(Xk, boxes, obn, scale, flip, params, ncls))
     avg = test_time.im_detect_bbox_aug(m, passes, dev(boxes), dev(obn), x_layout="NCHW").cpu().numpy()
     assert rel(avg, T.tta_average(wants)) <= 1e-3
-
-
-# ---------------------------------------------------------------------------------------------- N1 + N2 vs the reference's driver
-@pytest.mark.parametrize("i", [0, 1, 2])
-def test_tta_and_nms_vs_reference_driver(golden_dir, i):
-    """tests/golden/test_wsl.npz: the reference's own im_detect_bbox_aug + box_results_with_nms_and_limit, run unmodified
-    with the shipped flickr_voc config around a deterministic pseudo head (tests/golden/make_golden_test_wsl.py; CPU
-    counterpart tests/test_test_wsl_golden.py).  Here the product's device-side wrapper runs around the SAME pseudo head:
-    projection, flip, dedup, gather, inverse scatter, the float32 TTA sum and mean must give the reference's averaged
-    scores bit for bit, and the device NMS + limit the reference's detections (as sets per class: the reference lists
-    a class's detections by descending score, the product in proposal order)."""
-    import importlib.util
-    from nafwebsod_b200 import test_time
-    from oracle import roi_data_oracle as RD
-    g = np.load(os.path.join(golden_dir, "test_wsl.npz"))
-    spec = importlib.util.spec_from_file_location("make_golden_test_wsl", os.path.join(golden_dir, "make_golden_test_wsl.py"))
-    maker = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(maker)
-    K = int(g["num_classes"])
-
-    class PseudoHead:
-        """Stands for WeblyHeadModel: scores depend on the fed RoI rows and obn scores only."""
-        def __init__(self):
-            self.blobs = {}
-
-        def FeedBlobs(self, conv5, rois, obn, labels_oh=None, roi_offsets=None, x_layout="NHWC"):
-            assert roi_offsets is None                         # sync=True: exactly the unique rows are fed
-            self.blobs.update(rois=rois, obn_scores=obn)
-
-        def RunTestNet(self, want_cls_prob=True):
-            s = maker.pseudo_cls_prob(self.blobs["rois"].cpu().numpy(), self.blobs["obn_scores"].cpu().numpy(), K)
-            self.blobs["rois_pred"] = dev(s[:, 1:])
-            return self.blobs["rois_pred"]
-
-    h, w = (int(v) for v in g["case%d_im_shape" % i][:2])
-    boxes, obn = dev(g["case%d_boxes" % i]), dev(g["case%d_obn" % i])
-    model, dedup = PseudoHead(), float(g["dedup_boxes"])
-    s1 = test_time.im_detect_bbox(model, None, RD.im_scale_for(h, w, int(g["test_scale"]), int(g["test_max_size"])), boxes, obn,
-                                  dedup_boxes=dedup)
-    assert model.blobs["rois"].shape[0] == g["case%d_single_fed_rois" % i].shape[0]
-    assert np.array_equal(model.blobs["rois"].cpu().numpy(), g["case%d_single_fed_rois" % i])
-    assert np.array_equal(model.blobs["obn_scores"].cpu().numpy(), g["case%d_single_fed_obn" % i].reshape(-1))
-    assert np.array_equal(s1.cpu().numpy(), g["case%d_single_scores" % i])
-    # the ten passes in the reference's order (core/test_wsl.py:211-256)
-    passes = [(None, RD.im_scale_for(h, w, int(g["test_scale"]), int(g["test_max_size"])), w)]
-    for s in g["aug_scales"]:
-        sc = RD.im_scale_for(h, w, int(s), int(g["aug_max_size"]))
-        passes += [(None, sc, None), (None, sc, w)]
-    passes.append((None, RD.im_scale_for(h, w, int(g["test_scale"]), int(g["test_max_size"])), None))
-    avg = test_time.im_detect_bbox_aug(model, passes, boxes, obn, dedup_boxes=dedup)
-    assert np.array_equal(avg.cpu().numpy(), g["case%d_aug_scores" % i])
-    _, _, cls_boxes = test_time.box_results_with_nms_and_limit(avg, boxes, score_thresh=float(g["score_thresh"]),
-                                                               nms_thresh=float(g["nms"]), detections_per_im=int(g["detections_per_im"]))
-    # Detections.  Proposals that collapse to one feature RoI get IDENTICAL scores, and the order in which the reference
-    # visits tied scores is whatever NumPy's introsort leaves (cython_nms.pyx:45 `scores.argsort()[::-1]`); the device NMS
-    # visits ties higher-row-first.  A tied pair of near-duplicate boxes may therefore keep the other member: per class the
-    # kept SCORES must equal the reference's, and the kept rows must equal the oracle run with the device's tie order.
-    counts = list(g["case%d_det_counts" % i])
-    assert [int(c.shape[0]) for c in cls_boxes] == counts
-    want = np.concatenate([g["case%d_det_boxes" % i], g["case%d_det_scores" % i][:, None]], axis=1)
-
-    def nms_row_desc(dets, thresh):
-        import ctypes
-        if dets.shape[0] == 0:
-            return np.zeros((0,), np.int64)
-        dets = np.ascontiguousarray(dets, dtype=np.float32)
-        n = dets.shape[0]
-        order = np.lexsort((-np.arange(n), -dets[:, 4])).astype(np.int64)
-        keep = np.empty(n, np.uint8)
-        T._load().nawsod_oracle_nms(dets.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), n,
-                                    order.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), ctypes.c_float(thresh),
-                                    keep.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)))
-        return np.where(keep != 0)[0]
-    _, _, ocls, _ = T.box_results_with_nms_and_limit(g["case%d_aug_scores" % i], g["case%d_boxes" % i], K,
-                                                     score_thresh=float(g["score_thresh"]), nms_thresh=float(g["nms"]),
-                                                     detections_per_im=int(g["detections_per_im"]), nms_fn=nms_row_desc)
-    start = 0
-    canon = lambda a: a[np.lexsort(a.T[::-1])]
-    for j in range(K):
-        mine = cls_boxes[j].cpu().numpy()
-        assert np.array_equal(np.sort(mine[:, 4]), np.sort(want[start:start + counts[j], 4])), "class %d scores" % j
-        assert np.array_equal(canon(mine), canon(ocls[j])), "class %d rows" % j
-        start += counts[j]

@@ -4,7 +4,7 @@ add_spatial_entropy_weight, add_cls_pred, add_cross_entropy_loss and RoIFeatureT
 /root/reference and executed operator by operator on an eager NumPy workspace, with the reference's own code for the
 operators that live in its tree.  This pins the WIRING of SURVEY.md section 8 rows a3-a8 (which operator, on which blobs,
 in which order, with which axes / flags) to the reference; the arithmetic of the Caffe2 built-ins stays a float32
-restatement of their documented defaults.  The GPU test of the same vectors is tests/test_gpu_head.py."""
+restatement of their documented defaults.  The GPU test of the same vectors is in tests/test_gpu_zzz_reference_vectors.py."""
 import os
 
 import numpy as np

@@ -4,7 +4,7 @@ box_results_with_nms_and_limit were imported unmodified and run with the shipped
 workspace whose net is a deterministic pseudo head.  Pins rows N1 / N2 of SURVEY.md section 8f -- projection to the input
 scale, the float64 hash dedup (DEDUP_BOXES 0.125) and its inverse map, flipping, the ten passes of the flickr test-time
 augmentation in the reference's order, float32 score averaging, thresholding + NMS + the detections-per-image limit --
-to reference code.  The GPU counterpart is tests/test_gpu_test_time.py::test_tta_and_nms_vs_reference_driver."""
+to reference code.  The GPU counterpart is tests/test_gpu_zzz_reference_vectors.py::test_tta_and_nms_vs_reference_driver."""
 import importlib.util
 import os
 
