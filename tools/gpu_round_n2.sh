@@ -7,7 +7,7 @@ OUT=gpurun_out; mkdir -p $OUT
 T0=$(date +%s); el() { echo "[$(( $(date +%s) - T0 )) s] $*"; }
 nvidia-smi topo -m > $OUT/${TAG}_topo.txt 2>&1
 el "pytest dp"
-timeout 150 python -m pytest tests/test_gpu_dp.py -m gpu -x -q --timeout 140 -p no:cacheprovider > $OUT/${TAG}_pytest_dp.log 2>&1
+timeout 150 python -m pytest tests/test_gpu_zzzz_dp_2gpu.py -m gpu -x -q --timeout 140 -p no:cacheprovider > $OUT/${TAG}_pytest_dp.log 2>&1
 echo "pytest exit $?" | tee -a $OUT/${TAG}_pytest_dp.log; tail -n 3 $OUT/${TAG}_pytest_dp.log
 for sync in auto sharded allreduce; do
   el "bench N=$N sync=$sync"
