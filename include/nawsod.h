@@ -144,6 +144,11 @@ int nawsod_fc_bwd_w_stacks(const void* dY, int64_t lddy, int64_t sdY, const void
                            int64_t lddw, int64_t sdW, float* db, int64_t sdb, int flags,
                            void* stream);
 
+/* FCGradient's db alone: db[s][N] (float) = column sums of dY[s][M,N] -- what nawsod_fc_bwd_w[_stacks] computes when db is
+ * given, as a call of its own so that a caller can take the (HBM-bound) sums off the stream the GEMMs run on. */
+int nawsod_fc_bias_grad(const void* dY, int64_t lddy, int64_t sdY, int S, int M, int N, int ab_dtype,
+                        float* db, int64_t sdb, int flags, void* stream);
+
 /* FCGradient's dW with the op that follows it in the step fused into the GEMM epilogue (gemm_fused.cu; the 822 MB fc6
  * gradient then never makes the round trip through HBM).  EXPERIMENTAL: opt-in on the host side until measured.
  *

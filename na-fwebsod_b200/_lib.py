@@ -35,6 +35,7 @@ PROTOTYPES = {
     "nawsod_fc_bwd_x_stacks": (_i, [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _i, _vp, _i64, _i64, _i, _i, _i, _i, _i,
                                     _vp, _i64, _i64, _i, _i, _vp]),
     "nawsod_fc_bwd_w_stacks": (_i, [_vp, _i64, _i64, _vp, _i64, _i64, _i, _i, _i, _i, _i, _vp, _i64, _i64, _vp, _i64, _i, _vp]),
+    "nawsod_fc_bias_grad": (_i, [_vp, _i64, _i64, _i, _i, _i, _i, _vp, _i64, _i, _vp]),
     "nawsod_fc_bwd_w_sgd": (_i, [_vp, _i64, _vp, _i64, _i, _i, _i, _i, _vp, _i64, _vp, _i, _vp, _vp, _vp, _i, _vp, _f, _f, _f, _i,
                                  _i64, _vp]),
     "nawsod_fc_bwd_w_scatter": (_i, [_vp, _i64, _vp, _i64, _i, _i, _i, _i, _vp, _i, _i, _i64, _vp, _vp]),

@@ -502,6 +502,15 @@ extern "C" int nawsod_fc_bwd_w_stacks(const void* dY, int64_t lddy, int64_t sdY,
   return fc_bias_grad(dY, lddy, sdY, S, M, N, ab_dtype, db, sdb, flags, st);
 }
 
+extern "C" int nawsod_fc_bias_grad(const void* dY, int64_t lddy, int64_t sdY, int S, int M, int N, int ab_dtype, float* db,
+                                   int64_t sdb, int flags, void* stream) {
+  NAWSOD_REQUIRE(S >= 1 && M > 0 && N > 0 && lddy >= N, NAWSOD_ERR_SHAPE, "fc_bias_grad: need S >= 1, M, N > 0 and lddy >= N");
+  NAWSOD_REQUIRE(ab_dtype == NAWSOD_BF16 || ab_dtype == NAWSOD_F32, NAWSOD_ERR_ARG, "fc_bias_grad: bad ab_dtype");
+  NAWSOD_REQUIRE(dY && db, NAWSOD_ERR_ARG, "fc_bias_grad: null pointer");
+  NAWSOD_REQUIRE(!(flags & ~NAWSOD_FC_ACCUMULATE), NAWSOD_ERR_ARG, "fc_bias_grad: only ACCUMULATE is valid");
+  return fc_bias_grad(dY, lddy, sdY, S, M, N, ab_dtype, db, sdb, flags, static_cast<cudaStream_t>(stream));
+}
+
 extern "C" int nawsod_fc_bwd_w(const void* dY, int64_t lddy, const void* A, int64_t lda, int M, int N, int K, int ab_dtype,
                                float* dW, int64_t lddw, float* db, int flags, void* stream) {
   return nawsod_fc_bwd_w_stacks(dY, lddy, 0, A, lda, 0, 1, M, N, K, ab_dtype, dW, lddw, 0, db, 0, flags, stream);

@@ -22,6 +22,8 @@ PyTorch is used for memory, streams and (in dp.py) NCCL plumbing only.
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 
@@ -60,6 +62,7 @@ class WeblyHeadModel:
         self._buf = {}
         self.profile = None        # dict name -> [(start_event, end_event)] when bench.py instruments a run
         self.iter_count = 0
+        self._bias_stream = None
         self._alloc_params()
 
     # ------------------------------------------------------------------ parameters
@@ -327,6 +330,22 @@ class WeblyHeadModel:
             bl["d_conv5"] = ops.RoIPoolFGradient(bl["conv5"], bl["rois"], bl["_argmax_roi_feat"],
                                                  d_feat.view(R, self.roi_size, self.roi_size, Cc),
                                                  boost=bl["obn_scores"], layout="NHWC")
+        # EXPERIMENTAL (NAWSOD_BIAS_SIDE_STREAM=1, off until measured): the bias gradients are HBM-bound column sums of
+        # dY (8 launches, ~2 % of the step between the tensor-bound GEMMs); all their inputs exist once the activation-
+        # gradient chain is enqueued, so they can run on a side stream beside the weight-gradient GEMMs.
+        side_bias = fc6_dw is None and self.flat_grad.is_cuda and os.environ.get("NAWSOD_BIAS_SIDE_STREAM", "0") == "1"
+        if side_bias:
+            if self._bias_stream is None:
+                self._bias_stream = torch.cuda.Stream(device=self.device)
+            ready = torch.cuda.Event()
+            ready.record()
+            self._bias_stream.wait_event(ready)
+            with torch.cuda.stream(self._bias_stream):
+                ops.FCBiasGradient(d6, self.g["b6"])
+                ops.FCBiasGradient(d73, self.g["b7"])
+                ops.FCBiasGradient(dl3, self.g["b8"])
+                bias_done = torch.cuda.Event()
+                bias_done.record()
         rows = self.S * H
         step = _round_up((rows + fc6_panels - 1) // fc6_panels, 256)
         for r0 in range(0, rows, step):
@@ -335,11 +354,14 @@ class WeblyHeadModel:
                 self._timed("fc6_bwd_w", lambda: fc6_dw(r0, r1, d6[:, r0:r1], bl["roi_feat"]))
             else:
                 self._timed("fc6_bwd_w", lambda: ops.FCGradientW(d6[:, r0:r1], bl["roi_feat"], dW=self.g["W6"][r0:r1],
-                                                                 db=self.g["b6"][r0:r1]))
+                                                                 db=None if side_bias else self.g["b6"][r0:r1],
+                                                                 want_db=not side_bias))
             if on_fc6_panel is not None:
                 on_fc6_panel(r0, r1)
-        ops.FCGradientW(dl3, a7, dW=self.g["W8"], db=self.g["b8"])
-        ops.FCGradientW(d73, a6, dW=self.g["W7"], db=self.g["b7"])
+        ops.FCGradientW(dl3, a7, dW=self.g["W8"], db=None if side_bias else self.g["b8"], want_db=not side_bias)
+        ops.FCGradientW(d73, a6, dW=self.g["W7"], db=None if side_bias else self.g["b7"], want_db=not side_bias)
+        if side_bias:
+            torch.cuda.current_stream(self.device).wait_event(bias_done)     # the biases' exchange / update follows
         if on_small_grads is not None:
             on_small_grads()
         return bl

@@ -502,6 +502,18 @@ def FCGradientW(dY, X, *, dW=None, db=None, want_db=True, accumulate=False):
     return dW, db
 
 
+def FCBiasGradient(dY, db, *, accumulate=False):
+    """db of ``FCGradient`` on its own: db [N] (or [S,N] for a stack dY [S,M,N]) = column sums of dY, float32 -- the same
+    kernel ``FCGradientW`` runs for its ``db``, callable on another stream than the GEMMs."""
+    S, M, N, lddy, sdY = _mat3(dY, "dY")
+    if db.dtype != torch.float32 or not db.is_cuda or db.shape[-1] != N or db.stride(-1) != 1 or db.numel() != S * N:
+        raise RuntimeError("FCBiasGradient: db must be float32 with %d elements per stack" % N)
+    sdb = db.stride(0) if db.dim() == 2 and S > 1 else 0
+    _lib.call("nawsod_fc_bias_grad", _ptr(dY), lddy, sdY, S, M, N, _ab(dY.dtype), _ptr(db), sdb,
+              _lib.FC_ACCUMULATE if accumulate else 0, _stream(), extra_kernels=S)
+    return db
+
+
 def _dw_operands(who, dY, X):
     M, N, lddy = _mat(dY, "dY")
     M2, K, lda = _mat(X, "X")

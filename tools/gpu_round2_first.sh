@@ -23,6 +23,10 @@ el "bench fused SGD"
 NAWSOD_FUSED_SGD=1 timeout 200 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-isolated \
     > $OUT/${TAG}_bench_n1_fused_sgd.json 2> $OUT/${TAG}_bench_n1_fused_sgd.err; echo "exit $?"
 cut -c1-400 $OUT/${TAG}_bench_n1_fused_sgd.json; tail -n 3 $OUT/${TAG}_bench_n1_fused_sgd.err
+el "bench bias gradients on a side stream"
+NAWSOD_BIAS_SIDE_STREAM=1 timeout 200 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-isolated \
+    > $OUT/${TAG}_bench_n1_bias_side.json 2> $OUT/${TAG}_bench_n1_bias_side.err; echo "exit $?"
+cut -c1-200 $OUT/${TAG}_bench_n1_bias_side.json
 for c in 148 296 592; do
   el "bench sgd_max_ctas=$c"
   NAWSOD_TUNING=sgd_max_ctas=$c timeout 200 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-isolated \
