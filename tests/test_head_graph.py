@@ -153,3 +153,19 @@ def test_host_update_wiring_matches_the_reference_builder(gold, monkeypatch):
     for kw, want in zip(seen, (want_w, want_w, want_b)):
         assert (kw["momentum"], 1.0, float(kw["gpu_num"]), kw["lr_mult"], kw["weight_decay"]) == tuple(want)
         assert kw["iter_count"] == 5
+
+
+def test_exported_parameter_names_are_the_builders_blob_names(gold):
+    """Checkpoint contract (detectron/utils/net_wsl.py:140-181 saves every parameter under its blob name): the names the
+    host model exports are exactly the weight / bias blobs the reference's builders hand to their FC operators."""
+    import torch
+    from nafwebsod_b200.heads import WeblyHeadModel
+    fc = [str(t) for t in gold["case0_trace"] if str(t).startswith("FC(")]
+    blobs = set()
+    for t in fc:
+        _, w, b = t[3:t.index(")")].split(",")
+        blobs |= {w, b}
+    m = WeblyHeadModel(21, 16, 7, 64, noise=True, dtype=torch.float32, device="cpu")
+    exported = m.export_reference_params()
+    assert set(exported) == blobs, set(exported) ^ blobs
+    assert tuple(exported["_[noisy]_fc6_w"].shape) == (64, 16 * 49) and tuple(exported["noisy_fc8d_b"].shape) == (20,)
