@@ -42,6 +42,44 @@ def _load_roi_data_maker():
     return mod
 
 
+def head_case_params(ncls, Cc, hidden, seed):
+    """The case's parameters, regenerated from its seed instead of being stored (they dominate the file size): the oracle's
+    synthetic initialisation (gauss 0.01 / Xavier, zero biases), the narrow layers scaled so that activations keep the
+    statistics of the 25088- and 4096-wide originals.  Keys use the oracle's `noisy_` prefix."""
+    from oracle import nawsod_oracle as O
+    params = O.synth_params(ncls - 1, Cc * 49, hidden, noise=True, seed=seed + 2)
+    for k in list(params):
+        if k.endswith("fc6_w"):
+            params[k] = (params[k] * F32(np.sqrt(25088.0 / (Cc * 49)))).astype(F32)
+        if k.endswith("fc7_w"):
+            params[k] = (params[k] * F32(np.sqrt(4096.0 / hidden))).astype(F32)
+    return params
+
+
+def param_checksums(params):
+    return np.array([np.asarray(params[k], np.float64).sum() for k in sorted(params)], np.float64)
+
+
+def load_case(gold, i):
+    """(X, rois, obn, labels, params, masks-or-None, cfg dict) of golden case i -- what both the CPU and the GPU test feed.
+    Needs the oracle package only (not /root/reference)."""
+    ncls, hidden, soft, train, Cc, seed = (int(v) for v in gold["case%d_cfg" % i])
+    pre = "case%d_in_" % i
+    params = head_case_params(ncls, Cc, hidden, seed)
+    if not np.array_equal(param_checksums(params), gold["case%d_param_checksums" % i]):
+        raise RuntimeError("the regenerated parameters of golden case %d differ from the ones the vectors were made with" % i)
+    R = gold[pre + "rois"].shape[0]
+    masks = None
+    if train:
+        masks = {}
+        for k in gold.files:
+            if k.startswith(pre + "maskbits_"):
+                name = k[len(pre) + 9:].replace("_[noisy]_", "noisy_")
+                masks[name] = np.unpackbits(gold[k])[:R * hidden].reshape(R, hidden).astype(F32)
+    cfg = dict(ncls=ncls, hidden=hidden, soft=bool(soft), train=bool(train), Cc=Cc, seed=seed)
+    return gold[pre + "X"], gold[pre + "rois"], gold[pre + "obn"], gold[pre + "labels"], params, masks, cfg
+
+
 class EagerNet:
     """`model.net` / `model.param_init_net`: attribute access yields an operator that executes immediately."""
 
@@ -279,12 +317,7 @@ def build_case(rng, mods, cfg, *, Cc, Hc, Wc, R, hidden, ncls, soft, train, seed
         a, b = rng.choice(C, 2, replace=False)
         labels[:] = 0
         labels[0, a], labels[0, b] = lam, F32(1) - lam
-    params = O.synth_params(C, Cc * 49, hidden, noise=True, seed=seed + 2)
-    for k in list(params):                                      # scale the narrow layers so activations stay O(1)
-        if k.endswith("fc6_w"):
-            params[k] = (params[k] * F32(np.sqrt(25088.0 / (Cc * 49)))).astype(F32)
-        if k.endswith("fc7_w"):
-            params[k] = (params[k] * F32(np.sqrt(4096.0 / hidden))).astype(F32)
+    params = head_case_params(ncls, Cc, hidden, seed)
     ws = {"conv5_3": X, "rois": rois, "obn_scores": obn, "labels_oh": labels}
     for k, v in params.items():                                 # the oracle's 'noisy_' prefix -> the reference's blob names
         name = k
@@ -310,8 +343,8 @@ def build_case(rng, mods, cfg, *, Cc, Hc, Wc, R, hidden, ncls, soft, train, seed
     if train:
         webly.add_webly_losses(model)
     inputs = dict(X=X, rois=rois, obn=obn, labels=labels)
-    inputs.update({"param_" + k: v for k, v in params.items()})
-    inputs.update({"mask_" + k: v for k, v in masks.items()})
+    inputs.update({"maskbits_" + k: np.packbits(v.astype(np.uint8)) for k, v in masks.items()})
+    inputs["__param_checksums"] = param_checksums(params)
     keep = ["roi_feat", "fc6", "fc7", "_[noisy]_fc6", "_[noisy]_fc7", "fc8c", "fc8d", "noisy_fc8c", "noisy_fc8d", "rois_pred",
             "rois_pred_noise", "cls_prob", "cls_prob_noise", "rois_J", "rois_pred_E", "rois_pred_D", "rois_pred_hatE_sum",
             "rois_pred_hatE_sum_norm", "rois_class_weight", "rois_class_weight_noise", "cross_entropy", "cross_entropy_noise",
@@ -390,19 +423,20 @@ def main():
     mods = (webly, wsl_heads, reference_roi_feature_transform())
     rng = np.random.default_rng(2024)
     out = {}
-    cases = [dict(Cc=16, Hc=12, Wc=16, R=96, hidden=64, ncls=21, soft=False, train=True, seed=11),
+    cases = [dict(Cc=16, Hc=12, Wc=16, R=96, hidden=256, ncls=21, soft=False, train=True, seed=11),
              dict(Cc=8, Hc=10, Wc=14, R=130, hidden=32, ncls=81, soft=True, train=True, seed=21),
              dict(Cc=16, Hc=12, Wc=16, R=64, hidden=64, ncls=21, soft=False, train=False, seed=31)]
     for i, c in enumerate(cases):
         inputs, outputs, trace, losses = build_case(rng, mods, cfg, **c)
         pre = "case%d_" % i
+        out[pre + "param_checksums"] = inputs.pop("__param_checksums")
         for k, v in inputs.items():
             out[pre + "in_" + k] = v
         for k, v in outputs.items():
             out[pre + "out_" + k] = v
         out[pre + "trace"] = np.array(trace)
         out[pre + "losses"] = np.array(losses)
-        out[pre + "cfg"] = np.array([c["ncls"], c["hidden"], int(c["soft"]), int(c["train"])], np.int32)
+        out[pre + "cfg"] = np.array([c["ncls"], c["hidden"], int(c["soft"]), int(c["train"]), c["Cc"], c["seed"]], np.int32)
         print("case", i, c, "->", len(trace), "operators;", {k: v.shape for k, v in outputs.items() if k in ("rois_pred", "cls_prob", "loss_cls")})
     out["cases"] = np.int32(len(cases))
     out.update(build_optimizer_case(rng, cfg))

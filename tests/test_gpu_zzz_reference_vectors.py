@@ -58,14 +58,15 @@ def test_head_forward_vs_reference_graph_builders(golden_dir):
     """fp32/TF32 path against tests/golden/head_graph.npz -- the blobs the reference's OWN graph builders produce when they
     are executed operator by operator (tests/golden/make_golden_head_graph.py; CPU counterpart tests/test_head_graph.py).
     Forward quantities, tolerance of the fp32/TF32 path (rel <= 1e-3)."""
-    import os
+    import importlib.util
     from nafwebsod_b200.heads import WeblyHeadModel
     g = np.load(os.path.join(golden_dir, "head_graph.npz"))
-    pre = "case0_in_"
-    params = {k[len(pre) + 6:]: g[k] for k in g.files if k.startswith(pre + "param_")}
-    masks = {k[len(pre) + 5:].replace("_[noisy]_", "noisy_"): g[k].astype(np.uint8) for k in g.files if k.startswith(pre + "mask_")}
-    ncls, hidden = int(g["case0_cfg"][0]), int(g["case0_cfg"][1])
-    X, rois, obn, L = g[pre + "X"], g[pre + "rois"], g[pre + "obn"], g[pre + "labels"]
+    spec = importlib.util.spec_from_file_location("make_golden_head_graph", os.path.join(golden_dir, "make_golden_head_graph.py"))
+    maker = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(maker)
+    X, rois, obn, L, params, masks, cfg = maker.load_case(g, 0)
+    masks = {k: v.astype(np.uint8) for k, v in masks.items()}
+    ncls, hidden = cfg["ncls"], cfg["hidden"]
     m = WeblyHeadModel(ncls, X.shape[1], 7, hidden, noise=True, entropy=True, mean_loss=True, dtype=torch.float32)
     m.load_reference_params(params)
     m.FeedBlobs(t(X), t(rois), t(obn), t(L), x_layout="NCHW")

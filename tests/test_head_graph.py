@@ -18,12 +18,20 @@ def gold(golden_dir):
     return np.load(os.path.join(golden_dir, "head_graph.npz"))
 
 
+def _maker():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden_head_graph", os.path.join(os.path.dirname(os.path.abspath(__file__)),
+                                                                                       "golden", "make_golden_head_graph.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)                 # NumPy + the oracle package only; /root/reference is touched by its main() alone
+    return mod
+
+
 def case_inputs(gold, i):
-    pre = "case%d_in_" % i
-    params = {k[len(pre) + 6:]: gold[k] for k in gold.files if k.startswith(pre + "param_")}
-    masks = {k[len(pre) + 5:].replace("_[noisy]_", "noisy_"): gold[k] for k in gold.files if k.startswith(pre + "mask_")}
-    ncls, hidden, soft, train = (int(v) for v in gold["case%d_cfg" % i])
-    return gold[pre + "X"], gold[pre + "rois"], gold[pre + "obn"], gold[pre + "labels"], params, (masks or None), train
+    """Inputs of golden case i: the stored blobs, the bit-packed dropout masks, the parameters regenerated from the case's
+    seed (checksums stored in the file guard the regeneration)."""
+    X, rois, obn, L, params, masks, cfg = _maker().load_case(gold, i)
+    return X, rois, obn, L, params, masks, cfg["train"]
 
 
 def out(gold, i, name):
