@@ -541,7 +541,10 @@ __device__ __forceinline__ void rows2_bins(const Rows2Roi& g, TOut* yout, int32_
   }
 }
 
-template <typename TIn, typename TOut, bool kSmem, bool kArgmax>
+// kSkipIdle (experimental, tuning knob pool_skip_idle, off by default): RoIs arrive grouped by image, so of the N CTAs that
+// share a (slab, chunk) usually one finds work; with kSkipIdle the others return BEFORE staging 120 KB of map (at N = 2 a
+// third of the launch's CTA time).  A compile-time switch, so the default instantiation is the verified kernel unchanged.
+template <typename TIn, typename TOut, bool kSmem, bool kArgmax, bool kSkipIdle = false>
 __global__ void __launch_bounds__(1024, 1) roi_pool_fwd_rows2_kernel(const PoolParams p) {
   constexpr int VEC = Vec<TIn>::N;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -552,6 +555,11 @@ __global__ void __launch_bounds__(1024, 1) roi_pool_fwd_rows2_kernel(const PoolP
   const int r0 = chunk * p.rois_per_chunk;
   const int r1 = min(p.R, r0 + p.rois_per_chunk);
   if (threadIdx.x == 0) next_roi = r0;
+  if (kSkipIdle) {
+    int mine = 0;
+    for (int r = r0 + threadIdx.x; r < r1; r += blockDim.x) mine |= (static_cast<int>(__ldg(p.rois + (size_t)r * 5)) == n) ? 1 : 0;
+    if (!__syncthreads_or(mine)) return;
+  }
 
   Rows2Roi g;
   const unsigned char* src;
@@ -763,6 +771,13 @@ int launch_pool_fwd2(const PoolParams& p, size_t smem_bytes, dim3 grid, int thre
   // bin-row kernel: one warp holds a whole row of bins (h-bounds on lanes 0..7, w-bounds on lanes 8..31)
   const int slots = 32 / (p.SC / Vec<TIn>::N);
   if (p.PH <= 8 && p.PW <= 8 && slots == 8 && get_tuning("pool_generic", 0) == 0 && get_tuning("pool_rows2", kPoolRows2Default) != 0) {
+    if (kSmem && get_tuning("pool_skip_idle", 0) != 0) {
+      auto k = roi_pool_fwd_rows2_kernel<TIn, TOut, kSmem, kArgmax, true>;
+      NAWSOD_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+      k<<<grid, threads, smem_bytes, st>>>(p);
+      NAWSOD_LAUNCH_OK();
+      return NAWSOD_OK;
+    }
     auto k = roi_pool_fwd_rows2_kernel<TIn, TOut, kSmem, kArgmax>;
     if (kSmem) NAWSOD_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
     k<<<grid, threads, smem_bytes, st>>>(p);

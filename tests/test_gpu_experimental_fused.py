@@ -186,3 +186,30 @@ def test_bias_gradients_on_a_side_stream(monkeypatch):
     assert torch.equal(a[:nw], b[:nw])
     scale = a[nw:].abs().max().item()
     assert scale > 0 and (a[nw:] - b[nw:]).abs().max().item() <= 1e-5 * scale
+
+
+@pytest.mark.parametrize("argmax", [False, True])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_pool_skip_idle_ctas_is_bit_identical(dtype, argmax):
+    """pool_skip_idle = 1: CTAs whose chunk holds no RoI of their image return before staging the map.  Two images, RoIs
+    grouped by image (the loader's order) and, as a torture case, interleaved: values and argmax equal the default kernel."""
+    import nafwebsod_b200 as pkg
+    from oracle import nawsod_oracle as O            # inputs only
+    ops = _ops()
+    X = torch.from_numpy(O.synth_conv5(2, 512, 38, 50, seed=0)).cuda()
+    Xcl = ops.to_channels_last(X, dtype)
+    grouped = np.concatenate([O.synth_rois(1000, 608, 800, b, seed=1 + b) for b in range(2)])
+    inter = grouped[np.random.default_rng(3).permutation(2000)]
+    obn = torch.from_numpy((np.random.default_rng(9).random(2000) + 1).astype(np.float32)).cuda()
+    for rois in (grouped, inter):
+        r = torch.from_numpy(np.ascontiguousarray(rois)).cuda()
+        kw = dict(spatial_scale=1 / 16, is_test=not argmax, boost=obn, x_layout="NHWC", y_layout="NHWC", out_dtype=dtype)
+        Y0, A0 = ops.RoIPoolF(Xcl, r, **kw)
+        pkg.set_tuning("pool_skip_idle", 1)
+        try:
+            Y1, A1 = ops.RoIPoolF(Xcl, r, **kw)
+        finally:
+            pkg.set_tuning("pool_skip_idle", 0)
+        assert torch.equal(Y0.view(torch.int16 if dtype == torch.bfloat16 else torch.int32),
+                           Y1.view(torch.int16 if dtype == torch.bfloat16 else torch.int32))
+        assert (A0 is None and A1 is None) or torch.equal(A0, A1)
