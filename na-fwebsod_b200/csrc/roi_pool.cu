@@ -544,7 +544,10 @@ __device__ __forceinline__ void rows2_bins(const Rows2Roi& g, TOut* yout, int32_
 // kSkipIdle (experimental, tuning knob pool_skip_idle, off by default): RoIs arrive grouped by image, so of the N CTAs that
 // share a (slab, chunk) usually one finds work; with kSkipIdle the others return BEFORE staging 120 KB of map (at N = 2 a
 // third of the launch's CTA time).  A compile-time switch, so the default instantiation is the verified kernel unchanged.
-template <typename TIn, typename TOut, bool kSmem, bool kArgmax, bool kSkipIdle = false>
+// kPrefetchRoi (experimental, knob pool_prefetch_roi): the warp claims and loads the NEXT RoI's coordinates before it starts
+// on the current one, so the global-load latency of the RoI fetch (6 % of the stall samples, on the two SHFLs that broadcast
+// a freshly loaded RoI) is hidden behind a whole RoI of work.
+template <typename TIn, typename TOut, bool kSmem, bool kArgmax, bool kSkipIdle = false, bool kPrefetchRoi = false>
 __global__ void __launch_bounds__(1024, 1) roi_pool_fwd_rows2_kernel(const PoolParams p) {
   constexpr int VEC = Vec<TIn>::N;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -593,13 +596,31 @@ __global__ void __launch_bounds__(1024, 1) roi_pool_fwd_rows2_kernel(const PoolP
   const float fdiv = static_cast<float>(is_h ? PH : PW);
   const int lim = is_h ? H : W;
 
+  int r_next = 0;
+  float coord_next = 0.f;
+  if (kPrefetchRoi) {
+    if (lane == 0) r_next = atomicAdd(&next_roi, 1);
+    r_next = __shfl_sync(0xffffffffu, r_next, 0);
+    if (r_next < r1) coord_next = __ldg(p.rois + (size_t)r_next * 5 + min(lane, 4));
+  }
   while (true) {
     int r = 0;
-    if (lane == 0) r = atomicAdd(&next_roi, 1);
-    r = __shfl_sync(0xffffffffu, r, 0);
-    if (r >= r1) break;
+    float coord_pf = 0.f;
+    if (kPrefetchRoi) {
+      r = r_next;
+      coord_pf = coord_next;
+      if (r >= r1) break;
+      r_next = 0;
+      if (lane == 0) r_next = atomicAdd(&next_roi, 1);
+      r_next = __shfl_sync(0xffffffffu, r_next, 0);
+      if (r_next < r1) coord_next = __ldg(p.rois + (size_t)r_next * 5 + min(lane, 4));
+    } else {
+      if (lane == 0) r = atomicAdd(&next_roi, 1);
+      r = __shfl_sync(0xffffffffu, r, 0);
+      if (r >= r1) break;
+    }
     // lane l (1..4) owns coordinate l of the RoI; detectron/ops/roi_loop_pool_op.cu:42-45
-    const float coord = __ldg(p.rois + (size_t)r * 5 + min(lane, 4));
+    const float coord = kPrefetchRoi ? coord_pf : __ldg(p.rois + (size_t)r * 5 + min(lane, 4));
     if (static_cast<int>(__shfl_sync(0xffffffffu, coord, 0)) != n) continue;
     const int rounded = static_cast<int>(roundf(coord * p.scale));
     const int roi_start_w = __shfl_sync(0xffffffffu, rounded, 1);
@@ -771,12 +792,17 @@ int launch_pool_fwd2(const PoolParams& p, size_t smem_bytes, dim3 grid, int thre
   // bin-row kernel: one warp holds a whole row of bins (h-bounds on lanes 0..7, w-bounds on lanes 8..31)
   const int slots = 32 / (p.SC / Vec<TIn>::N);
   if (p.PH <= 8 && p.PW <= 8 && slots == 8 && get_tuning("pool_generic", 0) == 0 && get_tuning("pool_rows2", kPoolRows2Default) != 0) {
-    if (kSmem && get_tuning("pool_skip_idle", 0) != 0) {
-      auto k = roi_pool_fwd_rows2_kernel<TIn, TOut, kSmem, kArgmax, true>;
-      NAWSOD_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-      k<<<grid, threads, smem_bytes, st>>>(p);
-      NAWSOD_LAUNCH_OK();
-      return NAWSOD_OK;
+    if constexpr (kSmem) {                           // experimental variants (staged maps only)
+      const bool skip_idle = get_tuning("pool_skip_idle", 0) != 0, prefetch = get_tuning("pool_prefetch_roi", 0) != 0;
+      if (skip_idle || prefetch) {
+        auto k = (skip_idle && prefetch) ? roi_pool_fwd_rows2_kernel<TIn, TOut, true, kArgmax, true, true>
+                 : skip_idle             ? roi_pool_fwd_rows2_kernel<TIn, TOut, true, kArgmax, true, false>
+                                         : roi_pool_fwd_rows2_kernel<TIn, TOut, true, kArgmax, false, true>;
+        NAWSOD_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+        k<<<grid, threads, smem_bytes, st>>>(p);
+        NAWSOD_LAUNCH_OK();
+        return NAWSOD_OK;
+      }
     }
     auto k = roi_pool_fwd_rows2_kernel<TIn, TOut, kSmem, kArgmax>;
     if (kSmem) NAWSOD_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));

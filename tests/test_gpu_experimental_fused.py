@@ -188,11 +188,13 @@ def test_bias_gradients_on_a_side_stream(monkeypatch):
     assert scale > 0 and (a[nw:] - b[nw:]).abs().max().item() <= 1e-5 * scale
 
 
+@pytest.mark.parametrize("knobs", [{"pool_skip_idle": 1}, {"pool_prefetch_roi": 1}, {"pool_skip_idle": 1, "pool_prefetch_roi": 1}])
 @pytest.mark.parametrize("argmax", [False, True])
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
-def test_pool_skip_idle_ctas_is_bit_identical(dtype, argmax):
-    """pool_skip_idle = 1: CTAs whose chunk holds no RoI of their image return before staging the map.  Two images, RoIs
-    grouped by image (the loader's order) and, as a torture case, interleaved: values and argmax equal the default kernel."""
+def test_pool_experimental_variants_are_bit_identical(dtype, argmax, knobs):
+    """pool_skip_idle = 1: CTAs whose chunk holds no RoI of their image return before staging the map; pool_prefetch_roi = 1:
+    a warp claims and loads its next RoI before working on the current one.  Two images, RoIs grouped by image (the
+    loader's order) and, as a torture case, interleaved: values and argmax equal the default kernel."""
     import nafwebsod_b200 as pkg
     from oracle import nawsod_oracle as O            # inputs only
     ops = _ops()
@@ -205,11 +207,13 @@ def test_pool_skip_idle_ctas_is_bit_identical(dtype, argmax):
         r = torch.from_numpy(np.ascontiguousarray(rois)).cuda()
         kw = dict(spatial_scale=1 / 16, is_test=not argmax, boost=obn, x_layout="NHWC", y_layout="NHWC", out_dtype=dtype)
         Y0, A0 = ops.RoIPoolF(Xcl, r, **kw)
-        pkg.set_tuning("pool_skip_idle", 1)
+        for k, v in knobs.items():
+            pkg.set_tuning(k, v)
         try:
             Y1, A1 = ops.RoIPoolF(Xcl, r, **kw)
         finally:
-            pkg.set_tuning("pool_skip_idle", 0)
+            for k in knobs:
+                pkg.set_tuning(k, 0)
         assert torch.equal(Y0.view(torch.int16 if dtype == torch.bfloat16 else torch.int32),
                            Y1.view(torch.int16 if dtype == torch.bfloat16 else torch.int32))
         assert (A0 is None and A1 is None) or torch.equal(A0, A1)
