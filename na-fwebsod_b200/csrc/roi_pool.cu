@@ -541,13 +541,50 @@ __device__ __forceinline__ void rows2_bins(const Rows2Roi& g, TOut* yout, int32_
   }
 }
 
+// Experimental (knob pool_lean): rows2_bins<kEmpty = false> for PH == 7 with the seven bin rows unrolled.  The row bounds
+// are fetched with seven SHFLs up front (in the rolled loop every bin starts with a SHFL whose result the very next ISETP
+// needs: 17 % of the stall samples of the r1j capture), the share bit is a constant shift, and the output pointers are
+// compile-time multiples of the bin stride.  Same scan order and arithmetic as rows2_bins.
+template <typename TIn, typename TOut, bool kArgmax, int NC>
+__device__ __forceinline__ void rows3_bins(const Rows2Roi& g, TOut* yout, int32_t* aout) {
+  constexpr int VEC = Vec<TIn>::N;
+  using Scan = typename std::conditional<sizeof(TIn) == 4, ScanF32<kArgmax>, ScanBF16<kArgmax>>::type;
+  int hend[7];
+#pragma unroll
+  for (int ph = 0; ph < 7; ++ph) hend[ph] = __shfl_sync(0xffffffffu, g.bend, ph);
+  int next_h = __shfl_sync(0xffffffffu, g.bstart, 0);      // map row `rowp` points at; `cached` = row next_h - 1
+  const unsigned char* rowp = g.col_src + (size_t)next_h * g.row_bytes;
+  int idx0 = next_h * g.W + g.wstart;
+  Scan cached;
+  cached.init(false);
+#pragma unroll
+  for (int ph = 0; ph < 7; ++ph) {
+    Scan sc;
+    sc.select((g.share_mask >> ph) & 1u, cached);
+#pragma unroll 1
+    for (; next_h < hend[ph]; ++next_h, rowp += g.row_bytes, idx0 += g.W) {
+      cached.init(false);
+      rows2_scan_row<Scan, NC>(cached, rowp, idx0, g.o1, g.o2, g.o3, g.ncmax, g.last, g.cell_bytes);
+      sc.merge(cached);
+    }
+    float maxv[VEC];
+    int maxi[VEC];
+    sc.result(false, maxv, maxi);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) maxv[k] = __fmul_rn(maxv[k], g.s);
+    store_vals<VEC>(yout + (size_t)ph * g.bin_stride, maxv);
+    if (kArgmax) store_idx<VEC>(aout + (size_t)ph * g.bin_stride, maxi);
+  }
+}
+
 // kSkipIdle (experimental, tuning knob pool_skip_idle, off by default): RoIs arrive grouped by image, so of the N CTAs that
 // share a (slab, chunk) usually one finds work; with kSkipIdle the others return BEFORE staging 120 KB of map (at N = 2 a
 // third of the launch's CTA time).  A compile-time switch, so the default instantiation is the verified kernel unchanged.
 // kPrefetchRoi (experimental, knob pool_prefetch_roi): the warp claims and loads the NEXT RoI's coordinates before it starts
 // on the current one, so the global-load latency of the RoI fetch (6 % of the stall samples, on the two SHFLs that broadcast
 // a freshly loaded RoI) is hidden behind a whole RoI of work.
-template <typename TIn, typename TOut, bool kSmem, bool kArgmax, bool kSkipIdle = false, bool kPrefetchRoi = false>
+template <typename TIn, typename TOut, bool kSmem, bool kArgmax, bool kSkipIdle = false, bool kPrefetchRoi = false,
+          bool kUnrollBins = false>
 __global__ void __launch_bounds__(1024, 1) roi_pool_fwd_rows2_kernel(const PoolParams p) {
   constexpr int VEC = Vec<TIn>::N;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -656,6 +693,7 @@ __global__ void __launch_bounds__(1024, 1) roi_pool_fwd_rows2_kernel(const PoolP
 #define NAWSOD_ROWS2(NC_)                                                        \
   do {                                                                           \
     if (any_empty) rows2_bins<TIn, TOut, kArgmax, NC_, true>(g, yout, aout);     \
+    else if (kUnrollBins && PH == 7) rows3_bins<TIn, TOut, kArgmax, NC_>(g, yout, aout); \
     else rows2_bins<TIn, TOut, kArgmax, NC_, false>(g, yout, aout);              \
   } while (0)
     switch (g.ncmax) {                             // warp-uniform
@@ -793,9 +831,11 @@ int launch_pool_fwd2(const PoolParams& p, size_t smem_bytes, dim3 grid, int thre
   const int slots = 32 / (p.SC / Vec<TIn>::N);
   if (p.PH <= 8 && p.PW <= 8 && slots == 8 && get_tuning("pool_generic", 0) == 0 && get_tuning("pool_rows2", kPoolRows2Default) != 0) {
     if constexpr (kSmem) {                           // experimental variants (staged maps only)
-      const bool skip_idle = get_tuning("pool_skip_idle", 0) != 0, prefetch = get_tuning("pool_prefetch_roi", 0) != 0;
+      const bool lean = get_tuning("pool_lean", 0) != 0;    // skip idle CTAs + RoI prefetch + unrolled bin rows
+      const bool skip_idle = lean || get_tuning("pool_skip_idle", 0) != 0, prefetch = lean || get_tuning("pool_prefetch_roi", 0) != 0;
       if (skip_idle || prefetch) {
-        auto k = (skip_idle && prefetch) ? roi_pool_fwd_rows2_kernel<TIn, TOut, true, kArgmax, true, true>
+        auto k = lean                    ? roi_pool_fwd_rows2_kernel<TIn, TOut, true, kArgmax, true, true, true>
+                 : (skip_idle && prefetch) ? roi_pool_fwd_rows2_kernel<TIn, TOut, true, kArgmax, true, true>
                  : skip_idle             ? roi_pool_fwd_rows2_kernel<TIn, TOut, true, kArgmax, true, false>
                                          : roi_pool_fwd_rows2_kernel<TIn, TOut, true, kArgmax, false, true>;
         NAWSOD_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));

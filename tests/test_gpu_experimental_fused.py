@@ -188,13 +188,16 @@ def test_bias_gradients_on_a_side_stream(monkeypatch):
     assert scale > 0 and (a[nw:] - b[nw:]).abs().max().item() <= 1e-5 * scale
 
 
-@pytest.mark.parametrize("knobs", [{"pool_skip_idle": 1}, {"pool_prefetch_roi": 1}, {"pool_skip_idle": 1, "pool_prefetch_roi": 1}])
+@pytest.mark.parametrize("knobs", [{"pool_skip_idle": 1}, {"pool_prefetch_roi": 1}, {"pool_skip_idle": 1, "pool_prefetch_roi": 1},
+                                   {"pool_lean": 1}])
 @pytest.mark.parametrize("argmax", [False, True])
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
 def test_pool_experimental_variants_are_bit_identical(dtype, argmax, knobs):
     """pool_skip_idle = 1: CTAs whose chunk holds no RoI of their image return before staging the map; pool_prefetch_roi = 1:
-    a warp claims and loads its next RoI before working on the current one.  Two images, RoIs grouped by image (the
-    loader's order) and, as a torture case, interleaved: values and argmax equal the default kernel."""
+    a warp claims and loads its next RoI before working on the current one; pool_lean = 1: both plus the seven bin rows
+    unrolled (rows3_bins).  Two images, RoIs grouped by image (the loader's order) and, as a torture case, interleaved, plus
+    the config-3 RoI mixture (tiny, clipped, outside, inverted boxes -> the empty-bin path): values and argmax equal the
+    default kernel."""
     import nafwebsod_b200 as pkg
     from oracle import nawsod_oracle as O            # inputs only
     ops = _ops()
@@ -203,7 +206,14 @@ def test_pool_experimental_variants_are_bit_identical(dtype, argmax, knobs):
     grouped = np.concatenate([O.synth_rois(1000, 608, 800, b, seed=1 + b) for b in range(2)])
     inter = grouped[np.random.default_rng(3).permutation(2000)]
     obn = torch.from_numpy((np.random.default_rng(9).random(2000) + 1).astype(np.float32)).cuda()
-    for rois in (grouped, inter):
+    rng = np.random.default_rng(4)
+    mixed = grouped.copy()
+    kind = rng.integers(0, 6, 2000)
+    mixed[kind == 0, 3:] = mixed[kind == 0, 1:3] + rng.integers(0, 30, (int((kind == 0).sum()), 2))      # tiny
+    mixed[kind == 1, 1:] = (-60, -35, 200, 150)                                                        # overhanging
+    mixed[kind == 2, 1:] = (900, 700, 1000, 800)                                                       # outside the map
+    mixed[kind == 3, 1:] = mixed[kind == 3][:, [3, 4, 1, 2]]                                           # inverted
+    for rois in (grouped, inter, mixed.astype(np.float32)):
         r = torch.from_numpy(np.ascontiguousarray(rois)).cuda()
         kw = dict(spatial_scale=1 / 16, is_test=not argmax, boost=obn, x_layout="NHWC", y_layout="NHWC", out_dtype=dtype)
         Y0, A0 = ops.RoIPoolF(Xcl, r, **kw)
