@@ -140,6 +140,69 @@ class WeblyHeadModel:
             self.p["b8_%d" % s][C:].copy_(get(b + "fc8d_b"))
         self.sync_shadow()
 
+    def _param_targets(self):
+        """Reference blob name -> (parameter view, momentum view, transform applied to a loaded array)."""
+        H, C, out = self.H, self.C, {}
+        mom = {k: self.flat_mom[self._slices[k][0]: self._slices[k][0] + self._slices[k][1]].view(self._slices[k][2])
+               for k in self._slices}
+        mom["b8"] = mom["b8"][:, :2 * C]
+        ident = lambda v: v
+        for s in range(self.S):
+            a, b = self._ref_names(s)
+            rows = slice(s * H, (s + 1) * H)
+            out[a + "fc6_w"] = (self.p["W6"][rows], mom["W6"][rows], self._k_permute)
+            out[a + "fc6_b"] = (self.p["b6"][rows], mom["b6"][rows], ident)
+            out[a + "fc7_w"] = (self.p["W7"][s], mom["W7"][s], ident)
+            out[a + "fc7_b"] = (self.p["b7"][s], mom["b7"][s], ident)
+            out[b + "fc8c_w"] = (self.p["W8"][s][:C], mom["W8"][s][:C], ident)
+            out[b + "fc8d_w"] = (self.p["W8"][s][C:], mom["W8"][s][C:], ident)
+            out[b + "fc8c_b"] = (self.p["b8"][s][:C], mom["b8"][s][:C], ident)
+            out[b + "fc8d_b"] = (self.p["b8"][s][C:], mom["b8"][s][C:], ident)
+        return out
+
+    def initialize_from_weights(self, src_blobs):
+        """``initialize_gpu_from_weights_file`` (detectron/utils/net_wsl.py:53-137) for the head's parameters, given the
+        unpickled blob dictionary (the ``'blobs'`` sub-dictionary when present, :67-70).  Per parameter blob, in model
+        order: a blob named ``_[xyz]_foo`` that is NOT in the file is initialised from ``foo`` (:79-88 -- how the noisy
+        fc6 / fc7 start from the ImageNet VGG16 weights of the clean stack); a source blob that is missing altogether
+        leaves the current initialisation (:89-91); ``<name>_momentum`` is loaded along when present (:93, 115-119); a
+        shape mismatch is an error (:105-111).  Returns the list of (destination, source, with_momentum) loaded."""
+        if "blobs" in src_blobs:
+            src_blobs = src_blobs["blobs"]
+        loaded = []
+        for name, (pv, mv, xf) in self._param_targets().items():
+            src_name = name[name.find("]_") + 2:] if (name.find("]_") >= 0 and name not in src_blobs) else name
+            if src_name not in src_blobs:
+                continue
+            def as_tensor(v):
+                v = torch.from_numpy(np.ascontiguousarray(v)) if isinstance(v, np.ndarray) else v
+                return v.to(self.device, torch.float32)
+            ref_shape = tuple(self._k_unpermute(pv).shape) if xf == self._k_permute else tuple(pv.shape)
+            w = as_tensor(src_blobs[src_name])
+            if tuple(w.shape) != ref_shape:
+                raise RuntimeError("blob %s with shape %s does not match weights file shape %s of %s" % (
+                    name, ref_shape, tuple(w.shape), src_name))
+            pv.copy_(xf(w))
+            has_momentum = src_name + "_momentum" in src_blobs
+            if has_momentum:
+                mv.copy_(xf(as_tensor(src_blobs[src_name + "_momentum"])))
+            loaded.append((name, src_name, has_momentum))
+        if self.flat_param.is_cuda:
+            self.sync_shadow()
+        return loaded
+
+    def weights_file_blobs(self):
+        """The ``blobs`` dictionary ``save_model_to_weights_file`` pickles for the head (detectron/utils/net_wsl.py:140-181):
+        every parameter under its unscoped blob name and ``<name>_momentum`` for every trainable parameter, in the
+        reference's layouts (fc6 K-order ``c*49 + bin``).  Feeding the result to ``initialize_from_weights`` restores the
+        state exactly.  (In data-parallel runs call ``dp.gather_master_state()`` first.)"""
+        blobs = {}
+        for name, (pv, mv, xf) in self._param_targets().items():
+            back = self._k_unpermute if xf == self._k_permute else (lambda v: v)
+            blobs[name] = back(pv).detach().cpu().numpy().copy()
+            blobs[name + "_momentum"] = back(mv).detach().cpu().numpy().copy()
+        return blobs
+
     def sync_shadow(self):
         if self.dtype == torch.bfloat16:
             ops.to_bf16(self.flat_param.view(1, -1), out=self.flat_lp.view(1, -1))

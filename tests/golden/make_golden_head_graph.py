@@ -405,6 +405,48 @@ def build_optimizer_case(rng, cfg):
     return out
 
 
+def build_weights_init_case(rng):
+    """initialize_gpu_from_weights_file (utils/net_wsl.py:53-137) run unmodified against a dictionary workspace: which
+    source blob initialises which parameter blob (the `]_` rule for `_[noisy]_fc6/fc7`, missing blobs left alone, momentum
+    loaded along, unused blobs preserved)."""
+    import contextlib
+    import detectron.utils.net_wsl as nu
+    params = ["fc6_w", "fc6_b", "fc7_w", "fc7_b", "_[noisy]_fc6_w", "_[noisy]_fc6_b", "_[noisy]_fc7_w", "_[noisy]_fc7_b",
+              "fc8c_w", "fc8c_b", "fc8d_w", "fc8d_b", "noisy_fc8c_w", "noisy_fc8c_b", "noisy_fc8d_w", "noisy_fc8d_b"]
+    Cc, hidden, C = 4, 8, 5
+    shapes = {"fc6_w": (hidden, Cc * 49), "fc6_b": (hidden,), "fc7_w": (hidden, hidden), "fc7_b": (hidden,),
+              "fc8c_w": (C, hidden), "fc8c_b": (C,), "fc8d_w": (C, hidden), "fc8d_b": (C,)}
+    # an ImageNet-style file: the clean fc6 / fc7 only (+ a momentum blob, + a conv blob this model does not use), and one
+    # explicitly stored noisy blob that must win over the `]_` rule
+    src = {k: rng.standard_normal(shapes[k]).astype(F32) for k in ("fc6_w", "fc6_b", "fc7_w", "fc7_b")}
+    src["fc7_w_momentum"] = rng.standard_normal(shapes["fc7_w"]).astype(F32)
+    src["_[noisy]_fc7_b"] = rng.standard_normal(shapes["fc7_b"]).astype(F32)
+    src["conv1_1_w"] = rng.standard_normal((3,)).astype(F32)
+    ws = {}
+
+    class Model:
+        pass
+    model = Model()
+    model.params = list(params)
+    model.GetComputedParams = lambda: []
+    nu.load_object = lambda f: {"blobs": dict(src)}
+    nu.workspace.Blobs = lambda: list(ws)
+    nu.workspace.FeedBlob = lambda name, value: ws.__setitem__(str(name), np.array(value))
+    nu.workspace.FetchBlob = lambda name: ws[str(name)]
+    nu.core.ScopedName = lambda s: s
+    nu.c2_utils.UnscopeName = lambda s: s
+    nu.c2_utils.NamedCudaScope = lambda gpu_id: contextlib.nullcontext()
+    nu.c2_utils.CpuScope = lambda: contextlib.nullcontext()
+    nu.initialize_gpu_from_weights_file(model, "weights.pkl", gpu_id=0)
+    out = {"winit_params": np.array(params), "winit_cfg": np.array([Cc, hidden, C], np.int32),
+           "winit_ws_names": np.array(sorted(ws))}
+    for k, v in src.items():
+        out["winit_src_" + k] = v
+    for k, v in ws.items():
+        out["winit_ws_" + k] = v
+    return out
+
+
 def main():
     maker = _load_roi_data_maker()
     sys.meta_path.insert(0, maker._Absent())
@@ -440,6 +482,7 @@ def main():
         print("case", i, c, "->", len(trace), "operators;", {k: v.shape for k, v in outputs.items() if k in ("rois_pred", "cls_prob", "loss_cls")})
     out["cases"] = np.int32(len(cases))
     out.update(build_optimizer_case(rng, cfg))
+    out.update(build_weights_init_case(rng))
     np.savez_compressed(os.path.join(HERE, "head_graph.npz"), **out)
     print("wrote head_graph.npz (%d arrays)" % len(out))
 

@@ -209,3 +209,40 @@ def test_tf32_rounding_points_leave_headroom_on_the_gpu_case(gold):
     assert 1e-5 < worst <= 6e-4, worst                  # TF32 does cost ~5e-4 here -- and no more
     assert rel(got["class_weight_noise"], out(gold, 0, "rois_class_weight_noise")) <= 5e-4
     assert abs(got["loss_cls"] - out(gold, 0, "loss_cls")) <= 2e-4 * abs(out(gold, 0, "loss_cls"))
+
+
+def test_weights_file_initialisation_follows_the_reference(gold):
+    """heads.WeblyHeadModel.initialize_from_weights against initialize_gpu_from_weights_file (utils/net_wsl.py:53-137) run
+    unmodified on a dictionary workspace: the `]_` rule (`_[noisy]_fc6/fc7` start from the clean stack's blobs unless the
+    file holds them), missing blobs keep their initialisation, momentum blobs are loaded along."""
+    import torch
+    from nafwebsod_b200.heads import WeblyHeadModel
+    Cc, hidden, C = (int(v) for v in gold["winit_cfg"])
+    src = {k[len("winit_src_"):]: gold[k] for k in gold.files if k.startswith("winit_src_")}
+    ws = {k[len("winit_ws_"):]: gold[k] for k in gold.files if k.startswith("winit_ws_") and k != "winit_ws_names"}
+    m = WeblyHeadModel(C + 1, Cc, 7, hidden, noise=True, dtype=torch.float32, device="cpu")
+    loaded = m.initialize_from_weights({"blobs": src})
+    params = m.export_reference_params()
+    assert set(params) == set(str(p) for p in gold["winit_params"])
+    fed = {k for k in ws if not k.startswith("__preserve__/") and not k.endswith("_momentum")}
+    assert {d for d, _, _ in loaded} == fed
+    for name, value in params.items():
+        if name in fed:
+            assert np.array_equal(value.numpy(), ws[name]), name
+        else:
+            assert float(value.abs().sum()) == 0.0, name                  # not in the file: initialisation untouched
+    targets = m._param_targets()
+    for name in ("fc7_w", "_[noisy]_fc7_w"):
+        assert np.array_equal(targets[name][1].numpy(), ws[name + "_momentum"]), name
+    assert float(targets["fc6_w"][1].abs().sum()) == 0.0
+    # the explicitly stored noisy blob wins over the rule; the clean one fills the noisy fc6 / fc7 weights
+    assert ("_[noisy]_fc7_b", "_[noisy]_fc7_b", False) in loaded and ("_[noisy]_fc6_w", "fc6_w", False) in loaded
+    with pytest.raises(RuntimeError, match="does not match"):
+        m.initialize_from_weights({"fc7_w": np.zeros((3, 3), np.float32)})
+
+    # save_model_to_weights_file's dictionary (utils/net_wsl.py:140-181) round-trips through the loader
+    blobs = m.weights_file_blobs()
+    assert set(blobs) == set(params) | {p + "_momentum" for p in params}
+    m2 = WeblyHeadModel(C + 1, Cc, 7, hidden, noise=True, dtype=torch.float32, device="cpu")
+    m2.initialize_from_weights({"blobs": blobs, "cfg": "unused"})
+    assert torch.equal(m2.flat_param, m.flat_param) and torch.equal(m2.flat_mom, m.flat_mom)
