@@ -36,6 +36,20 @@ def _round_up(v, a):
     return (v + a - 1) // a * a
 
 
+def lr_change_correction(cur_lr, new_lr, scale_momentum=True, threshold=1.1):
+    """Factor ``_SetNewLr`` scales every ``<param>_momentum`` blob by when the learning rate goes from ``cur_lr`` to
+    ``new_lr`` (detectron/modeling/detector.py:528-560, 581-586; both float32 like the reference's blob and schedule):
+    ``new_lr / cur_lr`` if SOLVER.SCALE_MOMENTUM, ``cur_lr > 1e-7`` and the change ratio exceeds the threshold, else 1."""
+    cur_lr, new_lr = np.float32(cur_lr), np.float32(new_lr)
+    if cur_lr == new_lr:
+        return np.float32(1.0)
+    eps = 1e-10
+    ratio = max(new_lr / max(cur_lr, eps), cur_lr / max(new_lr, eps))
+    if scale_momentum and cur_lr > 1e-7 and ratio > threshold:
+        return np.float32(new_lr / cur_lr)
+    return np.float32(1.0)
+
+
 class WeblyHeadModel:
     """State + eager execution of the NA-fWebSOD head (``noise=True``) or plain WSDDN head.
 
@@ -62,6 +76,7 @@ class WeblyHeadModel:
         self._buf = {}
         self.profile = None        # dict name -> [(start_event, end_event)] when bench.py instruments a run
         self.iter_count = 0
+        self._lr_host = np.float32(0.0)     # value of the `lr` blob (UpdateWorkspaceLr keeps it; starts at 0 like the reference's)
         self._bias_stream = None
         self._alloc_params()
 
@@ -456,9 +471,22 @@ class WeblyHeadModel:
         return bl["cls_prob"]
 
     # ------------------------------------------------------------------ optimizer (single GPU; dp.py adds the all-reduce)
-    def UpdateWorkspaceLr(self, lr):
-        """detectron/modeling/detector.py:509-537: write the `lr` blob."""
-        self.lr.fill_(float(lr))
+    def UpdateWorkspaceLr(self, lr, scale_momentum=True, scale_momentum_threshold=1.1):
+        """``DetectionModelHelper.UpdateWorkspaceLr`` (detectron/modeling/detector.py:509-560): write the ``lr`` blob and,
+        when the rate changes by more than SOLVER.SCALE_MOMENTUM_THRESHOLD (1.1) from a rate above 1e-7, scale the update
+        history of every trainable parameter by ``new_lr / cur_lr`` (``_CorrectMomentum``: V := mu*V + lr*grad is not
+        independent of lr) -- at the flickr schedule's 1e-3 -> 1e-4 step all momenta are multiplied by 0.1.  The current
+        rate is tracked on the host (the blob starts at 0, optimizer_wsl.py:81-85, so the first call only writes it).
+        Returns the factor applied to the momenta (1.0 when they were left alone)."""
+        new_lr, cur_lr = np.float32(lr), self._lr_host
+        factor = lr_change_correction(cur_lr, new_lr, scale_momentum, scale_momentum_threshold)
+        if cur_lr != new_lr:
+            self.lr.fill_(float(new_lr))
+            self._lr_host = new_lr
+        if factor != 1.0:
+            s = torch.full((1,), float(factor), dtype=torch.float32, device=self.device)
+            ops.RoIFeatureBoost(self.flat_mom.view(1, -1), s, out=self.flat_mom.view(1, -1))   # Scale([m] -> [m]) in place
+        return float(factor)
 
     def param_update(self, momentum=0.9, weight_decay=5e-4, gpu_num=1, iter_size=1):
         """``ACMWeightDecayMomentumSGDUpdate`` for every parameter (detectron/modeling/optimizer_wsl.py:96-137):

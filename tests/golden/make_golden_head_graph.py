@@ -447,6 +447,54 @@ def build_weights_init_case(rng):
     return out
 
 
+def build_lr_change_case(cfg):
+    """DetectionModelHelper.UpdateWorkspaceLr / _SetNewLr / _CorrectMomentum and _get_lr_change_ratio
+    (modeling/detector.py:509-586) as plain functions on a dictionary workspace: for a sequence of learning rates, the value
+    the `lr` blob takes and the factor every `<param>_momentum` blob is scaled by (or 1.0 when the reference leaves the
+    update history alone)."""
+    import ast
+    import contextlib
+    import logging
+    import textwrap
+    import types
+    src = open("/root/reference/detectron/modeling/detector.py").read()
+    tree = ast.parse(src)
+    lines = src.split("\n")
+    code = []
+    for node in ast.walk(tree):
+        if isinstance(node, ast.FunctionDef) and node.name in ("UpdateWorkspaceLr", "_SetNewLr", "_CorrectMomentum", "_get_lr_change_ratio"):
+            code.append(textwrap.dedent("\n".join(lines[node.lineno - 1: node.end_lineno])))
+    assert len(code) == 4
+    ws = {"gpu_0/lr": np.array([0.0], F32), "gpu_0/fc6_w_momentum": np.ones(3, F32)}
+    scales = []
+
+    def run_once(op):
+        scales.append(op["scale"])
+        ws[op["out"]] = (ws[op["in"]] * F32(op["scale"])).astype(F32)      # caffe2 Scale: float argument, float32 arithmetic
+    one_gpu = types.SimpleNamespace(NUM_GPUS=1, SOLVER=cfg.SOLVER)          # the blobs of gpu_0 stand for every replica
+    ns = {"np": np, "cfg": one_gpu, "logger": logging.getLogger("lr"),
+          "workspace": types.SimpleNamespace(FetchBlob=lambda n: ws[n], FeedBlob=lambda n, v: ws.__setitem__(n, np.array(v)),
+                                             RunOperatorOnce=run_once),
+          "core": types.SimpleNamespace(CreateOperator=lambda typ, i, o, scale: {"type": typ, "in": i[0], "out": o[0], "scale": scale}),
+          "c2_utils": types.SimpleNamespace(CudaScope=lambda i: contextlib.nullcontext())}
+    for c in code:
+        exec(compile(c, "/root/reference/detectron/modeling/detector.py", "exec"), ns)
+    helper = types.SimpleNamespace(TrainableParams=lambda gpu_id=-1: ["gpu_0/fc6_w"])
+    helper._SetNewLr = lambda cur, new: ns["_SetNewLr"](helper, cur, new)
+    helper._CorrectMomentum = lambda corr: ns["_CorrectMomentum"](helper, corr)
+    seq = [F32(1e-3), F32(1e-3), F32(1e-4), F32(1.05e-4), F32(5e-8), F32(1e-3), F32(2e-3), F32(1e-5)]
+    lr_after, factor = [], []
+    for it, new_lr in enumerate(seq):
+        before = ws["gpu_0/fc6_w_momentum"].copy()
+        n_scales = len(scales)
+        ns["UpdateWorkspaceLr"](helper, it, new_lr)
+        lr_after.append(ws["gpu_0/lr"][0])
+        factor.append(F32(scales[-1]) if len(scales) > n_scales else F32(1.0))
+        assert np.array_equal(ws["gpu_0/fc6_w_momentum"], (before * factor[-1]).astype(F32))
+    assert cfg.SOLVER.SCALE_MOMENTUM and cfg.SOLVER.SCALE_MOMENTUM_THRESHOLD == 1.1
+    return {"lrseq_new": np.array(seq, F32), "lrseq_blob": np.array(lr_after, F32), "lrseq_momentum_factor": np.array(factor, F32)}
+
+
 def main():
     maker = _load_roi_data_maker()
     sys.meta_path.insert(0, maker._Absent())
@@ -483,6 +531,7 @@ def main():
     out["cases"] = np.int32(len(cases))
     out.update(build_optimizer_case(rng, cfg))
     out.update(build_weights_init_case(rng))
+    out.update(build_lr_change_case(cfg))
     np.savez_compressed(os.path.join(HERE, "head_graph.npz"), **out)
     print("wrote head_graph.npz (%d arrays)" % len(out))
 

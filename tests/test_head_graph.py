@@ -246,3 +246,18 @@ def test_weights_file_initialisation_follows_the_reference(gold):
     m2 = WeblyHeadModel(C + 1, Cc, 7, hidden, noise=True, dtype=torch.float32, device="cpu")
     m2.initialize_from_weights({"blobs": blobs, "cfg": "unused"})
     assert torch.equal(m2.flat_param, m.flat_param) and torch.equal(m2.flat_mom, m.flat_mom)
+
+
+def test_lr_change_scales_the_update_history_like_the_reference(gold):
+    """heads.lr_change_correction / WeblyHeadModel.UpdateWorkspaceLr against DetectionModelHelper.UpdateWorkspaceLr,
+    _SetNewLr and _CorrectMomentum (modeling/detector.py:509-586) run on a dictionary workspace: the `lr` blob after each
+    call and the factor the momentum blobs were scaled by (0.1 at the schedule's 1e-3 -> 1e-4 step; none for a change
+    below 10 %, from a rate <= 1e-7, or on the very first call from the blob's initial 0)."""
+    from nafwebsod_b200.heads import lr_change_correction
+    cur = np.float32(0.0)
+    for new, blob, factor in zip(gold["lrseq_new"], gold["lrseq_blob"], gold["lrseq_momentum_factor"]):
+        got = lr_change_correction(cur, new)
+        assert np.float32(got) == factor, (cur, new, got, factor)
+        cur = new
+        assert cur == blob
+    assert lr_change_correction(np.float32(1e-3), np.float32(1e-4), scale_momentum=False) == 1.0
