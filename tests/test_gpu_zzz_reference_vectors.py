@@ -167,3 +167,21 @@ def test_tta_and_nms_vs_reference_driver(golden_dir, i):
         assert np.array_equal(np.sort(mine[:, 4]), np.sort(want[start:start + counts[j], 4])), "class %d scores" % j
         assert np.array_equal(canon(mine), canon(ocls[j])), "class %d rows" % j
         start += counts[j]
+
+
+def test_update_workspace_lr_scales_the_momenta_on_the_device(golden_dir):
+    """WeblyHeadModel.UpdateWorkspaceLr through the reference's learning-rate sequence (tests/golden/head_graph.npz,
+    `lrseq_*`: DetectionModelHelper._SetNewLr / _CorrectMomentum run on a dictionary workspace): the `lr` blob and the
+    momentum buffer after every call, bit for bit (Scale is one float32 multiply per element)."""
+    from nafwebsod_b200.heads import WeblyHeadModel
+    g = np.load(os.path.join(golden_dir, "head_graph.npz"))
+    m = WeblyHeadModel(7, 16, 7, 64, noise=True, dtype=torch.bfloat16)
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    m.flat_mom.normal_(0.0, 1e-3, generator=gen)
+    want = m.flat_mom.clone()
+    for new, blob, factor in zip(g["lrseq_new"], g["lrseq_blob"], g["lrseq_momentum_factor"]):
+        got = m.UpdateWorkspaceLr(new)
+        assert np.float32(got) == factor
+        want = want * float(factor) if factor != 1.0 else want
+        assert m.lr.item() == float(blob)
+        assert torch.equal(m.flat_mom, want)
