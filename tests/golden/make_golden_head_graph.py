@@ -22,6 +22,13 @@ reference's code.  What the interpreter supplies is the arithmetic of each opera
     max-subtracted Softmax, NumPy-style broadcasting) -- the one part that stays a restatement.
 The operator trace (type + blob names, in emission order) is stored next to the blobs, so the test can also show that the
 oracle covers every operator the builders emit.
+
+The same file holds three more reference-run cases around the head's parameters: `opt_*` -- add_single_gpu_param_update_ops
+(modeling/optimizer_wsl.py:75-137) on the eager helper, the update net run three times through the reference's CPU operator;
+`winit_*` -- initialize_gpu_from_weights_file (utils/net_wsl.py:53-137) on a dictionary workspace; `lrseq_*` --
+UpdateWorkspaceLr / _SetNewLr / _CorrectMomentum (modeling/detector.py:509-586) over a sequence of learning rates.
+Inputs that are cheap to regenerate are not stored: `load_case()` rebuilds a case's parameters from its seed (checksums in
+the file guard the regeneration) and unpacks the bit-packed dropout masks.
 """
 import importlib.util
 import os
