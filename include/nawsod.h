@@ -352,6 +352,16 @@ int nawsod_bagging_mixup(const float* x0, const float* x1, int64_t n, float lam0
 int nawsod_set_column(float* a, int rows, int64_t ld, int col, float value, void* stream);
 int nawsod_convert_mcg_boxes(const double* bboxes, int R, uint16_t* boxes_out, void* stream);
 
+/* N4 (second half)  the frozen VGG16 conv body in channels-last bf16 (detectron/modeling/VGG16.py:9-58; Caffe2 Conv / Relu /
+ *   MaxPool, forward only: TRAIN.FREEZE_CONV_BODY).  EXPERIMENTAL: compiled, not yet run on hardware.  A 3x3 convolution
+ *   is nawsod_im2col3x3 followed by nawsod_fc_fwd with NAWSOD_FC_RELU on the patch matrix (W permuted to [Cout, (kh,kw,c)]).
+ *   nawsod_im2col3x3   X [N,H,W,C] bf16 -> cols [N*H*W, 9*C] bf16, K-order (kh, kw, c); stride 1, pad = dilation
+ *                      (1 or 2, the combinations VGG16.py:10-56 uses), zeros outside the image; C % 8 == 0.
+ *   nawsod_maxpool2x2  MaxPool(kernel=2, pad=0, stride) on [N,H,W,C] bf16 -> [N,(H-2)/stride+1,(W-2)/stride+1,C];
+ *                      stride 2 (pool1-3, pool4 of the 1/16 body) or 1 (pool4 with WSL.DILATION 2, VGG16.py:40-41). */
+int nawsod_im2col3x3(const void* X, int N, int H, int W, int C, int dilation, void* cols, void* stream);
+int nawsod_maxpool2x2(const void* X, int N, int H, int W, int C, int stride, void* Y, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

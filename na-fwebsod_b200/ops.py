@@ -798,3 +798,47 @@ def convert_mcg_boxes(bboxes):
     out = torch.empty((bboxes.shape[0], 4), dtype=torch.int16, device=bboxes.device)
     _lib.call("nawsod_convert_mcg_boxes", _ptr(bboxes), bboxes.shape[0], _ptr(out), _stream())
     return out
+
+
+# --------------------------------------------------------------------------------------------
+# N4: the frozen VGG16 conv body in channels-last bf16 (EXPERIMENTAL -- see csrc/conv_body.cu)
+# --------------------------------------------------------------------------------------------
+def _nhwc_bf16(X, name):
+    _req(X, name, torch.bfloat16, 4)
+    if not X.is_contiguous():
+        raise RuntimeError("%s must be a contiguous channels-last [N,H,W,C] tensor" % name)
+    return X.shape
+
+
+def Im2Col3x3(X, *, dilation=1, out=None):
+    """Patch matrix of a 3x3 / stride 1 / pad = dilation convolution: X [N,H,W,C] bf16 -> [N*H*W, 9*C] bf16 with the
+    K-order (kh, kw, c); taps outside the image are zeros (Caffe2 ``Conv`` zero padding, modeling/VGG16.py:10-56)."""
+    N, H, W, C = _nhwc_bf16(X, "X")
+    cols = torch.empty((N * H * W, 9 * C), dtype=torch.bfloat16, device=X.device) if out is None else out
+    _req(cols, "out", torch.bfloat16, 2)
+    if tuple(cols.shape) != (N * H * W, 9 * C) or not cols.is_contiguous():
+        raise RuntimeError("Im2Col3x3: out must be a contiguous [%d, %d] matrix" % (N * H * W, 9 * C))
+    _lib.call("nawsod_im2col3x3", _ptr(X), N, H, W, C, int(dilation), _ptr(cols), _stream())
+    return cols
+
+
+def Conv3x3Relu(X, Wmat, b, *, dilation=1, relu=True, cols=None):
+    """``Conv(kernel=3, pad=dilation, stride=1, dilation)`` + ``Relu`` on a channels-last bf16 map: the patch matrix times
+    ``Wmat`` [Cout, 9*Cin] (the reference's [Cout, Cin, 3, 3] weight permuted to (kh, kw, c)) on the tcgen05 GEMM, bias
+    and ReLU in its epilogue.  Returns Y [N,H,W,Cout] bf16 -- the next layer's input as is."""
+    N, H, W, C = _nhwc_bf16(X, "X")
+    if Wmat.dim() != 2 or Wmat.shape[1] != 9 * C:
+        raise RuntimeError("Conv3x3Relu: Wmat must be [Cout, %d], got %s" % (9 * C, tuple(Wmat.shape)))
+    cols = Im2Col3x3(X, dilation=dilation, out=cols)
+    Y = FC(cols, Wmat, b, relu=relu, out_dtype=torch.bfloat16)
+    return Y.view(N, H, W, Wmat.shape[0])
+
+
+def MaxPool2x2(X, *, stride=2):
+    """``MaxPool(kernel=2, pad=0, stride)`` on a channels-last bf16 map (Caffe2 floor output size)."""
+    N, H, W, C = _nhwc_bf16(X, "X")
+    if H < 2 or W < 2:
+        raise RuntimeError("MaxPool2x2: the map must be at least 2 x 2")
+    Y = torch.empty((N, (H - 2) // stride + 1, (W - 2) // stride + 1, C), dtype=torch.bfloat16, device=X.device)
+    _lib.call("nawsod_maxpool2x2", _ptr(X), N, H, W, C, int(stride), _ptr(Y), _stream())
+    return Y

@@ -16,6 +16,10 @@ el "pytest (experimental fused kernels)"
 NAWSOD_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_experimental_fused.py -m gpu -q --timeout 120 -p no:cacheprovider \
     > $OUT/${TAG}_pytest_fused.log 2>&1
 echo "pytest exit $?" | tee -a $OUT/${TAG}_pytest_fused.log; tail -n 25 $OUT/${TAG}_pytest_fused.log
+el "pytest (experimental conv body: im2col / max-pool kernels + the VGG16 body on the tcgen05 GEMM)"
+NAWSOD_EXPERIMENTAL=1 timeout 200 python -m pytest tests/test_gpu_experimental_conv_body.py -m gpu -q --timeout 120 -p no:cacheprovider \
+    > $OUT/${TAG}_pytest_conv_body.log 2>&1
+echo "pytest exit $?" | tee -a $OUT/${TAG}_pytest_conv_body.log; tail -n 15 $OUT/${TAG}_pytest_conv_body.log
 el "bench default"
 timeout 300 python bench.py --steps 20 --warmup 5 > $OUT/${TAG}_bench_n1.json 2> $OUT/${TAG}_bench_n1.err; echo "exit $?"
 cut -c1-400 $OUT/${TAG}_bench_n1.json
