@@ -39,6 +39,8 @@ for c in 148 296 592; do
 done
 el "pool microbenchmark (incl. the pool_skip_idle / pool_prefetch_roi / pool_lean variants)"
 timeout 200 python tools/microbench.py pool2 > $OUT/${TAG}_microbench_pool.log 2>&1; echo "exit $?"; grep "skip_idle\|prefetch\|lean\|{}:" $OUT/${TAG}_microbench_pool.log | cut -c1-160
+el "conv body microbenchmark (experimental)"
+timeout 200 python tools/microbench.py convbody > $OUT/${TAG}_microbench_convbody.log 2>&1; echo "exit $?"; cut -c1-200 $OUT/${TAG}_microbench_convbody.log
 el "ncu launch list (fused)"
 NAWSOD_FUSED_SGD=1 timeout 240 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
     --log-file $OUT/${TAG}_ncu_launches_fused.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-isolated \

@@ -180,6 +180,34 @@ def bench_testtime():
         print("nms+limit R=%d K=20: GPU med %.3f ms, CPU oracle (1 core) %.1f ms" % (R, med, cpu_ms), flush=True)
 
 
+def bench_convbody():
+    """EXPERIMENTAL frozen VGG16 conv body (csrc/conv_body.cu + the tcgen05 GEMM): whole body and its two kernel kinds on
+    flickr-sized images (short side 480 / 688; WSL.DILATION 2).  FLOPs = 2 * 9 * Cin * Cout per output pixel and layer."""
+    from nafwebsod_b200.conv_body import VGG16ConvBody, body_ops
+    from oracle import conv_body_oracle as CB
+    body = VGG16ConvBody(dilation=2)
+    body.load_reference_params(CB.synth_params(0))
+    for (H, W) in [(480, 640), (688, 912)]:
+        body.feed_image(torch.randn(1, 3, H, W, device="cuda") * 50)
+        flops, h, w = 0, H, W
+        for kind, _, _, a in body_ops(2):
+            if kind == "Conv":
+                flops += 2 * 9 * a["dim_in"] * a["dim_out"] * h * w
+            elif kind == "MaxPool":
+                h, w = (h - 2) // a["stride"] + 1, (w - 2) // a["stride"] + 1
+        med, best = timeit(lambda: body.run(), iters=10)
+        print("convbody %dx%d -> conv5 %dx%d: med %.3f ms best %.3f ms  %.1f GFLOP  %.0f TFLOP/s (%.1f%% of %.0f)" % (
+            H, W, h, w, med, best, flops / 1e9, flops / med / 1e9, 100 * flops / med / 1e9 / PEAKS["bf16_tflops"], PEAKS["bf16_tflops"]), flush=True)
+        x = torch.randn(1, H // 2, W // 2, 128, device="cuda").to(torch.bfloat16)
+        med, _ = timeit(lambda: ops.Im2Col3x3(x))
+        nbytes = x.numel() * 2 * 10
+        print("  im2col3x3 %dx%dx128: med %.1f us  %.0f GB/s (%.1f%% of %.0f)" % (H // 2, W // 2, med * 1e3, nbytes / med / 1e6,
+              100 * nbytes / med / 1e6 / PEAKS["hbm_gbs"], PEAKS["hbm_gbs"]), flush=True)
+        med, _ = timeit(lambda: ops.MaxPool2x2(x))
+        nbytes = x.numel() * 2 * 1.25
+        print("  maxpool2x2 %dx%dx128: med %.1f us  %.0f GB/s" % (H // 2, W // 2, med * 1e3, nbytes / med / 1e6), flush=True)
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["pool", "poolbwd", "mil", "sgd"]
     for w in which:
