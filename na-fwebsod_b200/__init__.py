@@ -11,8 +11,8 @@ __all__ = ["_lib", "ops", "LIB_PATH", "set_tuning"]
 
 
 def __getattr__(name):
-    # ops / heads / dp / test_time / roi_data / loader import torch; load them lazily so `import nafwebsod_b200` stays cheap
-    if name in ("ops", "heads", "dp", "test_time", "roi_data", "loader"):
+    # ops / heads / dp / test_time / roi_data / loader / torch_ops / conv_body import torch; load them lazily so `import nafwebsod_b200` stays cheap
+    if name in ("ops", "heads", "dp", "test_time", "roi_data", "loader", "torch_ops", "conv_body"):
         import importlib
         return importlib.import_module("." + name, __name__)
     raise AttributeError(name)
