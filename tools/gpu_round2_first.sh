@@ -23,6 +23,11 @@ echo "pytest exit $?" | tee -a $OUT/${TAG}_pytest_conv_body.log; tail -n 15 $OUT
 el "bench default"
 timeout 300 python bench.py --steps 20 --warmup 5 > $OUT/${TAG}_bench_n1.json 2> $OUT/${TAG}_bench_n1.err; echo "exit $?"
 cut -c1-400 $OUT/${TAG}_bench_n1.json
+for v in "--dtype tf32" "--head wsddn"; do      # fp32 (TF32) path and the single-stack WSDDN head
+  n=$(echo $v | tr -d ' -'); el "bench $v"
+  timeout 200 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-isolated $v > $OUT/${TAG}_bench_n1_$n.json 2> $OUT/${TAG}_bench_n1_$n.err; echo "exit $?"
+  cut -c1-200 $OUT/${TAG}_bench_n1_$n.json
+done
 el "bench fused SGD"
 NAWSOD_FUSED_SGD=1 timeout 200 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-isolated \
     > $OUT/${TAG}_bench_n1_fused_sgd.json 2> $OUT/${TAG}_bench_n1_fused_sgd.err; echo "exit $?"
