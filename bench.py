@@ -360,16 +360,35 @@ def gpu_arm(args):
 
     # ---- model: random-init weights of the reference architecture (no checkpoints offline) ----
     model = WeblyHeadModel(NUM_CLASSES, C5, 7, 4096, noise=noise, dtype=dtype, device=dev)
-    g = torch.Generator(device=dev).manual_seed(2)
-    nw = model.n_weights
-    model.flat_param[:nw].normal_(0.0, 0.01, generator=g)          # gauss_fill(0.01); biases stay 0
-    for s in range(model.S):                                        # XavierFill for fc8
-        lim = float(np.sqrt(3.0 / 4096))
-        model.p["W8_%d" % s].uniform_(-lim, lim, generator=g)
-    model.sync_shadow()
+
+    def init_parameters():
+        g = torch.Generator(device=dev).manual_seed(2)
+        nw = model.n_weights
+        model.flat_param.zero_()
+        model.flat_mom.zero_()
+        model.iter_count = 0
+        model.flat_param[:nw].normal_(0.0, 0.01, generator=g)          # gauss_fill(0.01); biases stay 0
+        for s in range(model.S):                                        # XavierFill for fc8
+            lim = float(np.sqrt(3.0 / 4096))
+            model.p["W8_%d" % s].uniform_(-lim, lim, generator=g)
+        model.sync_shadow()
+
+    init_parameters()
+    os.environ.setdefault("NAWSOD_P2P_TIMEOUT_MS", "10000")    # peer-exchange watchdog: a 5 ms step never waits this long
     dp = DataParallelHead(model, fc6_panels=args.fc6_panels, sync=args.dp_sync)
     dp.broadcast_parameters()
     model.UpdateWorkspaceLr(1e-3)
+
+    def exchange_timed_out():
+        """Peer exchange only: did a wait kernel's watchdog fire on any rank?  (Synchronises; same answer on every rank.)"""
+        if not hasattr(dp.exchange, "status"):
+            return False
+        dp.flush()
+        torch.cuda.synchronize()
+        bad = dp.exchange.status.to(torch.int32).clone()
+        if world > 1:
+            dist.all_reduce(bad, op=dist.ReduceOp.MAX)
+        return int(bad.item()) != 0
 
     # ---- this rank's shard of the synthetic batch (weak scaling: 2 images per GPU) ----
     X, rois, obn, L, offs = synth_inputs(IMAGES_PER_GPU, ROIS_PER_IMAGE, seed=1000 * rank)
@@ -409,8 +428,20 @@ def gpu_arm(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()               # before the warm-up: nvidia-smi needs a moment to deliver its first sample
+    sync_all()                        # every rank enters the first step together (the peer exchange's watchdog counts from there)
     for i in range(args.warmup):
         step_resident(i)
+        if i == 0 and args.dp_sync == "auto" and exchange_timed_out():
+            # sync=auto chose the peer-mapped exchange (its dry run passed) but a peer did not deliver inside the first real
+            # step: restart the run on the NCCL schedule instead of timing a broken exchange (the line records it)
+            if rank == 0:
+                sys.stderr.write("bench: p2p watchdog fired in the first step; falling back to --dp-sync sharded\n")
+            why = "%s; watchdog fired in the first training step -> NCCL sharded" % dp.p2p_selftest
+            init_parameters()
+            dp = DataParallelHead(model, fc6_panels=args.fc6_panels, sync="sharded")
+            dp.p2p_selftest = why
+            dp.broadcast_parameters()
+            step_resident(0)
     t_mark0 = time.time()
     model.profile = {}
     launches0 = _lib.launch_count

@@ -220,7 +220,7 @@ class P2PExchange:
                 raise RuntimeError("bucket of %d elements does not split into %d 32-byte aligned slices" % (n, self.world))
         self.index = {o: i for i, (o, _, _) in enumerate(self.plan)}
         self.update_fn = update_fn
-        self.timeout_ms = timeout_ms
+        self.timeout_ms = int(os.environ.get("NAWSOD_P2P_TIMEOUT_MS", timeout_ms))     # watchdog of every wait kernel
         dev = flat_grad.device
         nb, W = len(self.plan), self.world
         self.stage = torch.empty(flat_grad.numel(), dtype=torch.float32, device=dev)
