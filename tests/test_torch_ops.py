@@ -153,3 +153,26 @@ def test_losses_and_update_route_their_arguments(oracle_backed_ops):
     m2, p2, _, _ = O.acm_sgd_update(g, m.copy(), np.float32(1e-2), p.copy(), np.zeros_like(g), momentum=0.9, weight_decay=5e-4, lr_mult=2.0,
                                     iter_size=1, gpu_num=2, iter_count=3)
     assert np.array_equal(tm.numpy(), m2) and np.array_equal(tp.numpy(), p2) and not np.array_equal(p2, p) and np.isfinite(p2).all()
+
+
+def test_opcheck_on_the_oracle_stand_ins(oracle_backed_ops):
+    """torch.library.opcheck (schema incl. the in-place annotations of the SGD op, autograd registration, fake-tensor shape
+    functions against real outputs) -- runnable on the CPU because the stand-ins accept CPU tensors."""
+    from torch.library import opcheck
+    rng = np.random.default_rng(2)
+    utils = ("test_schema", "test_autograd_registration", "test_faketensor")
+    X = _t(O.synth_conv5(1, 8, 10, 12, seed=3)).requires_grad_()
+    rois = _t(O.synth_rois(6, 160, 192, seed=4))
+    opcheck(torch.ops.nawsod.RoIPoolF.default, (X, rois, 7, 7, 1.0 / 16), test_utils=utils)
+    Y = torch.rand(6, 8, 7, 7, requires_grad=True)
+    opcheck(torch.ops.nawsod.RoIFeatureBoost.default, (Y, torch.rand(6, 1) + 1), test_utils=utils)
+    opcheck(torch.ops.nawsod.FC.default, (torch.rand(6, 392, requires_grad=True), torch.rand(5, 392, requires_grad=True),
+                                          torch.rand(5, requires_grad=True)), test_utils=utils)
+    P = (torch.rand(1, 5) * 0.9 + 0.05).requires_grad_()
+    Lh = (torch.rand(1, 5) < 0.4).float()
+    opcheck(torch.ops.nawsod.WeightedCrossEntropyWithLogits.default, (P, Lh, torch.rand(1, 5), True), test_utils=utils)
+    opcheck(torch.ops.nawsod.CrossEntropyWithLogits.default, (P, Lh, False), test_utils=utils)
+    opcheck(torch.ops.nawsod.MinEntropyLoss.default, (torch.rand(9, 5, requires_grad=True), Lh), test_utils=utils)
+    g, m, p = (_t(rng.standard_normal(16).astype(np.float32)) for _ in range(3))
+    opcheck(torch.ops.nawsod.ACMWeightDecayMomentumSGDUpdate.default, (g, m, torch.tensor([1e-2]), p, None, 0.9, 1, 1, 1.0, 5e-4, 1),
+            test_utils=("test_schema", "test_faketensor"))
