@@ -94,3 +94,32 @@ def test_weight_permutation_matches_the_patch_order():
         y = cols.reshape(2 * 6 * 7, 9 * cp) @ wm.reshape(cout, 9 * cp).T
         want = Fn.conv2d(torch.from_numpy(x), torch.from_numpy(w), padding=dil, dilation=dil).numpy().transpose(0, 2, 3, 1)
         np.testing.assert_allclose(y.reshape(2, 6, 7, cout), want, rtol=1e-4, atol=1e-4)
+
+
+def test_product_weight_layout_on_the_host(gold):
+    """VGG16ConvBody.load_reference_params (pure tensor code: runs on the CPU): GEMM operand [Cout, (kh, kw, c)] in bf16 with
+    conv1_1's three planes zero-padded to eight, biases float32; wrong shapes are refused like the reference's
+    initialize_gpu_from_weights_file (utils/net_wsl.py:105-111)."""
+    import torch
+    from nafwebsod_b200.conv_body import VGG16ConvBody
+    params = CB.synth_params(int(gold["seed"]))
+    body = VGG16ConvBody(dilation=2, device="cpu")
+    body.load_reference_params(params)
+    assert sorted(body.w) == sorted(k[:-2] for k in params if k.endswith("_w")) and len(body.w) == 13
+    for name, cin in (("conv1_1", 3), ("conv3_2", 256), ("conv5_3", 512)):
+        w = params[name + "_w"]
+        cout, cp = w.shape[0], (cin + 7) // 8 * 8
+        got = body.w[name]
+        assert got.dtype == torch.bfloat16 and tuple(got.shape) == (cout, 9 * cp) and got.is_contiguous()
+        want = np.zeros((cout, 3, 3, cp), np.float32)
+        want[..., :cin] = w.transpose(0, 2, 3, 1)
+        assert torch.equal(got.float(), torch.from_numpy(want.reshape(cout, 9 * cp)).to(torch.bfloat16).float())
+        assert body.b[name].dtype == torch.float32 and np.array_equal(body.b[name].numpy(), params[name + "_b"])
+    bad = dict(params)
+    bad["conv2_1_w"] = params["conv2_1_w"][:, :32]
+    with pytest.raises(RuntimeError, match="conv2_1"):
+        VGG16ConvBody(dilation=1, device="cpu").load_reference_params(bad)
+    with pytest.raises(RuntimeError, match="DILATION"):
+        VGG16ConvBody(dilation=3, device="cpu")
+    with pytest.raises(RuntimeError, match="CUDA"):
+        body.feed_image(torch.zeros(1, 3, 8, 8))
