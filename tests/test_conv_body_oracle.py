@@ -123,3 +123,41 @@ def test_product_weight_layout_on_the_host(gold):
         VGG16ConvBody(dilation=3, device="cpu")
     with pytest.raises(RuntimeError, match="CUDA"):
         body.feed_image(torch.zeros(1, 3, 8, 8))
+
+
+@pytest.mark.parametrize("tag,dil", [("d2", 2), ("d1", 1)])
+def test_product_body_plumbing_on_stand_in_kernels(gold, monkeypatch, tag, dil):
+    """VGG16ConvBody.run() with the two device entry points replaced -- in this test only -- by torch CPU stand-ins that
+    consume exactly what the kernels consume (channels-last bf16 map, the [Cout, (kh,kw,c)] bf16 operand, float32 bias):
+    the layer sequence, the dilation / stride arguments, the padded first layer and the return values must reproduce the
+    oracle evaluated on the same bf16-rounded inputs (what the GPU test asserts of the real kernels)."""
+    import torch
+    import torch.nn.functional as Fn
+    from nafwebsod_b200 import ops
+    from nafwebsod_b200.conv_body import VGG16ConvBody, add_VGG16_conv5_body_origin
+
+    def conv(X, Wmat, b, *, dilation=1, relu=True, cols=None):
+        cout, cp = Wmat.shape[0], X.shape[3]
+        w = Wmat.float().reshape(cout, 3, 3, cp).permute(0, 3, 1, 2).contiguous()
+        y = Fn.conv2d(X.float().permute(0, 3, 1, 2).contiguous(), w, b, padding=dilation, dilation=dilation)
+        return (torch.relu(y) if relu else y).permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+
+    def pool(X, *, stride=2):
+        return Fn.max_pool2d(X.float().permute(0, 3, 1, 2).contiguous(), 2, stride).permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+    monkeypatch.setattr(ops, "Conv3x3Relu", conv)
+    monkeypatch.setattr(ops, "MaxPool2x2", pool)
+    params = CB.synth_params(int(gold["seed"]))
+    body = VGG16ConvBody(dilation=dil, device="cpu")
+    body.load_reference_params(params)
+    x = torch.zeros((1,) + gold["data"].shape[2:] + (8,), dtype=torch.bfloat16)        # what feed_image builds on the device
+    x[..., :3] = torch.from_numpy(gold["data"]).permute(0, 2, 3, 1).to(torch.bfloat16)
+    body.blobs["data"] = x
+    y, dim, scale = add_VGG16_conv5_body_origin(body)
+    assert (dim, scale) == (512, float(gold[tag + "_spatial_scale"])) and y.dtype == torch.bfloat16 and body.blobs["conv5_3"] is y
+    want, _, _, _ = CB.conv5_body(gold["data"], params, dil, round_bf16=True)
+    got = y.float().numpy().transpose(0, 3, 1, 2)
+    assert got.shape == want.shape
+    rel = np.linalg.norm(got.astype(np.float64) - want) / np.linalg.norm(want.astype(np.float64))
+    assert rel <= 1e-6, rel            # same torch functions at the same rounding points: equal up to the padded first layer's sum order
+    _, _, _ = body.run(keep=("pool4",))
+    assert tuple(body.blobs["pool4"].shape[1:3]) == tuple(gold[tag + "_pool4"].shape[2:])
