@@ -24,13 +24,28 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+
+def _cpu_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+if "reference" in sys.argv[1:]:
+    # The CPU arm uses every host core: torchrun exports OMP_NUM_THREADS=1 to its workers, which
+    # would throttle the BLAS / OpenMP legs nine-fold -- override it BEFORE NumPy (and its BLAS) is loaded.
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS", "NUMEXPR_NUM_THREADS"):
+        os.environ[_v] = str(_cpu_threads())
+
 import numpy as np  # noqa: E402
 
 METRIC = "RoIs/sec (fwd+bwd, WSDDN head)"
 UNIT = "RoIs/s"
 IMAGES_PER_GPU, ROIS_PER_IMAGE, NUM_CLASSES = 2, 2000, 21
 C5, H5, W5 = 512, 38, 50
-CPU_SAMPLE_ROIS = 1000        # CPU legs: one image x 1000 of its 2000 RoIs per step (about 2 s per step on 16 cores)
+CPU_SAMPLE_ROIS = 1000        # cpu_baseline leg of the GPU arm: one image x 1000 of its 2000 RoIs per step (~1 s on 16 cores)
+REF_BUDGET_S = 420.0          # reference arm: wall-clock budget of the timed steps (a slow box runs fewer steps and says so)
 
 
 _JSON_OUT = None
@@ -128,45 +143,87 @@ def cpu_head_step(X, rois, obn, L, params, masks):
     return float(out["loss_cls"]) + float(out["loss_cls_noise"])
 
 
-def cpu_problem(rois_n, seed=0):
+def cpu_problem(rois_n, seed=0, params=None):
     from oracle import nawsod_oracle as O
     X, rois, obn, L, _ = synth_inputs(1, rois_n, seed)
-    params = O.synth_params(NUM_CLASSES - 1, C5 * 49, 4096, noise=True, seed=2)
+    if params is None:
+        params = O.synth_params(NUM_CLASSES - 1, C5 * 49, 4096, noise=True, seed=2)
     rng = np.random.default_rng(3)
     masks = {k: (rng.random((rois_n, 4096)) < 0.5).astype(np.float32) for k in ("drop6", "drop7", "noisy_drop6", "noisy_drop7")}
     return X, rois, obn, L, params, masks
 
 
-def run_cpu(steps, warmup, sample_rois):
-    prob = cpu_problem(sample_rois)
+def run_cpu(steps, warmup, sample_rois, images=1, budget_s=None):
+    """`steps` timed passes of `images` independent one-image problems of `sample_rois` RoIs each (the reference runs one
+    image per net, wsl_heads.py:214).  Returns (RoIs/s, per-step seconds list, steps actually timed)."""
+    probs = []
+    for b in range(images):                                  # the images share one set of parameters
+        probs.append(cpu_problem(sample_rois, seed=10 * b, params=probs[0][4] if probs else None))
     for _ in range(warmup):
-        cpu_head_step(*prob)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        cpu_head_step(*prob)
-    dt = time.perf_counter() - t0
-    return sample_rois * steps / dt, dt / steps
+        for prob in probs:
+            cpu_head_step(*prob)
+    per = []
+    for i in range(steps):
+        t0 = time.perf_counter()
+        for prob in probs:
+            cpu_head_step(*prob)
+        per.append(time.perf_counter() - t0)
+        if budget_s is not None and sum(per) + per[-1] > budget_s and i + 1 < steps:
+            break
+    return images * sample_rois * len(per) / sum(per), per, len(per)
+
+
+def cpu_forward_only(rois_n, repeats=5):
+    """BASELINE config 1: head FORWARD on the CPU, 1 image x `rois_n` RoIs, clean stack only, dropout off (test net)."""
+    from oracle import nawsod_oracle as O
+    from oracle import c_oracle as CO
+    X, rois, obn, L, params, _ = cpu_problem(rois_n)
+
+    def fwd():
+        Y, _ = CO.roi_pool_f(X, rois, 1.0 / 16)
+        feat = O.roi_feature_boost(Y, obn).reshape(Y.shape[0], -1)
+        a = O.fc_stack_forward(feat, params["fc6_w"], params["fc6_b"], params["fc7_w"], params["fc7_b"], None, None)
+        c, d = O.fc(a["drop7"], params["fc8c_w"], params["fc8c_b"]), O.fc(a["drop7"], params["fc8d_w"], params["fc8d_b"])
+        return O.test_cls_prob(O.wsl_outputs(c, d)[2])
+    fwd()
+    ts = []
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        fwd()
+        ts.append(time.perf_counter() - t0)
+    return rois_n / float(np.median(ts)), float(np.median(ts))
 
 
 def reference_arm(args):
+    """The reference's CPU path on this box's host cores: the SAME workload per step as the GPU arm (BASELINE config 2:
+    2 images x 2000 RoIs, two-stack head, fwd+bwd, fp32), --steps / --warmup honoured, all host threads.  Caffe2 cannot be
+    installed here, so the operators are the oracle port: the reference's own .cc operators where they
+    compile (oracle/_ref), C/OpenMP RoIPoolF, NumPy/BLAS for the Caffe2 built-ins."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    cores = os.cpu_count() or 1
-    sample = CPU_SAMPLE_ROIS
-    steps, warmup = max(1, min(args.steps, 10)), max(1, min(args.warmup, 2))
-    value, per = run_cpu(steps, warmup, sample)
-    desc = ("1 image x %d RoIs per step (of the 2 x 2000 workload), 512x38x50 map, 20 classes, two-stack head, fwd+bwd, fp32; "
-            "oracle port of the reference's CPU algorithm (Caffe2 itself is not installable here): C/OpenMP RoIPoolF + NumPy/BLAS") % sample
+    cores = _cpu_threads()
+    rpi = args.ref_rois_per_image
+    value, per, done = run_cpu(args.steps, args.warmup, rpi, images=IMAGES_PER_GPU, budget_s=REF_BUDGET_S)
+    c1_value, c1_s = cpu_forward_only(rpi)
+    desc = ("%d images x %d RoIs per step = the GPU arm's per-GPU workload (not a sub-sample), 512x38x50 map, 20 classes, two-stack head, "
+            "fwd+bwd, fp32, %d timed steps%s; oracle port of the reference's CPU algorithm (Caffe2 itself is not installable here): "
+            "C/OpenMP RoIPoolF + NumPy/BLAS, %d threads") % (
+                IMAGES_PER_GPU, rpi, done, "" if done == args.steps else " (of %d requested: %.0f s budget)" % (args.steps, REF_BUDGET_S), cores)
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
-        "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": _workload(True), "global_rois_per_step": args.gpus * IMAGES_PER_GPU * ROIS_PER_IMAGE,
-                   "parallelism": "host cores of rank 0 (the reference's CPU path does not shard)",
-                   "sample": desc},
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": done, "warmup": args.warmup,
+        "ms_per_step": float(np.mean(per)) * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": _workload(True), "global_rois_per_step": IMAGES_PER_GPU * rpi,
+                   "parallelism": "host cores of rank 0 (the reference's CPU path does not shard; at N > 1 the other ranks exit)",
+                   "sample": desc, "threads": cores,
+                   "step_s": {"min": float(np.min(per)), "median": float(np.median(per)), "max": float(np.max(per))}},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        # BASELINE.json configs[0]: the reference's own CPU-runnable case (forward only, 1 image x 2000 RoIs, clean stack)
+        "config1_cpu_forward": {"value": c1_value, "unit": "RoIs/s (fwd only)", "s_per_image": c1_s, "cores": cores,
+                                "sample": "1 image x %d RoIs, median of 5" % rpi},
     }
     _emit(line)
     return 0
@@ -245,11 +302,13 @@ class ClockSampler:
 
 
 def assemble_line(*, steps, warmup, world, R, S, bf16, noise, ms_total, ms_e2e, h2d_bytes, d2h_bytes, launches, clocks, kernel_ms,
-                  n_panels, iso, cpu, loss, dp_info):
+                  n_panels, iso, cpu, loss, dp_info, timing=None, tf32=None):
     """The ONE JSON line of the GPU arm from the run's raw measurements (pure: no CUDA, no torch -- tests/test_bench_contract.py
     runs it on the CPU).  ms_total / ms_e2e: device time of the `steps` timed steps of the resident / end-to-end leg (max over
-    ranks); kernel_ms: mean CUDA-event duration per launch of fc6_fwd, fc6_bwd_w (one row panel), roi_pool_f, mil_head inside
-    the timed steps; iso: isolated RoIPoolF timings (rank 0) or {}; dp_info: sync / fc6_panels / p2p_selftest / fused."""
+    ranks; the median block when the region was repeated, see `timing`); kernel_ms: mean CUDA-event duration per launch of
+    fc6_fwd, fc6_bwd_w (one row panel), roi_pool_f, mil_head inside the timed steps; iso: isolated RoIPoolF timings (rank 0)
+    or {}; dp_info: sync / fc6_panels / p2p_selftest / fused; timing: {"value": ..., "e2e": ...} block / per-step spread;
+    tf32: {"ms_total", "steps", "kernel_ms", "n_panels"} of the fp32 (TF32 tensor path) run of the same workload, or None."""
     peaks = _peaks()
     ms_step = ms_total / steps
     value = world * R * steps / (ms_total * 1e-3)
@@ -273,7 +332,8 @@ def assemble_line(*, steps, warmup, world, R, S, bf16, noise, ms_total, ms_e2e, 
     roofline = {
         "kernel": "gemm_tcgen05_kernel<256,MN,MN> (fc6 weight gradient, dY^T.X, both stacks in one GEMM)",
         "bound": "tensor", "achieved": fc6_flops / (t_bww_total * 1e-3) / 1e12 if t_bww_total else None, "peak": tensor_peak,
-        "unit": "TFLOP/s", "traffic": traffic, "launches_per_step": n_panels,
+        "unit": "TFLOP/s", "traffic": traffic, "traffic_source": "ncu --set full capture of one such launch (profiles/ncu_traffic.json)",
+        "launches_per_step": n_panels,
         # a panel launch reads its columns of dY and all pooled features and writes its rows of dW (fp32)
         "algorithmic_bytes_per_launch": (R * (S * 4096) * es + R * (C5 * 49) * es * n_panels + (S * 4096) * (C5 * 49) * 4) / n_panels,
         "peak_source": peaks["source"] + ("; sustained bf16" if bf16 else "; TF32 = bf16/2"),
@@ -289,6 +349,22 @@ def assemble_line(*, steps, warmup, world, R, S, bf16, noise, ms_total, ms_e2e, 
         "mil_head": {"ms": t_mil},
         "step_tensor_frac": _flops_per_roi(noise) * R / (ms_step * 1e-3) / 1e12 / tensor_peak,
     }
+    if tf32:
+        # the reference's precision (fp32 end to end: Caffe2 FC = sgemm) on the TF32 tensor path; peak = bf16 / 2
+        t32_peak = peaks["tf_sustained"] * 0.5
+        ms32 = tf32["ms_total"] / tf32["steps"]
+        f32, w32 = tf32["kernel_ms"].get("fc6_fwd"), tf32["kernel_ms"].get("fc6_bwd_w")
+        w32 = w32 * tf32["n_panels"] if w32 else None
+        kernels["tf32_step"] = {
+            "note": "same workload, fp32 storage + kind::tf32 GEMMs (operands pre-rounded to nearest TF32), resident inputs",
+            "ms_per_step": ms32, "rois_per_s": R * tf32["steps"] / (tf32["ms_total"] * 1e-3), "steps": tf32["steps"],
+            "peak_tflops": t32_peak,
+            "fc6_fwd": {"ms": f32, "tflops": fc6_flops / (f32 * 1e-3) / 1e12 if f32 else None,
+                        "frac_tensor": fc6_flops / (f32 * 1e-3) / 1e12 / t32_peak if f32 else None},
+            "fc6_bwd_w": {"ms": w32, "panels": tf32["n_panels"], "tflops": fc6_flops / (w32 * 1e-3) / 1e12 if w32 else None,
+                          "frac_tensor": fc6_flops / (w32 * 1e-3) / 1e12 / t32_peak if w32 else None},
+            "step_tensor_frac": _flops_per_roi(noise) * R / (ms32 * 1e-3) / 1e12 / t32_peak,
+        }
     if iso:
         # algorithmic bytes: Y + (argmax when the conv body trains) + rois + the map read once
         b_step = pool_bytes
@@ -304,9 +380,8 @@ def assemble_line(*, steps, warmup, world, R, S, bf16, noise, ms_total, ms_e2e, 
                 "p2p": "peer-mapped (CUDA IPC over NVSwitch) scatter of fp32 grads into the owner's staging + fused reduce/SGD on the owner "
                        "+ scatter of the bf16 operands back, ordered by flag kernels",
                 "allreduce": "NCCL all-reduce fp32 grads + full SGD"}
-    fc6_update = {"sgd": "EXPERIMENTAL: fused into the fc6 weight-gradient GEMM epilogue (NAWSOD_FUSED_SGD=1)",
-                  "scatter": "on the owner rank of each slice; EXPERIMENTAL: the GEMM epilogue stores its tiles into the owners' "
-                             "peer-mapped staging (NAWSOD_P2P_FUSED_SCATTER=1)"}
+    fc6_update = {"scatter": "on the owner rank of each slice; the fc6 weight-gradient GEMM's epilogue stores its tiles into "
+                             "the owners' peer-mapped staging (gemm_scatter.cu, NAWSOD_P2P_FUSED_SCATTER=1)"}
     return {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -321,6 +396,7 @@ def assemble_line(*, steps, warmup, world, R, S, bf16, noise, ms_total, ms_e2e, 
                                                 else "on the owner rank of each slice")},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),
                 "ms_per_step": ms_e2e / steps},
+        "timing": timing,
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,
@@ -406,12 +482,16 @@ def gpu_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, tail=None):
+    def timed(fn, steps, tail=None, step_events=None):
         sync_all()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         for i in range(steps):
             fn(i)
+            if step_events is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                step_events.append(e)
         dp.flush()                      # the last step's parameter exchange belongs to the timed region
         b.record()
         if tail is not None:
@@ -420,7 +500,33 @@ def gpu_arm(args):
         ms = torch.tensor([a.elapsed_time(b)], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        if step_events is not None:
+            step_events.insert(0, a)
         return ms.item()
+
+    def timed_blocks(run_block, steps):
+        """EXACTLY `steps` steps per timed block (barrier + synchronize on both sides, max over ranks).  A block of a few ms
+        per step is over in < 0.1 s, where one host hiccup dominates: the block is repeated until >= 1 s has been timed
+        (at most 15 blocks, the count agreed across ranks through the max-reduced first block) and the MEDIAN block is
+        reported, with the spread of the blocks and of the individual steps beside it."""
+        blocks, per_step = [], []
+
+        def one():
+            ev = []
+            ms, extra = run_block(steps, ev)
+            blocks.append(ms)
+            per_step.extend(ev[i].elapsed_time(ev[i + 1]) for i in range(len(ev) - 1))
+            return extra
+        extra = one()
+        n = int(min(15, max(1, np.ceil(1000.0 / max(blocks[0], 1e-3)))))
+        for _ in range(n - 1):
+            extra = one()
+        order = sorted(range(len(blocks)), key=lambda i: blocks[i])
+        med = blocks[order[len(order) // 2]]
+        stats = {"blocks": len(blocks), "steps_per_block": steps,
+                 "block_ms_per_step": {"min": min(blocks) / steps, "median": med / steps, "max": max(blocks) / steps},
+                 "step_ms_this_rank": {"min": float(np.min(per_step)), "median": float(np.median(per_step)), "max": float(np.max(per_step))}}
+        return med, stats, extra
 
     # ---- resident-input leg (value) ----
     feed_from_host()                      # inputs now live in HBM (channels-last bf16 map etc.)
@@ -445,9 +551,9 @@ def gpu_arm(args):
     t_mark0 = time.time()
     model.profile = {}
     launches0 = _lib.launch_count
-    ms_total = timed(step_resident, args.steps)
+    ms_total, value_stats, _ = timed_blocks(lambda k, ev: (timed(step_resident, k, step_events=ev), None), args.steps)
     t_mark1 = time.time()
-    launches = _lib.launch_count - launches0
+    launches = (_lib.launch_count - launches0) // value_stats["blocks"]          # per block of `steps` steps
     prof, model.profile = model.profile, None
 
     # ---- end-to-end leg: host buffers in, loss out, every step ----
@@ -457,7 +563,7 @@ def gpu_arm(args):
     # loss of the previous step only.  Every step's H2D and D2H copies are issued and completed inside the timed region.
     from nafwebsod_b200.loader import BlobsQueue, LossFetcher
 
-    def run_e2e(steps, seed0=0):
+    def run_e2e(steps, ev=None, seed0=0):
         queue, fetch = BlobsQueue(model, capacity=2, x_layout="NCHW"), LossFetcher(lag=1)
 
         def step(i):
@@ -468,13 +574,13 @@ def gpu_arm(args):
                 queue.enqueue_blobs(hX, hrois, hobn, hL, hoffs)      # prefetch: overlaps this step's kernels
             bl = dp.step(dropout_seed=seed0 + i + 1)
             fetch.push(bl["loss"])                                    # D2H read of the step's result
-        ms = timed(step, steps, tail=fetch.wait_all)
+        ms = timed(step, steps, tail=fetch.wait_all, step_events=ev)
         assert queue.h2d_bytes == steps * h2d_bytes
         return ms, fetch
 
     run_e2e(max(2, args.warmup // 2))
     t_mark2 = time.time()
-    ms_e2e, fetch = run_e2e(args.steps)
+    ms_e2e, e2e_stats, fetch = timed_blocks(run_e2e, args.steps)
     losses = fetch.values
     # clocks are sampled across BOTH timed regions (resident + end-to-end) so that short runs still
     # collect samples under load
@@ -528,6 +634,27 @@ def gpu_arm(args):
             out_dtype=torch.float32))
         del x32
 
+    # ---- the reference's precision: fp32 storage on the TF32 tensor path, same workload (one GPU only; SURVEY.md 8d config 2
+    # asks for both) -- reported inside the one line as kernels.tf32_step
+    tf32 = None
+    if world == 1 and dtype == torch.bfloat16 and not args.no_tf32:
+        dp.flush(); torch.cuda.synchronize()
+        main_model, main_dp = model, dp
+        model = WeblyHeadModel(NUM_CLASSES, C5, 7, 4096, noise=noise, dtype=torch.float32, device=dev)
+        init_parameters()
+        dp = DataParallelHead(model, fc6_panels=args.fc6_panels, sync=args.dp_sync)
+        model.UpdateWorkspaceLr(1e-3)
+        feed_from_host()
+        for i in range(3):
+            step_resident(i)
+        model.profile = {}
+        ms32 = timed(step_resident, args.steps)
+        prof32, model.profile = model.profile, None
+        mean = lambda ev: sum(a.elapsed_time(b) for a, b in ev) / max(len(ev), 1) if ev else None
+        tf32 = {"ms_total": ms32, "steps": args.steps, "kernel_ms": {k: mean(prof32.get(k, [])) for k in ("fc6_fwd", "fc6_bwd_w")},
+                "n_panels": max(1, len(prof32.get("fc6_bwd_w", [])) // max(args.steps, 1))}
+        model, dp = main_model, main_dp
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -539,18 +666,18 @@ def gpu_arm(args):
         return sum(a.elapsed_time(b) for a, b in ev) / max(len(ev), 1) if ev else None
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
+        cores = _cpu_threads()
         sample = CPU_SAMPLE_ROIS
-        v, per = run_cpu(5, 1, sample)
+        v, per, _ = run_cpu(5, 1, sample)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": "5 steps of 1 image x %d RoIs (bounded sample of the 2 x 2000 workload), fp32 oracle port: C/OpenMP RoIPoolF + NumPy/BLAS "
-                         "FC stack + MIL/loss restatement, %.2f s per step" % (sample, per)}
+                         "FC stack + MIL/loss restatement, %.2f s per step" % (sample, float(np.median(per)))}
     line = assemble_line(
         steps=args.steps, warmup=args.warmup, world=world, R=R, S=model.S, bf16=dtype == torch.bfloat16, noise=noise,
         ms_total=ms_total, ms_e2e=ms_e2e, h2d_bytes=h2d_bytes, d2h_bytes=d2h_bytes, launches=launches, clocks=clocks,
         kernel_ms={k: avg_ms(k) for k in ("fc6_fwd", "fc6_bwd_w", "roi_pool_f", "mil_head")},
-        n_panels=max(1, len(prof.get("fc6_bwd_w", [])) // max(args.steps, 1)), iso=iso, cpu=cpu,
-        loss=[float(x) for x in losses[-1].flatten().tolist()],
+        n_panels=max(1, len(prof.get("fc6_bwd_w", [])) // max(args.steps * value_stats["blocks"], 1)), iso=iso, cpu=cpu,
+        loss=[float(x) for x in losses[-1].flatten().tolist()], timing={"value": value_stats, "e2e": e2e_stats}, tf32=tf32,
         dp_info={"sync": dp.sync, "fc6_panels": dp.fc6_panels, "p2p_selftest": dp.p2p_selftest, "fused": dp._fused_mode()})
     _emit(line)
     if world > 1:
@@ -572,8 +699,11 @@ def main():
                     help="N>1 gradient exchange: auto = p2p when the ranks can map each other's memory, else NCCL sharded; allreduce = the reference's schedule")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-isolated", action="store_true", help="skip the isolated RoIPoolF timing after the timed regions")
+    ap.add_argument("--ref-rois-per-image", type=int, default=ROIS_PER_IMAGE, help=argparse.SUPPRESS)   # tests shrink the CPU arm
+    ap.add_argument("--no-tf32", action="store_true", help="skip the fp32 / TF32 run of the same workload (kernels.tf32_step)")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3)
+    if args.impl == "ours":
+        args.warmup = max(args.warmup, 3)          # timing rule: at least three warm-up steps on the device
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if not (args.impl == "ours" and world == 1 and args.gpus > 1):      # the torchrun re-launch keeps the parent's stdout
         _protect_stdout()

@@ -145,30 +145,18 @@ int nawsod_fc_bwd_w_stacks(const void* dY, int64_t lddy, int64_t sdY, const void
                            void* stream);
 
 /* FCGradient's db alone: db[s][N] (float) = column sums of dY[s][M,N] -- what nawsod_fc_bwd_w[_stacks] computes when db is
- * given, as a call of its own so that a caller can take the (HBM-bound) sums off the stream the GEMMs run on. */
+ * given, as a call of its own (FCGradient's db output without its dW). */
 int nawsod_fc_bias_grad(const void* dY, int64_t lddy, int64_t sdY, int S, int M, int N, int ab_dtype,
                         float* db, int64_t sdb, int flags, void* stream);
 
-/* FCGradient's dW with the op that follows it in the step fused into the GEMM epilogue (gemm_fused.cu; the 822 MB fc6
- * gradient then never makes the round trip through HBM).  EXPERIMENTAL: opt-in on the host side until measured.
+/* FCGradient's dW with the send leg of the data-parallel exchange fused into the GEMM epilogue (gemm_scatter.cu).
  *
- * nawsod_fc_bwd_w_sgd      FCGradient (dW, db) + ACMWeightDecayMomentumSGDUpdate of W (iter_size 1;
- *     detectron/ops/acm_weightdecay_momentum_sgd_op.h:48-112, wiring modeling/optimizer_wsl.py:127-136) on ONE GPU:
- *     m, p [N,K] (row pitch ldw) are updated in place from the tile the epilogue just accumulated, p_shadow receives
- *     the updated parameter in the operands' type (shadow_dtype must equal ab_dtype: bf16, or float = TF32-rounded).
- *     dW may be NULL (the gradient is then not stored); db as in nawsod_fc_bwd_w (its update stays with the caller).
- *     Results are bit-identical to nawsod_fc_bwd_w followed by nawsod_sgd_update.
  * nawsod_fc_bwd_w_scatter  FCGradient (dW, db) + the send leg of the data-parallel reduce-scatter that replaces
  *     NCCLAllreduce (modeling/optimizer_wsl.py:52-72): rows [k*rows_per_owner, (k+1)*rows_per_owner) of dW are stored
  *     to owner_dW[k] (row k*rows_per_owner first, row pitch ldw) -- the local gradient slice for the calling rank,
  *     peer-mapped staging memory (nawsod_p2p_open_mem_handle) for the others -- tile by tile from the epilogue.
  *     rows_per_owner must be a multiple of 128 (one output tile has one owner).  The caller publishes the
  *     sequence number afterwards (nawsod_p2p_signal in stream order). */
-int nawsod_fc_bwd_w_sgd(const void* dY, int64_t lddy, const void* A, int64_t lda, int M, int N, int K,
-                        int ab_dtype, float* dW, int64_t ldw, float* db, int flags, float* m, float* p,
-                        void* p_shadow, int shadow_dtype, const float* lr, float momentum,
-                        float weight_decay, float lr_mult, int gpu_num, int64_t iter_count,
-                        void* stream);
 int nawsod_fc_bwd_w_scatter(const void* dY, int64_t lddy, const void* A, int64_t lda, int M, int N,
                             int K, int ab_dtype, float* const* owner_dW, int n_owners,
                             int rows_per_owner, int64_t ldw, float* db, void* stream);
@@ -242,11 +230,13 @@ int nawsod_sgd_update(const float* g, float* m, const float* lr, float* p, float
 /* a10 + a11 on the owner rank of a parameter slice: the gradient is the sum, in the order given, of
  *   n_grads contributions (the rank's own slice and the copies its peers deposited), followed by the
  *   same update as nawsod_sgd_update with iter_size 1 (the reference all-reduces, then updates:
- *   modeling/optimizer_wsl.py:52-72, 96-137). */
+ *   modeling/optimizer_wsl.py:52-72, 96-137).  abort_flag (optional, device uint32): when the word is
+ *   non-zero at launch time -- the status word of a nawsod_p2p_wait whose watchdog fired -- the call
+ *   leaves m, p and the shadow untouched instead of updating from an incomplete sum. */
 int nawsod_sgd_update_reduce(const float* const* grads, int n_grads, float* m, const float* lr,
                              float* p, int64_t n, float momentum, float weight_decay,
                              float lr_mult, int gpu_num, int64_t iter_count, void* p_shadow,
-                             int shadow_dtype, void* stream);
+                             int shadow_dtype, const void* abort_flag, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * a11: peer-to-peer plumbing of the gradient exchange (replaces the NCCLAllreduce ops of

@@ -439,6 +439,8 @@ extern "C" int nawsod_fc_fwd_stacks(const void* A, int64_t lda, int64_t sA, cons
   NAWSOD_REQUIRE(!(flags & NAWSOD_FC_ACCUMULATE), NAWSOD_ERR_ARG, "fc_fwd: ACCUMULATE is a bwd_w flag");
   NAWSOD_REQUIRE(!(flags & NAWSOD_FC_ROUND_TF32) || y_dtype == NAWSOD_F32, NAWSOD_ERR_ARG, "fc_fwd: ROUND_TF32 needs a float output");
   NAWSOD_REQUIRE(ldy >= N && (!mask || ldmask >= N), NAWSOD_ERR_SHAPE, "fc_fwd: ldy / ldmask smaller than N");
+  NAWSOD_REQUIRE(!(flags & NAWSOD_FC_DROPOUT) || mask || dropout_seed != 0, NAWSOD_ERR_ARG,
+                 "fc_fwd: DROPOUT needs a mask or a non-zero dropout_seed (it would only scale the activations by 2)");
   EpiParams ep{};
   ep.out = Y; ep.ldo = ldy; ep.out_dtype = y_dtype; ep.bias = bias; ep.mask = (flags & NAWSOD_FC_DROPOUT) ? mask : nullptr;
   ep.ldmask = ldmask; ep.act = nullptr; ep.flags = flags; ep.seed = dropout_seed; ep.M = M; ep.N = N; ep.K = K;

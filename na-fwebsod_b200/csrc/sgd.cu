@@ -21,6 +21,7 @@ struct SgdArgs {
   int first_call;   // iter_count == 0: m and acc start from zero whatever the buffers hold (.h:62-69)
   int do_update;    // (iter_count + 1) % iter_size == 0
   int use_acc;      // iter_size > 1 or acc buffer given
+  const uint32_t* abort_flag;   // optional: a non-zero word (the exchange's watchdog status) turns the launch into a no-op
 };
 
 __device__ __forceinline__ float rna_tf32(float x) {
@@ -49,6 +50,9 @@ __device__ __forceinline__ void sgd_elem(float g, float& m, float& p, float& acc
 }
 
 __global__ void __launch_bounds__(256) sgd_kernel(const SgdArgs a) {
+  // a peer's contribution never arrived (p2p_wait's watchdog fired): leave m / p / shadow untouched rather than
+  // update from an incomplete sum; the host sees the same word and raises (dp.P2PExchange.check)
+  if (a.abort_flag && *reinterpret_cast<const volatile uint32_t*>(a.abort_flag) != 0u) return;
   const float LR = __fmul_rn(a.lr[0], a.lr_mult);
   const int64_t n4 = a.n / 4;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -104,7 +108,7 @@ using namespace nawsod;
 
 static int sgd_launch(const float* const* grads, int n_grads, float* m, const float* lr, float* p, float* acc, int64_t n,
                       float momentum, float weight_decay, float lr_mult, int iter_size, int gpu_num,
-                      int64_t iter_count, void* p_shadow, int shadow_dtype, void* stream) {
+                      int64_t iter_count, void* p_shadow, int shadow_dtype, const void* abort_flag, void* stream) {
   const float* g = grads[0];
   NAWSOD_REQUIRE(n >= 0, NAWSOD_ERR_SHAPE, "sgd_update: negative n");
   NAWSOD_REQUIRE(iter_size >= 1 && gpu_num >= 1 && iter_count >= 0, NAWSOD_ERR_ARG,
@@ -131,6 +135,7 @@ static int sgd_launch(const float* const* grads, int n_grads, float* m, const fl
   a.first_call = iter_count == 0;
   a.do_update = ((iter_count + 1) % iter_size) == 0;
   a.use_acc = acc != nullptr;
+  a.abort_flag = static_cast<const uint32_t*>(abort_flag);
   const int64_t work = std::max<int64_t>(n / 4, 1);
   // sgd_max_ctas: when the update runs beside the tensor-core GEMMs it only has to keep up with them;
   // a narrower grid leaves the memory system's queues to the GEMM epilogues
@@ -146,15 +151,16 @@ extern "C" int nawsod_sgd_update(const float* g, float* m, const float* lr, floa
                                  int64_t iter_count, void* p_shadow, int shadow_dtype, void* stream) {
   const float* grads[1] = {g};
   return sgd_launch(grads, 1, m, lr, p, acc, n, momentum, weight_decay, lr_mult, iter_size, gpu_num, iter_count,
-                    p_shadow, shadow_dtype, stream);
+                    p_shadow, shadow_dtype, nullptr, stream);
 }
 
 extern "C" int nawsod_sgd_update_reduce(const float* const* grads, int n_grads, float* m, const float* lr, float* p,
                                         int64_t n, float momentum, float weight_decay, float lr_mult, int gpu_num,
-                                        int64_t iter_count, void* p_shadow, int shadow_dtype, void* stream) {
+                                        int64_t iter_count, void* p_shadow, int shadow_dtype, const void* abort_flag,
+                                        void* stream) {
   NAWSOD_REQUIRE(grads && n_grads >= 1 && n_grads <= kMaxGradSources, NAWSOD_ERR_ARG,
                  "sgd_update_reduce: need 1..%d gradient sources", kMaxGradSources);
   NAWSOD_REQUIRE(n == 0 || grads[0], NAWSOD_ERR_ARG, "sgd_update_reduce: null gradient source");
   return sgd_launch(grads, n_grads, m, lr, p, nullptr, n, momentum, weight_decay, lr_mult, 1, gpu_num, iter_count,
-                    p_shadow, shadow_dtype, stream);
+                    p_shadow, shadow_dtype, abort_flag, stream);
 }

@@ -82,11 +82,22 @@ def rank_slice(offset: int, length: int, world: int, rank: int):
 
 
 def slices_aligned(length: int, world: int) -> bool:
-    """A bucket is exchanged in per-rank slices only if it splits evenly into slices of a multiple of 8 elements:
+    """A bucket can be exchanged in per-rank slices only if it splits evenly into slices of a multiple of 8 elements:
     the update kernel moves 16-byte vectors of the fp32 buffers AND of the bf16 operand shadow, so every slice must
-    start on a 16-byte boundary in both (2 x 4096 + 8192 + 80 bias floats over 4 or 8 ranks do not).  Other buckets
-    take the whole-bucket all-reduce with a redundant update on every rank."""
+    start on a 16-byte boundary in both.  Other buckets take the whole-bucket all-reduce with a redundant update on
+    every rank."""
     return length % world == 0 and (length // world) % 8 == 0
+
+
+def bucket_is_sliced(length: int, tag: str, world: int) -> bool:
+    """Whether a bucket's update is split over the ranks (reduce-scatter -> update of the owned slice -> all-gather of
+    the GEMM operands) or REPLICATED (every rank reduces all W contributions and updates the whole bucket).
+
+    The "biases" bucket is always replicated, whatever its alignment: the forward pass reads b6 / b7 / b8 from the
+    fp32 MASTERS (heads.py: ``self.p["b*"]`` are views of flat_param), and the sliced schedules only send the
+    GEMM-operand shadow back -- a rank would keep training on stale copies of every bias outside its own slice.  The
+    bucket is 66 KB; replicating its update costs nothing and keeps masters, momenta and shadow current everywhere."""
+    return tag != "biases" and slices_aligned(length, world)
 
 
 class GradientExchange:
@@ -111,8 +122,8 @@ class GradientExchange:
         self.in_flight = False
         self.bytes_out = 0      # gradient bytes handed to the collective (per step accounting by the caller)
 
-    def _divisible(self, length):
-        return slices_aligned(length, self.world)
+    def _sliced(self, length, tag):
+        return bucket_is_sliced(length, tag, self.world)
 
     def launch(self, offset: int, length: int, tag: str):
         """Call once the kernels producing flat[offset:offset+length] are enqueued on the current stream."""
@@ -135,14 +146,15 @@ class GradientExchange:
             if not self.sharded:
                 dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group)
                 return
-            if self._divisible(length):
+            sliced = self._sliced(length, tag)
+            if sliced:
                 so, sn = rank_slice(offset, length, self.world, self.rank)
                 dist.reduce_scatter_tensor(self.flat[so: so + sn], view, op=dist.ReduceOp.SUM, group=self.group)
-            else:                      # uneven or misaligned slices: whole-bucket all-reduce, every rank updates the bucket redundantly
-                dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group)
+            else:                      # replicated bucket (the biases; uneven or misaligned slices): whole-bucket
+                dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group)      # all-reduce, redundant update
                 so, sn = offset, length
             self.update_fn(offset, length, tag, so, sn)
-            if self._divisible(length):
+            if sliced:
                 dist.all_gather_into_tensor(self.out[offset: offset + length], self.out[so: so + sn], group=self.group)
 
     def finish(self):
@@ -215,8 +227,8 @@ class P2PExchange:
         self.flat, self.out, self.group = flat_grad, flat_out, group
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         self.plan = [(o, n, t) for o, n, t in plan if n > 0]
-        for o, n, _ in self.plan:
-            if not slices_aligned(n, self.world):
+        for o, n, t in self.plan:
+            if not bucket_is_sliced(n, t, self.world) and (t != "biases" or n % 4):
                 raise RuntimeError("bucket of %d elements does not split into %d 32-byte aligned slices" % (n, self.world))
         self.index = {o: i for i, (o, _, _) in enumerate(self.plan)}
         self.update_fn = update_fn
@@ -224,12 +236,22 @@ class P2PExchange:
         dev = flat_grad.device
         nb, W = len(self.plan), self.world
         self.stage = torch.empty(flat_grad.numel(), dtype=torch.float32, device=dev)
+        # replicated buckets (the biases, see bucket_is_sliced): every rank receives every rank's WHOLE contribution
+        # -> slot [rank] of a W x L area, one per replicated bucket, carved from one allocation
+        self.rep_off, rep_total = {}, 0
+        for o, n, t in self.plan:
+            if not bucket_is_sliced(n, t, self.world):
+                self.rep_off[o] = rep_total
+                rep_total += n * W
+        self.rep_stage = torch.empty(max(rep_total, 4), dtype=torch.float32, device=dev)
         self.flags = torch.zeros(2 * nb * W, dtype=torch.int32, device=dev)
         self.status = torch.zeros(1, dtype=torch.int32, device=dev)
         torch.cuda.synchronize(dev)
         self.peer_stage, e1 = _share_with_peers(self.stage, group)
         self.peer_flags, e2 = _share_with_peers(self.flags, group)
         self.peer_out, e3 = _share_with_peers(self.out, group)
+        self.peer_rep, e4 = _share_with_peers(self.rep_stage, group)
+        e3 = e3 or e4
         torch.cuda.synchronize(dev)
         ok = torch.tensor([0 if (e1 or e2 or e3) else 1], dtype=torch.int32, device=dev)
         dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)          # also the setup barrier
@@ -250,6 +272,8 @@ class P2PExchange:
         self.in_flight = False
         self.bytes_out = 0
         self.profile = None      # list of (label, bucket, event) while a caller instruments one step
+        self._status_host = torch.zeros(1, dtype=torch.int32).pin_memory()     # lagged copy of the watchdog word
+        self._status_ev = None
 
     def _flag_ptrs(self, kind, b):
         W, nb = self.world, len(self.plan)
@@ -273,7 +297,9 @@ class P2PExchange:
         if length <= 0:
             return
         b = self.index[offset]
-        W, rank, n = self.world, self.rank, length // self.world
+        W, rank = self.world, self.rank
+        replicated = offset in self.rep_off       # every rank gets every contribution and updates the whole bucket
+        n = length if replicated else length // W
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(self.flat.device))
         self.in_flight = True
@@ -285,7 +311,11 @@ class P2PExchange:
             with torch.cuda.stream(self.send_stream):
                 prof.append(("ready", b, self._mark()))
         peers = [(rank + i) % W for i in range(1, W)]             # staggered targets
-        rs_copies = [(self.peer_stage[k] + 4 * (offset + rank * n), self.flat.data_ptr() + 4 * (offset + k * n), 4 * n) for k in peers]
+        if replicated:
+            ro = self.rep_off[offset]
+            rs_copies = [(self.peer_rep[k] + 4 * (ro + rank * n), self.flat.data_ptr() + 4 * offset, 4 * n) for k in peers]
+        else:
+            rs_copies = [(self.peer_stage[k] + 4 * (offset + rank * n), self.flat.data_ptr() + 4 * (offset + k * n), 4 * n) for k in peers]
         self.bytes_out += 4 * n * (W - 1)
         if prescattered:
             # the producer GEMM stored its tiles at owner_ptrs(): all that is left of the scatter leg is the signal
@@ -308,17 +338,21 @@ class P2PExchange:
                     prof.append(("sent", b, self._mark()))
         # update side: wait for the W contributions, reduce + SGD on the owned slice, publish the operands
         self.stream.wait_event(ev)
-        so = offset + rank * n
+        so = offset if replicated else offset + rank * n
         with torch.cuda.stream(self.stream):
             fb = (self.RS * len(self.plan) + b) * W
             ops.p2p_wait(self.flags[fb: fb + W], self.seq, self.timeout_ms, self.status)
             if prof is not None:
                 prof.append(("arrived", b, self._mark()))
-            grads = [self.flat[so: so + n] if r == rank else self.stage[offset + r * n: offset + (r + 1) * n] for r in range(W)]
+            if replicated:       # the same W addends in the same (rank) order on every rank: replicas stay bit-identical
+                grads = [self.flat[so: so + n] if r == rank else self.rep_stage[ro + r * n: ro + (r + 1) * n] for r in range(W)]
+            else:
+                grads = [self.flat[so: so + n] if r == rank else self.stage[offset + r * n: offset + (r + 1) * n] for r in range(W)]
             self.update_fn(offset, length, tag, so, n, grads)
             if prof is not None:
                 prof.append(("updated", b, self._mark()))
-            ag_copies = [(self.peer_out[k] + es_out * so, self.out.data_ptr() + es_out * so, es_out * n) for k in peers]
+            # operand leg; a replicated bucket has nothing to send back, its AG flag only says "staging consumed"
+            ag_copies = [] if replicated else [(self.peer_out[k] + es_out * so, self.out.data_ptr() + es_out * so, es_out * n) for k in peers]
             if self.engine == "sm":
                 ops.p2p_scatter([c[1] for c in ag_copies], [c[0] for c in ag_copies], es_out * n, self._flag_ptrs(self.AG, b), self.seq, 64 + b)
             upd = torch.cuda.Event()
@@ -360,6 +394,9 @@ class P2PExchange:
             ops.p2p_wait(self.flags[nb * W: 2 * nb * W], self.seq, self.timeout_ms, self.status)
             if self.profile is not None:
                 self.profile.append(("all operands here", -1, self._mark()))
+            self._status_host.copy_(self.status, non_blocking=True)
+            self._status_ev = torch.cuda.Event()
+            self._status_ev.record()
         cur = torch.cuda.current_stream(self.flat.device)
         cur.wait_stream(self.stream)
         cur.wait_stream(self.send_stream)
@@ -395,7 +432,10 @@ class P2PExchange:
             for off, length, tag in self.plan:
                 self.launch(off, length, tag)
             self.finish()
-            for off, length, _ in self.plan:
+            for off, length, tag in self.plan:
+                if not bucket_is_sliced(length, tag, W):      # replicated: this rank updated (filled) all of it itself
+                    expect(self.out[off: off + length], float(rank + 1))
+                    continue
                 n = length // W
                 for r in range(W):
                     expect(self.out[off + r * n: off + (r + 1) * n], float(r + 1))
@@ -414,6 +454,12 @@ class P2PExchange:
         if int(ok.item()) == 1:
             return True, "ok"
         return False, msg or "failed on a peer"
+
+    def poll(self):
+        """Non-blocking check, one finish() behind: raises once the copy of the watchdog word that the last COMPLETED
+        finish() took is non-zero (the owner's update kernels have skipped their work since, see abort_flag)."""
+        if self._status_ev is not None and self._status_ev.query() and int(self._status_host[0]) != 0:
+            raise RuntimeError("p2p exchange: a peer did not deliver within %d ms; parameters were left un-updated" % self.timeout_ms)
 
     def check(self):
         """Host-side check of the watchdog word (synchronises)."""
@@ -449,11 +495,8 @@ class DataParallelHead:
         self.comm_sms = int(os.environ.get("NAWSOD_COMM_SMS", "0")) if comm_sms is None else comm_sms
         self._hyper = dict(momentum=0.9, weight_decay=5e-4)
         self.p2p_selftest = None                     # outcome of P2PExchange.self_test() when it ran ("ok" or the reason)
-        # EXPERIMENTAL (gemm_fused.cu), off until measured: fc6 weight gradient fused with the SGD update (one GPU) or with
-        # the scatter to the owner ranks (p2p); NAWSOD_FUSED_KEEP_GRAD=1 also stores the fc6 gradient (parity runs)
-        self.fused_sgd = os.environ.get("NAWSOD_FUSED_SGD", "0") == "1"
+        # gemm_scatter.cu: the fc6 weight-gradient GEMM stores its tiles straight into the owner ranks' staging (p2p only)
         self.fused_scatter = os.environ.get("NAWSOD_P2P_FUSED_SCATTER", "0") == "1"
-        self.fused_keep_grad = os.environ.get("NAWSOD_FUSED_KEEP_GRAD", "0") == "1"
         if self.world > 1 and sync in ("p2p", "auto") and model.flat_grad.is_cuda:
             # "auto": the peer-mapped path when every rank can set it up (one NVLink / NVSwitch box), else NCCL
             requested = sync
@@ -490,6 +533,8 @@ class DataParallelHead:
         if self.exchange is None and (self.world > 1 or self.fc6_panels > 1):
             self.exchange = GradientExchange(model.flat_grad, model.flat_lp, group, sharded=(sync != "allreduce"),
                                              update_fn=self._update_slice)
+        # UpdateWorkspaceLr / RunTestNet / export_* / weights_file_blobs on the model join the update pipeline first
+        model.pre_mutation_hooks.append(self.flush)
 
     # ------------------------------------------------------------------ parameters
     def broadcast_parameters(self):
@@ -506,7 +551,7 @@ class DataParallelHead:
         if self.world == 1 or not self.master_sharded:
             return
         for off, length, _ in self.plan:
-            if length <= 0 or not slices_aligned(length, self.world):
+            if length <= 0 or not bucket_is_sliced(length, _, self.world):
                 continue          # updated redundantly on every rank: already complete everywhere
             so, sn = rank_slice(off, length, self.world, self.rank)
             for flat in (self.model.flat_param, self.model.flat_mom):
@@ -527,18 +572,26 @@ class DataParallelHead:
         if grads is None:
             ops.ACMWeightDecayMomentumSGDUpdate(m.flat_grad[so: so + sn], m.flat_mom[so: so + sn], m.lr,
                                                 m.flat_param[so: so + sn], None, **kw)
-        else:
-            ops.ACMWeightDecayMomentumSGDUpdateReduce(grads, m.flat_mom[so: so + sn], m.lr, m.flat_param[so: so + sn], **kw)
+        else:        # a wait kernel whose watchdog fired sets the status word: the update is then skipped, step() raises
+            ops.ACMWeightDecayMomentumSGDUpdateReduce(grads, m.flat_mom[so: so + sn], m.lr, m.flat_param[so: so + sn],
+                                                      abort_flag=getattr(self.exchange, "status", None), **kw)
 
     def _limit_gemm_grid(self, on: bool):
         if self.model.flat_grad.is_cuda and self.comm_sms > 0:
             from . import _lib
             _lib.set_tuning("gemm_max_ctas", max(1, _sm_count(self.model.flat_grad.device) - self.comm_sms) if on else 0)
 
-    def step(self, dropout_seed=0, dropout_masks=None, momentum=0.9, weight_decay=5e-4):
+    def step(self, dropout_seed=None, dropout_masks=None, momentum=0.9, weight_decay=5e-4, dropout=True):
+        """Dropout is on by default like the reference's training net (seed derived from the iteration count when none
+        is given; ``dropout=False`` disables it); every rank draws its own keep pattern: seed * world + rank."""
         m = self.model
+        if dropout and dropout_masks is None:
+            base = m.iter_count + 1 if dropout_seed is None else int(dropout_seed)
+            if base <= 0:
+                raise RuntimeError("dropout_seed must be positive (pass dropout=False to train without Dropout)")
+            dropout_seed = base * self.world + self.rank
         if self.exchange is None:
-            bl = m.RunTrainStep(dropout_masks=dropout_masks, dropout_seed=dropout_seed)
+            bl = m.RunTrainStep(dropout_masks=dropout_masks, dropout_seed=dropout_seed, dropout=dropout)
             m.param_update(momentum=momentum, weight_decay=weight_decay, gpu_num=1)
             return bl
         from . import ops
@@ -550,27 +603,20 @@ class DataParallelHead:
             ex.finish()
             self._limit_gemm_grid(False)
             if self.sync == "p2p":
+                ex.poll()                            # a lost peer surfaces here, one step late, without a host sync
                 ex.begin_step()
 
         fused = self._fused_mode()
 
         def on_panel(r0, r1):
             self._limit_gemm_grid(True)              # GEMMs launched from here on share the GPU with NCCL
-            if fused == "sgd":
-                return                               # the panel's GEMM already updated its rows of W6
-            ex.launch(r0 * cols, (r1 - r0) * cols, "fc6_panel", **({"prescattered": True} if fused == "scatter" else {}))
+            ex.launch(r0 * cols, (r1 - r0) * cols, "fc6_panel", **({"prescattered": True} if fused else {}))
 
         def fc6_dw(r0, r1, dY, feat):
             rows, lo, hi = r1 - r0, r0 * cols, r1 * cols
-            if fused == "sgd":
-                ops.FCGradientWSGD(dY, feat, m.flat_mom[lo:hi].view(rows, cols), m.lr, m.flat_param[lo:hi].view(rows, cols),
-                                   m.flat_lp[lo:hi].view(rows, cols), dW=m.g["W6"][r0:r1] if self.fused_keep_grad else None,
-                                   db=m.g["b6"][r0:r1], momentum=momentum, gpu_num=1, lr_mult=1.0, weight_decay=weight_decay,
-                                   iter_count=m.iter_count)
-            else:
-                ops.FCGradientWScatter(dY, feat, ex.owner_ptrs(lo, hi - lo), rows // self.world, cols, db=m.g["b6"][r0:r1])
+            ops.FCGradientWScatter(dY, feat, ex.owner_ptrs(lo, hi - lo), rows // self.world, cols, db=m.g["b6"][r0:r1])
 
-        bl = m.RunTrainStep(dropout_masks=dropout_masks, dropout_seed=dropout_seed, fc6_panels=self.fc6_panels,
+        bl = m.RunTrainStep(dropout_masks=dropout_masks, dropout_seed=dropout_seed, dropout=dropout, fc6_panels=self.fc6_panels,
                             on_fc6_panel=on_panel, on_before_params=before_params, fc6_dw=fc6_dw if fused else None,
                             on_small_grads=lambda: ex.launch(small[0], small[1], "small_weights"))
         ex.launch(biases[0], biases[1], "biases")
@@ -584,12 +630,10 @@ class DataParallelHead:
         return bl
 
     def _fused_mode(self):
-        """Which experimental fused fc6 weight-gradient kernel this step uses: "sgd" (one GPU: GEMM + update), "scatter"
-        (p2p: GEMM + scatter to the owners; every panel must split into whole 128-row tiles per owner) or None."""
+        """"scatter" when this step's fc6 weight-gradient panels use the GEMM fused with the scatter to the owner ranks
+        (p2p only; every panel must split into whole 128-row tiles per owner), else None."""
         if not self.model.flat_grad.is_cuda:
             return None
-        if self.sync == "local" and self.fused_sgd and self.exchange is not None:
-            return "sgd"
         if self.sync == "p2p" and self.fused_scatter:
             rows_total = self.model._slices["W6"][2][0]
             step = ((rows_total + self.fc6_panels - 1) // self.fc6_panels + 255) // 256 * 256

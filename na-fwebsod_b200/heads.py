@@ -77,7 +77,9 @@ class WeblyHeadModel:
         self.profile = None        # dict name -> [(start_event, end_event)] when bench.py instruments a run
         self.iter_count = 0
         self._lr_host = np.float32(0.0)     # value of the `lr` blob (UpdateWorkspaceLr keeps it; starts at 0 like the reference's)
-        self._bias_stream = None
+        # callables that join work still in flight on side streams (dp.DataParallelHead registers its flush(): the
+        # previous step's exchange / SGD pipeline reads `lr` and read-modify-writes the momenta and parameters there)
+        self.pre_mutation_hooks = []
         self._alloc_params()
 
     # ------------------------------------------------------------------ parameters
@@ -114,6 +116,12 @@ class WeblyHeadModel:
         self.p = views(self.flat_param)       # fp32 masters
         self.g = views(self.flat_grad)
         self.w = views(self.flat_lp)          # GEMM operands (bf16 shadow or the master)
+
+    def _join_side_streams(self):
+        """Before the host touches `lr`, the momenta or the parameters on the compute stream (or reads them back):
+        wait for every update that a data-parallel step still has in flight on its exchange stream."""
+        for hook in self.pre_mutation_hooks:
+            hook()
 
     def _ref_names(self, s):
         """Reference blob-name prefixes of stack s (detectron/modeling/webly_heads.py:490-498, 36-55)."""
@@ -184,6 +192,7 @@ class WeblyHeadModel:
         shape mismatch is an error (:105-111).  Returns the list of (destination, source, with_momentum) loaded."""
         if "blobs" in src_blobs:
             src_blobs = src_blobs["blobs"]
+        self._join_side_streams()
         loaded = []
         for name, (pv, mv, xf) in self._param_targets().items():
             src_name = name[name.find("]_") + 2:] if (name.find("]_") >= 0 and name not in src_blobs) else name
@@ -211,6 +220,7 @@ class WeblyHeadModel:
         every parameter under its unscoped blob name and ``<name>_momentum`` for every trainable parameter, in the
         reference's layouts (fc6 K-order ``c*49 + bin``).  Feeding the result to ``initialize_from_weights`` restores the
         state exactly.  (In data-parallel runs call ``dp.gather_master_state()`` first.)"""
+        self._join_side_streams()
         blobs = {}
         for name, (pv, mv, xf) in self._param_targets().items():
             back = self._k_unpermute if xf == self._k_permute else (lambda v: v)
@@ -238,9 +248,11 @@ class WeblyHeadModel:
     def export_reference_params(self):
         """Parameters under the reference's blob names and layouts (checkpoint contract,
         detectron/utils/net_wsl.py:140-181)."""
+        self._join_side_streams()
         return self._export(self.p)
 
     def export_reference_grads(self):
+        self._join_side_streams()
         return self._export(self.g)
 
     def _timed(self, name, fn):
@@ -280,8 +292,12 @@ class WeblyHeadModel:
             self.blobs["labels_oh"] = labels_oh
 
     # ------------------------------------------------------------------ forward pieces
-    def _fc_stack(self, dropout_masks=None, dropout_seed=0, stacks=None, on_before_params=None):
-        """RoIFeatureTransform -> RoIFeatureBoost -> (fc6 -> Relu -> Dropout -> fc7 -> Relu -> Dropout) per stack."""
+    def _fc_stack(self, dropout_masks=None, dropout_seed=None, stacks=None, on_before_params=None, dropout=True):
+        """RoIFeatureTransform -> RoIFeatureBoost -> (fc6 -> Relu -> Dropout -> fc7 -> Relu -> Dropout) per stack.
+
+        Dropout follows ``DropoutIfTraining`` (detectron/modeling/wsl_heads.py:1259-1267): ALWAYS on (ratio 0.5) when the
+        model trains -- from the injected masks (parity runs), else from ``dropout_seed``, else from a seed derived from
+        the iteration count; only an explicit ``dropout=False`` turns it off (the oracle comparisons without masks)."""
         bl, H = self.blobs, self.H
         stacks = list(range(self.S)) if stacks is None else stacks
         need_argmax = self.train and not self.freeze_conv_body
@@ -298,9 +314,13 @@ class WeblyHeadModel:
         nS = len(stacks)
         drop6 = self._scratch("drop6", (R, nS * H), self.dtype)
         drop7 = self._scratch("drop7", (R, nS * H), self.dtype)
-        # Dropout is active in training when a mask is injected or a seed is given
-        # (DropoutIfTraining, detectron/modeling/wsl_heads.py:1259-1267); otherwise it is the identity.
-        use_drop = self.train and (dropout_masks is not None or dropout_seed != 0)
+        use_drop = bool(self.train and dropout)
+        if use_drop and dropout_masks is None:
+            if dropout_seed is None:
+                dropout_seed = self.iter_count + 1
+            if int(dropout_seed) <= 0:
+                raise RuntimeError("dropout_seed must be positive (pass dropout=False to train without Dropout)")
+        dropout_seed = int(dropout_seed or 0)
         self._dropped = use_drop
         m6 = m7 = None
         if use_drop and dropout_masks is not None:
@@ -348,8 +368,8 @@ class WeblyHeadModel:
         return logits
 
     # ------------------------------------------------------------------ the reference's builder names
-    def RunTrainStep(self, dropout_masks=None, dropout_seed=0, need_dX=False, fc6_panels=1, on_small_grads=None,
-                     on_fc6_panel=None, on_before_params=None, fc6_dw=None):
+    def RunTrainStep(self, dropout_masks=None, dropout_seed=None, need_dX=False, fc6_panels=1, on_small_grads=None,
+                     on_fc6_panel=None, on_before_params=None, fc6_dw=None, dropout=True):
         """One fwd+bwd pass of the head on the fed blobs (the slice of ``workspace.RunNet(net)``,
         detectron/utils/train_wsl.py:59, that lies between conv5 and the parameter gradients).
         Gradients land in ``self.g`` / ``self.flat_grad``; returns the blob dict.
@@ -361,13 +381,12 @@ class WeblyHeadModel:
         gradients of fc6 are complete with the last panel, all others with ``on_small_grads``.
         ``on_before_params()`` fires after RoI pooling, right before the first parameter read (fc6):
         the place to join a parameter update that is still in flight from the previous step.
-        ``fc6_dw(r0, r1, dY_panel, roi_feat)`` (experimental) replaces the plain ``FCGradientW`` of an fc6 row panel,
-        e.g. by the GEMM fused with the SGD update or with the scatter to the rows' owner ranks (dp.py); it must
-        also produce ``self.g["b6"][r0:r1]``."""
+        ``fc6_dw(r0, r1, dY_panel, roi_feat)`` replaces the plain ``FCGradientW`` of an fc6 row panel by the GEMM
+        fused with the scatter to the rows' owner ranks (dp.py); it must also produce ``self.g["b6"][r0:r1]``."""
         if not self.train:
             raise RuntimeError("RunTrainStep on a test-mode model")
         bl, H, C, C2 = self.blobs, self.H, self.C, 2 * self.C
-        drop6, drop7 = self._fc_stack(dropout_masks, dropout_seed, on_before_params=on_before_params)
+        drop6, drop7 = self._fc_stack(dropout_masks, dropout_seed, on_before_params=on_before_params, dropout=dropout)
         logits = self._fc8(drop7)
         R = drop7.shape[0]
         ld = logits.shape[2]
@@ -408,22 +427,6 @@ class WeblyHeadModel:
             bl["d_conv5"] = ops.RoIPoolFGradient(bl["conv5"], bl["rois"], bl["_argmax_roi_feat"],
                                                  d_feat.view(R, self.roi_size, self.roi_size, Cc),
                                                  boost=bl["obn_scores"], layout="NHWC")
-        # EXPERIMENTAL (NAWSOD_BIAS_SIDE_STREAM=1, off until measured): the bias gradients are HBM-bound column sums of
-        # dY (8 launches, ~2 % of the step between the tensor-bound GEMMs); all their inputs exist once the activation-
-        # gradient chain is enqueued, so they can run on a side stream beside the weight-gradient GEMMs.
-        side_bias = fc6_dw is None and self.flat_grad.is_cuda and os.environ.get("NAWSOD_BIAS_SIDE_STREAM", "0") == "1"
-        if side_bias:
-            if self._bias_stream is None:
-                self._bias_stream = torch.cuda.Stream(device=self.device)
-            ready = torch.cuda.Event()
-            ready.record()
-            self._bias_stream.wait_event(ready)
-            with torch.cuda.stream(self._bias_stream):
-                ops.FCBiasGradient(d6, self.g["b6"])
-                ops.FCBiasGradient(d73, self.g["b7"])
-                ops.FCBiasGradient(dl3, self.g["b8"])
-                bias_done = torch.cuda.Event()
-                bias_done.record()
         rows = self.S * H
         step = _round_up((rows + fc6_panels - 1) // fc6_panels, 256)
         for r0 in range(0, rows, step):
@@ -432,14 +435,11 @@ class WeblyHeadModel:
                 self._timed("fc6_bwd_w", lambda: fc6_dw(r0, r1, d6[:, r0:r1], bl["roi_feat"]))
             else:
                 self._timed("fc6_bwd_w", lambda: ops.FCGradientW(d6[:, r0:r1], bl["roi_feat"], dW=self.g["W6"][r0:r1],
-                                                                 db=None if side_bias else self.g["b6"][r0:r1],
-                                                                 want_db=not side_bias))
+                                                                 db=self.g["b6"][r0:r1]))
             if on_fc6_panel is not None:
                 on_fc6_panel(r0, r1)
-        ops.FCGradientW(dl3, a7, dW=self.g["W8"], db=None if side_bias else self.g["b8"], want_db=not side_bias)
-        ops.FCGradientW(d73, a6, dW=self.g["W7"], db=None if side_bias else self.g["b7"], want_db=not side_bias)
-        if side_bias:
-            torch.cuda.current_stream(self.device).wait_event(bias_done)     # the biases' exchange / update follows
+        ops.FCGradientW(dl3, a7, dW=self.g["W8"], db=self.g["b8"])
+        ops.FCGradientW(d73, a6, dW=self.g["W7"], db=self.g["b7"])
         if on_small_grads is not None:
             on_small_grads()
         return bl
@@ -450,6 +450,7 @@ class WeblyHeadModel:
         ``want_cls_prob=False`` stops at ``rois_pred`` (test_time.im_detect_bbox builds cls_prob while it
         maps the scores back to the original boxes)."""
         bl, C, C2 = self.blobs, self.C, 2 * self.C
+        self._join_side_streams()
         was_train, self.train = self.train, False
         try:
             _, drop7 = self._fc_stack(stacks=[0])
@@ -480,6 +481,10 @@ class WeblyHeadModel:
         Returns the factor applied to the momenta (1.0 when they were left alone)."""
         new_lr, cur_lr = np.float32(lr), self._lr_host
         factor = lr_change_correction(cur_lr, new_lr, scale_momentum, scale_momentum_threshold)
+        if cur_lr != new_lr or factor != 1.0:
+            # the reference calls this before every RunNet; the previous step's update pipeline (dp.py) may still be
+            # reading `lr` / rewriting the momenta on its side stream -- join it before either changes
+            self._join_side_streams()
         if cur_lr != new_lr:
             self.lr.fill_(float(new_lr))
             self._lr_host = new_lr
@@ -514,9 +519,9 @@ def add_VGG16_roi_2fc_head(model, blob_in=None, dim_in=None, spatial_scale=None,
 
 
 def add_VGG16_roi_2fc_noise_head(model, blob_in=None, dim_in=None, spatial_scale=None, prefix="", dropout_masks=None,
-                                 dropout_seed=0):
+                                 dropout_seed=None, dropout=True):
     """detectron/modeling/webly_heads.py:463-502.  Returns ([drop7, noisy drop7], [4096, 4096])."""
-    _, drop7 = model._fc_stack(dropout_masks, dropout_seed)
+    _, drop7 = model._fc_stack(dropout_masks, dropout_seed, dropout=dropout)
     H = model.H
     return [drop7[:, s * H:(s + 1) * H] for s in range(model.S)], [H] * model.S
 

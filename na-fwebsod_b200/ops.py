@@ -319,11 +319,12 @@ def ACMWeightDecayMomentumSGDUpdate(g, m, lr, p, acc, *, momentum=0.9, iter_size
 
 
 def ACMWeightDecayMomentumSGDUpdateReduce(grads, m, lr, p, *, momentum=0.9, gpu_num=1, lr_mult=1.0, weight_decay=0.0,
-                                          iter_count=0, p_shadow=None):
+                                          iter_count=0, p_shadow=None, abort_flag=None):
     """Data-parallel owner's update: ``g = grads[0] + grads[1] + ...`` (in that order: the ranks'
     contributions to this parameter slice), then ``ACMWeightDecayMomentumSGDUpdate`` with
     iter_size 1 -- i.e. the reference's NCCLAllreduce + update pair (modeling/optimizer_wsl.py:52-72,
-    96-137) restricted to the slice this rank owns, in one pass over HBM."""
+    96-137) restricted to the slice this rank owns, in one pass over HBM.  ``abort_flag`` (int32 CUDA word): a
+    non-zero value at launch time (a peer exchange whose watchdog fired) makes the call a no-op."""
     n = m.numel()
     for t, nme in ((m, "m"), (p, "p")):
         _req(t, nme, torch.float32)
@@ -339,7 +340,7 @@ def ACMWeightDecayMomentumSGDUpdateReduce(grads, m, lr, p, *, momentum=0.9, gpu_
     table = (ctypes.c_void_p * len(grads))(*[g.data_ptr() for g in grads])
     _lib.call("nawsod_sgd_update_reduce", table, len(grads), _ptr(m), _ptr(lr), _ptr(p), n, float(momentum),
               float(weight_decay), float(lr_mult), int(gpu_num), int(iter_count), _ptr(p_shadow),
-              _DT[p_shadow.dtype] if p_shadow is not None else F32, _stream())
+              _DT[p_shadow.dtype] if p_shadow is not None else F32, _ptr(abort_flag), _stream())
     return m, p
 
 
@@ -435,6 +436,8 @@ def FC(X, W, b=None, *, relu=False, dropout_mask=None, dropout=False, dropout_se
     _same_stacks("FC", S, S2, S3)
     if N2 != N or M3 != M:
         raise RuntimeError("FC: out has the wrong shape")
+    if dropout and dropout_mask is None and not dropout_seed:
+        raise RuntimeError("FC: dropout=True needs a dropout_mask or a non-zero dropout_seed")
     flags = (_lib.FC_RELU if relu else 0) | \
             (_lib.FC_DROPOUT if (dropout or dropout_mask is not None or dropout_seed) else 0) | \
             (_lib.FC_ROUND_TF32 if round_tf32 else 0)
@@ -527,39 +530,8 @@ def _dw_bias(who, db, N):
         raise RuntimeError("%s: db must be a contiguous float32 CUDA tensor with %d elements" % (who, N))
 
 
-def FCGradientWSGD(dY, X, m, lr, p, p_shadow, *, dW=None, db=None, accumulate=False, momentum=0.9, gpu_num=1, lr_mult=1.0,
-                   weight_decay=0.0, iter_count=0):
-    """EXPERIMENTAL.  ``FCGradient`` (dW, db) fused with ``ACMWeightDecayMomentumSGDUpdate([dW, m, lr, p] -> [m, p])`` of
-    the weight (iter_size 1; modeling/optimizer_wsl.py:127-136): the update runs in the GEMM epilogue on the tile it just
-    accumulated, so the gradient is never re-read (and with ``dW=None`` never written).  ``m``, ``p`` [N,K] float32 and
-    ``p_shadow`` (the GEMM-operand copy of ``p``, in the operands' dtype) are updated in place; bit-identical to
-    ``FCGradientW`` followed by the stand-alone update.  ``db`` is only computed, its update stays with the caller."""
-    M, N, K, lddy, lda = _dw_operands("FCGradientWSGD", dY, X)
-    ld = None
-    for t, nme, dt in ((m, "m", torch.float32), (p, "p", torch.float32), (p_shadow, "p_shadow", dY.dtype), (dW, "dW", torch.float32)):
-        if t is None and nme == "dW":
-            continue
-        r, c, l = _mat(t, nme)
-        if t.dtype != dt or (r, c) != (N, K):
-            raise RuntimeError("FCGradientWSGD: %s must be %s [%d,%d]" % (nme, dt, N, K))
-        if ld is not None and l != ld:
-            raise RuntimeError("FCGradientWSGD: m, p, p_shadow and dW must share one row pitch")
-        ld = l
-    _req(lr, "lr", torch.float32)
-    if lr.numel() != 1:
-        raise RuntimeError("lr must have one element")
-    if accumulate and dW is None:
-        raise RuntimeError("FCGradientWSGD: accumulate needs the gradient buffer dW")
-    _dw_bias("FCGradientWSGD", db, N)
-    _lib.call("nawsod_fc_bwd_w_sgd", _ptr(dY), lddy, _ptr(X), lda, M, N, K, _ab(dY.dtype), _ptr(dW), ld, _ptr(db),
-              _lib.FC_ACCUMULATE if accumulate else 0, _ptr(m), _ptr(p), _ptr(p_shadow), _DT[p_shadow.dtype], _ptr(lr),
-              float(momentum), float(weight_decay), float(lr_mult), int(gpu_num), int(iter_count), _stream(),
-              extra_kernels=1 if db is not None else 0)
-    return dW, db
-
-
 def FCGradientWScatter(dY, X, owner_ptrs, rows_per_owner, ldw, *, db=None):
-    """EXPERIMENTAL.  ``FCGradient`` (dW, db) whose epilogue stores rows ``[k*rows_per_owner, (k+1)*rows_per_owner)`` of
+    """``FCGradient`` (dW, db) whose epilogue stores rows ``[k*rows_per_owner, (k+1)*rows_per_owner)`` of
     dW straight to ``owner_ptrs[k]`` (device addresses: this rank's own gradient slice, or a peer's staging memory mapped
     with ``nawsod_p2p_open_mem_handle``) -- the GEMM and the send leg of the reduce-scatter that replaces the reference's
     ``NCCLAllreduce`` (modeling/optimizer_wsl.py:52-72) as one kernel.  The caller signals the owners afterwards."""

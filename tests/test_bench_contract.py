@@ -10,12 +10,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def _run(env_extra):
     env = dict(os.environ, **env_extra)
-    return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "1", "--steps", "1",
-                           "--warmup", "1"], capture_output=True, text=True, env=env, timeout=600)
+    return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "1", "--steps", "2",
+                           "--warmup", "1", "--ref-rois-per-image", "250"], capture_output=True, text=True, env=env, timeout=600)
 
 
 def test_reference_arm_prints_one_json_line():
-    r = _run({})
+    r = _run({"OMP_NUM_THREADS": "1"})          # what torchrun exports to its workers: the arm must override it
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
     assert len(lines) == 1, r.stdout
@@ -26,6 +26,9 @@ def test_reference_arm_prints_one_json_line():
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "RoIs" in cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "RoIs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "model" not in d["config"]
+    assert d["steps"] == 2 and d["warmup"] == 1                               # --steps / --warmup honoured
+    assert d["config"]["threads"] == len(os.sched_getaffinity(0)) == cb["cores"]
+    assert d["config1_cpu_forward"]["value"] > 0
 
 
 def test_reference_arm_other_ranks_stay_silent():
@@ -68,7 +71,11 @@ def test_gpu_arm_line_assembly():
     # unpanelled launch: the other capture; an uncaptured panel count: unknown
     common = dict(steps=2, warmup=3, world=1, R=R, S=2, bf16=True, noise=True, ms_total=8.0, ms_e2e=9.0, h2d_bytes=1, d2h_bytes=1, launches=1,
                   clocks=None, kernel_ms={"fc6_bwd_w": 1.2}, iso={}, cpu=None, loss=[0.0],
-                  dp_info={"sync": "local", "fc6_panels": 1, "p2p_selftest": None, "fused": "sgd"})
+                  dp_info={"sync": "p2p", "fc6_panels": 1, "p2p_selftest": None, "fused": "scatter"})
     assert bench.assemble_line(n_panels=1, **common)["roofline"]["traffic"] > 3e9
     assert bench.assemble_line(n_panels=2, **common)["roofline"]["traffic"] is None
-    assert "EXPERIMENTAL" in bench.assemble_line(n_panels=1, **common)["config"]["fc6_update"]
+    assert "gemm_scatter.cu" in bench.assemble_line(n_panels=1, **common)["config"]["fc6_update"]
+    # the fp32 / TF32 run of the same workload rides in the same line
+    t = bench.assemble_line(n_panels=4, tf32={"ms_total": 160.0, "steps": 20, "kernel_ms": {"fc6_fwd": 2.2, "fc6_bwd_w": 0.8}, "n_panels": 4},
+                            **common)["kernels"]["tf32_step"]
+    assert t["ms_per_step"] == 8.0 and abs(t["rois_per_s"] - 500000.0) < 1e-6 and 0 < t["fc6_fwd"]["frac_tensor"] < 1.5

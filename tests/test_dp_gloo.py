@@ -85,15 +85,18 @@ def _worker(rank, world, port, sync, panels, out):
             if sync == "allreduce":
                 update(0, N_WEIGHTS, "weights", 0, N_WEIGHTS)
                 update(N_WEIGHTS, N_TOTAL - N_WEIGHTS, "biases", N_WEIGHTS, N_TOTAL - N_WEIGHTS)
+        # what the NEXT forward pass would read on this rank, with no gather in between: the operand shadow of the
+        # weights and the fp32 MASTERS of the biases (heads.py reads b6 / b7 / b8 from flat_param)
+        visible = np.concatenate([shadow[:N_WEIGHTS].numpy(), p[N_WEIGHTS:].numpy()]).copy()
         if sync == "sharded":
             # operands are complete everywhere; masters only on their owner until gathered
-            for off, n, _ in plan:
-                if n % world:
-                    continue                          # non-divisible bucket: every rank updated all of it
+            for off, n, tag in plan:
+                if not dp.bucket_is_sliced(n, tag, world):
+                    continue                          # replicated bucket (biases, non-divisible): every rank updated all of it
                 so, sn = dp.rank_slice(off, n, world, rank)
                 for flat in (p, m):
                     dist.all_gather_into_tensor(flat[off:off + n], flat[so:so + sn])
-        out[rank] = (p.numpy().copy(), m.numpy().copy(), shadow.numpy().copy())
+        out[rank] = (p.numpy().copy(), m.numpy().copy(), shadow.numpy().copy(), visible)
     finally:
         dist.destroy_process_group()
 
@@ -109,11 +112,14 @@ def _run(sync, panels, world=2):
 def test_exchange_matches_reference_schedule(sync, panels):
     res = _run(sync, panels)
     p_ref, m_ref = _reference(2, 3)
-    for p, m, shadow in res:
+    for p, m, shadow, visible in res:
         # the same fp32 operations in the same order: bit-exact
         assert np.array_equal(p, p_ref)
         assert np.array_equal(m, m_ref)
         assert np.array_equal(shadow, p_ref)
+        # ... and already BEFORE any gather of the master state, everything a forward pass reads (operand shadow of
+        # the weights, fp32 masters of the biases) is the reference schedule's on every rank: no stale biases
+        assert np.array_equal(visible, p_ref)
     assert np.array_equal(res[0][0], res[1][0])
 
 
@@ -125,10 +131,11 @@ def test_sharded_exchange_other_world_sizes(world, panels):
     last bit: parameters agree to 1e-6 relative, and bit-exactly ACROSS ranks (replicas must not diverge)."""
     res = _run("sharded", panels, world=world)
     p_ref, m_ref = _reference(world, 3)
-    for p, m, shadow in res:
+    for p, m, shadow, visible in res:
         np.testing.assert_allclose(p, p_ref, rtol=1e-6, atol=1e-7)
         np.testing.assert_allclose(m, m_ref, rtol=1e-5, atol=1e-7)
         assert np.array_equal(shadow, p)
+        assert np.array_equal(visible, p)             # forward-visible state current on every rank without a gather
     for r in range(1, world):
         assert np.array_equal(res[0][0], res[r][0]) and np.array_equal(res[0][2], res[r][2])
 
@@ -184,6 +191,11 @@ def _selftest_worker(rank, world, port, corrupt_rank, out):
                 self.seq = 0
 
             def launch(self, offset, length, tag):
+                if not dp.bucket_is_sliced(length, tag, world):           # replicated (the biases): everyone gets everything
+                    parts = [torch.empty(length) for _ in range(world)]
+                    dist.all_gather(parts, self.flat[offset: offset + length].clone())
+                    self.update_fn(offset, length, tag, offset, length, parts)
+                    return
                 n = length // world
                 mine = [self.flat[offset + k * n: offset + (k + 1) * n].clone() for k in range(world)]
                 if rank == corrupt_rank and tag == "small_weights":

@@ -56,7 +56,7 @@ def _run(dtype, prob, noise=True, entropy=True, use_masks=True):
     m = WeblyHeadModel(L.shape[1] + 1, Cc, 7, Hd, noise=noise, entropy=entropy, dtype=dtype)
     m.load_reference_params(params)
     m.FeedBlobs(t(X), t(rois), t(obn), t(L), torch.tensor(offs, dtype=torch.int32, device="cuda"), x_layout="NCHW")
-    bl = m.RunTrainStep(dropout_masks={k: t(v) for k, v in masks.items()} if use_masks else None)
+    bl = m.RunTrainStep(dropout_masks={k: t(v) for k, v in masks.items()} if use_masks else None, dropout=use_masks)
     torch.cuda.synchronize()
     return m, bl
 
