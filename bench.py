@@ -307,7 +307,7 @@ def assemble_line(*, steps, warmup, world, R, S, bf16, noise, ms_total, ms_e2e, 
     runs it on the CPU).  ms_total / ms_e2e: device time of the `steps` timed steps of the resident / end-to-end leg (max over
     ranks; the median block when the region was repeated, see `timing`); kernel_ms: mean CUDA-event duration per launch of
     fc6_fwd, fc6_bwd_w (one row panel), roi_pool_f, mil_head inside the timed steps; iso: isolated RoIPoolF timings (rank 0)
-    or {}; dp_info: sync / fc6_panels / p2p_selftest / fused; timing: {"value": ..., "e2e": ...} block / per-step spread;
+    or {}; dp_info: sync / fc6_panels / p2p_selftest / engine; timing: {"value": ..., "e2e": ...} block / per-step spread;
     tf32: {"ms_total", "steps", "kernel_ms", "n_panels"} of the fp32 (TF32 tensor path) run of the same workload, or None."""
     peaks = _peaks()
     ms_step = ms_total / steps
@@ -380,8 +380,6 @@ def assemble_line(*, steps, warmup, world, R, S, bf16, noise, ms_total, ms_e2e, 
                 "p2p": "peer-mapped (CUDA IPC over NVSwitch) scatter of fp32 grads into the owner's staging + fused reduce/SGD on the owner "
                        "+ scatter of the bf16 operands back, ordered by flag kernels",
                 "allreduce": "NCCL all-reduce fp32 grads + full SGD"}
-    fc6_update = {"scatter": "on the owner rank of each slice; the fc6 weight-gradient GEMM's epilogue stores its tiles into "
-                             "the owners' peer-mapped staging (gemm_scatter.cu, NAWSOD_P2P_FUSED_SCATTER=1)"}
     return {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -392,8 +390,8 @@ def assemble_line(*, steps, warmup, world, R, S, bf16, noise, ms_total, ms_e2e, 
                    "l2": "working set per step (weights 0.5 GB bf16 + 0.96 GB fp32 grads + activations) >> 126 MB L2; no flush needed",
                    "fc6_panels": dp_info["fc6_panels"],
                    "p2p_selftest": dp_info["p2p_selftest"],
-                   "fc6_update": fc6_update.get(dp_info["fused"], "stand-alone SGD kernel per row panel on a side stream" if world == 1
-                                                else "on the owner rank of each slice")},
+                   "p2p_engine": dp_info.get("engine"),
+                   "fc6_update": "stand-alone SGD kernel per row panel on a side stream" if world == 1 else "on the owner rank of each slice"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),
                 "ms_per_step": ms_e2e / steps},
         "timing": timing,
@@ -563,8 +561,14 @@ def gpu_arm(args):
     # loss of the previous step only.  Every step's H2D and D2H copies are issued and completed inside the timed region.
     from nafwebsod_b200.loader import BlobsQueue, LossFetcher
 
+    # one queue / fetcher for the whole leg: their device and pinned buffers are rings allocated on first use, so the timed
+    # blocks run allocation-free (the warm-up block below performs the allocations)
+    queue, fetch_ring = BlobsQueue(model, capacity=2, x_layout="NCHW"), LossFetcher(lag=1)
+
     def run_e2e(steps, ev=None, seed0=0):
-        queue, fetch = BlobsQueue(model, capacity=2, x_layout="NCHW"), LossFetcher(lag=1)
+        fetch = fetch_ring
+        fetch.values = []
+        bytes0 = queue.h2d_bytes
 
         def step(i):
             if i == 0:
@@ -575,7 +579,7 @@ def gpu_arm(args):
             bl = dp.step(dropout_seed=seed0 + i + 1)
             fetch.push(bl["loss"])                                    # D2H read of the step's result
         ms = timed(step, steps, tail=fetch.wait_all, step_events=ev)
-        assert queue.h2d_bytes == steps * h2d_bytes
+        assert queue.h2d_bytes - bytes0 == steps * h2d_bytes
         return ms, fetch
 
     run_e2e(max(2, args.warmup // 2))
@@ -678,7 +682,8 @@ def gpu_arm(args):
         kernel_ms={k: avg_ms(k) for k in ("fc6_fwd", "fc6_bwd_w", "roi_pool_f", "mil_head")},
         n_panels=max(1, len(prof.get("fc6_bwd_w", [])) // max(args.steps * value_stats["blocks"], 1)), iso=iso, cpu=cpu,
         loss=[float(x) for x in losses[-1].flatten().tolist()], timing={"value": value_stats, "e2e": e2e_stats}, tf32=tf32,
-        dp_info={"sync": dp.sync, "fc6_panels": dp.fc6_panels, "p2p_selftest": dp.p2p_selftest, "fused": dp._fused_mode()})
+        dp_info={"sync": dp.sync, "fc6_panels": dp.fc6_panels, "p2p_selftest": dp.p2p_selftest,
+                 "engine": getattr(dp.exchange, "engine", None)})
     _emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -149,18 +149,6 @@ int nawsod_fc_bwd_w_stacks(const void* dY, int64_t lddy, int64_t sdY, const void
 int nawsod_fc_bias_grad(const void* dY, int64_t lddy, int64_t sdY, int S, int M, int N, int ab_dtype,
                         float* db, int64_t sdb, int flags, void* stream);
 
-/* FCGradient's dW with the send leg of the data-parallel exchange fused into the GEMM epilogue (gemm_scatter.cu).
- *
- * nawsod_fc_bwd_w_scatter  FCGradient (dW, db) + the send leg of the data-parallel reduce-scatter that replaces
- *     NCCLAllreduce (modeling/optimizer_wsl.py:52-72): rows [k*rows_per_owner, (k+1)*rows_per_owner) of dW are stored
- *     to owner_dW[k] (row k*rows_per_owner first, row pitch ldw) -- the local gradient slice for the calling rank,
- *     peer-mapped staging memory (nawsod_p2p_open_mem_handle) for the others -- tile by tile from the epilogue.
- *     rows_per_owner must be a multiple of 128 (one output tile has one owner).  The caller publishes the
- *     sequence number afterwards (nawsod_p2p_signal in stream order). */
-int nawsod_fc_bwd_w_scatter(const void* dY, int64_t lddy, const void* A, int64_t lda, int M, int N,
-                            int K, int ab_dtype, float* const* owner_dW, int n_owners,
-                            int rows_per_owner, int64_t ldw, float* db, void* stream);
-
 /* Operand staging for the GEMMs above: float -> bf16, and float -> nearest-TF32 (kept in a
  * float container; dst may alias src) of a [rows, cols] matrix. */
 int nawsod_convert_f32_to_bf16(const float* src, int64_t ld_src, int64_t rows, int64_t cols,

@@ -36,7 +36,6 @@ PROTOTYPES = {
                                     _vp, _i64, _i64, _i, _i, _vp]),
     "nawsod_fc_bwd_w_stacks": (_i, [_vp, _i64, _i64, _vp, _i64, _i64, _i, _i, _i, _i, _i, _vp, _i64, _i64, _vp, _i64, _i, _vp]),
     "nawsod_fc_bias_grad": (_i, [_vp, _i64, _i64, _i, _i, _i, _i, _vp, _i64, _i, _vp]),
-    "nawsod_fc_bwd_w_scatter": (_i, [_vp, _i64, _vp, _i64, _i, _i, _i, _i, _vp, _i, _i, _i64, _vp, _vp]),
     "nawsod_convert_f32_to_bf16": (_i, [_vp, _i64, _i64, _i64, _vp, _i64, _vp]),
     "nawsod_mil_workspace_bytes": (_i64, [_i, _i, _i]),
     "nawsod_mil_head_fwd_bwd": (_i, [_vp] * 4 + [_i64] + [_vp] * 3 + [_i, _i, _i, _i] + [_vp] * 11 + [_i64, _vp, _vp]),
@@ -75,7 +74,7 @@ PROTOTYPES = {
 KERNELS_PER_CALL = {
     "nawsod_transpose_batched": 1, "nawsod_roi_pool_f_fwd": 1, "nawsod_roi_pool_f_bwd": 1, "nawsod_roi_feature_boost": 1,
     "nawsod_fc_fwd": 1, "nawsod_fc_bwd_x": 1, "nawsod_fc_bwd_w": 1, "nawsod_fc_fwd_stacks": 1, "nawsod_fc_bwd_x_stacks": 1,
-    "nawsod_fc_bwd_w_stacks": 1, "nawsod_fc_bwd_w_scatter": 1, "nawsod_convert_f32_to_bf16": 1,
+    "nawsod_fc_bwd_w_stacks": 1, "nawsod_convert_f32_to_bf16": 1,
     "nawsod_round_to_tf32": 1, "nawsod_mil_head_fwd_bwd": 1, "nawsod_roi_iou": 1, "nawsod_cross_entropy_fwd": 1,
     "nawsod_cross_entropy_bwd": 1, "nawsod_sgd_update": 1, "nawsod_sgd_update_reduce": 1, "nawsod_p2p_signal": 1, "nawsod_p2p_scatter": 1,
     "nawsod_p2p_wait": 1,

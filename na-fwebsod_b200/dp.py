@@ -57,10 +57,13 @@ def n_weights_w6_padded(n: int, align: int = 64) -> int:
     return (n + align - 1) // align * align
 
 
-def bucket_plan(n_weights_w6: int, w6_rows: int, w6_cols: int, n_weights: int, n_total: int, panels: int, align_rows: int = 256):
-    """Ordered exchange buckets (offset, length, tag) over the flat gradient buffer laid out as
-    [W6 | other weights | biases], in the order the backward pass completes them: fc6 row panels,
-    then the fc7/fc8 weights, then the biases.  Every element is covered exactly once."""
+def bucket_plan(n_weights_w6: int, w6_rows: int, w6_cols: int, n_weights: int, n_total: int, panels: int, align_rows: int = 256,
+                n_bias_fc6: int = 0):
+    """Exchange buckets (offset, length, tag) tiling the flat gradient buffer laid out as [W6 | other weights | biases]:
+    fc6 row panels, the fc7/fc8 weights, then the biases -- in two buckets when ``n_bias_fc6`` (the padded length of b6,
+    which leads the bias block) is given: "biases_fc6" is complete with the last fc6 panel and is, with the panels, all
+    the NEXT step's fc6 needs, so that step can start while "small_weights" and the remaining "biases" are still in
+    flight.  Every element is covered exactly once."""
     assert n_weights_w6 == w6_rows * w6_cols
     plan = []
     step = ((w6_rows + panels - 1) // panels + align_rows - 1) // align_rows * align_rows
@@ -69,7 +72,11 @@ def bucket_plan(n_weights_w6: int, w6_rows: int, w6_cols: int, n_weights: int, n
         plan.append((r0 * w6_cols, (r1 - r0) * w6_cols, "fc6_panel"))
     w6p = n_weights_w6_padded(n_weights_w6)
     plan.append((w6p, n_weights - w6p, "small_weights"))
-    plan.append((n_weights, n_total - n_weights, "biases"))
+    if 0 < n_bias_fc6 < n_total - n_weights:
+        plan.append((n_weights, n_bias_fc6, "biases_fc6"))
+        plan.append((n_weights + n_bias_fc6, n_total - n_weights - n_bias_fc6, "biases"))
+    else:
+        plan.append((n_weights, n_total - n_weights, "biases"))
     return plan
 
 
@@ -97,7 +104,7 @@ def bucket_is_sliced(length: int, tag: str, world: int) -> bool:
     fp32 MASTERS (heads.py: ``self.p["b*"]`` are views of flat_param), and the sliced schedules only send the
     GEMM-operand shadow back -- a rank would keep training on stale copies of every bias outside its own slice.  The
     bucket is 66 KB; replicating its update costs nothing and keeps masters, momenta and shadow current everywhere."""
-    return tag != "biases" and slices_aligned(length, world)
+    return not tag.startswith("biases") and slices_aligned(length, world)
 
 
 class GradientExchange:
@@ -157,8 +164,9 @@ class GradientExchange:
             if sliced:
                 dist.all_gather_into_tensor(self.out[offset: offset + length], self.out[so: so + sn], group=self.group)
 
-    def finish(self):
-        """Make the current (compute) stream wait for every outstanding bucket."""
+    def finish(self, tags=None):
+        """Make the current (compute) stream wait for every outstanding bucket (``tags`` is accepted for interface parity
+        with P2PExchange.finish and ignored: the collectives of one stream complete in order anyway)."""
         if self.cuda and self.in_flight:
             torch.cuda.current_stream(self.flat.device).wait_stream(self.stream)
         self.in_flight = False
@@ -228,7 +236,7 @@ class P2PExchange:
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         self.plan = [(o, n, t) for o, n, t in plan if n > 0]
         for o, n, t in self.plan:
-            if not bucket_is_sliced(n, t, self.world) and (t != "biases" or n % 4):
+            if not bucket_is_sliced(n, t, self.world) and (not t.startswith("biases") or n % 4):
                 raise RuntimeError("bucket of %d elements does not split into %d 32-byte aligned slices" % (n, self.world))
         self.index = {o: i for i, (o, _, _) in enumerate(self.plan)}
         self.update_fn = update_fn
@@ -274,6 +282,8 @@ class P2PExchange:
         self.profile = None      # list of (label, bucket, event) while a caller instruments one step
         self._status_host = torch.zeros(1, dtype=torch.int32).pin_memory()     # lagged copy of the watchdog word
         self._status_ev = None
+        self._done = [None] * len(self.plan)     # per bucket: event on the update stream behind its publish
+        self._joined = set()                     # buckets of the step in flight the compute stream has already joined
 
     def _flag_ptrs(self, kind, b):
         W, nb = self.world, len(self.plan)
@@ -283,16 +293,7 @@ class P2PExchange:
     def begin_step(self):
         self.seq += 1
 
-    def owner_ptrs(self, offset: int, length: int):
-        """Where this rank's contribution to slice k of the bucket belongs, for k = 0..W-1 (device addresses): its own
-        gradient buffer for the slice it owns, slot [bucket][my rank] of the owner's staging area otherwise.  A GEMM whose
-        epilogue stores there (ops.FCGradientWScatter) has done the scatter leg; launch(..., prescattered=True) then
-        only publishes the sequence number."""
-        n = length // self.world
-        return [self.flat.data_ptr() + 4 * (offset + k * n) if k == self.rank else self.peer_stage[k] + 4 * (offset + self.rank * n)
-                for k in range(self.world)]
-
-    def launch(self, offset: int, length: int, tag: str, prescattered: bool = False):
+    def launch(self, offset: int, length: int, tag: str):
         from . import ops
         if length <= 0:
             return
@@ -317,14 +318,7 @@ class P2PExchange:
         else:
             rs_copies = [(self.peer_stage[k] + 4 * (offset + rank * n), self.flat.data_ptr() + 4 * (offset + k * n), 4 * n) for k in peers]
         self.bytes_out += 4 * n * (W - 1)
-        if prescattered:
-            # the producer GEMM stored its tiles at owner_ptrs(): all that is left of the scatter leg is the signal
-            self.send_stream.wait_event(ev)
-            with torch.cuda.stream(self.send_stream):
-                ops.p2p_signal(self._flag_ptrs(self.RS, b), self.seq)
-                if prof is not None:
-                    prof.append(("sent", b, self._mark()))
-        elif self.engine == "sm":
+        if self.engine == "sm":
             self.send_stream.wait_event(ev)
             with torch.cuda.stream(self.send_stream):
                 ops.p2p_scatter([c[1] for c in rs_copies], [c[0] for c in rs_copies], 4 * n, self._flag_ptrs(self.RS, b), self.seq, b)
@@ -361,9 +355,11 @@ class P2PExchange:
             self._fan_out(self.ag_streams, upd, self.stream, ag_copies)
             with torch.cuda.stream(self.stream):
                 ops.p2p_signal(self._flag_ptrs(self.AG, b), self.seq)
-        if prof is not None:
-            with torch.cuda.stream(self.stream):
+        with torch.cuda.stream(self.stream):
+            if prof is not None:
                 prof.append(("published", b, self._mark()))
+            self._done[b] = torch.cuda.Event()
+            self._done[b].record()
 
     def _fan_out(self, streams, after, join, copies):
         """Issue the peer copies round-robin over a few streams (their per-copy set-up latencies overlap, the
@@ -385,22 +381,43 @@ class P2PExchange:
         e.record()
         return e
 
-    def finish(self):
+    def finish(self, tags=None):
+        """Make the current (compute) stream wait until the buckets with the given tags (default: all) are complete HERE:
+        this rank's own update of them has run and every peer's operand slice of them has landed (their AG flags carry
+        the step's sequence number).  An owner signals AG only after it consumed its staging area, so having joined ALL
+        buckets also licenses the next step's writes into the peers' staging; step() joins the buckets in two groups --
+        what fc6 reads before fc6, the rest before fc7 -- so the tail of the exchange hides behind the next step's RoI
+        pooling and fc6 GEMM."""
         from . import ops
         if not self.in_flight:
             return
         nb, W = len(self.plan), self.world
-        with torch.cuda.stream(self.stream):
-            ops.p2p_wait(self.flags[nb * W: 2 * nb * W], self.seq, self.timeout_ms, self.status)
-            if self.profile is not None:
-                self.profile.append(("all operands here", -1, self._mark()))
+        want = [i for i, (_, _, t) in enumerate(self.plan) if (tags is None or t in tags) and i not in self._joined]
+        cur = torch.cuda.current_stream(self.flat.device)
+        # contiguous runs of bucket indices -> one wait kernel each, on the COMPUTE stream (nothing else is held up)
+        runs = []
+        for i in want:
+            if runs and runs[-1][1] == i:
+                runs[-1][1] = i + 1
+            else:
+                runs.append([i, i + 1])
+        for lo, hi in runs:
+            if self._done[hi - 1] is not None:
+                cur.wait_event(self._done[hi - 1])          # the update stream runs the buckets in launch order
+            ops.p2p_wait(self.flags[(nb + lo) * W: (nb + hi) * W], self.seq, self.timeout_ms, self.status)
+        self._joined.update(want)
+        if self.profile is not None and want:
+            self.profile.append(("joined %s" % ("all" if tags is None else "+".join(sorted(tags))), -1, self._mark()))
+        if len(self._joined) == nb:
+            for i in range(nb):
+                if self._done[i] is not None:
+                    cur.wait_event(self._done[i])
+            cur.wait_stream(self.send_stream)
             self._status_host.copy_(self.status, non_blocking=True)
             self._status_ev = torch.cuda.Event()
             self._status_ev.record()
-        cur = torch.cuda.current_stream(self.flat.device)
-        cur.wait_stream(self.stream)
-        cur.wait_stream(self.send_stream)
-        self.in_flight = False
+            self._joined = set()
+            self.in_flight = False
 
     def self_test(self, timeout_ms=3000):
         """One dry run of the whole bucket pipeline on recognisable data, so that a world size this box has not run
@@ -489,14 +506,13 @@ class DataParallelHead:
         self.fc6_panels = fc6_panels
         off, n, shp = model._slices["W6"]
         assert off == 0
-        self.plan = bucket_plan(n, shp[0], shp[1], model.n_weights, model.n_total, self.fc6_panels)
+        nb6 = model._slices["b7"][0] - model._slices["b6"][0]          # padded length of b6, the head of the bias block
+        self.plan = bucket_plan(n, shp[0], shp[1], model.n_weights, model.n_total, self.fc6_panels, n_bias_fc6=nb6)
         self.exchange = None
         self.master_sharded = False
         self.comm_sms = int(os.environ.get("NAWSOD_COMM_SMS", "0")) if comm_sms is None else comm_sms
         self._hyper = dict(momentum=0.9, weight_decay=5e-4)
         self.p2p_selftest = None                     # outcome of P2PExchange.self_test() when it ran ("ok" or the reason)
-        # gemm_scatter.cu: the fc6 weight-gradient GEMM stores its tiles straight into the owner ranks' staging (p2p only)
-        self.fused_scatter = os.environ.get("NAWSOD_P2P_FUSED_SCATTER", "0") == "1"
         if self.world > 1 and sync in ("p2p", "auto") and model.flat_grad.is_cuda:
             # "auto": the peer-mapped path when every rank can set it up (one NVLink / NVSwitch box), else NCCL
             requested = sync
@@ -565,7 +581,7 @@ class DataParallelHead:
         Weights: wd, lr_mult 1; biases: no decay, lr_mult 2 (optimizer_wsl.py:106-123)."""
         from . import ops
         m = self.model
-        bias = tag == "biases"
+        bias = tag.startswith("biases")
         kw = dict(momentum=self._hyper["momentum"], gpu_num=self.world, lr_mult=2.0 if bias else 1.0,
                   weight_decay=0.0 if bias else self._hyper["weight_decay"], iter_count=m.iter_count,
                   p_shadow=m.flat_lp[so: so + sn])
@@ -597,27 +613,34 @@ class DataParallelHead:
         from . import ops
         ex, cols = self.exchange, m._slices["W6"][2][1]
         self._hyper = dict(momentum=momentum, weight_decay=weight_decay)
-        small, biases = self.plan[-2], self.plan[-1]
+        by_tag = {t: (o, n) for o, n, t in self.plan}
+        small, biases, bias6 = by_tag["small_weights"], by_tag["biases"], by_tag.get("biases_fc6")
 
-        def before_params():                         # RoI pooling needs no parameters: join the previous exchange after it
-            ex.finish()
+        p2p = self.sync == "p2p"
+
+        def before_fc6():                            # RoI pooling needs no parameters: join the previous exchange after it
+            if p2p:
+                ex.finish(tags=("fc6_panel", "biases_fc6"))     # all that fc6 reads; the rest lands while fc6 runs
+            else:
+                ex.finish()
             self._limit_gemm_grid(False)
-            if self.sync == "p2p":
+
+        def before_fc7():
+            if p2p:
+                ex.finish()                          # fc7 / fc8 weights and biases of the previous step
                 ex.poll()                            # a lost peer surfaces here, one step late, without a host sync
                 ex.begin_step()
 
-        fused = self._fused_mode()
+        rows_total = m._slices["W6"][2][0]
 
         def on_panel(r0, r1):
             self._limit_gemm_grid(True)              # GEMMs launched from here on share the GPU with NCCL
-            ex.launch(r0 * cols, (r1 - r0) * cols, "fc6_panel", **({"prescattered": True} if fused else {}))
-
-        def fc6_dw(r0, r1, dY, feat):
-            rows, lo, hi = r1 - r0, r0 * cols, r1 * cols
-            ops.FCGradientWScatter(dY, feat, ex.owner_ptrs(lo, hi - lo), rows // self.world, cols, db=m.g["b6"][r0:r1])
+            ex.launch(r0 * cols, (r1 - r0) * cols, "fc6_panel")
+            if r1 == rows_total and bias6 is not None:
+                ex.launch(bias6[0], bias6[1], "biases_fc6")      # b6's gradient is complete with the last panel
 
         bl = m.RunTrainStep(dropout_masks=dropout_masks, dropout_seed=dropout_seed, dropout=dropout, fc6_panels=self.fc6_panels,
-                            on_fc6_panel=on_panel, on_before_params=before_params, fc6_dw=fc6_dw if fused else None,
+                            on_fc6_panel=on_panel, on_before_params=before_fc6, on_before_fc7=before_fc7,
                             on_small_grads=lambda: ex.launch(small[0], small[1], "small_weights"))
         ex.launch(biases[0], biases[1], "biases")
         if self.sync == "allreduce":
@@ -628,19 +651,6 @@ class DataParallelHead:
             self.master_sharded = self.world > 1
             m.iter_count += 1
         return bl
-
-    def _fused_mode(self):
-        """"scatter" when this step's fc6 weight-gradient panels use the GEMM fused with the scatter to the owner ranks
-        (p2p only; every panel must split into whole 128-row tiles per owner), else None."""
-        if not self.model.flat_grad.is_cuda:
-            return None
-        if self.sync == "p2p" and self.fused_scatter:
-            rows_total = self.model._slices["W6"][2][0]
-            step = ((rows_total + self.fc6_panels - 1) // self.fc6_panels + 255) // 256 * 256
-            panels = [min(rows_total, r0 + step) - r0 for r0 in range(0, rows_total, step)]
-            if all(r % (128 * self.world) == 0 for r in panels):
-                return "scatter"
-        return None
 
     def flush(self):
         """Join the exchange stream (end of a timed region, before reading parameters)."""

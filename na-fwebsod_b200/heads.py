@@ -292,7 +292,8 @@ class WeblyHeadModel:
             self.blobs["labels_oh"] = labels_oh
 
     # ------------------------------------------------------------------ forward pieces
-    def _fc_stack(self, dropout_masks=None, dropout_seed=None, stacks=None, on_before_params=None, dropout=True):
+    def _fc_stack(self, dropout_masks=None, dropout_seed=None, stacks=None, on_before_params=None, dropout=True,
+                  on_before_fc7=None):
         """RoIFeatureTransform -> RoIFeatureBoost -> (fc6 -> Relu -> Dropout -> fc7 -> Relu -> Dropout) per stack.
 
         Dropout follows ``DropoutIfTraining`` (detectron/modeling/wsl_heads.py:1259-1267): ALWAYS on (ratio 0.5) when the
@@ -332,6 +333,8 @@ class WeblyHeadModel:
             feat, self.w["W6"][s0 * H:s1 * H], self.p["b6"][s0 * H:s1 * H], relu=True, dropout=use_drop,
             dropout_mask=m6, dropout_seed=(dropout_seed * 4 + 1) if (use_drop and m6 is None) else 0, out=drop6,
             round_tf32=self.tf32))
+        if on_before_fc7 is not None:
+            on_before_fc7()               # first read of the fc7 / fc8 parameters follows
         if nS == self.S:      # all stacks: one launch ([S, R, H] views of the column blocks; nothing is copied)
             ops.FC(self._stacked(drop6, nS), self.w["W7"], self.p["b7"], relu=True, dropout=use_drop,
                    dropout_mask=None if m7 is None else torch.stack(m7),
@@ -369,7 +372,7 @@ class WeblyHeadModel:
 
     # ------------------------------------------------------------------ the reference's builder names
     def RunTrainStep(self, dropout_masks=None, dropout_seed=None, need_dX=False, fc6_panels=1, on_small_grads=None,
-                     on_fc6_panel=None, on_before_params=None, fc6_dw=None, dropout=True):
+                     on_fc6_panel=None, on_before_params=None, dropout=True, on_before_fc7=None):
         """One fwd+bwd pass of the head on the fed blobs (the slice of ``workspace.RunNet(net)``,
         detectron/utils/train_wsl.py:59, that lies between conv5 and the parameter gradients).
         Gradients land in ``self.g`` / ``self.flat_grad``; returns the blob dict.
@@ -380,13 +383,13 @@ class WeblyHeadModel:
         weight-gradient GEMMs); ``on_small_grads()`` fires once those are enqueued.  The bias
         gradients of fc6 are complete with the last panel, all others with ``on_small_grads``.
         ``on_before_params()`` fires after RoI pooling, right before the first parameter read (fc6):
-        the place to join a parameter update that is still in flight from the previous step.
-        ``fc6_dw(r0, r1, dY_panel, roi_feat)`` replaces the plain ``FCGradientW`` of an fc6 row panel by the GEMM
-        fused with the scatter to the rows' owner ranks (dp.py); it must also produce ``self.g["b6"][r0:r1]``."""
+        the place to join a parameter update that is still in flight from the previous step; ``on_before_fc7()`` fires
+        before the first read of the fc7 / fc8 parameters (their update may land while fc6 runs)."""
         if not self.train:
             raise RuntimeError("RunTrainStep on a test-mode model")
         bl, H, C, C2 = self.blobs, self.H, self.C, 2 * self.C
-        drop6, drop7 = self._fc_stack(dropout_masks, dropout_seed, on_before_params=on_before_params, dropout=dropout)
+        drop6, drop7 = self._fc_stack(dropout_masks, dropout_seed, on_before_params=on_before_params, dropout=dropout,
+                                      on_before_fc7=on_before_fc7)
         logits = self._fc8(drop7)
         R = drop7.shape[0]
         ld = logits.shape[2]
@@ -431,11 +434,8 @@ class WeblyHeadModel:
         step = _round_up((rows + fc6_panels - 1) // fc6_panels, 256)
         for r0 in range(0, rows, step):
             r1 = min(rows, r0 + step)
-            if fc6_dw is not None:
-                self._timed("fc6_bwd_w", lambda: fc6_dw(r0, r1, d6[:, r0:r1], bl["roi_feat"]))
-            else:
-                self._timed("fc6_bwd_w", lambda: ops.FCGradientW(d6[:, r0:r1], bl["roi_feat"], dW=self.g["W6"][r0:r1],
-                                                                 db=self.g["b6"][r0:r1]))
+            self._timed("fc6_bwd_w", lambda: ops.FCGradientW(d6[:, r0:r1], bl["roi_feat"], dW=self.g["W6"][r0:r1],
+                                                             db=self.g["b6"][r0:r1]))
             if on_fc6_panel is not None:
                 on_fc6_panel(r0, r1)
         ops.FCGradientW(dl3, a7, dW=self.g["W8"], db=self.g["b8"])

@@ -517,34 +517,6 @@ def FCBiasGradient(dY, db, *, accumulate=False):
     return db
 
 
-def _dw_operands(who, dY, X):
-    M, N, lddy = _mat(dY, "dY")
-    M2, K, lda = _mat(X, "X")
-    if M != M2 or dY.dtype != X.dtype:
-        raise RuntimeError("%s: dY and X do not match" % who)
-    return M, N, K, lddy, lda
-
-
-def _dw_bias(who, db, N):
-    if db is not None and (db.dtype != torch.float32 or not db.is_cuda or db.numel() != N or not db.is_contiguous()):
-        raise RuntimeError("%s: db must be a contiguous float32 CUDA tensor with %d elements" % (who, N))
-
-
-def FCGradientWScatter(dY, X, owner_ptrs, rows_per_owner, ldw, *, db=None):
-    """``FCGradient`` (dW, db) whose epilogue stores rows ``[k*rows_per_owner, (k+1)*rows_per_owner)`` of
-    dW straight to ``owner_ptrs[k]`` (device addresses: this rank's own gradient slice, or a peer's staging memory mapped
-    with ``nawsod_p2p_open_mem_handle``) -- the GEMM and the send leg of the reduce-scatter that replaces the reference's
-    ``NCCLAllreduce`` (modeling/optimizer_wsl.py:52-72) as one kernel.  The caller signals the owners afterwards."""
-    M, N, K, lddy, lda = _dw_operands("FCGradientWScatter", dY, X)
-    if not owner_ptrs or any(int(a) == 0 for a in owner_ptrs):
-        raise RuntimeError("FCGradientWScatter: need one non-null destination per owner")
-    _dw_bias("FCGradientWScatter", db, N)
-    table = (ctypes.c_void_p * len(owner_ptrs))(*[int(a) for a in owner_ptrs])
-    _lib.call("nawsod_fc_bwd_w_scatter", _ptr(dY), lddy, _ptr(X), lda, M, N, K, _ab(dY.dtype), table, len(owner_ptrs),
-              int(rows_per_owner), int(ldw), _ptr(db), _stream(), extra_kernels=1 if db is not None else 0)
-    return db
-
-
 def to_bf16(src, out=None):
     """float32 [rows, cols] (may be a column slice) -> bfloat16, by the library's conversion kernel."""
     rows, cols, lds = _mat(src, "src")

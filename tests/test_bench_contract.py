@@ -52,7 +52,7 @@ def test_gpu_arm_line_assembly():
             kernel_ms={"fc6_fwd": k["fc6_fwd"]["ms"], "fc6_bwd_w": k["fc6_bwd_w"]["ms"] / 4, "roi_pool_f": k["roi_pool_f"]["ms"],
                        "mil_head": k["mil_head"]["ms"]},
             n_panels=4, iso={"step_config": 0.0809, "fp32_train": 0.238} if world == 1 else {}, cpu=rec["cpu_baseline"] if world == 1 else None,
-            loss=rec["loss"], dp_info={"sync": sync, "fc6_panels": 4, "p2p_selftest": selftest, "fused": None})
+            loss=rec["loss"], dp_info={"sync": sync, "fc6_panels": 4, "p2p_selftest": selftest, "engine": "ce" if sync == "p2p" else None})
         d = json.loads(json.dumps(line))
         assert d["metric"] == "RoIs/sec (fwd+bwd, WSDDN head)" and d["unit"] == "RoIs/s" and d["n_gpus"] == world
         assert d["higher_is_better"] is True and d["scaling"] == "weak" and d["vs_baseline"] is None and d["dtype"] == "bf16"
@@ -71,10 +71,9 @@ def test_gpu_arm_line_assembly():
     # unpanelled launch: the other capture; an uncaptured panel count: unknown
     common = dict(steps=2, warmup=3, world=1, R=R, S=2, bf16=True, noise=True, ms_total=8.0, ms_e2e=9.0, h2d_bytes=1, d2h_bytes=1, launches=1,
                   clocks=None, kernel_ms={"fc6_bwd_w": 1.2}, iso={}, cpu=None, loss=[0.0],
-                  dp_info={"sync": "p2p", "fc6_panels": 1, "p2p_selftest": None, "fused": "scatter"})
+                  dp_info={"sync": "local", "fc6_panels": 1, "p2p_selftest": None, "engine": None})
     assert bench.assemble_line(n_panels=1, **common)["roofline"]["traffic"] > 3e9
     assert bench.assemble_line(n_panels=2, **common)["roofline"]["traffic"] is None
-    assert "gemm_scatter.cu" in bench.assemble_line(n_panels=1, **common)["config"]["fc6_update"]
     # the fp32 / TF32 run of the same workload rides in the same line
     t = bench.assemble_line(n_panels=4, tf32={"ms_total": 160.0, "steps": 20, "kernel_ms": {"fc6_fwd": 2.2, "fc6_bwd_w": 0.8}, "n_panels": 4},
                             **common)["kernels"]["tf32_step"]

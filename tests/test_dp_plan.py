@@ -1,6 +1,6 @@
 """Host arithmetic of the data-parallel exchange that needs neither a GPU nor a process group: the bucket plan of the
 bench's parameter layout splits into 16-byte aligned per-rank slices for 2, 4 and 8 ranks (so `sync=auto` can select the
-peer path there), the fused-scatter precondition, and where P2PExchange.owner_ptrs() points."""
+peer path there), and the split of the bias block into the bucket fc6 needs and the rest."""
 import pytest
 
 from nafwebsod_b200 import dp
@@ -34,22 +34,16 @@ def test_bench_buckets_split_into_aligned_slices(world, C):
         so, sn = dp.rank_slice(off, n, world, world - 1)
         assert so + sn == off + n and (so * 4) % 16 == 0 and (so * 2) % 16 == 0
     assert covered == n_total
-    # the GEMM-fused scatter needs whole 128-row tiles per owner in every fc6 panel
     panel_rows = [n // cols for _, n, tag in plan if tag == "fc6_panel"]
-    assert sum(panel_rows) == rows and all(r % (128 * world) == 0 for r in panel_rows)
+    assert sum(panel_rows) == rows
 
 
-def test_owner_ptrs_address_the_owners_slot_for_this_rank():
-    class FakeFlat:
-        def data_ptr(self):
-            return 1 << 20
-
-    ex = dp.P2PExchange.__new__(dp.P2PExchange)
-    ex.world, ex.rank, ex.flat = 4, 2, FakeFlat()
-    ex.peer_stage = [0x10000000 * (k + 1) for k in range(4)]
-    offset, length = 4096, 4 * 1000
-    n = length // 4
-    ptrs = ex.owner_ptrs(offset, length)
-    assert ptrs[2] == (1 << 20) + 4 * (offset + 2 * n)                      # own slice: the local gradient buffer
-    for k in (0, 1, 3):                                                     # owner k's staging, slot of rank 2
-        assert ptrs[k] == ex.peer_stage[k] + 4 * (offset + 2 * n)
+def test_bias_block_splits_into_what_fc6_needs_and_the_rest():
+    n_w6, rows, cols, n_weights, n_total = bench_layout()
+    plan = dp.bucket_plan(n_w6, rows, cols, n_weights, n_total, panels=4, n_bias_fc6=8192)
+    tags = [t for _, _, t in plan]
+    assert tags == ["fc6_panel"] * 4 + ["small_weights", "biases_fc6", "biases"]
+    assert sum(n for _, n, _ in plan) == n_total and plan[-2][:2] == (n_weights, 8192) and plan[-1][0] == n_weights + 8192
+    for world in (2, 4, 8):                      # both bias buckets are replicated, whatever their alignment
+        assert not dp.bucket_is_sliced(plan[-1][1], "biases", world) and not dp.bucket_is_sliced(8192, "biases_fc6", world)
+        assert dp.bucket_is_sliced(plan[0][1], "fc6_panel", world)

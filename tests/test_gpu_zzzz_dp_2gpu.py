@@ -38,18 +38,14 @@ def _worker(rank, world, port, out):
         from nafwebsod_b200.dp import DataParallelHead
         from oracle import nawsod_oracle as O
         res = {}
-        variants = ("allreduce", "sharded", "p2p") + (("p2p_fused",) if os.environ.get("NAWSOD_EXPERIMENTAL") == "1" else ())
-        for variant in variants:
-            sync = "p2p" if variant == "p2p_fused" else variant
-            # experimental: the fc6 weight-gradient GEMM stores its tiles straight into the owners' staging areas
-            os.environ["NAWSOD_P2P_FUSED_SCATTER"] = "1" if variant == "p2p_fused" else "0"
+        for variant in ("allreduce", "sharded", "p2p"):
+            sync = variant
             m = WeblyHeadModel(7, 64, 7, 256, noise=True, dtype=torch.bfloat16, device=dev)
             g = torch.Generator(device=dev).manual_seed(5)
             m.flat_param[:m.n_weights].normal_(0.0, 0.02, generator=g)
             m.sync_shadow()
             m.UpdateWorkspaceLr(1e-2)
             dp = DataParallelHead(m, fc6_panels=4, sync=sync)
-            assert (dp._fused_mode() == "scatter") == (variant == "p2p_fused")
             dp.broadcast_parameters()
             X = O.synth_conv5(1, 64, 20, 25, seed=10 + rank)
             rois = O.synth_rois(256, 320, 400, seed=20 + rank)
@@ -97,9 +93,3 @@ def test_sharded_exchange_matches_allreduce_schedule():
     assert np.abs(pa - pp).max() <= 1e-3 * upd and np.abs(ma - mp_).max() <= 1e-3 * upd
     assert np.abs(la - lp).max() <= 2e-2 * np.abs(la).max()
     assert np.allclose(r0["allreduce"][3], r0["p2p"][3], rtol=1e-3)
-
-    if "p2p_fused" in r0:
-        # same contributions, same owner-side summation order: the fused scatter must not change a bit
-        for r in (r0, r1):
-            for a, b in zip(r["p2p"], r["p2p_fused"]):
-                assert np.array_equal(a, b), "GEMM-fused scatter differs from GEMM + scatter kernel"
