@@ -253,6 +253,11 @@ int nawsod_p2p_signal(void* const* flag_ptrs, int n, uint32_t value, void* strea
  * for launches that may overlap in time). */
 int nawsod_p2p_scatter(const void* const* srcs, void* const* dsts, int npeers, int64_t bytes,
                        void* const* flag_ptrs, int nflags, uint32_t value, int slot, void* stream);
+/* The same contract, moved by the TMA unit: bulk asynchronous copies global -> shared -> (peer) global issued by one
+ * thread per CTA (one warp, ~25 KB of shared memory: it fits beside a persistent GEMM CTA and takes no issue slots or
+ * LSU bandwidth from it). */
+int nawsod_p2p_scatter_tma(const void* const* srcs, void* const* dsts, int npeers, int64_t bytes,
+                           void* const* flag_ptrs, int nflags, uint32_t value, int slot, void* stream);
 int nawsod_p2p_wait(const void* flags, int n, uint32_t value, int64_t timeout_ms, void* status,
                     void* stream);
 

@@ -541,50 +541,20 @@ __device__ __forceinline__ void rows2_bins(const Rows2Roi& g, TOut* yout, int32_
   }
 }
 
-// Experimental (knob pool_lean): rows2_bins<kEmpty = false> for PH == 7 with the seven bin rows unrolled.  The row bounds
-// are fetched with seven SHFLs up front (in the rolled loop every bin starts with a SHFL whose result the very next ISETP
-// needs: 17 % of the stall samples of the r1j capture), the share bit is a constant shift, and the output pointers are
-// compile-time multiples of the bin stride.  Same scan order and arithmetic as rows2_bins.
-template <typename TIn, typename TOut, bool kArgmax, int NC>
-__device__ __forceinline__ void rows3_bins(const Rows2Roi& g, TOut* yout, int32_t* aout) {
-  constexpr int VEC = Vec<TIn>::N;
-  using Scan = typename std::conditional<sizeof(TIn) == 4, ScanF32<kArgmax>, ScanBF16<kArgmax>>::type;
-  int hend[7];
-#pragma unroll
-  for (int ph = 0; ph < 7; ++ph) hend[ph] = __shfl_sync(0xffffffffu, g.bend, ph);
-  int next_h = __shfl_sync(0xffffffffu, g.bstart, 0);      // map row `rowp` points at; `cached` = row next_h - 1
-  const unsigned char* rowp = g.col_src + (size_t)next_h * g.row_bytes;
-  int idx0 = next_h * g.W + g.wstart;
-  Scan cached;
-  cached.init(false);
-#pragma unroll
-  for (int ph = 0; ph < 7; ++ph) {
-    Scan sc;
-    sc.select((g.share_mask >> ph) & 1u, cached);
-#pragma unroll 1
-    for (; next_h < hend[ph]; ++next_h, rowp += g.row_bytes, idx0 += g.W) {
-      cached.init(false);
-      rows2_scan_row<Scan, NC>(cached, rowp, idx0, g.o1, g.o2, g.o3, g.ncmax, g.last, g.cell_bytes);
-      sc.merge(cached);
-    }
-    float maxv[VEC];
-    int maxi[VEC];
-    sc.result(false, maxv, maxi);
-#pragma unroll
-    for (int k = 0; k < VEC; ++k) maxv[k] = __fmul_rn(maxv[k], g.s);
-    store_vals<VEC>(yout + (size_t)ph * g.bin_stride, maxv);
-    if (kArgmax) store_idx<VEC>(aout + (size_t)ph * g.bin_stride, maxi);
-  }
-}
-
-// kSkipIdle (experimental, tuning knob pool_skip_idle, off by default): RoIs arrive grouped by image, so of the N CTAs that
-// share a (slab, chunk) usually one finds work; with kSkipIdle the others return BEFORE staging 120 KB of map (at N = 2 a
-// third of the launch's CTA time).  A compile-time switch, so the default instantiation is the verified kernel unchanged.
-// kPrefetchRoi (experimental, knob pool_prefetch_roi): the warp claims and loads the NEXT RoI's coordinates before it starts
-// on the current one, so the global-load latency of the RoI fetch (6 % of the stall samples, on the two SHFLs that broadcast
-// a freshly loaded RoI) is hidden behind a whole RoI of work.
-template <typename TIn, typename TOut, bool kSmem, bool kArgmax, bool kSkipIdle = false, bool kPrefetchRoi = false,
-          bool kUnrollBins = false>
+// kSkipIdle (staged maps; tuning knob pool_skip_idle, default 1): RoIs arrive grouped by image, so of the N CTAs that share a
+// (slab, chunk) usually one finds work; with kSkipIdle the others return BEFORE staging 120 KB of map (at N = 2 a third of
+// the launch's CTA time; measured 79.9 -> 73.7 us bf16, 139.3 -> 131.1 us bf16 + argmax, profiles/r2a_microbench_pool.log).
+//
+// Measured and REMOVED in round 2 (profiles/r2a_microbench_pool.log, r2e / r2g_microbench_pool_*.log, r2g_ncu_pool_rows4_summary.txt):
+// a one-RoI-ahead prefetch of the RoI coordinates (no change), the seven bin rows unrolled (slower: instruction cache), and a
+// rebuilt bf16 / no-argmax kernel ("rows4": 32-bit shared addresses, three-input packed maxima, no -inf fill or selects,
+// packed-bf16 FMA boost, then a ping-pong prefetch of the next map row, then 4- / 5-cell specialisations).  Its three builds
+// ran 42.8-46.1 M warp instructions with very different schedules and all took 73-78 us -- the same as this kernel.  The bound
+// they share is the LSU / shared-memory pipe: 11.7 M shared wavefronts (2.1 M of them bank conflicts between the two bin columns
+// of a quarter-warp, whose cell parities are data dependent) + the output stores keep l1tex at 72 % of peak over the whole launch
+// and ~85 % while the SMs are active; reading each RoI's window out of a 64-byte-per-cell slab costs ~6 bytes of shared-memory
+// traffic per byte written (bin columns overlap by a cell, windows are clamped to the widest column of the warp).
+template <typename TIn, typename TOut, bool kSmem, bool kArgmax, bool kSkipIdle = false>
 __global__ void __launch_bounds__(1024, 1) roi_pool_fwd_rows2_kernel(const PoolParams p) {
   constexpr int VEC = Vec<TIn>::N;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -633,31 +603,13 @@ __global__ void __launch_bounds__(1024, 1) roi_pool_fwd_rows2_kernel(const PoolP
   const float fdiv = static_cast<float>(is_h ? PH : PW);
   const int lim = is_h ? H : W;
 
-  int r_next = 0;
-  float coord_next = 0.f;
-  if (kPrefetchRoi) {
-    if (lane == 0) r_next = atomicAdd(&next_roi, 1);
-    r_next = __shfl_sync(0xffffffffu, r_next, 0);
-    if (r_next < r1) coord_next = __ldg(p.rois + (size_t)r_next * 5 + min(lane, 4));
-  }
   while (true) {
     int r = 0;
-    float coord_pf = 0.f;
-    if (kPrefetchRoi) {
-      r = r_next;
-      coord_pf = coord_next;
-      if (r >= r1) break;
-      r_next = 0;
-      if (lane == 0) r_next = atomicAdd(&next_roi, 1);
-      r_next = __shfl_sync(0xffffffffu, r_next, 0);
-      if (r_next < r1) coord_next = __ldg(p.rois + (size_t)r_next * 5 + min(lane, 4));
-    } else {
-      if (lane == 0) r = atomicAdd(&next_roi, 1);
-      r = __shfl_sync(0xffffffffu, r, 0);
-      if (r >= r1) break;
-    }
+    if (lane == 0) r = atomicAdd(&next_roi, 1);
+    r = __shfl_sync(0xffffffffu, r, 0);
+    if (r >= r1) break;
     // lane l (1..4) owns coordinate l of the RoI; detectron/ops/roi_loop_pool_op.cu:42-45
-    const float coord = kPrefetchRoi ? coord_pf : __ldg(p.rois + (size_t)r * 5 + min(lane, 4));
+    const float coord = __ldg(p.rois + (size_t)r * 5 + min(lane, 4));
     if (static_cast<int>(__shfl_sync(0xffffffffu, coord, 0)) != n) continue;
     const int rounded = static_cast<int>(roundf(coord * p.scale));
     const int roi_start_w = __shfl_sync(0xffffffffu, rounded, 1);
@@ -693,7 +645,6 @@ __global__ void __launch_bounds__(1024, 1) roi_pool_fwd_rows2_kernel(const PoolP
 #define NAWSOD_ROWS2(NC_)                                                        \
   do {                                                                           \
     if (any_empty) rows2_bins<TIn, TOut, kArgmax, NC_, true>(g, yout, aout);     \
-    else if (kUnrollBins && PH == 7) rows3_bins<TIn, TOut, kArgmax, NC_>(g, yout, aout); \
     else rows2_bins<TIn, TOut, kArgmax, NC_, false>(g, yout, aout);              \
   } while (0)
     switch (g.ncmax) {                             // warp-uniform
@@ -830,14 +781,9 @@ int launch_pool_fwd2(const PoolParams& p, size_t smem_bytes, dim3 grid, int thre
   // bin-row kernel: one warp holds a whole row of bins (h-bounds on lanes 0..7, w-bounds on lanes 8..31)
   const int slots = 32 / (p.SC / Vec<TIn>::N);
   if (p.PH <= 8 && p.PW <= 8 && slots == 8 && get_tuning("pool_generic", 0) == 0 && get_tuning("pool_rows2", kPoolRows2Default) != 0) {
-    if constexpr (kSmem) {                           // experimental variants (staged maps only)
-      const bool lean = get_tuning("pool_lean", 0) != 0;    // skip idle CTAs + RoI prefetch + unrolled bin rows
-      const bool skip_idle = lean || get_tuning("pool_skip_idle", 0) != 0, prefetch = lean || get_tuning("pool_prefetch_roi", 0) != 0;
-      if (skip_idle || prefetch) {
-        auto k = lean                    ? roi_pool_fwd_rows2_kernel<TIn, TOut, true, kArgmax, true, true, true>
-                 : (skip_idle && prefetch) ? roi_pool_fwd_rows2_kernel<TIn, TOut, true, kArgmax, true, true>
-                 : skip_idle             ? roi_pool_fwd_rows2_kernel<TIn, TOut, true, kArgmax, true, false>
-                                         : roi_pool_fwd_rows2_kernel<TIn, TOut, true, kArgmax, false, true>;
+    if constexpr (kSmem) {
+      if (get_tuning("pool_skip_idle", 1) != 0) {
+        auto k = roi_pool_fwd_rows2_kernel<TIn, TOut, true, kArgmax, true>;
         NAWSOD_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
         k<<<grid, threads, smem_bytes, st>>>(p);
         NAWSOD_LAUNCH_OK();

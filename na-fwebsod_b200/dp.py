@@ -267,10 +267,11 @@ class P2PExchange:
             raise RuntimeError("peer mapping failed on at least one rank: %s" % (e1 or e2 or e3 or "on a peer"))
         self.stream = torch.cuda.Stream(device=dev, priority=-1)
         self.send_stream = torch.cuda.Stream(device=dev, priority=-1)
-        # "sm": one co-resident scatter kernel per bucket and leg (default); "ce": copy-engine transfers
+        # "tma": one co-resident scatter kernel per bucket and leg whose bytes the TMA unit moves (bulk copies through shared
+        # memory, one thread per CTA); "sm": the same with SM loads / stores; "ce": copy-engine transfers
         self.engine = os.environ.get("NAWSOD_P2P_ENGINE", "sm")
-        if self.engine not in ("sm", "ce"):
-            raise RuntimeError("NAWSOD_P2P_ENGINE must be 'sm' or 'ce'")
+        if self.engine not in ("tma", "sm", "ce"):
+            raise RuntimeError("NAWSOD_P2P_ENGINE must be 'tma', 'sm' or 'ce'")
         if len(self.plan) > 64:
             raise RuntimeError("at most 64 exchange buckets")
         nfan = int(os.environ.get("NAWSOD_P2P_COPY_STREAMS", "3"))
@@ -318,10 +319,12 @@ class P2PExchange:
         else:
             rs_copies = [(self.peer_stage[k] + 4 * (offset + rank * n), self.flat.data_ptr() + 4 * (offset + k * n), 4 * n) for k in peers]
         self.bytes_out += 4 * n * (W - 1)
-        if self.engine == "sm":
+        kernel_engine = self.engine in ("sm", "tma")
+        if kernel_engine:
             self.send_stream.wait_event(ev)
             with torch.cuda.stream(self.send_stream):
-                ops.p2p_scatter([c[1] for c in rs_copies], [c[0] for c in rs_copies], 4 * n, self._flag_ptrs(self.RS, b), self.seq, b)
+                ops.p2p_scatter([c[1] for c in rs_copies], [c[0] for c in rs_copies], 4 * n, self._flag_ptrs(self.RS, b), self.seq, b,
+                                tma=self.engine == "tma")
                 if prof is not None:
                     prof.append(("sent", b, self._mark()))
         else:
@@ -347,11 +350,12 @@ class P2PExchange:
                 prof.append(("updated", b, self._mark()))
             # operand leg; a replicated bucket has nothing to send back, its AG flag only says "staging consumed"
             ag_copies = [] if replicated else [(self.peer_out[k] + es_out * so, self.out.data_ptr() + es_out * so, es_out * n) for k in peers]
-            if self.engine == "sm":
-                ops.p2p_scatter([c[1] for c in ag_copies], [c[0] for c in ag_copies], es_out * n, self._flag_ptrs(self.AG, b), self.seq, 64 + b)
+            if kernel_engine:
+                ops.p2p_scatter([c[1] for c in ag_copies], [c[0] for c in ag_copies], es_out * n, self._flag_ptrs(self.AG, b), self.seq, 64 + b,
+                                tma=self.engine == "tma")
             upd = torch.cuda.Event()
             upd.record()
-        if self.engine != "sm":
+        if not kernel_engine:
             self._fan_out(self.ag_streams, upd, self.stream, ag_copies)
             with torch.cuda.stream(self.stream):
                 ops.p2p_signal(self._flag_ptrs(self.AG, b), self.seq)

@@ -358,13 +358,15 @@ def p2p_signal(flag_ptrs, value: int):
     _lib.call("nawsod_p2p_signal", table, len(flag_ptrs), int(value) & 0xFFFFFFFF, _stream())
 
 
-def p2p_scatter(srcs, dsts, nbytes: int, flag_ptrs, value: int, slot: int):
-    """One SM-driven launch: copy ``nbytes`` from srcs[i] to dsts[i] (raw addresses, local or peer-mapped) for every
-    peer, then publish ``value`` into the flag words."""
+def p2p_scatter(srcs, dsts, nbytes: int, flag_ptrs, value: int, slot: int, tma: bool = False):
+    """One launch: copy ``nbytes`` from srcs[i] to dsts[i] (raw addresses, local or peer-mapped) for every peer, then
+    publish ``value`` into the flag words.  ``tma=False``: SM-driven 16-byte loads / posted stores; ``tma=True``: bulk
+    asynchronous copies through shared memory issued by one thread per CTA (the TMA unit moves the bytes)."""
     ts = (ctypes.c_void_p * max(len(srcs), 1))(*srcs)
     td = (ctypes.c_void_p * max(len(dsts), 1))(*dsts)
     tf = (ctypes.c_void_p * max(len(flag_ptrs), 1))(*flag_ptrs)
-    _lib.call("nawsod_p2p_scatter", ts, td, len(srcs), int(nbytes), tf, len(flag_ptrs), int(value) & 0xFFFFFFFF, int(slot), _stream())
+    _lib.call("nawsod_p2p_scatter_tma" if tma else "nawsod_p2p_scatter", ts, td, len(srcs), int(nbytes), tf, len(flag_ptrs),
+              int(value) & 0xFFFFFFFF, int(slot), _stream())
 
 
 def p2p_wait(flags, value: int, timeout_ms: int = 20000, status=None):

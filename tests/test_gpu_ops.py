@@ -83,6 +83,25 @@ def test_roi_pool_bf16_path():
     assert np.array_equal(A.cpu().numpy(), Ao.transpose(0, 2, 3, 1))
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_roi_pool_rois_interleaved_across_images(dtype):
+    """The kernels filter RoIs by batch index inside every (slab, chunk, image) CTA and CTAs whose chunk holds no RoI of
+    their image leave before staging the map (pool_skip_idle): RoIs grouped by image (the loader's order) and randomly
+    interleaved across three images must both equal the oracle."""
+    ops = _ops()
+    X = O.synth_conv5(3, 128, 38, 50, seed=0)
+    grouped = np.concatenate([O.synth_rois(400, 608, 800, b, seed=1 + b) for b in range(3)])
+    inter = grouped[np.random.default_rng(3).permutation(grouped.shape[0])]
+    Xd = dev(X).to(dtype)
+    Xr = Xd.float().cpu().numpy()
+    Xcl = Xd.permute(0, 2, 3, 1).contiguous()
+    for rois in (grouped, inter):
+        Yo, Ao = CO.roi_pool_f(Xr, rois, 1 / 16)
+        Y, A = ops.RoIPoolF(Xcl, dev(rois), spatial_scale=1 / 16, x_layout="NHWC", y_layout="NHWC")
+        assert np.array_equal(Y.float().cpu().numpy(), Yo.transpose(0, 2, 3, 1))
+        assert np.array_equal(A.cpu().numpy(), Ao.transpose(0, 2, 3, 1))
+
+
 def _mixed_rois(R, img_h, img_w, batch, seed):
     """RoI mixture of BASELINE config 3: MCG-like boxes, boxes smaller than one cell / one bin row
     (bins repeat a map row), full-image boxes, boxes hanging over the border or fully outside,
@@ -113,7 +132,7 @@ def _mixed_rois(R, img_h, img_w, batch, seed):
 
 @pytest.mark.parametrize("knobs", [{}, {"pool_rows2": 0}, {"pool_rows2": 0, "pool_rowcache": 0}, {"pool_generic": 1},
                                    {"pool_force_global": 1}, {"pool_slab_bytes": 32 * 1024}, {"pool_rows2": 1}, {"pool_rows2": 2},
-                                   {"pool_rows2": 2, "pool_force_global": 1}, {"pool_chunks": 3}])
+                                   {"pool_rows2": 2, "pool_force_global": 1}, {"pool_chunks": 3}, {"pool_skip_idle": 0}])
 @pytest.mark.parametrize("cfg", [(2, 512, 38, 50, 1 / 16, 16), (1, 128, 75, 125, 1 / 16, 16), (1, 64, 60, 80, 1 / 8, 8),
                                  (1, 32, 150, 250, 1 / 8, 8)])      # the largest config-3 map: short side 1200, max side 2000 at 1/8
 def test_roi_pool_mixed_rois_all_variants(cfg, knobs):
@@ -147,7 +166,7 @@ def test_roi_pool_mixed_rois_all_variants(cfg, knobs):
         assert np.array_equal(Y3.float().cpu().numpy(), Yob.transpose(0, 2, 3, 1))
     finally:
         for k in knobs:
-            pkg.set_tuning(k, {"pool_rowcache": 1, "pool_slab_bytes": 200 * 1024, "pool_rows2": -1}.get(k, 0))
+            pkg.set_tuning(k, {"pool_rowcache": 1, "pool_slab_bytes": 200 * 1024, "pool_rows2": -1, "pool_skip_idle": 1}.get(k, 0))
 
 
 def test_roi_pool_empty_and_errors():

@@ -70,13 +70,13 @@ def bench_pool2():
         boost = torch.rand(R, device="cuda") + 1
         es = 4 if dt == torch.float32 else 2
         alg = R * (C * 49 * es + (C * 49 * 4 if train else 0) + 20) + N * C * H * W * es
-        for knobs in [dict(), dict(pool_rows2=0), dict(pool_skip_idle=1), dict(pool_prefetch_roi=1), dict(pool_skip_idle=1, pool_prefetch_roi=1), dict(pool_lean=1), dict(pool_chunks=9), dict(pool_chunks=18), dict(pool_chunks=27),
+        for knobs in [dict(), dict(pool_skip_idle=0), dict(pool_rows2=0), dict(pool_chunks=9), dict(pool_chunks=18), dict(pool_chunks=27),
                       dict(pool_chunks=36)]:
             for k, v in knobs.items():
                 pkg.set_tuning(k, v)
             med, best = timeit(lambda: ops.RoIPoolF(Xcl, rois, boost=boost, is_test=not train, x_layout="NHWC", y_layout="NHWC"))
             pkg.set_tuning("pool_rows2", -1); pkg.set_tuning("pool_threads", 0); pkg.set_tuning("pool_chunks", 0)
-            pkg.set_tuning("pool_skip_idle", 0); pkg.set_tuning("pool_prefetch_roi", 0); pkg.set_tuning("pool_lean", 0)
+            pkg.set_tuning("pool_skip_idle", 1)
             print("pool N=%d R=%d %dx%d %s train=%d %s: med %.1f us best %.1f us  %.0f GB/s (%.1f%% of %.0f)  %.2f M RoIs/s" % (
                 N, R, H, W, str(dt)[6:], train, knobs, med * 1e3, best * 1e3, alg / med / 1e6, 100 * alg / med / 1e6 / PEAKS["hbm_gbs"],
                 PEAKS["hbm_gbs"], R / med / 1e3), flush=True)

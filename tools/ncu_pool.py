@@ -7,7 +7,7 @@ import bench
 for kv in filter(None, os.environ.get("NAWSOD_TUNING", "").split(",")):      # e.g. NAWSOD_TUNING=pool_rows2=1
     k, v = kv.split("=")
     pkg.set_tuning(k, int(v))
-X, rois, obn, L, offs = bench.synth_inputs(1, 2000, 0)
+X, rois, obn, L, offs = bench.synth_inputs(2, 2000, 0)        # BASELINE config 2: 2 images x 2000 RoIs
 Xd = torch.from_numpy(X).cuda(); r = torch.from_numpy(rois).cuda(); b = torch.from_numpy(obn).cuda()
 for dt, train in ((torch.float32, True), (torch.bfloat16, False)):
     Xcl = ops.to_channels_last(Xd, dt)
