@@ -273,7 +273,7 @@ int nawsod_p2p_wait(const void* flags, int n, uint32_t value, int64_t timeout_ms
  *                         np.unique(hashes, return_index, return_inverse) (core/test_wsl.py:125-133):
  *                         index[u] = first row with the u-th smallest hash (entries u >= num_unique
  *                         repeat index[0]), inv_index[r] = rank of row r's hash, num_unique[0].
- *                         R <= 8192.  All outputs are device arrays; roi_offsets (or NULL) receives
+ *                         R <= 16384 (the shipped TEST.PROPOSAL_LIMIT is 9999).  All outputs are device arrays; roi_offsets (or NULL) receives
  *                         {0, num_unique}, the row range nawsod_mil_head_fwd_bwd takes for one image, so the
  *                         head can run on the unique set without a host round trip.
  *   nawsod_gather_rows    dst[i,:] = src[index[i],:]   (rois / obn_scores / boxes of the unique set)

@@ -20,7 +20,7 @@ namespace {
 
 constexpr int kPostThreads = 1024;
 constexpr int kMaxSortRois = 16384;   // NMS: 16384 * (8 + 1) B of sort keys + flags fit the 227 KB of one SM
-constexpr int kMaxDedupRois = 8192;   // dedup: 8192 * (8 + 4 + 4) B (hash, row, rank); config 5 sweeps up to 8000 RoIs
+constexpr int kMaxDedupRois = 16384;  // dedup: 16384 * (8 + 4) B (hash, row) = 192 KB; the shipped TEST.PROPOSAL_LIMIT is 9999 (configs/flickr_voc/na_wsddn_V-16-C5_1x.yaml:39)
 
 __host__ __device__ inline int next_pow2(int v) {
   int p = 1;
@@ -134,16 +134,29 @@ dedup_rois_kernel(const float* __restrict__ rois, int R, float dedup_scale, int3
   }
   __syncthreads();
   bitonic_sort_pairs<long long>(key, pay, P);
-  // run heads -> ranks.  The flags overwrite nothing we still need: they live in a third array.
-  int* rank = reinterpret_cast<int*>(post_smem + (size_t)P * (sizeof(long long) + sizeof(int)));
-  for (int i = threadIdx.x; i < R; i += blockDim.x) rank[i] = (i == 0 || key[i] != key[i - 1]) ? 1 : 0;
+  // run heads -> ranks, without a rank array (shared memory holds the 12-byte pairs of up to 16384 RoIs and nothing else):
+  // every thread owns a contiguous chunk of the sorted sequence, counts the run heads in it, the chunk counts are scanned,
+  // and a second walk over the chunk hands out the ranks.
+  const int T = blockDim.x, t = threadIdx.x;
+  const int per = (R + T - 1) / T;
+  const int cb = min(R, t * per), ce = min(R, cb + per);
+  int heads = 0;
+  for (int i = cb; i < ce; ++i) heads += (i == 0 || key[i] != key[i - 1]) ? 1 : 0;
+  chunk_sums[t] = heads;
   __syncthreads();
-  const int total = block_exclusive_scan(rank, R, chunk_sums);     // rank[i] = #heads before i
-  for (int i = threadIdx.x; i < R; i += blockDim.x) {
+  for (int off = 1; off < T; off <<= 1) {
+    const int add = t >= off ? chunk_sums[t - off] : 0;
+    __syncthreads();
+    chunk_sums[t] += add;
+    __syncthreads();
+  }
+  const int total = chunk_sums[T - 1];
+  int u = t ? chunk_sums[t - 1] : 0;             // number of run heads before this chunk
+  for (int i = cb; i < ce; ++i) {
     const bool head = (i == 0 || key[i] != key[i - 1]);
-    const int u = head ? rank[i] : rank[i] - 1;                     // rank of the run this element belongs to
-    if (head) index[u] = pay[i];
-    inv_index[pay[i]] = u;
+    if (head) index[u] = pay[i];                 // first occurrence: (hash, original index) sorts it to the run's front
+    inv_index[pay[i]] = head ? u : u - 1;        // rank of the run this element belongs to
+    u += head ? 1 : 0;
   }
   __syncthreads();
   const int first = pay[0];
@@ -428,11 +441,11 @@ extern "C" int nawsod_dedup_rois(const float* rois, int R, float dedup_scale, in
   NAWSOD_REQUIRE(rois && index && inv_index && num_unique, NAWSOD_ERR_ARG, "dedup_rois: null pointer");
   NAWSOD_REQUIRE(dedup_scale > 0.f, NAWSOD_ERR_ARG, "dedup_rois: DEDUP_BOXES must be > 0");
   const int P = next_pow2(R);
-  const size_t smem = (size_t)P * (sizeof(long long) + 2 * sizeof(int));
+  const size_t smem = (size_t)P * (sizeof(long long) + sizeof(int));
   static bool attr_set = false;
   if (!attr_set) {
     NAWSOD_CUDA_OK(cudaFuncSetAttribute(dedup_rois_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)((size_t)kMaxDedupRois * (sizeof(long long) + 2 * sizeof(int)))));
+                                        (int)((size_t)kMaxDedupRois * (sizeof(long long) + sizeof(int)))));
     attr_set = true;
   }
   dedup_rois_kernel<<<1, kPostThreads, smem, static_cast<cudaStream_t>(stream)>>>(rois, R, dedup_scale, index, inv_index,

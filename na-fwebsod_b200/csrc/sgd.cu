@@ -49,6 +49,11 @@ __device__ __forceinline__ void sgd_elem(float g, float& m, float& p, float& acc
   acc = ac;
 }
 
+// kPre: number of extra gradient sources whose loads are issued TOGETHER before the first add (0: the plain update; 7 / 15: the
+// data-parallel owner's reduction over up to 8 / 16 ranks).  The contributions may live in PEER memory (the pull exchange reads
+// the ranks' gradient slices in place over NVLink, ~1-2 us per load): a load -> add -> load chain would serialise that latency
+// once per rank; with all of a vector's loads in flight at once it is paid once.  The adds still run in rank order.
+template <int kPre>
 __global__ void __launch_bounds__(256) sgd_kernel(const SgdArgs a) {
   // a peer's contribution never arrived (p2p_wait's watchdog fired): leave m / p / shadow untouched rather than
   // update from an incomplete sum; the host sees the same word and raises (dp.P2PExchange.check)
@@ -59,9 +64,16 @@ __global__ void __launch_bounds__(256) sgd_kernel(const SgdArgs a) {
   const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   for (int64_t i = t0; i < n4; i += stride) {
     float4 g = __ldcs(reinterpret_cast<const float4*>(a.g) + i);
-    for (int e = 0; e < a.n_extra; ++e) {      // fixed (rank) order: the sum is deterministic
-      const float4 x = __ldcs(reinterpret_cast<const float4*>(a.extra[e]) + i);
-      g.x = __fadd_rn(g.x, x.x); g.y = __fadd_rn(g.y, x.y); g.z = __fadd_rn(g.z, x.z); g.w = __fadd_rn(g.w, x.w);
+    if (kPre > 0) {
+      float4 x[kPre > 0 ? kPre : 1];
+#pragma unroll
+      for (int e = 0; e < kPre; ++e)
+        if (e < a.n_extra) x[e] = __ldcv(reinterpret_cast<const float4*>(a.extra[e]) + i);   // never from a stale L1 line
+#pragma unroll
+      for (int e = 0; e < kPre; ++e)             // fixed (rank) order: the sum is deterministic
+        if (e < a.n_extra) {
+          g.x = __fadd_rn(g.x, x[e].x); g.y = __fadd_rn(g.y, x[e].y); g.z = __fadd_rn(g.z, x[e].z); g.w = __fadd_rn(g.w, x[e].w);
+        }
     }
     float4 m = a.first_call ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldcs(reinterpret_cast<const float4*>(a.m) + i);
     float4 p = __ldcs(reinterpret_cast<const float4*>(a.p) + i);
@@ -141,7 +153,10 @@ static int sgd_launch(const float* const* grads, int n_grads, float* m, const fl
   // a narrower grid leaves the memory system's queues to the GEMM epilogues
   const int64_t cap = get_tuning("sgd_max_ctas", 0);
   const int blocks = (int)std::min<int64_t>((work + 255) / 256, cap > 0 ? cap : (int64_t)sm_count() * 16);
-  sgd_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (a.n_extra == 0) sgd_kernel<0><<<blocks, 256, 0, st>>>(a);
+  else if (a.n_extra <= 7) sgd_kernel<7><<<blocks, 256, 0, st>>>(a);
+  else sgd_kernel<15><<<blocks, 256, 0, st>>>(a);
   NAWSOD_LAUNCH_OK();
   return NAWSOD_OK;
 }

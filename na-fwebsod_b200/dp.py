@@ -243,7 +243,15 @@ class P2PExchange:
         self.timeout_ms = int(os.environ.get("NAWSOD_P2P_TIMEOUT_MS", timeout_ms))     # watchdog of every wait kernel
         dev = flat_grad.device
         nb, W = len(self.plan), self.world
-        self.stage = torch.empty(flat_grad.numel(), dtype=torch.float32, device=dev)
+        # reduce-scatter leg: "pull" -- the owner's update kernel reads the ranks' gradient slices IN PLACE over NVLink (the
+        # producers only publish "my bucket is complete"); "push" -- producers copy their slices into the owner's staging
+        # area (engine-driven copies), the owner reduces from local memory.  Pull needs no staging memory (958 MB), no copy
+        # kernels beside the GEMMs and saves the staging's HBM write + re-read (1.7 GB per step and GPU at 8 ranks).
+        self.rs_mode = os.environ.get("NAWSOD_P2P_RS", "pull")
+        if self.rs_mode not in ("pull", "push"):
+            raise RuntimeError("NAWSOD_P2P_RS must be 'pull' or 'push'")
+        pull = self.rs_mode == "pull"
+        self.stage = torch.empty(4 if pull else flat_grad.numel(), dtype=torch.float32, device=dev)
         # replicated buckets (the biases, see bucket_is_sliced): every rank receives every rank's WHOLE contribution
         # -> slot [rank] of a W x L area, one per replicated bucket, carved from one allocation
         self.rep_off, rep_total = {}, 0
@@ -251,7 +259,7 @@ class P2PExchange:
             if not bucket_is_sliced(n, t, self.world):
                 self.rep_off[o] = rep_total
                 rep_total += n * W
-        self.rep_stage = torch.empty(max(rep_total, 4), dtype=torch.float32, device=dev)
+        self.rep_stage = torch.empty(4 if pull else max(rep_total, 4), dtype=torch.float32, device=dev)
         self.flags = torch.zeros(2 * nb * W, dtype=torch.int32, device=dev)
         self.status = torch.zeros(1, dtype=torch.int32, device=dev)
         torch.cuda.synchronize(dev)
@@ -259,7 +267,8 @@ class P2PExchange:
         self.peer_flags, e2 = _share_with_peers(self.flags, group)
         self.peer_out, e3 = _share_with_peers(self.out, group)
         self.peer_rep, e4 = _share_with_peers(self.rep_stage, group)
-        e3 = e3 or e4
+        self.peer_grad, e5 = _share_with_peers(self.flat, group) if pull else (None, None)
+        e3 = e3 or e4 or e5
         torch.cuda.synchronize(dev)
         ok = torch.tensor([0 if (e1 or e2 or e3) else 1], dtype=torch.int32, device=dev)
         dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)          # also the setup barrier
@@ -318,9 +327,18 @@ class P2PExchange:
             rs_copies = [(self.peer_rep[k] + 4 * (ro + rank * n), self.flat.data_ptr() + 4 * offset, 4 * n) for k in peers]
         else:
             rs_copies = [(self.peer_stage[k] + 4 * (offset + rank * n), self.flat.data_ptr() + 4 * (offset + k * n), 4 * n) for k in peers]
-        self.bytes_out += 4 * n * (W - 1)
+        self.bytes_out += 4 * n * (W - 1)          # bytes of this rank's gradient that cross NVLink (pushed, or read by the owners)
         kernel_engine = self.engine in ("sm", "tma")
-        if kernel_engine:
+        pull = self.rs_mode == "pull"
+        if pull:
+            # nothing to copy: tell every rank that this bucket of my gradient buffer is complete (it stays untouched until
+            # all owners have published this step's operands, i.e. until they have read it: see finish())
+            self.send_stream.wait_event(ev)
+            with torch.cuda.stream(self.send_stream):
+                ops.p2p_signal(self._flag_ptrs(self.RS, b), self.seq)
+                if prof is not None:
+                    prof.append(("sent", b, self._mark()))
+        elif kernel_engine:
             self.send_stream.wait_event(ev)
             with torch.cuda.stream(self.send_stream):
                 ops.p2p_scatter([c[1] for c in rs_copies], [c[0] for c in rs_copies], 4 * n, self._flag_ptrs(self.RS, b), self.seq, b,
@@ -341,7 +359,9 @@ class P2PExchange:
             ops.p2p_wait(self.flags[fb: fb + W], self.seq, self.timeout_ms, self.status)
             if prof is not None:
                 prof.append(("arrived", b, self._mark()))
-            if replicated:       # the same W addends in the same (rank) order on every rank: replicas stay bit-identical
+            if pull:             # every rank's copy of [so, so + n) of the gradient buffer, read in place (peers: over NVLink)
+                grads = [self.flat[so: so + n] if r == rank else self.peer_grad[r] + 4 * so for r in range(W)]
+            elif replicated:     # the same W addends in the same (rank) order on every rank: replicas stay bit-identical
                 grads = [self.flat[so: so + n] if r == rank else self.rep_stage[ro + r * n: ro + (r + 1) * n] for r in range(W)]
             else:
                 grads = [self.flat[so: so + n] if r == rank else self.stage[offset + r * n: offset + (r + 1) * n] for r in range(W)]
@@ -440,7 +460,12 @@ class P2PExchange:
             bad.add_(((lo != value) | (hi != value)).to(torch.int32))
 
         def check_and_publish(off, length, tag, so, n, grads):
+            from . import ops
             for r, g in enumerate(grads):
+                if isinstance(g, int):           # pull mode: a peer's gradient slice, mapped into this process
+                    tmp = torch.empty(n, dtype=torch.float32, device=dev)
+                    ops.p2p_copy(tmp.data_ptr(), g, 4 * n)
+                    g = tmp
                 expect(g, float(r + 1))
             self.out[so: so + n].fill_(float(rank + 1))
 

@@ -323,7 +323,9 @@ def ACMWeightDecayMomentumSGDUpdateReduce(grads, m, lr, p, *, momentum=0.9, gpu_
     """Data-parallel owner's update: ``g = grads[0] + grads[1] + ...`` (in that order: the ranks'
     contributions to this parameter slice), then ``ACMWeightDecayMomentumSGDUpdate`` with
     iter_size 1 -- i.e. the reference's NCCLAllreduce + update pair (modeling/optimizer_wsl.py:52-72,
-    96-137) restricted to the slice this rank owns, in one pass over HBM.  ``abort_flag`` (int32 CUDA word): a
+    96-137) restricted to the slice this rank owns, in one pass over HBM.  A gradient source may be a tensor or the raw
+    device address of ``m.numel()`` floats (a peer's gradient slice mapped into this process: the kernel then reads it
+    over NVLink, all sources' loads in flight together).  ``abort_flag`` (int32 CUDA word): a
     non-zero value at launch time (a peer exchange whose watchdog fired) makes the call a no-op."""
     n = m.numel()
     for t, nme in ((m, "m"), (p, "p")):
@@ -332,12 +334,16 @@ def ACMWeightDecayMomentumSGDUpdateReduce(grads, m, lr, p, *, momentum=0.9, gpu_
     if not grads or p.numel() != n:
         raise RuntimeError("need at least one gradient source and matching m / p sizes")
     for i, g in enumerate(grads):
+        if isinstance(g, int):                  # raw device address of n floats (a peer-mapped gradient slice)
+            if g == 0 or g % 16:
+                raise RuntimeError("grads[%d]: null or misaligned device address" % i)
+            continue
         _req(g, "grads[%d]" % i, torch.float32)
         if g.numel() != n:
             raise RuntimeError("grads[%d] has %d elements, expected %d" % (i, g.numel(), n))
     if p_shadow is not None:
         _req(p_shadow, "p_shadow", (torch.bfloat16, torch.float32))
-    table = (ctypes.c_void_p * len(grads))(*[g.data_ptr() for g in grads])
+    table = (ctypes.c_void_p * len(grads))(*[g if isinstance(g, int) else g.data_ptr() for g in grads])
     _lib.call("nawsod_sgd_update_reduce", table, len(grads), _ptr(m), _ptr(lr), _ptr(p), n, float(momentum),
               float(weight_decay), float(lr_mult), int(gpu_num), int(iter_count), _ptr(p_shadow),
               _DT[p_shadow.dtype] if p_shadow is not None else F32, _ptr(abort_flag), _stream())

@@ -38,7 +38,8 @@ def _mcg_boxes(R, img_h, img_w, seed, dup_frac=0.25):
 
 
 # ---------------------------------------------------------------------------------------------- N1
-@pytest.mark.parametrize("R", [1, 7, 500, 2000, 4000, 8000])
+# 9999 = TEST.PROPOSAL_LIMIT of the shipped configs (configs/flickr_voc/na_wsddn_V-16-C5_1x.yaml:39); 16384 = the kernel's capacity
+@pytest.mark.parametrize("R", [1, 7, 500, 2000, 4000, 8000, 9999, 16384])
 def test_project_and_dedup_match_numpy(R):
     ops = _ops()
     boxes = _mcg_boxes(R, 375, 500, seed=R) if R > 8 else _mcg_boxes(16, 375, 500, seed=R)[:R]
@@ -63,8 +64,8 @@ def test_project_and_dedup_match_numpy(R):
 
 def test_dedup_errors():
     ops = _ops()
-    with pytest.raises(RuntimeError, match="R=9000"):
-        ops.dedup_rois(torch.zeros((9000, 5), device="cuda"))
+    with pytest.raises(RuntimeError, match="R=16385"):
+        ops.dedup_rois(torch.zeros((16385, 5), device="cuda"))
     with pytest.raises(RuntimeError):
         ops.dedup_rois(torch.zeros((10, 4), device="cuda"))
 

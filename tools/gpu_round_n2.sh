@@ -3,7 +3,7 @@
 # against the oracle's reference schedule) and bench.py under torchrun for each exchange schedule / engine.
 #   gpurun --gpus 2 --timeout 420 -- 'bash tools/gpu_round_n2.sh r2b 2'
 set -u
-TAG="${1:-r2}"; N="${2:-2}"
+TAG="${1:-r2}"; N="${2:-2}"; shift 2 || true
 OUT=gpurun_out; mkdir -p $OUT
 T0=$(date +%s); el() { echo "[$(( $(date +%s) - T0 )) s] $*"; }
 nvidia-smi topo -m > $OUT/${TAG}_topo.txt 2>&1
@@ -18,9 +18,16 @@ run() {   # name, extra env (VAR=VALUE words), extra bench args
   echo "exit $?"; python tools/bench_brief.py $OUT/${TAG}_bench_n${N}_${name}.json
   grep -a "p2p timeline" $OUT/${TAG}_bench_n${N}_${name}.err | cut -c1-1500
 }
-run auto_sm "NAWSOD_P2P_PROFILE=1"
-run auto_ce "NAWSOD_P2P_ENGINE=ce NAWSOD_P2P_PROFILE=1"
-run fused_scatter "NAWSOD_P2P_FUSED_SCATTER=1 NAWSOD_P2P_PROFILE=1"
-run sharded "NAWSOD_X=0" --dp-sync sharded
-run allreduce "NAWSOD_X=0" --dp-sync allreduce
+for v in "$@"; do
+  case $v in
+    pull_sm)   run pull_sm "NAWSOD_P2P_RS=pull NAWSOD_P2P_ENGINE=sm NAWSOD_P2P_PROFILE=1" ;;
+    pull_sm32) run pull_sm32 "NAWSOD_P2P_RS=pull NAWSOD_P2P_ENGINE=sm NAWSOD_TUNING=p2p_ctas=32 NAWSOD_P2P_PROFILE=1" ;;
+    pull_tma)  run pull_tma "NAWSOD_P2P_RS=pull NAWSOD_P2P_ENGINE=tma NAWSOD_P2P_PROFILE=1" ;;
+    pull_ce)   run pull_ce "NAWSOD_P2P_RS=pull NAWSOD_P2P_ENGINE=ce NAWSOD_P2P_PROFILE=1" ;;
+    push_sm)   run push_sm "NAWSOD_P2P_RS=push NAWSOD_P2P_ENGINE=sm NAWSOD_P2P_PROFILE=1" ;;
+    push_ce)   run push_ce "NAWSOD_P2P_RS=push NAWSOD_P2P_ENGINE=ce NAWSOD_P2P_PROFILE=1" ;;
+    sharded)   run sharded "NAWSOD_X=0" --dp-sync sharded ;;
+    allreduce) run allreduce "NAWSOD_X=0" --dp-sync allreduce ;;
+  esac
+done
 el "done"
