@@ -690,6 +690,129 @@ def gpu_arm(args):
     return 0
 
 
+# ------------------------------------------------------------------------------------------------
+# BASELINE configs 3 and 5 (one GPU; `--config 3` / `--config 5`): not the driver's headline line, but the same harness,
+# one JSON line each, so that the numbers are reproducible from a tracked command (profiles/ keeps the outputs)
+# ------------------------------------------------------------------------------------------------
+def _event_ms(fn, iters, warmup=3):
+    import torch
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    return float(np.median(ts)), float(np.min(ts))
+
+
+def _mixed_rois(r, img_h, img_w, seed):
+    """Config 3's RoI mixture: MCG-like boxes from 16 px to the full image (window areas 1 ... ~10^4 cells)."""
+    rng = np.random.default_rng(seed)
+    x1 = np.floor(rng.random(r) * (img_w - 17))
+    y1 = np.floor(rng.random(r) * (img_h - 17))
+    side = np.exp(rng.uniform(np.log(16.0), np.log(float(max(img_h, img_w))), r))       # log-uniform sizes
+    ar = np.exp(rng.uniform(np.log(0.5), np.log(2.0), r))
+    bw, bh = np.floor(side * np.sqrt(ar)), np.floor(side / np.sqrt(ar))
+    return np.stack([np.zeros(r), x1, y1, np.minimum(x1 + bw, img_w - 1), np.minimum(y1 + bh, img_h - 1)], axis=1).astype(np.float32)
+
+
+def gpu_config3(args):
+    """flickr_coco shape (configs/flickr_coco/na_wsddn_V-16-C5_1x.yaml): 80 classes, 4000 proposals per image, one image per
+    step (the reference's 1 image / GPU), conv5 maps of the multi-scale training (short side 480 ... 1200, max side 2000)
+    at 1/16 and, for the largest, at 1/8 (WSL.DILATION 2), RoI sizes from 16 px to the full image; NA two-stack head,
+    bf16, fwd + bwd + SGD, resident inputs."""
+    import torch
+    from nafwebsod_b200 import _lib
+    from nafwebsod_b200.heads import WeblyHeadModel
+    from nafwebsod_b200.dp import DataParallelHead
+    _lib.load()
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    peaks = _peaks()
+    ncls, R = 81, 4000
+    model = WeblyHeadModel(ncls, C5, 7, 4096, noise=True, dtype=torch.bfloat16, device=dev)
+    g = torch.Generator(device=dev).manual_seed(2)
+    model.flat_param[:model.n_weights].normal_(0.0, 0.01, generator=g)
+    model.sync_shadow()
+    model.UpdateWorkspaceLr(1e-3)
+    dp = DataParallelHead(model, fc6_panels=args.fc6_panels)
+    cases = []
+    for (h, w, stride, what) in ((30, 40, 16, "short side 480"), (43, 57, 16, "short side 688"), (54, 72, 16, "short side 864"),
+                                 (75, 125, 16, "short side 1200, max side 2000"), (150, 250, 8, "short side 1200, max side 2000 at 1/8 (WSL.DILATION 2)")):
+        X = torch.from_numpy(synth_conv5(1, C5, h, w, seed=h)).to(dev)
+        rois = torch.from_numpy(_mixed_rois(R, h * stride, w * stride, seed=w)).to(dev)
+        obn = (torch.rand(R, device=dev) + 1)
+        L = torch.zeros(1, ncls - 1, device=dev); L[0, 17] = 1
+        model.spatial_scale = 1.0 / stride
+        model.FeedBlobs(X, rois, obn, L, x_layout="NCHW")
+        model.profile = {}
+        med, best = _event_ms(lambda: dp.step(), args.steps, warmup=args.warmup)
+        dp.flush(); torch.cuda.synchronize()
+        prof, model.profile = model.profile, None
+        mean = lambda k: float(np.mean([a.elapsed_time(b) for a, b in prof.get(k, [])])) if prof.get(k) else None
+        pool_bytes = R * (C5 * 49 * 2 + 20) + C5 * h * w * 2
+        t_pool = mean("roi_pool_f")
+        cases.append({"map": "%dx%d @1/%d" % (h, w, stride), "what": what, "ms_per_step": med, "rois_per_s": R / (med * 1e-3),
+                      "step_tensor_frac": _flops_per_roi(True, C=ncls - 1) * R / (med * 1e-3) / 1e12 / peaks["tf_sustained"],
+                      "roi_pool_f": {"ms": t_pool, "gbs": pool_bytes / (t_pool * 1e-3) / 1e9 if t_pool else None,
+                                     "frac_hbm": pool_bytes / (t_pool * 1e-3) / 1e9 / peaks["hbm"] if t_pool else None},
+                      "mil_head_ms": mean("mil_head"), "fc6_fwd_ms": mean("fc6_fwd")})
+    worst = min(c["rois_per_s"] for c in cases)
+    _emit({"metric": METRIC, "value": worst, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": max(c["ms_per_step"] for c in cases), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "bf16", "data": "synthetic",
+           "config": {"workload": "BASELINE config 3 (flickr_coco shape): 1 image x 4000 RoIs per step, 80 classes, NA two-stack head fwd+bwd+SGD, "
+                                  "conv5 maps of the multi-scale schedule, RoIs 16 px ... full image; `value` = the slowest map",
+                      "l2": "working set per step >> 126 MB L2"},
+           "cases": cases})
+    return 0
+
+
+def gpu_config5(args):
+    """Test-time-augmented inference (core/test_wsl.py:181-281): forward only, 5 scales x {orig, hflip} = 10 passes per
+    image through test_time.im_detect_bbox_aug (projection, dedup, head forward, inverse scatter, averaging on the GPU),
+    then threshold + NMS + limit; proposal-count sweep 500 ... 8000 (+ the shipped TEST.PROPOSAL_LIMIT 9999), bf16."""
+    import torch
+    from nafwebsod_b200 import _lib, ops, test_time
+    from nafwebsod_b200.heads import WeblyHeadModel
+    _lib.load()
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    m = WeblyHeadModel(NUM_CLASSES, C5, 7, 4096, dtype=torch.bfloat16, train=False, device=dev)
+    g = torch.Generator(device=dev).manual_seed(2)
+    m.flat_param[:m.n_weights].normal_(0.0, 0.01, generator=g)
+    m.sync_shadow()
+    img_h, img_w = 375, 500                                   # a VOC-sized image
+    scales = [688, 480, 576, 864, 1200]                       # TEST.SCALE, then TEST.BBOX_AUG.SCALES
+    maps = {}
+    for sc_px in scales:
+        sc = sc_px / float(min(img_h, img_w))
+        h, w = int(np.ceil(img_h * sc / 16)), int(np.ceil(img_w * sc / 16))
+        maps[sc_px] = (torch.from_numpy(synth_conv5(1, C5, h, w, seed=sc_px)).to(dev).permute(0, 2, 3, 1).contiguous().to(torch.bfloat16), sc)
+    order = [(688, True)] + [(sc_px, f) for sc_px in scales[1:] for f in (False, True)] + [(688, False)]
+    passes = [(maps[sc_px][0], maps[sc_px][1], img_w if f else None) for sc_px, f in order]
+    cases = []
+    for R in (500, 1000, 2000, 4000, 8000, 9999):
+        boxes = torch.from_numpy(synth_rois(R, img_h, img_w, 0, seed=R)[:, 1:].copy()).to(dev)
+        obn = torch.rand(R, device=dev)
+        med, _ = _event_ms(lambda: test_time.im_detect_bbox_aug(m, passes, boxes, obn, sync=False), max(5, args.steps // 2))
+        scores = test_time.im_detect_bbox_aug(m, passes, boxes, obn, sync=False)
+        nms_ms, _ = _event_ms(lambda: ops.nms_and_limit(scores, boxes, score_thresh=1e-9, nms_thresh=0.5, detections_per_im=100), 10)
+        cases.append({"rois": R, "passes": len(passes), "ms_per_image": med, "roi_passes_per_s": R * len(passes) / (med * 1e-3),
+                      "images_per_s": 1e3 / (med + nms_ms), "nms_and_limit_ms": nms_ms})
+    ref = [c for c in cases if c["rois"] == 2000][0]
+    _emit({"metric": "RoI-passes/sec (forward only, 10-pass test-time augmentation)", "value": ref["roi_passes_per_s"], "unit": "RoI-passes/s",
+           "n_gpus": 1, "steps": args.steps, "warmup": 3, "ms_per_step": ref["ms_per_image"], "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+           "config": {"workload": "BASELINE config 5: test-time-augmented inference, 5 scales x {orig, hflip} on a 375x500 image, 20 classes, "
+                                  "DEDUP_BOXES 1/16, no host round trip per pass; `value` at 2000 RoIs per image; sweep in `cases`"},
+           "cases": cases})
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -702,6 +825,8 @@ def main():
     ap.add_argument("--comm-sms", type=int, default=0, help="N>1: SMs the GEMMs leave to NCCL during the exchange (0 = no reservation)")
     ap.add_argument("--dp-sync", default="auto", choices=["auto", "sharded", "p2p", "allreduce"],
                     help="N>1 gradient exchange: auto = p2p when the ranks can map each other's memory, else NCCL sharded; allreduce = the reference's schedule")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 5],
+                    help="BASELINE.json configuration: 2 = the headline (default; 4 = the same under --gpus N), 3 = flickr_coco shape, 5 = TTA inference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-isolated", action="store_true", help="skip the isolated RoIPoolF timing after the timed regions")
     ap.add_argument("--ref-rois-per-image", type=int, default=ROIS_PER_IMAGE, help=argparse.SUPPRESS)   # tests shrink the CPU arm
@@ -714,6 +839,10 @@ def main():
         _protect_stdout()
     if args.impl == "reference":
         return reference_arm(args)
+    if args.config == 3:
+        return gpu_config3(args)
+    if args.config == 5:
+        return gpu_config5(args)
     if args.gpus != world:
         if world == 1 and args.gpus > 1:
             # convenience: re-launch under torchrun on one node

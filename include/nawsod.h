@@ -115,6 +115,19 @@ int nawsod_fc_fwd(const void* A, int64_t lda, const void* W, int64_t ldw, const 
                   const uint8_t* mask, int64_t ldmask, uint64_t dropout_seed, int M, int N, int K,
                   int ab_dtype, void* Y, int64_t ldy, int y_dtype, int flags, void* stream);
 
+/* nawsod_fc_fwd whose weight reads are GATED on the data-parallel peer exchange (a11): rows
+ *   [g * gate_rows, (g + 1) * gate_rows) of W are read only once the gate_nflags device words
+ *   gate_flags[g * gate_nflags ...] have reached gate_seq (the "operands of exchange bucket g have
+ *   landed" flags of nawsod_p2p_scatter / nawsod_p2p_signal), g < gate_groups; gate_rows a multiple of
+ *   256.  The kernel starts on the row groups that are there and meets the others as they arrive, so
+ *   the tail of one step's exchange hides behind the next step's fc6.  A flag that does not arrive
+ *   within gate_timeout_ms sets *gate_status (device uint32, may be NULL) and the kernel proceeds. */
+int nawsod_fc_fwd_gated(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
+                        const uint8_t* mask, int64_t ldmask, uint64_t dropout_seed, int M, int N,
+                        int K, int ab_dtype, void* Y, int64_t ldy, int y_dtype, int flags,
+                        const void* gate_flags, int gate_groups, int gate_nflags, int gate_rows,
+                        uint32_t gate_seq, int64_t gate_timeout_ms, void* gate_status, void* stream);
+
 int nawsod_fc_bwd_x(const void* dY, int64_t lddy, const void* W, int64_t ldw,
                     const void* act_below, int64_t ldact, int act_dtype,
                     const uint8_t* mask_below, int64_t ldmask, int M, int N, int K,
@@ -253,11 +266,6 @@ int nawsod_p2p_signal(void* const* flag_ptrs, int n, uint32_t value, void* strea
  * for launches that may overlap in time). */
 int nawsod_p2p_scatter(const void* const* srcs, void* const* dsts, int npeers, int64_t bytes,
                        void* const* flag_ptrs, int nflags, uint32_t value, int slot, void* stream);
-/* The same contract, moved by the TMA unit: bulk asynchronous copies global -> shared -> (peer) global issued by one
- * thread per CTA (one warp, ~25 KB of shared memory: it fits beside a persistent GEMM CTA and takes no issue slots or
- * LSU bandwidth from it). */
-int nawsod_p2p_scatter_tma(const void* const* srcs, void* const* dsts, int npeers, int64_t bytes,
-                           void* const* flag_ptrs, int nflags, uint32_t value, int slot, void* stream);
 int nawsod_p2p_wait(const void* flags, int n, uint32_t value, int64_t timeout_ms, void* status,
                     void* stream);
 

@@ -28,6 +28,8 @@ PROTOTYPES = {
     "nawsod_roi_pool_f_bwd": (_i, [_vp, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp]),
     "nawsod_roi_feature_boost": (_i, [_vp, _vp, _i, _i64, _vp, _vp]),
     "nawsod_fc_fwd": (_i, [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _c.c_uint64, _i, _i, _i, _i, _vp, _i64, _i, _i, _vp]),
+    "nawsod_fc_fwd_gated": (_i, [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _c.c_uint64, _i, _i, _i, _i, _vp, _i64, _i, _i,
+                                 _vp, _i, _i, _i, _c.c_uint32, _i64, _vp, _vp]),
     "nawsod_fc_bwd_x": (_i, [_vp, _i64, _vp, _i64, _vp, _i64, _i, _vp, _i64, _i, _i, _i, _i, _vp, _i64, _i, _i, _vp]),
     "nawsod_fc_bwd_w": (_i, [_vp, _i64, _vp, _i64, _i, _i, _i, _i, _vp, _i64, _vp, _i, _vp]),
     "nawsod_fc_fwd_stacks": (_i, [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _vp, _i64, _i64, _c.c_uint64, _i, _i, _i, _i, _i,
@@ -52,7 +54,6 @@ PROTOTYPES = {
     "nawsod_p2p_copy": (_i, [_vp, _vp, _i64, _vp]),
     "nawsod_p2p_signal": (_i, [_vp, _i, _c.c_uint32, _vp]),
     "nawsod_p2p_scatter": (_i, [_vp, _vp, _i, _i64, _vp, _i, _c.c_uint32, _i, _vp]),
-    "nawsod_p2p_scatter_tma": (_i, [_vp, _vp, _i, _i64, _vp, _i, _c.c_uint32, _i, _vp]),
     "nawsod_p2p_wait": (_i, [_vp, _i, _c.c_uint32, _i64, _vp, _vp]),
     "nawsod_project_rois": (_i, [_vp, _i, _c.c_double, _c.c_double, _i, _vp, _vp, _vp, _vp]),
     "nawsod_dedup_rois": (_i, [_vp, _i, _f, _vp, _vp, _vp, _vp, _vp]),
@@ -74,10 +75,10 @@ PROTOTYPES = {
 # kernels launched per C-ABI call (bench.py reports the count of OUR kernels in the timed region)
 KERNELS_PER_CALL = {
     "nawsod_transpose_batched": 1, "nawsod_roi_pool_f_fwd": 1, "nawsod_roi_pool_f_bwd": 1, "nawsod_roi_feature_boost": 1,
-    "nawsod_fc_fwd": 1, "nawsod_fc_bwd_x": 1, "nawsod_fc_bwd_w": 1, "nawsod_fc_fwd_stacks": 1, "nawsod_fc_bwd_x_stacks": 1,
+    "nawsod_fc_fwd": 1, "nawsod_fc_fwd_gated": 1, "nawsod_fc_bwd_x": 1, "nawsod_fc_bwd_w": 1, "nawsod_fc_fwd_stacks": 1, "nawsod_fc_bwd_x_stacks": 1,
     "nawsod_fc_bwd_w_stacks": 1, "nawsod_convert_f32_to_bf16": 1,
     "nawsod_round_to_tf32": 1, "nawsod_mil_head_fwd_bwd": 1, "nawsod_roi_iou": 1, "nawsod_cross_entropy_fwd": 1,
-    "nawsod_cross_entropy_bwd": 1, "nawsod_sgd_update": 1, "nawsod_sgd_update_reduce": 1, "nawsod_p2p_signal": 1, "nawsod_p2p_scatter": 1, "nawsod_p2p_scatter_tma": 1,
+    "nawsod_cross_entropy_bwd": 1, "nawsod_sgd_update": 1, "nawsod_sgd_update_reduce": 1, "nawsod_p2p_signal": 1, "nawsod_p2p_scatter": 1,
     "nawsod_p2p_wait": 1,
     "nawsod_project_rois": 1, "nawsod_dedup_rois": 1, "nawsod_gather_rows": 1, "nawsod_scatter_scores": 1,
     "nawsod_scores_finalize": 1, "nawsod_nms_and_limit": 2, "nawsod_min_entropy_loss_fwd": 1, "nawsod_min_entropy_loss_bwd": 2,

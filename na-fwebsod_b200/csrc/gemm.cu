@@ -36,7 +36,34 @@ struct EpiParams {
   // live in the 3-D tensor maps
   int nbatch;
   long long so, sbias, smask, sact;
+  // Optional weight gate (data-parallel peer exchange): rows [g * gate_rows, (g + 1) * gate_rows) of the B operand (W) may only
+  // be read once the gate_nflags words gate_flags[g * gate_nflags ...] have reached gate_seq -- the "operands of exchange
+  // bucket g have landed" flags the owner ranks publish (p2p.cu).  The TMA producer checks them when its tiles enter a new
+  // row group, so the GEMM starts on the weights that are there and meets the rest as they arrive.
+  const uint32_t* gate_flags; int gate_nflags, gate_rows; uint32_t gate_seq;
+  unsigned long long gate_timeout_ns; uint32_t* gate_status;
 };
+
+// spin (one thread) until all n flags have reached `value` (sequence numbers wrap); a watchdog turns a lost peer into a status
+// word instead of a hung GPU
+__device__ __forceinline__ void gate_wait(const uint32_t* flags, int n, uint32_t value, unsigned long long timeout_ns, uint32_t* status) {
+  unsigned long long t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (int i = 0; i < n; ++i) {
+    unsigned ns = 32;
+    while (true) {
+      uint32_t v;
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + i) : "memory");
+      if (static_cast<int32_t>(v - value) >= 0) break;
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      if (t - t0 > timeout_ns) { if (status) atomicMax(status, 1u); break; }
+      __nanosleep(ns);
+      if (ns < 512) ns <<= 1;
+    }
+  }
+  asm volatile("fence.proxy.async;" ::: "memory");     // the TMA loads that follow read what the flags guard
+}
 
 template <int BN, bool A_MN, bool B_MN, int ES>
 __global__ void __launch_bounds__(kNumThreads, 1)
@@ -84,9 +111,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // ================= TMA producer =================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
+      int gate_open = -1;                        // row groups [0, gate_open] of W have been waited for
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int bi = tile / tiles_pb, tb = tile - bi * tiles_pb;
         const int m0 = (tb % num_m) * BLOCK_M, n0 = (tb / num_m) * BN;
+        if (ep.gate_flags) {                     // tiles arrive in ascending n0: groups open in order
+          const int need = (min(n0 + BN, ep.N) - 1) / ep.gate_rows;
+          for (; gate_open < need; ++gate_open)
+            gate_wait(ep.gate_flags + (size_t)(gate_open + 1) * ep.gate_nflags, ep.gate_nflags, ep.gate_seq, ep.gate_timeout_ns, ep.gate_status);
+        }
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t sa = smem_base + stage * C::STAGE_BYTES, sb = sa + C::A_BYTES;
@@ -446,6 +479,32 @@ extern "C" int nawsod_fc_fwd_stacks(const void* A, int64_t lda, int64_t sA, cons
   ep.ldmask = ldmask; ep.act = nullptr; ep.flags = flags; ep.seed = dropout_seed; ep.M = M; ep.N = N; ep.K = K;
   ep.nbatch = S; ep.so = sY; ep.sbias = sbias; ep.smask = smask; ep.sact = 0;
   const Operands o{A, lda, sA, W, ldw, sW};
+  return dispatch_gemm<false, false>(o, ep, ab_dtype, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int nawsod_fc_fwd_gated(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, const uint8_t* mask,
+                                   int64_t ldmask, uint64_t dropout_seed, int M, int N, int K, int ab_dtype, void* Y, int64_t ldy,
+                                   int y_dtype, int flags, const void* gate_flags, int gate_groups, int gate_nflags, int gate_rows,
+                                   uint32_t gate_seq, int64_t gate_timeout_ms, void* gate_status, void* stream) {
+  if (int rc = check_common("fc_fwd_gated", M, N, K, ab_dtype)) return rc;
+  NAWSOD_REQUIRE(A && W && Y, NAWSOD_ERR_ARG, "fc_fwd_gated: null pointer");
+  NAWSOD_REQUIRE(y_dtype == NAWSOD_F32 || y_dtype == NAWSOD_BF16, NAWSOD_ERR_ARG, "fc_fwd_gated: bad y_dtype");
+  NAWSOD_REQUIRE(!(flags & NAWSOD_FC_ACCUMULATE), NAWSOD_ERR_ARG, "fc_fwd_gated: ACCUMULATE is a bwd_w flag");
+  NAWSOD_REQUIRE(!(flags & NAWSOD_FC_ROUND_TF32) || y_dtype == NAWSOD_F32, NAWSOD_ERR_ARG, "fc_fwd_gated: ROUND_TF32 needs a float output");
+  NAWSOD_REQUIRE(ldy >= N && (!mask || ldmask >= N), NAWSOD_ERR_SHAPE, "fc_fwd_gated: ldy / ldmask smaller than N");
+  NAWSOD_REQUIRE(!(flags & NAWSOD_FC_DROPOUT) || mask || dropout_seed != 0, NAWSOD_ERR_ARG,
+                 "fc_fwd_gated: DROPOUT needs a mask or a non-zero dropout_seed");
+  NAWSOD_REQUIRE(gate_flags && gate_groups >= 1 && gate_nflags >= 1 && gate_rows > 0 && gate_rows % 256 == 0 &&
+                     (int64_t)gate_groups * gate_rows >= N && gate_timeout_ms > 0,
+                 NAWSOD_ERR_ARG, "fc_fwd_gated: need gate flags, groups * rows covering N = %d, rows a multiple of 256, a time-out", N);
+  EpiParams ep{};
+  ep.out = Y; ep.ldo = ldy; ep.out_dtype = y_dtype; ep.bias = bias; ep.mask = (flags & NAWSOD_FC_DROPOUT) ? mask : nullptr;
+  ep.ldmask = ldmask; ep.act = nullptr; ep.flags = flags; ep.seed = dropout_seed; ep.M = M; ep.N = N; ep.K = K;
+  ep.nbatch = 1;
+  ep.gate_flags = static_cast<const uint32_t*>(gate_flags); ep.gate_nflags = gate_nflags; ep.gate_rows = gate_rows;
+  ep.gate_seq = gate_seq; ep.gate_timeout_ns = (unsigned long long)gate_timeout_ms * 1000000ull;
+  ep.gate_status = static_cast<uint32_t*>(gate_status);
+  const Operands o{A, lda, 0, W, ldw, 0};
   return dispatch_gemm<false, false>(o, ep, ab_dtype, static_cast<cudaStream_t>(stream));
 }
 

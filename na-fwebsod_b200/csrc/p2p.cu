@@ -102,85 +102,19 @@ __global__ void __launch_bounds__(kScatterThreads) p2p_scatter_kernel(const Scat
 }
 
 
-// TMA-driven scatter: the same contract as p2p_scatter_kernel (copy `bytes` from src[i] to dst[i] for every peer, then publish
-// the sequence number), but the bytes are moved by the SM's TMA unit with bulk asynchronous copies -- global -> shared ->
-// peer global -- issued by ONE thread per CTA.  It exists because the SM-driven kernel, co-resident with the persistent
-// tcgen05 GEMMs, costs them issue slots and LSU bandwidth (8 GPUs: fc6 weight-gradient GEMMs 1.32 -> 2.0-2.3 ms per step with
-// the SM scatter running beside them, profiles/r2c_bench_n8_*.json), while the copy engines leave the GEMMs alone but sustain
-// only ~360 GB/s of egress when eight ranks scatter at once.  A CTA is one warp, ~25 KB of shared memory (it fits beside a
-// GEMM CTA's 193 KB) and a handful of instructions per 8 KB moved.
-constexpr int kTmaChunk = 8192;
-constexpr int kTmaStages = 3;
-
-__device__ __forceinline__ uint32_t smem_addr(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-
-__global__ void __launch_bounds__(32) p2p_scatter_tma_kernel(const ScatterArgs a) {
-  __shared__ __align__(128) unsigned char buf[kTmaStages][kTmaChunk];
-  __shared__ __align__(8) unsigned long long bar[kTmaStages];
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < kTmaStages; ++s)
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&bar[s])));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    const long long per_peer = (a.bytes + kTmaChunk - 1) / kTmaChunk;
-    const long long total = per_peer * a.npeers;
-    const long long n = total > blockIdx.x ? (total - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;   // chunks of this CTA
-    // chunk j of this CTA = global chunk c = blockIdx.x + j * gridDim.x: peer c % npeers, piece c / npeers (all links busy)
-    auto src_of = [&](long long j, const char*& sp, char*& dp, uint32_t& sz) {
-      const long long c = blockIdx.x + j * gridDim.x;
-      const int peer = static_cast<int>(c % a.npeers);
-      const long long off = (c / a.npeers) * kTmaChunk;
-      sp = a.src[peer] + off; dp = a.dst[peer] + off;
-      sz = static_cast<uint32_t>(min((long long)kTmaChunk, a.bytes - off));
-    };
-    auto load = [&](long long j) {
-      const char* sp; char* dp; uint32_t sz;
-      src_of(j, sp, dp, sz);
-      const int s = static_cast<int>(j % kTmaStages);
-      const uint32_t b = smem_addr(&bar[s]);
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(sz) : "memory");
-      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                   ::"r"(smem_addr(buf[s])), "l"(sp), "r"(sz), "r"(b) : "memory");
-    };
-    for (long long j = 0; j < n && j < kTmaStages - 1; ++j) load(j);
-    for (long long i = 0; i < n; ++i) {
-      const int s = static_cast<int>(i % kTmaStages);
-      // the stage chunk i + S - 1 will land in was last read by the store of chunk i - 1: wait until that read is done
-      if (i + kTmaStages - 1 < n) {
-        if (i > 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        load(i + kTmaStages - 1);
-      }
-      const uint32_t parity = static_cast<uint32_t>((i / kTmaStages) & 1);
-      uint32_t done;
-      do {
-        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
-                     : "=r"(done) : "r"(smem_addr(&bar[s])), "r"(parity) : "memory");
-      } while (!done);
-      const char* sp; char* dp; uint32_t sz;
-      src_of(i, sp, dp, sz);
-      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dp), "r"(smem_addr(buf[s])), "r"(sz) : "memory");
-      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    }
-    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");       // every store of this CTA has been performed
-    asm volatile("fence.proxy.async;" ::: "memory");
-    __threadfence_system();
-    const unsigned prev = atomicAdd(&g_scatter_done[a.slot], 1u);
-    if (prev == gridDim.x - 1) {                 // last CTA: every piece of every CTA is out -> publish
-      g_scatter_done[a.slot] = 0;
-      __threadfence_system();
-      for (int i = 0; i < a.nflags; ++i)
-        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.flag[i]), "r"(a.value) : "memory");
-    }
-  }
-}
-
+// Measured in round 2 and removed: a TMA-driven variant of this kernel (one warp per CTA issuing cp.async.bulk global -> shared ->
+// peer global through a 3 x 8 KB ring).  It moves the bytes without SM loads / stores, but it needs ~25 KB of shared memory per
+// CTA, and an SM whose shared-memory carve-out was sized for a persistent tcgen05 GEMM CTA (193 KB -> the 196 KB configuration)
+// has 2 KB left: the scatter CTAs could only start in the gaps between GEMM launches (8 GPUs: a 180 MB panel took 0.56 ms
+// instead of 0.3 ms, profiles/r2h_bench_n8_tma.json) and, with the next step's fc6 waiting inside the kernel for the operands
+// they carry, not at all.  This kernel needs no shared memory and co-resides.
 }  // namespace
 }  // namespace nawsod
 
 using namespace nawsod;
 
-static int scatter_launch(bool tma, const void* const* srcs, void* const* dsts, int npeers, int64_t bytes, void* const* flag_ptrs,
-                          int nflags, uint32_t value, int slot, void* stream) {
+extern "C" int nawsod_p2p_scatter(const void* const* srcs, void* const* dsts, int npeers, int64_t bytes,
+                                  void* const* flag_ptrs, int nflags, uint32_t value, int slot, void* stream) {
   NAWSOD_REQUIRE(npeers >= 0 && npeers <= kMaxPeers && nflags >= 0 && nflags <= kMaxPeers + 1 && slot >= 0 && slot < 128,
                  NAWSOD_ERR_ARG, "p2p_scatter: at most %d peers, %d flags, slot in [0, 128)", kMaxPeers, kMaxPeers + 1);
   NAWSOD_REQUIRE(bytes >= 0 && bytes % 16 == 0, NAWSOD_ERR_ALIGN, "p2p_scatter: byte count must be a multiple of 16");
@@ -196,24 +130,15 @@ static int scatter_launch(bool tma, const void* const* srcs, void* const* dsts, 
     a.flag[i] = static_cast<uint32_t*>(flag_ptrs[i]);
   }
   if (a.npeers == 0 && nflags == 0) return NAWSOD_OK;
-  const long long piece = tma ? (long long)kTmaChunk : (long long)kScatterThreads * 16 * kScatterUnroll;
+  const long long piece = (long long)kScatterThreads * 16 * kScatterUnroll;
   const long long total = std::max<long long>(1, ((bytes + piece - 1) / piece) * std::max(a.npeers, 0));
-  const long long want = get_tuning("p2p_ctas", 0) > 0 ? get_tuning("p2p_ctas", 0) : (tma ? 1LL : 2LL) * sm_count();
+  // 32 CTAs keep the links busy and leave the co-resident GEMMs most of their issue slots (8 GPUs: 5.07 ms per step against
+  // 5.15 ms with two CTAs per SM, profiles/r2c_bench_n8_sm32.json / _sm.json)
+  const long long want = get_tuning("p2p_ctas", 0) > 0 ? get_tuning("p2p_ctas", 0) : 32;
   const int grid = (int)std::max<long long>(1, std::min<long long>(total, want));
-  if (tma) p2p_scatter_tma_kernel<<<grid, 32, 0, static_cast<cudaStream_t>(stream)>>>(a);
-  else p2p_scatter_kernel<<<grid, kScatterThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  p2p_scatter_kernel<<<grid, kScatterThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
   NAWSOD_LAUNCH_OK();
   return NAWSOD_OK;
-}
-
-extern "C" int nawsod_p2p_scatter(const void* const* srcs, void* const* dsts, int npeers, int64_t bytes,
-                                  void* const* flag_ptrs, int nflags, uint32_t value, int slot, void* stream) {
-  return scatter_launch(false, srcs, dsts, npeers, bytes, flag_ptrs, nflags, value, slot, stream);
-}
-
-extern "C" int nawsod_p2p_scatter_tma(const void* const* srcs, void* const* dsts, int npeers, int64_t bytes,
-                                      void* const* flag_ptrs, int nflags, uint32_t value, int slot, void* stream) {
-  return scatter_launch(true, srcs, dsts, npeers, bytes, flag_ptrs, nflags, value, slot, stream);
 }
 
 extern "C" int nawsod_p2p_enable_peer_access(int peer_device) {

@@ -276,11 +276,13 @@ class P2PExchange:
             raise RuntimeError("peer mapping failed on at least one rank: %s" % (e1 or e2 or e3 or "on a peer"))
         self.stream = torch.cuda.Stream(device=dev, priority=-1)
         self.send_stream = torch.cuda.Stream(device=dev, priority=-1)
-        # "tma": one co-resident scatter kernel per bucket and leg whose bytes the TMA unit moves (bulk copies through shared
-        # memory, one thread per CTA); "sm": the same with SM loads / stores; "ce": copy-engine transfers
+        # b6's (tiny, replicated) update runs on a stream of its own: behind the last fc6 panel's update it would hold up
+        # the next step's fc6, which reads b6 but meets the W6 panels through its in-kernel gate
+        self.bias6_stream = torch.cuda.Stream(device=dev, priority=-1)
+        # "sm": one co-resident scatter kernel per bucket and leg (default); "ce": copy-engine transfers
         self.engine = os.environ.get("NAWSOD_P2P_ENGINE", "sm")
-        if self.engine not in ("tma", "sm", "ce"):
-            raise RuntimeError("NAWSOD_P2P_ENGINE must be 'tma', 'sm' or 'ce'")
+        if self.engine not in ("sm", "ce"):
+            raise RuntimeError("NAWSOD_P2P_ENGINE must be 'sm' or 'ce'")
         if len(self.plan) > 64:
             raise RuntimeError("at most 64 exchange buckets")
         nfan = int(os.environ.get("NAWSOD_P2P_COPY_STREAMS", "3"))
@@ -328,7 +330,7 @@ class P2PExchange:
         else:
             rs_copies = [(self.peer_stage[k] + 4 * (offset + rank * n), self.flat.data_ptr() + 4 * (offset + k * n), 4 * n) for k in peers]
         self.bytes_out += 4 * n * (W - 1)          # bytes of this rank's gradient that cross NVLink (pushed, or read by the owners)
-        kernel_engine = self.engine in ("sm", "tma")
+        kernel_engine = self.engine == "sm"
         pull = self.rs_mode == "pull"
         if pull:
             # nothing to copy: tell every rank that this bucket of my gradient buffer is complete (it stays untouched until
@@ -341,8 +343,7 @@ class P2PExchange:
         elif kernel_engine:
             self.send_stream.wait_event(ev)
             with torch.cuda.stream(self.send_stream):
-                ops.p2p_scatter([c[1] for c in rs_copies], [c[0] for c in rs_copies], 4 * n, self._flag_ptrs(self.RS, b), self.seq, b,
-                                tma=self.engine == "tma")
+                ops.p2p_scatter([c[1] for c in rs_copies], [c[0] for c in rs_copies], 4 * n, self._flag_ptrs(self.RS, b), self.seq, b)
                 if prof is not None:
                     prof.append(("sent", b, self._mark()))
         else:
@@ -352,9 +353,10 @@ class P2PExchange:
                 if prof is not None:
                     prof.append(("sent", b, self._mark()))
         # update side: wait for the W contributions, reduce + SGD on the owned slice, publish the operands
-        self.stream.wait_event(ev)
+        ustream = self.bias6_stream if tag == "biases_fc6" else self.stream
+        ustream.wait_event(ev)
         so = offset if replicated else offset + rank * n
-        with torch.cuda.stream(self.stream):
+        with torch.cuda.stream(ustream):
             fb = (self.RS * len(self.plan) + b) * W
             ops.p2p_wait(self.flags[fb: fb + W], self.seq, self.timeout_ms, self.status)
             if prof is not None:
@@ -371,15 +373,14 @@ class P2PExchange:
             # operand leg; a replicated bucket has nothing to send back, its AG flag only says "staging consumed"
             ag_copies = [] if replicated else [(self.peer_out[k] + es_out * so, self.out.data_ptr() + es_out * so, es_out * n) for k in peers]
             if kernel_engine:
-                ops.p2p_scatter([c[1] for c in ag_copies], [c[0] for c in ag_copies], es_out * n, self._flag_ptrs(self.AG, b), self.seq, 64 + b,
-                                tma=self.engine == "tma")
+                ops.p2p_scatter([c[1] for c in ag_copies], [c[0] for c in ag_copies], es_out * n, self._flag_ptrs(self.AG, b), self.seq, 64 + b)
             upd = torch.cuda.Event()
             upd.record()
         if not kernel_engine:
-            self._fan_out(self.ag_streams, upd, self.stream, ag_copies)
-            with torch.cuda.stream(self.stream):
+            self._fan_out(self.ag_streams, upd, ustream, ag_copies)
+            with torch.cuda.stream(ustream):
                 ops.p2p_signal(self._flag_ptrs(self.AG, b), self.seq)
-        with torch.cuda.stream(self.stream):
+        with torch.cuda.stream(ustream):
             if prof is not None:
                 prof.append(("published", b, self._mark()))
             self._done[b] = torch.cuda.Event()
@@ -426,8 +427,9 @@ class P2PExchange:
             else:
                 runs.append([i, i + 1])
         for lo, hi in runs:
-            if self._done[hi - 1] is not None:
-                cur.wait_event(self._done[hi - 1])          # the update stream runs the buckets in launch order
+            for i in range(lo, hi):
+                if self._done[i] is not None:
+                    cur.wait_event(self._done[i])
             ops.p2p_wait(self.flags[(nb + lo) * W: (nb + hi) * W], self.seq, self.timeout_ms, self.status)
         self._joined.update(want)
         if self.profile is not None and want:
@@ -442,6 +444,19 @@ class P2PExchange:
             self._status_ev.record()
             self._joined = set()
             self.in_flight = False
+
+    def fc6_gate(self):
+        """The ops.FC ``gate`` for the NEXT step's stacked fc6 forward while this step's exchange is still in flight: the
+        fc6 row panels are exchange buckets 0 .. P-1 in plan order, their "operands have landed" (AG) flags are consecutive
+        words, and every panel has the same number of rows -- or None when that does not hold or nothing is in flight."""
+        if not self.in_flight:
+            return None
+        panels = [(o, n) for o, n, t in self.plan if t == "fc6_panel"]
+        P = len(panels)
+        if P == 0 or any(t != "fc6_panel" for _, _, t in self.plan[:P]) or len({n for _, n in panels}) != 1:
+            return None
+        nb, W = len(self.plan), self.world
+        return dict(flags=self.flags[nb * W: (nb + P) * W], nflags=W, seq=self.seq, timeout_ms=self.timeout_ms, status=self.status)
 
     def self_test(self, timeout_ms=3000):
         """One dry run of the whole bucket pipeline on recognisable data, so that a world size this box has not run
@@ -542,6 +557,8 @@ class DataParallelHead:
         self.comm_sms = int(os.environ.get("NAWSOD_COMM_SMS", "0")) if comm_sms is None else comm_sms
         self._hyper = dict(momentum=0.9, weight_decay=5e-4)
         self.p2p_selftest = None                     # outcome of P2PExchange.self_test() when it ran ("ok" or the reason)
+        # p2p: the next step's fc6 forward waits for its weight panels inside the kernel instead of on the stream
+        self.gated_fc6 = os.environ.get("NAWSOD_P2P_GATED_FC6", "1") == "1"
         if self.world > 1 and sync in ("p2p", "auto") and model.flat_grad.is_cuda:
             # "auto": the peer-mapped path when every rank can set it up (one NVLink / NVSwitch box), else NCCL
             requested = sync
@@ -646,10 +663,22 @@ class DataParallelHead:
         small, biases, bias6 = by_tag["small_weights"], by_tag["biases"], by_tag.get("biases_fc6")
 
         p2p = self.sync == "p2p"
+        rows_w6 = m._slices["W6"][2][0]
+        panel_rows = ((rows_w6 + self.fc6_panels - 1) // self.fc6_panels + 255) // 256 * 256
+        cols_rows_ok = rows_w6 % panel_rows == 0 and by_tag.get("biases_fc6") is not None
 
         def before_fc6():                            # RoI pooling needs no parameters: join the previous exchange after it
+            m.fc6_gate = None
             if p2p:
-                ex.finish(tags=("fc6_panel", "biases_fc6"))     # all that fc6 reads; the rest lands while fc6 runs
+                gate = ex.fc6_gate() if self.gated_fc6 else None
+                if gate is not None and cols_rows_ok:
+                    # fc6 meets its weight panels INSIDE the kernel (the TMA producer waits for a panel's flags when its
+                    # tiles get there); the stream only joins b6, whose update runs on a stream of its own
+                    gate["rows"] = panel_rows
+                    m.fc6_gate = gate
+                    ex.finish(tags=("biases_fc6",))
+                else:
+                    ex.finish(tags=("fc6_panel", "biases_fc6"))     # all that fc6 reads; the rest lands while fc6 runs
             else:
                 ex.finish()
             self._limit_gemm_grid(False)

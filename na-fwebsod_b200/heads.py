@@ -80,6 +80,9 @@ class WeblyHeadModel:
         # callables that join work still in flight on side streams (dp.DataParallelHead registers its flush(): the
         # previous step's exchange / SGD pipeline reads `lr` and read-modify-writes the momenta and parameters there)
         self.pre_mutation_hooks = []
+        # set by dp.DataParallelHead for one step at a time: the ops.FC ``gate`` of the stacked fc6 forward (its weight rows
+        # arrive panel by panel from the previous step's exchange), or None
+        self.fc6_gate = None
         self._alloc_params()
 
     # ------------------------------------------------------------------ parameters
@@ -332,7 +335,7 @@ class WeblyHeadModel:
         self._timed("fc6_fwd", lambda: ops.FC(
             feat, self.w["W6"][s0 * H:s1 * H], self.p["b6"][s0 * H:s1 * H], relu=True, dropout=use_drop,
             dropout_mask=m6, dropout_seed=(dropout_seed * 4 + 1) if (use_drop and m6 is None) else 0, out=drop6,
-            round_tf32=self.tf32))
+            round_tf32=self.tf32, gate=self.fc6_gate if nS == self.S else None))
         if on_before_fc7 is not None:
             on_before_fc7()               # first read of the fc7 / fc8 parameters follows
         if nS == self.S:      # all stacks: one launch ([S, R, H] views of the column blocks; nothing is copied)

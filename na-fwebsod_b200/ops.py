@@ -364,15 +364,13 @@ def p2p_signal(flag_ptrs, value: int):
     _lib.call("nawsod_p2p_signal", table, len(flag_ptrs), int(value) & 0xFFFFFFFF, _stream())
 
 
-def p2p_scatter(srcs, dsts, nbytes: int, flag_ptrs, value: int, slot: int, tma: bool = False):
-    """One launch: copy ``nbytes`` from srcs[i] to dsts[i] (raw addresses, local or peer-mapped) for every peer, then
-    publish ``value`` into the flag words.  ``tma=False``: SM-driven 16-byte loads / posted stores; ``tma=True``: bulk
-    asynchronous copies through shared memory issued by one thread per CTA (the TMA unit moves the bytes)."""
+def p2p_scatter(srcs, dsts, nbytes: int, flag_ptrs, value: int, slot: int):
+    """One SM-driven launch: copy ``nbytes`` from srcs[i] to dsts[i] (raw addresses, local or peer-mapped) for every
+    peer, then publish ``value`` into the flag words."""
     ts = (ctypes.c_void_p * max(len(srcs), 1))(*srcs)
     td = (ctypes.c_void_p * max(len(dsts), 1))(*dsts)
     tf = (ctypes.c_void_p * max(len(flag_ptrs), 1))(*flag_ptrs)
-    _lib.call("nawsod_p2p_scatter_tma" if tma else "nawsod_p2p_scatter", ts, td, len(srcs), int(nbytes), tf, len(flag_ptrs),
-              int(value) & 0xFFFFFFFF, int(slot), _stream())
+    _lib.call("nawsod_p2p_scatter", ts, td, len(srcs), int(nbytes), tf, len(flag_ptrs), int(value) & 0xFFFFFFFF, int(slot), _stream())
 
 
 def p2p_wait(flags, value: int, timeout_ms: int = 20000, status=None):
@@ -422,12 +420,17 @@ def _same_stacks(who, *ss):
 
 
 def FC(X, W, b=None, *, relu=False, dropout_mask=None, dropout=False, dropout_seed=0, out=None, out_dtype=None,
-       round_tf32=False):
+       round_tf32=False, gate=None):
     """``FC([X, W, b] -> Y)`` with W [out, in] (Caffe2 layout), optionally fused with the
     ``Relu`` and ``Dropout(ratio=0.5, is_test=0)`` that follow it in the head
     (modeling/wsl_heads.py:674-679).  X may be a column slice of a wider matrix.  3-d operands
     ([S, ., .] strided views, b [S, N]) run the S stacks of the head as ONE launch; stack s draws its
-    seeded dropout bits from ``dropout_seed + s``."""
+    seeded dropout bits from ``dropout_seed + s``.
+
+    ``gate`` (2-d operands only) = dict(flags=int32 CUDA tensor [groups * nflags], nflags, rows, seq, timeout_ms, status):
+    rows ``[g*rows, (g+1)*rows)`` of W are read only once flags ``[g*nflags, (g+1)*nflags)`` have reached ``seq`` -- the
+    data-parallel peer exchange's "operands of bucket g have landed" words (dp.P2PExchange), so the GEMM runs on the weights
+    that are there and meets the rest as they arrive."""
     S, M, K, lda, sA = _mat3(X, "X")
     S2, N, K2, ldw, sW = _mat3(W, "W")
     if K != K2 or X.dtype != W.dtype:
@@ -455,6 +458,16 @@ def FC(X, W, b=None, *, relu=False, dropout_mask=None, dropout=False, dropout_se
             raise RuntimeError("dropout_mask must be uint8 (0/1)")
         S4, _, _, ldm, sm = _mat3(dropout_mask, "dropout_mask")
         _same_stacks("FC", S, S4)
+    if gate is not None:
+        if S != 1:
+            raise RuntimeError("FC: a gated launch takes 2-d operands")
+        gf = gate["flags"]
+        _req(gf, "gate flags", torch.int32)
+        groups = gf.numel() // int(gate["nflags"])
+        _lib.call("nawsod_fc_fwd_gated", _ptr(X), lda, _ptr(W), ldw, _ptr(b), _ptr(dropout_mask), ldm, int(dropout_seed), M, N, K,
+                  _ab(X.dtype), _ptr(Y), ldy, _DT[Y.dtype], flags, _ptr(gf), groups, int(gate["nflags"]), int(gate["rows"]),
+                  int(gate["seq"]) & 0xFFFFFFFF, int(gate.get("timeout_ms", 20000)), _ptr(gate.get("status")), _stream())
+        return Y
     _lib.call("nawsod_fc_fwd_stacks", _ptr(X), lda, sA, _ptr(W), ldw, sW, _ptr(b), sb, _ptr(dropout_mask), ldm, sm,
               int(dropout_seed), S, M, N, K, _ab(X.dtype), _ptr(Y), ldy, sY, _DT[Y.dtype], flags, _stream())
     return Y

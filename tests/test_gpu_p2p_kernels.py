@@ -1,6 +1,6 @@
 """Single-GPU checks of the peer-exchange kernels of na-fwebsod_b200/csrc/p2p.cu (the kernels only see addresses; between
-GPUs they run in tests/test_gpu_zzzz_dp_*.py): the SM-driven and the TMA-driven scatter move exactly the requested bytes
-to every destination and then publish the sequence number; the wait kernel returns once the flags carry it and reports
+GPUs they run in tests/test_gpu_zzzz_dp_*.py): the SM-driven scatter moves exactly the requested bytes
+to every destination and then publishes the sequence number; the wait kernel returns once the flags carry it and reports
 a time-out through the status word; the owner's update kernel skips its work once that word is set."""
 import pytest
 import torch
@@ -13,9 +13,8 @@ def _ops():
     return ops
 
 
-@pytest.mark.parametrize("tma", [False, True])
 @pytest.mark.parametrize("npeers,nbytes", [(1, 16), (3, 8192), (7, 8192 * 5 + 4080), (2, 3 * 1024 * 1024 + 16), (7, 25690112 // 8)])
-def test_scatter_moves_the_bytes_then_publishes(tma, npeers, nbytes):
+def test_scatter_moves_the_bytes_then_publishes(npeers, nbytes):
     ops = _ops()
     g = torch.Generator(device="cuda").manual_seed(nbytes % 9973)
     srcs = [torch.randint(0, 255, (nbytes,), dtype=torch.uint8, device="cuda", generator=g) for _ in range(npeers)]
@@ -24,7 +23,7 @@ def test_scatter_moves_the_bytes_then_publishes(tma, npeers, nbytes):
     flags = torch.zeros(npeers + 1, dtype=torch.int32, device="cuda")
     fptr = [flags.data_ptr() + 4 * i for i in range(npeers + 1)]
     for seq in (1, 2):                           # twice: the completion counter of the slot must reset itself
-        ops.p2p_scatter([s.data_ptr() for s in srcs], [d.data_ptr() + pad for d in dsts], nbytes, fptr, seq, 5, tma=tma)
+        ops.p2p_scatter([s.data_ptr() for s in srcs], [d.data_ptr() + pad for d in dsts], nbytes, fptr, seq, 5)
         status = torch.zeros(1, dtype=torch.int32, device="cuda")
         ops.p2p_wait(flags, seq, 2000, status)
         torch.cuda.synchronize()
@@ -40,11 +39,9 @@ def test_flag_only_launch_and_wait_timeout():
     ops = _ops()
     flags = torch.zeros(4, dtype=torch.int32, device="cuda")
     status = torch.zeros(1, dtype=torch.int32, device="cuda")
-    for tma in (False, True):                    # no bytes, flags only (the operand leg of a replicated bucket)
-        flags.zero_()
-        ops.p2p_scatter([], [], 0, [flags.data_ptr() + 4 * i for i in range(3)], 7, 9, tma=tma)
-        torch.cuda.synchronize()
-        assert flags.tolist() == [7, 7, 7, 0]
+    ops.p2p_scatter([], [], 0, [flags.data_ptr() + 4 * i for i in range(3)], 7, 9)     # no bytes, flags only (a replicated bucket's operand leg)
+    torch.cuda.synchronize()
+    assert flags.tolist() == [7, 7, 7, 0]
     ops.p2p_wait(flags, 7, 50, status)           # the fourth flag never arrives: the watchdog fires after 50 ms
     torch.cuda.synchronize()
     assert int(status.item()) == 1

@@ -21,8 +21,11 @@ run() {   # name, extra env (VAR=VALUE words), extra bench args
 for v in "$@"; do
   case $v in
     pull_sm)   run pull_sm "NAWSOD_P2P_RS=pull NAWSOD_P2P_ENGINE=sm NAWSOD_P2P_PROFILE=1" ;;
+    pull_sm_nogate) run pull_sm_nogate "NAWSOD_P2P_RS=pull NAWSOD_P2P_ENGINE=sm NAWSOD_P2P_GATED_FC6=0 NAWSOD_P2P_PROFILE=1" ;;
+    pull_ce_p8) run pull_ce_p8 "NAWSOD_P2P_RS=pull NAWSOD_P2P_ENGINE=ce NAWSOD_P2P_PROFILE=1" --fc6-panels 8 ;;
+    pull_sm_p8) run pull_sm_p8 "NAWSOD_P2P_RS=pull NAWSOD_P2P_ENGINE=sm NAWSOD_P2P_PROFILE=1" --fc6-panels 8 ;;
     pull_sm32) run pull_sm32 "NAWSOD_P2P_RS=pull NAWSOD_P2P_ENGINE=sm NAWSOD_TUNING=p2p_ctas=32 NAWSOD_P2P_PROFILE=1" ;;
-    pull_tma)  run pull_tma "NAWSOD_P2P_RS=pull NAWSOD_P2P_ENGINE=tma NAWSOD_P2P_PROFILE=1" ;;
+    pull_sm32_p8) run pull_sm32_p8 "NAWSOD_P2P_RS=pull NAWSOD_P2P_ENGINE=sm NAWSOD_TUNING=p2p_ctas=32 NAWSOD_P2P_PROFILE=1" --fc6-panels 8 ;;
     pull_ce)   run pull_ce "NAWSOD_P2P_RS=pull NAWSOD_P2P_ENGINE=ce NAWSOD_P2P_PROFILE=1" ;;
     push_sm)   run push_sm "NAWSOD_P2P_RS=push NAWSOD_P2P_ENGINE=sm NAWSOD_P2P_PROFILE=1" ;;
     push_ce)   run push_ce "NAWSOD_P2P_RS=push NAWSOD_P2P_ENGINE=ce NAWSOD_P2P_PROFILE=1" ;;

@@ -21,14 +21,14 @@ run() {   # name, extra env (VAR=VALUE words), extra bench args
 for v in "$@"; do
   case $v in
     pull_sm)   run pull_sm "NAWSOD_P2P_RS=pull NAWSOD_P2P_ENGINE=sm NAWSOD_P2P_PROFILE=1" ;;
+    pull_sm_nogate) run pull_sm_nogate "NAWSOD_P2P_RS=pull NAWSOD_P2P_ENGINE=sm NAWSOD_P2P_GATED_FC6=0 NAWSOD_P2P_PROFILE=1" ;;
+    pull_ce_p8) run pull_ce_p8 "NAWSOD_P2P_RS=pull NAWSOD_P2P_ENGINE=ce NAWSOD_P2P_PROFILE=1" --fc6-panels 8 ;;
+    pull_sm_p8) run pull_sm_p8 "NAWSOD_P2P_RS=pull NAWSOD_P2P_ENGINE=sm NAWSOD_P2P_PROFILE=1" --fc6-panels 8 ;;
     pull_sm32) run pull_sm32 "NAWSOD_P2P_RS=pull NAWSOD_P2P_ENGINE=sm NAWSOD_TUNING=p2p_ctas=32 NAWSOD_P2P_PROFILE=1" ;;
-    pull_tma)  run pull_tma "NAWSOD_P2P_RS=pull NAWSOD_P2P_ENGINE=tma NAWSOD_P2P_PROFILE=1" ;;
+    pull_sm32_p8) run pull_sm32_p8 "NAWSOD_P2P_RS=pull NAWSOD_P2P_ENGINE=sm NAWSOD_TUNING=p2p_ctas=32 NAWSOD_P2P_PROFILE=1" --fc6-panels 8 ;;
     pull_ce)   run pull_ce "NAWSOD_P2P_RS=pull NAWSOD_P2P_ENGINE=ce NAWSOD_P2P_PROFILE=1" ;;
     pull_sm_sgd296) run pull_sm_sgd296 "NAWSOD_P2P_RS=pull NAWSOD_P2P_ENGINE=sm NAWSOD_TUNING=p2p_ctas=32,sgd_max_ctas=296 NAWSOD_P2P_PROFILE=1" ;;
     sm)        run sm "NAWSOD_P2P_RS=push NAWSOD_P2P_ENGINE=sm NAWSOD_P2P_PROFILE=1" ;;
-    tma)       run tma "NAWSOD_P2P_RS=push NAWSOD_P2P_ENGINE=tma NAWSOD_P2P_PROFILE=1" ;;
-    tma64)     run tma64 "NAWSOD_P2P_ENGINE=tma NAWSOD_TUNING=p2p_ctas=64 NAWSOD_P2P_PROFILE=1" ;;
-    tma_p8)    run tma_p8 "NAWSOD_P2P_ENGINE=tma NAWSOD_P2P_PROFILE=1" --fc6-panels 8 ;;
     ce)        run ce "NAWSOD_P2P_RS=push NAWSOD_P2P_ENGINE=ce NAWSOD_P2P_PROFILE=1" ;;
     ce7)       run ce7 "NAWSOD_P2P_ENGINE=ce NAWSOD_P2P_COPY_STREAMS=7 NAWSOD_P2P_PROFILE=1" ;;
     sm32)      run sm32 "NAWSOD_P2P_RS=push NAWSOD_P2P_ENGINE=sm NAWSOD_TUNING=p2p_ctas=32 NAWSOD_P2P_PROFILE=1" ;;
