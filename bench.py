@@ -480,16 +480,20 @@ def gpu_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    host_ms = []                        # per timed block: host milliseconds spent enqueueing one step
+
     def timed(fn, steps, tail=None, step_events=None):
         sync_all()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
+        h0 = time.perf_counter()
         for i in range(steps):
             fn(i)
             if step_events is not None:
                 e = torch.cuda.Event(enable_timing=True)
                 e.record()
                 step_events.append(e)
+        host_ms.append((time.perf_counter() - h0) * 1e3 / max(steps, 1))      # host time to ENQUEUE a step (no sync inside)
         dp.flush()                      # the last step's parameter exchange belongs to the timed region
         b.record()
         if tail is not None:
@@ -508,6 +512,7 @@ def gpu_arm(args):
         (at most 15 blocks, the count agreed across ranks through the max-reduced first block) and the MEDIAN block is
         reported, with the spread of the blocks and of the individual steps beside it."""
         blocks, per_step = [], []
+        h_first = len(host_ms)
 
         def one():
             ev = []
@@ -523,7 +528,9 @@ def gpu_arm(args):
         med = blocks[order[len(order) // 2]]
         stats = {"blocks": len(blocks), "steps_per_block": steps,
                  "block_ms_per_step": {"min": min(blocks) / steps, "median": med / steps, "max": max(blocks) / steps},
-                 "step_ms_this_rank": {"min": float(np.min(per_step)), "median": float(np.median(per_step)), "max": float(np.max(per_step))}}
+                 "step_ms_this_rank": {"min": float(np.min(per_step)), "median": float(np.median(per_step)), "max": float(np.max(per_step))},
+                 # when this approaches ms_per_step the run is launch-bound: the GPU waits for the host
+                 "host_enqueue_ms_per_step_this_rank": float(np.median(host_ms[h_first:]))}
         return med, stats, extra
 
     # ---- resident-input leg (value) ----
@@ -683,7 +690,7 @@ def gpu_arm(args):
         n_panels=max(1, len(prof.get("fc6_bwd_w", [])) // max(args.steps * value_stats["blocks"], 1)), iso=iso, cpu=cpu,
         loss=[float(x) for x in losses[-1].flatten().tolist()], timing={"value": value_stats, "e2e": e2e_stats}, tf32=tf32,
         dp_info={"sync": dp.sync, "fc6_panels": dp.fc6_panels, "p2p_selftest": dp.p2p_selftest,
-                 "engine": getattr(dp.exchange, "engine", None)})
+                 "engine": ("%s/%s" % (getattr(dp.exchange, "rs_mode", "-"), dp.exchange.engine)) if hasattr(dp.exchange, "engine") else None})
     _emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -350,6 +350,13 @@ int nawsod_convert_mcg_boxes(const double* bboxes, int R, uint16_t* boxes_out, v
  *                      (1 or 2, the combinations VGG16.py:10-56 uses), zeros outside the image; C % 8 == 0.
  *   nawsod_maxpool2x2  MaxPool(kernel=2, pad=0, stride) on [N,H,W,C] bf16 -> [N,(H-2)/stride+1,(W-2)/stride+1,C];
  *                      stride 2 (pool1-3, pool4 of the 1/16 body) or 1 (pool4 with WSL.DILATION 2, VGG16.py:40-41). */
+/* Conv(3x3, stride 1, pad = dilation) + bias [+ Relu] as an implicit GEMM on the tcgen05 tensor cores: X [N,H,W,Cin] bf16
+ *   channels-last, Wmat [Cout, 9*Cin] bf16 with K-order (kh, kw, c), bias [Cout] float, Y [N,H,W,Cout] bf16.  The A operand
+ *   of a k-block is a shifted [8, 16, 64-channel] box of X loaded by ONE 4-D tiled TMA copy (out-of-bounds = the zero
+ *   padding): no patch matrix.  Cin % 64 == 0, Cout % 32 == 0, dilation 1 or 2.  Bit-identical to
+ *   nawsod_im2col3x3 + nawsod_fc_fwd. */
+int nawsod_conv3x3_relu(const void* X, int N, int H, int W, int Cin, const void* Wmat, const float* bias,
+                        int Cout, int dilation, int relu, void* Y, void* stream);
 int nawsod_im2col3x3(const void* X, int N, int H, int W, int C, int dilation, void* cols, void* stream);
 int nawsod_maxpool2x2(const void* X, int N, int H, int W, int C, int stride, void* Y, void* stream);
 

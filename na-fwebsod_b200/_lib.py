@@ -68,6 +68,7 @@ PROTOTYPES = {
     "nawsod_bagging_mixup": (_i, [_vp, _vp, _i64, _f, _f, _vp, _vp]),
     "nawsod_set_column": (_i, [_vp, _i, _i64, _i, _f, _vp]),
     "nawsod_convert_mcg_boxes": (_i, [_vp, _i, _vp, _vp]),
+    "nawsod_conv3x3_relu": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "nawsod_im2col3x3": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "nawsod_maxpool2x2": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),
 }
@@ -83,7 +84,7 @@ KERNELS_PER_CALL = {
     "nawsod_project_rois": 1, "nawsod_dedup_rois": 1, "nawsod_gather_rows": 1, "nawsod_scatter_scores": 1,
     "nawsod_scores_finalize": 1, "nawsod_nms_and_limit": 2, "nawsod_min_entropy_loss_fwd": 1, "nawsod_min_entropy_loss_bwd": 2,
     "nawsod_sample_rois": 1, "nawsod_image_labels": 1, "nawsod_bagging_mixup": 1, "nawsod_set_column": 1, "nawsod_convert_mcg_boxes": 1,
-    "nawsod_im2col3x3": 1, "nawsod_maxpool2x2": 1,
+    "nawsod_conv3x3_relu": 1, "nawsod_im2col3x3": 1, "nawsod_maxpool2x2": 1,
 }
 launch_count = 0
 

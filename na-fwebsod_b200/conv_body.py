@@ -1,16 +1,14 @@
 """Frozen VGG16 conv body feeding the head's RoIPoolF directly (second half).
 
-EXPERIMENTAL: the two kernels behind it (csrc/conv_body.cu) are compiled but have not run on hardware yet; their GPU
-tests only run with NAWSOD_EXPERIMENTAL=1.
-
 The reference's ``add_VGG16_conv5_body_origin`` (detectron/modeling/VGG16.py:9-58, MODEL.CONV_BODY of the flickr
 configs) is thirteen ``Conv(3x3, stride 1)`` + ``Relu`` pairs and the 2x2 ``MaxPool``s between the five groups, NCHW fp32
 on cuDNN, all frozen (TRAIN.FREEZE_CONV_BODY): forward only.  ``WSL.DILATION == 2`` (the shipped flickr value, yaml:64)
 keeps conv5 at 1/8 resolution: pool4 becomes kernel 2 / stride 1 and conv5_x get pad 2 / dilation 2 (VGG16.py:39-48).
 
 Here the body keeps its activations channels-last in bf16 end to end -- the layout ``heads.WeblyHeadModel.FeedBlobs``
-takes with ``x_layout='NHWC'`` -- so conv5_3 goes into RoIPoolF without a transpose or a cast.  Each convolution is one
-patch-matrix kernel plus the library's tcgen05 GEMM with bias + ReLU in its epilogue (ops.Conv3x3Relu).  The layer list
+takes with ``x_layout='NHWC'`` -- so conv5_3 goes into RoIPoolF without a transpose or a cast.  Each convolution is an
+implicit GEMM on the tcgen05 tensor cores (shifted 4-D TMA boxes of the map as the A operand, bias + ReLU in the epilogue;
+csrc/conv_body.cu); conv1_1 (three input planes padded to eight) keeps the patch-matrix form (ops.Conv3x3Relu).  The layer list
 below is the reference builder's own operator sequence (pinned by tests/golden/vgg16_body.npz, which records that builder
 run on a tracing model).  There is no CPU fallback.
 """
@@ -66,6 +64,7 @@ class VGG16ConvBody:
         self.dilation, self.device = dilation, torch.device(device)
         self.w, self.b = {}, {}
         self.blobs = {}
+        self.implicit = None          # None: implicit GEMM wherever Cin % 64 == 0 (ops.Conv3x3Relu); False: patch matrix everywhere
 
     @staticmethod
     def _cin_padded(cin):
@@ -108,7 +107,8 @@ class VGG16ConvBody:
         cur = {"data": self.blobs["data"]}
         for kind, src, dst, args in body_ops(self.dilation):
             if kind == "Conv":
-                cur = {dst: ops.Conv3x3Relu(cur[src], self.w[dst], self.b[dst], dilation=args["dilation"], relu=True)}
+                imp = None if self.implicit is None else (self.implicit and args["dim_in"] % 64 == 0)
+                cur = {dst: ops.Conv3x3Relu(cur[src], self.w[dst], self.b[dst], dilation=args["dilation"], relu=True, implicit=imp)}
             elif kind == "MaxPool":
                 cur = {dst: ops.MaxPool2x2(cur[src], stride=args["stride"])}
             # Relu: fused into the convolution's GEMM epilogue

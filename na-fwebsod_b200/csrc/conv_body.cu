@@ -1,22 +1,29 @@
-// Frozen VGG16 conv body in channels-last bf16 (row N4 of SURVEY.md section 8f; EXPERIMENTAL: compiled, not yet run).
+// Frozen VGG16 conv body in channels-last bf16 (row N4 of SURVEY.md section 8f).
 //
 // The reference builds conv1_1 .. conv5_3 with Caffe2 `Conv` (cuDNN, NCHW fp32) + `Relu` + `MaxPool`
 // (detectron/modeling/VGG16.py:9-58, the flickr configs' MODEL.CONV_BODY) and freezes all of it
-// (TRAIN.FREEZE_CONV_BODY, yaml:31), so the body is a forward-only producer of the head's conv5 map.  Here every 3x3
-// convolution is the library's tcgen05 FC GEMM (gemm.cu: bias + ReLU fused in its epilogue, bf16 channels-last output =
-// the next layer's input) over a patch matrix this file builds:
+// (TRAIN.FREEZE_CONV_BODY, yaml:31), so the body is a forward-only producer of the head's conv5 map.
 //
-//   nawsod_im2col3x3   X [N,H,W,C] bf16  ->  cols [N*H*W, 9*C] bf16, K-order (kh, kw, c), stride 1,
-//                      pad = dilation (the only combinations VGG16.py uses: pad 1 / dilation 1, pad 2 / dilation 2);
-//                      out-of-image taps are zeros.  Pure 16-byte copies: HBM-bound, 2 * 9 * C bytes written per pixel.
+//   nawsod_conv3x3_relu  Conv(3x3, stride 1, pad = dilation) + bias + Relu as an IMPLICIT GEMM on the tcgen05 tensor cores:
+//                      no patch matrix.  An output tile is 8 x 16 pixels (128 GEMM rows) x BN output channels; the
+//                      reduction runs over 9 taps x Cin / 64 channel blocks.  For tap (kh, kw) the A operand of a k-block is
+//                      the input map's [8, 16, 64-channel] box shifted by ((kh - 1) d, (kw - 1) d): ONE 4-D tiled TMA
+//                      load per k-block, whose out-of-bounds zero fill is the convolution's zero padding and whose shared-
+//                      memory image (128 rows of 128 swizzled bytes) is exactly the K-major operand tile tcgen05.mma reads.
+//                      The weights [Cout, (kh, kw, c)] are the K-major B operand as they lie.  Same warp roles, smem ring,
+//                      double-buffered TMEM accumulator and epilogue structure as gemm.cu.  Cin a multiple of 64 (all of
+//                      VGG16 but conv1_1, which keeps the patch-matrix path: K = 9 x 8 padded planes).
+//   nawsod_im2col3x3   X [N,H,W,C] bf16  ->  cols [N*H*W, 9*C] bf16, K-order (kh, kw, c), stride 1, pad = dilation
+//                      (conv1_1, and the reference form the implicit GEMM is tested against).
 //   nawsod_maxpool2x2  MaxPool(kernel=2, pad=0, stride=1|2) on a channels-last bf16 map (Caffe2's floor output size:
 //                      (H - 2) / stride + 1); packed bf16x2 maxima, 16 bytes per thread.
 //
-// The weights [Cout, Cin, 3, 3] are permuted once on the host to [Cout, (kh, kw, c)] (conv_body.py).  A TMA-im2col
-// implicit GEMM would remove the patch matrix's round trip through HBM (it is ~3x the layers' algorithmic bytes); this
-// first version reuses the verified GEMM unchanged.
+// Measured (profiles/r2a_microbench_convbody.log -> r2*_microbench_convbody.log): the patch-matrix body ran 1.0 ms for a
+// 480 x 640 image (235 TFLOP/s, 14 % of the tensor peak: the patch matrix moves ~10x the layers' algorithmic bytes).
+#include <cuda.h>
 #include <algorithm>
-#include "common.cuh"
+#include "gemm_tc.cuh"
+
 
 namespace nawsod {
 namespace {
@@ -69,6 +76,210 @@ __global__ void __launch_bounds__(kThreads) maxpool2x2_kernel(const uint4* __res
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// implicit-GEMM 3x3 convolution
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kTileH = 8, kTileW = 16;           // 128 output pixels per tile = the GEMM's BLOCK_M rows, row = h_local * 16 + w_local
+
+struct ConvParams {
+  int N, H, W, Cin, Cout, dil, relu;
+  const float* bias;
+  __nv_bfloat16* Y;                              // [N, H, W, Cout]
+};
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kNumThreads, 1)
+conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const ConvParams p) {
+  using C = Cfg<BN, 2>;
+  constexpr int BK = C::BK;                      // 64 channels = one 128-byte swizzle atom
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + C::STAGES * C::STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * C::STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * C::STAGES + 2 + a); };
+  const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * C::STAGES + 4);
+  volatile uint32_t* tmem_ptr_generic =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_w = (p.W + kTileW - 1) / kTileW, tiles_h = (p.H + kTileH - 1) / kTileH;
+  const int num_m = p.N * tiles_h * tiles_w;
+  const int num_n = (p.Cout + BN - 1) / BN;
+  const int num_tiles = num_m * num_n;
+  const int cblocks = p.Cin / BK;
+  const int num_kb = 9 * cblocks;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmW);
+    for (int s = 0; s < C::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"(C::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_generic;
+
+  // tile -> (image, first output row, first output column, first output channel); pixel tiles fastest, so the CTAs that run
+  // together share the weight tile through L2
+  auto tile_origin = [&](int tile, int& n, int& h0, int& w0, int& n0) {
+    const int tm = tile % num_m;
+    n0 = (tile / num_m) * BN;
+    n = tm / (tiles_h * tiles_w);
+    const int r = tm - n * tiles_h * tiles_w;
+    h0 = (r / tiles_w) * kTileH;
+    w0 = (r % tiles_w) * kTileW;
+  };
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        int n, h0, w0, n0;
+        tile_origin(tile, n, h0, w0, n0);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const int tap = kb / cblocks, c0 = (kb - tap * cblocks) * BK;
+          const int dh = (tap / 3 - 1) * p.dil, dw = (tap % 3 - 1) * p.dil;
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t sa = smem_base + stage * C::STAGE_BYTES, sb = sa + C::A_BYTES;
+          mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
+          // the shifted [8, 16, 64] box of the input map: rows / columns outside the image arrive as zeros (the padding)
+          tma_load_4d(sa, &tmX, full_bar(stage), c0, w0 + dw, h0 + dh, n);
+          tma_load_3d(sb, &tmW, full_bar(stage), kb * BK, n0, 0);
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(2, false, false, BLOCK_M, BN);
+      constexpr uint32_t kstep = 32 >> 4;
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * C::STAGE_BYTES, sb = sa + C::A_BYTES;
+          const uint64_t adesc = make_smem_desc(sa, 16, 1024, 2), bdesc = make_smem_desc(sb, 16, 1024, 2);
+#pragma unroll
+          for (int k = 0; k < BK / C::UMMA_K; ++k)
+            tc_mma<2>(tmem_d, adesc + (uint64_t)(k * kstep), bdesc + (uint64_t)(k * kstep), idesc, (kb | k) != 0);
+          tc_commit(empty_bar(stage));
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(tfull_bar(acc));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ================= epilogue (warps 2..5): bias + Relu -> bf16, 16-byte stores =================
+    const int q = warp & 3;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int n, h0, w0, n0;
+      tile_origin(tile, n, h0, w0, n0);
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const int ml = q * 32 + lane;
+      const int h = h0 + ml / kTileW, w = w0 + ml % kTileW;
+      const bool pix_ok = h < p.H && w < p.W;
+      __nv_bfloat16* const orow = p.Y + (((size_t)n * p.H + h) * p.W + w) * p.Cout;
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        if (n0 + c >= p.Cout) break;              // warp-uniform
+        uint32_t r[32];
+        __syncwarp();
+        tc_ld32(tmem_base + acc * BN + c + (static_cast<uint32_t>(q * 32) << 16), r);
+        tc_wait_ld();
+        if (pix_ok) {
+          const int co = n0 + c;                  // Cout is a multiple of 32 (host check): whole 32-column chunks
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + co + i));
+            v[i] = __uint_as_float(r[i]) + b4.x; v[i + 1] = __uint_as_float(r[i + 1]) + b4.y;
+            v[i + 2] = __uint_as_float(r[i + 2]) + b4.z; v[i + 3] = __uint_as_float(r[i + 3]) + b4.w;
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+          }
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            __nv_bfloat162 a0 = __floats2bfloat162_rn(v[i], v[i + 1]), a1 = __floats2bfloat162_rn(v[i + 2], v[i + 3]);
+            __nv_bfloat162 a2 = __floats2bfloat162_rn(v[i + 4], v[i + 5]), a3 = __floats2bfloat162_rn(v[i + 6], v[i + 7]);
+            *reinterpret_cast<uint4*>(orow + co + i) = make_uint4(*reinterpret_cast<uint32_t*>(&a0), *reinterpret_cast<uint32_t*>(&a1),
+                                                                  *reinterpret_cast<uint32_t*>(&a2), *reinterpret_cast<uint32_t*>(&a3));
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::TMEM_COLS) : "memory");
+  }
+}
+
+// 4-D tiled tensor map over the channels-last map X [N, H, W, C] (bf16): box [1, 8, 16, 64 channels], 128-byte swizzle,
+// out-of-bounds elements read as zero
+int make_tmap_nhwc(CUtensorMap* map, const void* X, int N, int H, int W, int Cch) {
+  EncodeTiledFn fn = get_encode_fn();
+  NAWSOD_REQUIRE(fn != nullptr, NAWSOD_ERR_CUDA, "cuTensorMapEncodeTiled is not available (no CUDA driver?)");
+  cuuint64_t gdim[4] = {(cuuint64_t)Cch, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t gstride[3] = {(cuuint64_t)Cch * 2, (cuuint64_t)W * Cch * 2, (cuuint64_t)H * W * Cch * 2};
+  cuuint32_t box[4] = {64, kTileW, kTileH, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(X), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  NAWSOD_REQUIRE(r == CUDA_SUCCESS, NAWSOD_ERR_CUDA, "cuTensorMapEncodeTiled (4-d) failed with %d", (int)r);
+  return NAWSOD_OK;
+}
+
+template <int BN>
+int launch_conv(const void* X, const void* Wm, const ConvParams& p, cudaStream_t st) {
+  using C = Cfg<BN, 2>;
+  CUtensorMap tmX, tmW;
+  if (int rc = make_tmap_nhwc(&tmX, X, p.N, p.H, p.W, p.Cin)) return rc;
+  if (int rc = make_tmap(&tmW, Wm, 2, p.Cout, 9LL * p.Cin, 9LL * p.Cin, BN, C::BK, false, 1, 0)) return rc;
+  auto kern = conv3x3_igemm_kernel<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    NAWSOD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int num_tiles = p.N * ((p.H + kTileH - 1) / kTileH) * ((p.W + kTileW - 1) / kTileW) * ((p.Cout + BN - 1) / BN);
+  kern<<<std::min(num_tiles, sm_count()), kNumThreads, C::SMEM_BYTES, st>>>(tmX, tmW, p);
+  NAWSOD_LAUNCH_OK();
+  return NAWSOD_OK;
+}
+
 int grid_for(int64_t total) {
   return (int)std::max<int64_t>(1, std::min<int64_t>((total + kThreads - 1) / kThreads, 16LL * sm_count()));
 }
@@ -77,6 +288,28 @@ int grid_for(int64_t total) {
 }  // namespace nawsod
 
 using namespace nawsod;
+
+extern "C" int nawsod_conv3x3_relu(const void* X, int N, int H, int W, int Cin, const void* Wmat, const float* bias, int Cout,
+                                   int dilation, int relu, void* Y, void* stream) {
+  NAWSOD_REQUIRE(N >= 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, NAWSOD_ERR_SHAPE, "conv3x3_relu: bad shape N=%d H=%d W=%d Cin=%d Cout=%d", N, H, W, Cin, Cout);
+  NAWSOD_REQUIRE(Cin % 64 == 0, NAWSOD_ERR_UNSUPPORTED, "conv3x3_relu: Cin=%d must be a multiple of 64 (one 128-byte channel block per k-step; "
+                 "use nawsod_im2col3x3 + nawsod_fc_fwd otherwise)", Cin);
+  NAWSOD_REQUIRE(Cout % 32 == 0, NAWSOD_ERR_UNSUPPORTED, "conv3x3_relu: Cout=%d must be a multiple of 32", Cout);
+  NAWSOD_REQUIRE(dilation == 1 || dilation == 2, NAWSOD_ERR_UNSUPPORTED, "conv3x3_relu: dilation must be 1 or 2 (pad = dilation)");
+  if (N == 0) return NAWSOD_OK;
+  NAWSOD_REQUIRE(X && Wmat && bias && Y, NAWSOD_ERR_ARG, "conv3x3_relu: null pointer");
+  NAWSOD_REQUIRE(aligned16(X) && aligned16(Wmat) && aligned16(bias) && aligned16(Y), NAWSOD_ERR_ALIGN, "conv3x3_relu: buffers must be 16-byte aligned");
+  ConvParams p;
+  p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.dil = dilation; p.relu = relu ? 1 : 0;
+  p.bias = bias; p.Y = static_cast<__nv_bfloat16*>(Y);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // BN = 256 only when that still gives every SM a tile; small maps (conv5 at 1/8) take narrower tiles
+  const long long mt = (long long)N * ((H + kTileH - 1) / kTileH) * ((W + kTileW - 1) / kTileW);
+  if (Cout % 256 == 0 && mt * (Cout / 256) >= 2LL * sm_count()) return launch_conv<256>(X, Wmat, p, st);
+  if (Cout % 128 == 0 && mt * (Cout / 128) >= sm_count()) return launch_conv<128>(X, Wmat, p, st);
+  if (Cout % 64 == 0) return launch_conv<64>(X, Wmat, p, st);
+  return launch_conv<128>(X, Wmat, p, st);        // Cout = 32 * odd: BN covers it with one guarded tile column
+}
 
 extern "C" int nawsod_im2col3x3(const void* X, int N, int H, int W, int C, int dilation, void* cols, void* stream) {
   NAWSOD_REQUIRE(N >= 0 && H > 0 && W > 0 && C > 0, NAWSOD_ERR_SHAPE, "im2col3x3: bad shape N=%d H=%d W=%d C=%d", N, H, W, C);

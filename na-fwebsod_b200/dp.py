@@ -247,7 +247,10 @@ class P2PExchange:
         # producers only publish "my bucket is complete"); "push" -- producers copy their slices into the owner's staging
         # area (engine-driven copies), the owner reduces from local memory.  Pull needs no staging memory (958 MB), no copy
         # kernels beside the GEMMs and saves the staging's HBM write + re-read (1.7 GB per step and GPU at 8 ranks).
-        self.rs_mode = os.environ.get("NAWSOD_P2P_RS", "pull")
+        # Measured (profiles/r2i..r2m_bench_n*_*.json; ms per step, push/ce | pull/ce | pull/sm | push/sm): 2 GPUs 4.33 | 4.46 |
+        # 4.55 | 4.81; 8 GPUs 5.50 | 4.93 | 4.99 | 5.01-5.15 -- the copy engines leave the GEMMs alone but sustain only ~360 GB/s
+        # of egress when eight ranks push at once; pulling needs a seventh of the engine-driven bytes (the operand leg only).
+        self.rs_mode = os.environ.get("NAWSOD_P2P_RS", "push" if self.world <= 2 else "pull")
         if self.rs_mode not in ("pull", "push"):
             raise RuntimeError("NAWSOD_P2P_RS must be 'pull' or 'push'")
         pull = self.rs_mode == "pull"
@@ -279,8 +282,9 @@ class P2PExchange:
         # b6's (tiny, replicated) update runs on a stream of its own: behind the last fc6 panel's update it would hold up
         # the next step's fc6, which reads b6 but meets the W6 panels through its in-kernel gate
         self.bias6_stream = torch.cuda.Stream(device=dev, priority=-1)
-        # "sm": one co-resident scatter kernel per bucket and leg (default); "ce": copy-engine transfers
-        self.engine = os.environ.get("NAWSOD_P2P_ENGINE", "sm")
+        # "ce": copy-engine transfers (default: no SM is taken from the GEMMs); "sm": one co-resident scatter kernel per bucket
+        # and leg
+        self.engine = os.environ.get("NAWSOD_P2P_ENGINE", "ce")
         if self.engine not in ("sm", "ce"):
             raise RuntimeError("NAWSOD_P2P_ENGINE must be 'sm' or 'ce'")
         if len(self.plan) > 64:

@@ -787,16 +787,32 @@ def Im2Col3x3(X, *, dilation=1, out=None):
     return cols
 
 
-def Conv3x3Relu(X, Wmat, b, *, dilation=1, relu=True, cols=None):
-    """``Conv(kernel=3, pad=dilation, stride=1, dilation)`` + ``Relu`` on a channels-last bf16 map: the patch matrix times
-    ``Wmat`` [Cout, 9*Cin] (the reference's [Cout, Cin, 3, 3] weight permuted to (kh, kw, c)) on the tcgen05 GEMM, bias
-    and ReLU in its epilogue.  Returns Y [N,H,W,Cout] bf16 -- the next layer's input as is."""
+def Conv3x3Relu(X, Wmat, b, *, dilation=1, relu=True, cols=None, implicit=None):
+    """``Conv(kernel=3, pad=dilation, stride=1, dilation)`` + ``Relu`` on a channels-last bf16 map; ``Wmat`` [Cout, 9*Cin]
+    is the reference's [Cout, Cin, 3, 3] weight permuted to (kh, kw, c).  Returns Y [N,H,W,Cout] bf16 -- the next layer's
+    input as is.
+
+    ``implicit`` (default: whenever Cin is a multiple of 64): the implicit GEMM of csrc/conv_body.cu -- shifted 4-D TMA
+    boxes of the map are the A operand, no patch matrix.  Otherwise (conv1_1's 8 padded planes, or ``implicit=False``):
+    the patch matrix (``Im2Col3x3``) times ``Wmat`` on the FC GEMM.  Both accumulate the same products in the same
+    order: bit-identical outputs."""
     N, H, W, C = _nhwc_bf16(X, "X")
     if Wmat.dim() != 2 or Wmat.shape[1] != 9 * C:
         raise RuntimeError("Conv3x3Relu: Wmat must be [Cout, %d], got %s" % (9 * C, tuple(Wmat.shape)))
+    Cout = Wmat.shape[0]
+    if implicit is None:
+        implicit = C % 64 == 0 and Cout % 32 == 0
+    if implicit:
+        _req(Wmat, "Wmat", torch.bfloat16, 2)
+        _req(b, "b", torch.float32, 1)
+        if b.numel() != Cout or not Wmat.is_contiguous():
+            raise RuntimeError("Conv3x3Relu: need a contiguous Wmat and a bias of %d elements" % Cout)
+        Y = torch.empty((N, H, W, Cout), dtype=torch.bfloat16, device=X.device)
+        _lib.call("nawsod_conv3x3_relu", _ptr(X), N, H, W, C, _ptr(Wmat), _ptr(b), Cout, int(dilation), 1 if relu else 0, _ptr(Y), _stream())
+        return Y
     cols = Im2Col3x3(X, dilation=dilation, out=cols)
     Y = FC(cols, Wmat, b, relu=relu, out_dtype=torch.bfloat16)
-    return Y.view(N, H, W, Wmat.shape[0])
+    return Y.view(N, H, W, Cout)
 
 
 def MaxPool2x2(X, *, stride=2):

@@ -1,11 +1,12 @@
-"""EXPERIMENTAL: the frozen VGG16 conv body in channels-last bf16 (na-fwebsod_b200/csrc/conv_body.cu + conv_body.py;
-SURVEY.md 8f row N4).  Written after the round's GPU budget was spent, so these tests only run with NAWSOD_EXPERIMENTAL=1:
-a kernel that has never executed must not be able to turn the regular suite red.
+"""The frozen VGG16 conv body in channels-last bf16 (na-fwebsod_b200/csrc/conv_body.cu + conv_body.py):
+3x3 convolutions as implicit GEMMs on the tcgen05 tensor cores (shifted 4-D TMA boxes of the map, no patch matrix), the
+patch-matrix form for conv1_1, the 2x2 max-pools.
 
 Parity bars: the patch matrix and the max-pool move / compare bf16 values -> bit-exact against NumPy on the same bf16
-inputs; a convolution and the whole body against the oracle evaluated on the same bf16-rounded inputs and weights
-(oracle.conv_body_oracle, torch CPU float32): relative L2 <= 1e-2 per convolution (the bf16 bar of north_star); the whole
-thirteen-layer body <= 1.5e-2 against the oracle on the same bf16 inputs and <= 2e-2 against the float32 run of the
+inputs; the implicit GEMM is bit-identical to the patch matrix times the same weights on the FC GEMM (same products, same
+accumulation order); a convolution and the whole body against the oracle evaluated on the same bf16-rounded inputs and
+weights (oracle.conv_body_oracle, torch CPU float32): relative L2 <= 1e-2 per convolution (the bf16 bar of north_star); the
+whole thirteen-layer body <= 1.5e-2 against the oracle on the same bf16 inputs and <= 2e-2 against the float32 run of the
 reference's builder (tests/golden/vgg16_body.npz) -- the measured noise floor of bf16 storage through thirteen layers is
 5e-3 / 7e-3 (see the comment in test_body_vs_reference_builder_run)."""
 import os
@@ -16,8 +17,7 @@ import torch
 
 from oracle import conv_body_oracle as CB
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("NAWSOD_EXPERIMENTAL") != "1", reason="experimental kernels: set NAWSOD_EXPERIMENTAL=1")]
+pytestmark = pytest.mark.gpu
 
 
 def _ops():
@@ -65,6 +65,24 @@ def test_errors():
         ops.MaxPool2x2(torch.zeros((1, 4, 4, 8), dtype=torch.bfloat16, device="cuda"), stride=3)
     with pytest.raises(RuntimeError):
         ops.Im2Col3x3(torch.zeros((1, 4, 4, 8), dtype=torch.float32, device="cuda"))
+
+
+@pytest.mark.parametrize("shape,cout,dil", [((1, 19, 23, 64), 128, 1), ((2, 8, 16, 64), 64, 1), ((1, 37, 50, 512), 512, 2),
+                                            ((1, 60, 80, 256), 512, 1), ((2, 9, 17, 128), 256, 2), ((1, 3, 5, 64), 32, 1)])
+def test_implicit_gemm_equals_patch_matrix_gemm(shape, cout, dil):
+    """Whole and ragged 8 x 16 pixel tiles, every tile width (BN = 64 / 128 / 256), both dilations, two images."""
+    ops = _ops()
+    N, H, W, cin = shape
+    rng = np.random.default_rng(H * W + cout)
+    x = _bf16(np.maximum(rng.standard_normal(shape), 0)).cuda()
+    wm = _bf16(rng.standard_normal((cout, 9 * cin)) * np.sqrt(2.0 / (9 * cin))).cuda()
+    b = torch.from_numpy((rng.standard_normal(cout) * 0.05).astype(np.float32)).cuda()
+    for relu in (True, False):
+        y0 = ops.Conv3x3Relu(x, wm, b, dilation=dil, relu=relu, implicit=False)
+        y1 = ops.Conv3x3Relu(x, wm, b, dilation=dil, relu=relu, implicit=True)
+        assert y1.shape == y0.shape and torch.equal(y0.view(torch.int16), y1.view(torch.int16))
+    with pytest.raises(RuntimeError, match="multiple of 64"):
+        ops.Conv3x3Relu(x[..., :8].contiguous(), wm[:, :72].contiguous(), b, implicit=True)
 
 
 @pytest.mark.parametrize("cin,cout,dil", [(64, 128, 1), (512, 512, 2), (8, 64, 1)])

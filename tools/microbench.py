@@ -195,9 +195,22 @@ def bench_convbody():
                 flops += 2 * 9 * a["dim_in"] * a["dim_out"] * h * w
             elif kind == "MaxPool":
                 h, w = (h - 2) // a["stride"] + 1, (w - 2) // a["stride"] + 1
-        med, best = timeit(lambda: body.run(), iters=10)
-        print("convbody %dx%d -> conv5 %dx%d: med %.3f ms best %.3f ms  %.1f GFLOP  %.0f TFLOP/s (%.1f%% of %.0f)" % (
-            H, W, h, w, med, best, flops / 1e9, flops / med / 1e9, 100 * flops / med / 1e9 / PEAKS["bf16_tflops"], PEAKS["bf16_tflops"]), flush=True)
+        for implicit in (True, False):
+            body.implicit = implicit
+            med, best = timeit(lambda: body.run(), iters=10)
+            print("convbody %dx%d -> conv5 %dx%d [%s]: med %.3f ms best %.3f ms  %.1f GFLOP  %.0f TFLOP/s (%.1f%% of %.0f)" % (
+                H, W, h, w, "implicit GEMM (4-D TMA boxes)" if implicit else "patch matrix + FC GEMM", med, best, flops / 1e9, flops / med / 1e9,
+                100 * flops / med / 1e9 / PEAKS["bf16_tflops"], PEAKS["bf16_tflops"]), flush=True)
+        body.implicit = None
+        x = body.blobs["data"]
+        for name, cin, cout, hh, ww, dil in (("conv1_2", 64, 64, H, W, 1), ("conv2_2", 128, 128, H // 2, W // 2, 1), ("conv3_3", 256, 256, H // 4, W // 4, 1),
+                                             ("conv4_3", 512, 512, H // 8, W // 8, 1), ("conv5_3", 512, 512, H // 8 - 1, W // 8 - 1, 2)):
+            xin = torch.relu(torch.randn(1, hh, ww, cin, device="cuda")).to(torch.bfloat16)
+            fl = 2.0 * 9 * cin * cout * hh * ww
+            m1, _ = timeit(lambda: ops.Conv3x3Relu(xin, body.w[name], body.b[name], dilation=dil, implicit=True), iters=10)
+            m0, _ = timeit(lambda: ops.Conv3x3Relu(xin, body.w[name], body.b[name], dilation=dil, implicit=False), iters=10)
+            print("  %s %dx%dx%d->%d: implicit %.1f us (%.0f TFLOP/s, %.1f%%)  patch matrix %.1f us" % (
+                name, hh, ww, cin, cout, m1 * 1e3, fl / m1 / 1e9, 100 * fl / m1 / 1e9 / PEAKS["bf16_tflops"], m0 * 1e3), flush=True)
         x = torch.randn(1, H // 2, W // 2, 128, device="cuda").to(torch.bfloat16)
         med, _ = timeit(lambda: ops.Im2Col3x3(x))
         nbytes = x.numel() * 2 * 10
