@@ -72,11 +72,15 @@ def box_results_with_nms_and_limit(scores, boxes, *, score_thresh=0.05, nms_thre
     the flickr configs).  scores [R, num_classes] and boxes [R,4] are CUDA tensors; the threshold, the
     per-class greedy NMS and the detections-per-image limit run on the GPU, and the reference's return
     values ``(scores, boxes, cls_boxes)`` are assembled from the keep mask (cls_boxes[j]: [n_j, 5]
-    rows of x1, y1, x2, y2, score in original proposal order; cls_boxes[0] is empty)."""
+    rows of x1, y1, x2, y2, score; cls_boxes[0] is empty).  Row order within a class: ASCENDING proposal row, which is
+    the reference's -- its Cython NMS returns ``np.where(suppressed == 0)[0]`` (utils/cython_nms.pyx:93), i.e. the kept
+    indices sorted ascending, not the descending-score visiting order, ``dets_j[keep]`` keeps that order
+    (core/test_wsl.py:838-846) and the detections-per-image filter preserves it (:852-860); pinned bit for bit by
+    tests/test_test_wsl_golden.py against the reference's own driver."""
     keep, num_keep, _ = ops.nms_and_limit(scores, boxes, score_thresh=score_thresh, nms_thresh=nms_thresh,
                                           detections_per_im=detections_per_im)
     K1 = scores.shape[1]
-    cls_idx, row_idx = torch.nonzero(keep, as_tuple=True)          # ascending (class, row): the reference's vstack order
+    cls_idx, row_idx = torch.nonzero(keep, as_tuple=True)          # ascending (class, row): np.where(suppressed == 0) per class, vstack over classes
     dets = torch.cat([boxes[row_idx], scores[row_idx, cls_idx].unsqueeze(1)], dim=1)
     counts = num_keep.cpu().tolist()
     cls_boxes, start = [], 0
