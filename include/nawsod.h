@@ -106,6 +106,9 @@ int nawsod_roi_feature_boost(const float* X, const float* S, int R, int64_t feat
  * nawsod_fc_bwd_w FCGradient's dW, db:
  *     dW[N,K] (float) = dY[M,N]^T . A[M,K];  db[N] (float) = sum_m dY[m,:] (db may be NULL).
  *     NAWSOD_FC_ACCUMULATE: add into dW / db instead of overwriting.
+ * NAWSOD_FC_ACCUMULATE on fwd / bwd_x (float outputs only): the prior contents of Y / dA are added to the
+ *     product BEFORE bias, activation, dropout and their gradients -- how the split-operand fp32 path
+ *     (nawsod_split_tf32 below) sums its three tensor-core passes x.y = lo.hi' + hi.lo' + hi.hi'.
  * NAWSOD_FC_ROUND_TF32 (fwd / bwd_x, float outputs): round the stored values to the nearest
  *     TF32 so that the next GEMM's tensor-core truncation is exact (keeps the fp32 path unbiased).
  * ------------------------------------------------------------------------------------- */
@@ -168,6 +171,12 @@ int nawsod_convert_f32_to_bf16(const float* src, int64_t ld_src, int64_t rows, i
                                void* dst, int64_t ld_dst, void* stream);
 int nawsod_round_to_tf32(const float* src, int64_t ld_src, int64_t rows, int64_t cols,
                          float* dst, int64_t ld_dst, void* stream);
+/* fp32 path at the reference's precision (Caffe2 FC = cuBLAS sgemm, modeling/wsl_heads.py:674-679) on the TF32
+ * tensor cores: src = hi + lo with hi = nearest TF32 of src (hi may alias src) and lo = nearest TF32 of the exact
+ * remainder (lo must not alias).  Three passes hi.hi' + lo.hi' + hi.lo' (NAWSOD_FC_ACCUMULATE) reproduce the fp32
+ * product to ~2^-21 relative; one pass (the TF32 path) stops at ~2^-11 per operand. */
+int nawsod_split_tf32(const float* src, int64_t ld_src, int64_t rows, int64_t cols, float* hi,
+                      int64_t ld_hi, float* lo, int64_t ld_lo, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * a5..a9: the two-stream MIL head, noise-aware class weights, weighted multi-label CE and

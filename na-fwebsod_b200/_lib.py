@@ -45,6 +45,7 @@ PROTOTYPES = {
     "nawsod_cross_entropy_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "nawsod_cross_entropy_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "nawsod_round_to_tf32": (_i, [_vp, _i64, _i64, _i64, _vp, _i64, _vp]),
+    "nawsod_split_tf32": (_i, [_vp, _i64, _i64, _i64, _vp, _i64, _vp, _i64, _vp]),
     "nawsod_sgd_update": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _f, _f, _f, _i, _i, _i64, _vp, _i, _vp]),
     "nawsod_sgd_update_reduce": (_i, [_vp, _i, _vp, _vp, _vp, _i64, _f, _f, _f, _i, _i64, _vp, _i, _vp, _vp]),
     "nawsod_p2p_enable_peer_access": (_i, [_i]),
@@ -78,7 +79,7 @@ KERNELS_PER_CALL = {
     "nawsod_transpose_batched": 1, "nawsod_roi_pool_f_fwd": 1, "nawsod_roi_pool_f_bwd": 1, "nawsod_roi_feature_boost": 1,
     "nawsod_fc_fwd": 1, "nawsod_fc_fwd_gated": 1, "nawsod_fc_bwd_x": 1, "nawsod_fc_bwd_w": 1, "nawsod_fc_fwd_stacks": 1, "nawsod_fc_bwd_x_stacks": 1,
     "nawsod_fc_bwd_w_stacks": 1, "nawsod_convert_f32_to_bf16": 1,
-    "nawsod_round_to_tf32": 1, "nawsod_mil_head_fwd_bwd": 1, "nawsod_roi_iou": 1, "nawsod_cross_entropy_fwd": 1,
+    "nawsod_round_to_tf32": 1, "nawsod_split_tf32": 1, "nawsod_mil_head_fwd_bwd": 1, "nawsod_roi_iou": 1, "nawsod_cross_entropy_fwd": 1,
     "nawsod_cross_entropy_bwd": 1, "nawsod_sgd_update": 1, "nawsod_sgd_update_reduce": 1, "nawsod_p2p_signal": 1, "nawsod_p2p_scatter": 1,
     "nawsod_p2p_wait": 1,
     "nawsod_project_rois": 1, "nawsod_dedup_rois": 1, "nawsod_gather_rows": 1, "nawsod_scatter_scores": 1,

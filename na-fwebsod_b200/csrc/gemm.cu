@@ -210,6 +210,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
           const bool full = ncols == 32;
+          if ((ep.flags & NAWSOD_FC_ACCUMULATE) && ep.out_dtype == NAWSOD_F32) {
+            // add what the output holds BEFORE bias / activation: the earlier passes of a split-operand (3 x TF32) product left
+            // their raw partial sums there, the weight-gradient GEMMs their running gradient
+            const float* o = reinterpret_cast<const float*>(out_b) + (size_t)m * ep.ldo + n;
+            if (vec_ok && full) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                const float4 o4 = *reinterpret_cast<const float4*>(o + i);
+                v[i] += o4.x; v[i + 1] += o4.y; v[i + 2] += o4.z; v[i + 3] += o4.w;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) if (i < ncols) v[i] += o[i];
+            }
+          }
           if (bias_b) {
             if (full && bias_vec) {
 #pragma unroll
@@ -278,10 +293,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
           if (ep.out_dtype == NAWSOD_F32) {
             float* o = reinterpret_cast<float*>(out_b) + (size_t)m * ep.ldo + n;
-            if (ep.flags & NAWSOD_FC_ACCUMULATE) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) if (i < ncols) v[i] += o[i];
-            }
             if (ep.flags & NAWSOD_FC_ROUND_TF32) {
 #pragma unroll
               for (int i = 0; i < 32; ++i) v[i] = round_tf32(v[i]);
@@ -358,6 +369,23 @@ __global__ void __launch_bounds__(256) round_tf32_kernel(const float* __restrict
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / cols, c = i - r * cols;
     dst[r * ld_dst + c] = round_tf32(src[r * ld_src + c]);
+  }
+}
+
+// x = hi + lo with hi = nearest TF32 of x and lo = nearest TF32 of the (exact) remainder: the operand pair of a split-operand
+// (3 x TF32) product, x.y ~ hi.hi' + lo.hi' + hi.lo' to ~2^-21 relative
+__global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict__ src, long long ld_src, long long rows,
+                                                        long long cols, float* __restrict__ hi, long long ld_hi,
+                                                        float* __restrict__ lo, long long ld_lo) {
+  const long long total = rows * cols;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols, c = i - r * cols;
+    const float x = src[r * ld_src + c];
+    // the 13 bits below the TF32 mantissa are masked explicitly: the remainder must be taken against exactly the value the
+    // tensor core will read (it ignores those bits)
+    const float h = __uint_as_float(__float_as_uint(round_tf32(x)) & 0xFFFFE000u);
+    hi[r * ld_hi + c] = h;
+    lo[r * ld_lo + c] = __uint_as_float(__float_as_uint(round_tf32(__fsub_rn(x, h))) & 0xFFFFE000u);
   }
 }
 
@@ -469,7 +497,7 @@ extern "C" int nawsod_fc_fwd_stacks(const void* A, int64_t lda, int64_t sA, cons
   NAWSOD_REQUIRE(S >= 1, NAWSOD_ERR_SHAPE, "fc_fwd: need at least one stack");
   NAWSOD_REQUIRE(A && W && Y, NAWSOD_ERR_ARG, "fc_fwd: null pointer");
   NAWSOD_REQUIRE(y_dtype == NAWSOD_F32 || y_dtype == NAWSOD_BF16, NAWSOD_ERR_ARG, "fc_fwd: bad y_dtype");
-  NAWSOD_REQUIRE(!(flags & NAWSOD_FC_ACCUMULATE), NAWSOD_ERR_ARG, "fc_fwd: ACCUMULATE is a bwd_w flag");
+  NAWSOD_REQUIRE(!(flags & NAWSOD_FC_ACCUMULATE) || y_dtype == NAWSOD_F32, NAWSOD_ERR_ARG, "fc_fwd: ACCUMULATE needs a float output");
   NAWSOD_REQUIRE(!(flags & NAWSOD_FC_ROUND_TF32) || y_dtype == NAWSOD_F32, NAWSOD_ERR_ARG, "fc_fwd: ROUND_TF32 needs a float output");
   NAWSOD_REQUIRE(ldy >= N && (!mask || ldmask >= N), NAWSOD_ERR_SHAPE, "fc_fwd: ldy / ldmask smaller than N");
   NAWSOD_REQUIRE(!(flags & NAWSOD_FC_DROPOUT) || mask || dropout_seed != 0, NAWSOD_ERR_ARG,
@@ -524,7 +552,7 @@ extern "C" int nawsod_fc_bwd_x_stacks(const void* dY, int64_t lddy, int64_t sdY,
   NAWSOD_REQUIRE(dY && W && dA, NAWSOD_ERR_ARG, "fc_bwd_x: null pointer");
   NAWSOD_REQUIRE(da_dtype == NAWSOD_F32 || da_dtype == NAWSOD_BF16, NAWSOD_ERR_ARG, "fc_bwd_x: bad da_dtype");
   NAWSOD_REQUIRE(!(flags & NAWSOD_FC_RELU) || act_below, NAWSOD_ERR_ARG, "fc_bwd_x: RELU needs act_below");
-  NAWSOD_REQUIRE(!(flags & NAWSOD_FC_ACCUMULATE), NAWSOD_ERR_ARG, "fc_bwd_x: ACCUMULATE is a bwd_w flag");
+  NAWSOD_REQUIRE(!(flags & NAWSOD_FC_ACCUMULATE) || da_dtype == NAWSOD_F32, NAWSOD_ERR_ARG, "fc_bwd_x: ACCUMULATE needs a float output");
   NAWSOD_REQUIRE(ldda >= K, NAWSOD_ERR_SHAPE, "fc_bwd_x: ldda smaller than K");
   EpiParams ep{};
   // GEMM view: out [M, K] = dY [M, N] . W [N, K]  -> reduction over N, "N" of the GEMM is K
@@ -597,6 +625,18 @@ extern "C" int nawsod_round_to_tf32(const float* src, int64_t ld_src, int64_t ro
   const long long total = rows * cols;
   const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)sm_count() * 8);
   round_tf32_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, ld_src, rows, cols, dst, ld_dst);
+  NAWSOD_LAUNCH_OK();
+  return NAWSOD_OK;
+}
+
+extern "C" int nawsod_split_tf32(const float* src, int64_t ld_src, int64_t rows, int64_t cols, float* hi, int64_t ld_hi, float* lo,
+                                 int64_t ld_lo, void* stream) {
+  NAWSOD_REQUIRE(rows >= 0 && cols >= 0 && ld_src >= cols && ld_hi >= cols && ld_lo >= cols, NAWSOD_ERR_SHAPE, "split_tf32: bad shape");
+  if (rows == 0 || cols == 0) return NAWSOD_OK;
+  NAWSOD_REQUIRE(src && hi && lo && lo != src && lo != hi, NAWSOD_ERR_ARG, "split_tf32: null pointer, or lo aliases src / hi");
+  const long long total = rows * cols;
+  const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)sm_count() * 8);
+  split_tf32_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, ld_src, rows, cols, hi, ld_hi, lo, ld_lo);
   NAWSOD_LAUNCH_OK();
   return NAWSOD_OK;
 }

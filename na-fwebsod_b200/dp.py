@@ -550,6 +550,10 @@ class DataParallelHead:
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        if getattr(model, "x3", False) and self.world > 1 and sync != "allreduce":
+            # the sharded / peer schedules replicate only the operand (high-part) shadow of a slice to the other ranks; the
+            # three-pass fp32 path re-splits the fp32 masters every step, so every rank must hold them: the reference's schedule
+            raise RuntimeError("precision='fp32' across ranks needs sync='allreduce' (masters replicated on every rank)")
         self.sync = sync
         self.fc6_panels = fc6_panels
         off, n, shp = model._slices["W6"]

@@ -59,9 +59,19 @@ class WeblyHeadModel:
 
     def __init__(self, num_classes=21, dim_in=512, roi_size=7, hidden_dim=4096, spatial_scale=1.0 / 16,
                  noise=True, entropy=True, mean_loss=True, dtype=torch.bfloat16, device="cuda", train=True,
-                 freeze_conv_body=True):
+                 freeze_conv_body=True, precision=None):
+        """``dtype`` is the storage type of the GEMM operands.  ``precision`` (float32 storage only): ``"tf32"`` (default) = one
+        tensor-core pass per product on operands rounded to the nearest TF32 (~1e-3 end to end); ``"fp32"`` = the reference's
+        precision (Caffe2 FC = sgemm, detectron/modeling/wsl_heads.py:674-679): every operand is kept as a TF32 (high, low)
+        pair and every product is summed from three passes (ops.FC ``X_lo`` / ``W_lo``), ~1e-5 end to end at a third of the
+        TF32 path's GEMM throughput -- the parity path, single-GPU schedules."""
         if dtype not in (torch.bfloat16, torch.float32):
             raise RuntimeError("dtype must be bfloat16 or float32 (TF32 tensor path)")
+        if precision is None:
+            precision = "bf16" if dtype == torch.bfloat16 else "tf32"
+        if precision not in ("bf16", "tf32", "fp32") or (precision == "bf16") != (dtype == torch.bfloat16):
+            raise RuntimeError("precision must be 'tf32' or 'fp32' with float32 storage, 'bf16' with bfloat16")
+        self.precision = precision
         self.num_classes = num_classes
         self.C = num_classes - 1
         self.dim_in, self.roi_size, self.H = dim_in, roi_size, hidden_dim
@@ -72,6 +82,7 @@ class WeblyHeadModel:
         self.dtype, self.device, self.train = dtype, torch.device(device), train
         self.freeze_conv_body = freeze_conv_body
         self.tf32 = dtype == torch.float32
+        self.x3 = precision == "fp32"       # split operands, three passes per product
         self.blobs = {}
         self._buf = {}
         self.profile = None        # dict name -> [(start_event, end_event)] when bench.py instruments a run
@@ -107,6 +118,7 @@ class WeblyHeadModel:
         self.flat_param, self.flat_grad, self.flat_mom = z(torch.float32), z(torch.float32), z(torch.float32)
         # GEMM-operand copy of the parameters: bf16, or float rounded to the nearest TF32
         self.flat_lp = z(self.dtype)
+        self.flat_lo = z(torch.float32) if self.x3 else None      # fp32 path: low parts of the parameters (flat_lp = high parts)
         self.lr = torch.zeros(1, dtype=torch.float32, device=self.device)   # the reference's `lr` blob
         view = lambda flat, k: flat[self._slices[k][0]: self._slices[k][0] + self._slices[k][1]].view(self._slices[k][2])
         def views(flat):
@@ -119,6 +131,7 @@ class WeblyHeadModel:
         self.p = views(self.flat_param)       # fp32 masters
         self.g = views(self.flat_grad)
         self.w = views(self.flat_lp)          # GEMM operands (bf16 shadow or the master)
+        self.wl = views(self.flat_lo) if self.x3 else {}
 
     def _join_side_streams(self):
         """Before the host touches `lr`, the momenta or the parameters on the compute stream (or reads them back):
@@ -232,7 +245,9 @@ class WeblyHeadModel:
         return blobs
 
     def sync_shadow(self):
-        if self.dtype == torch.bfloat16:
+        if self.x3:
+            ops.split_tf32(self.flat_param.view(1, -1), hi=self.flat_lp.view(1, -1), lo=self.flat_lo.view(1, -1))
+        elif self.dtype == torch.bfloat16:
             ops.to_bf16(self.flat_param.view(1, -1), out=self.flat_lp.view(1, -1))
         else:
             ops.round_to_tf32(self.flat_param.view(1, -1), out=self.flat_lp.view(1, -1))
@@ -277,6 +292,14 @@ class WeblyHeadModel:
             self._buf[name] = t
         return t
 
+    def _lo(self, name, buf):
+        """fp32 path: split ``buf`` [rows, cols] in place into its TF32 high part and a low part kept in scratch; None otherwise."""
+        if not self.x3:
+            return None
+        lo = self._scratch(name + "_lo", tuple(buf.shape), torch.float32)
+        ops.split_tf32(buf, hi=buf, lo=lo)
+        return lo
+
     # ------------------------------------------------------------------ inputs
     def FeedBlobs(self, data_conv5, rois, obn_scores, labels_oh=None, roi_offsets=None, x_layout="NHWC"):
         """Feed the head's input blobs (the contract of detectron/roi_data/wsl.py:20-58 downstream of
@@ -310,11 +333,22 @@ class WeblyHeadModel:
             is_test=not need_argmax, boost=bl["obn_scores"], x_layout="NHWC", y_layout="NHWC", out_dtype=self.dtype))
         R = roi_feat.shape[0]
         feat = roi_feat.view(R, self.D)
-        if self.tf32:
+        feat_lo = None
+        if self.x3:
+            feat_lo = self._lo("roi_feat", feat)
+        elif self.tf32:
             ops.round_to_tf32(feat, out=feat)     # GEMM operand: nearest-TF32 (the stand-alone RoIPoolF op stays exact)
-        bl["roi_feat"], bl["_argmax_roi_feat"] = feat, argmax
+        bl["roi_feat"], bl["_argmax_roi_feat"], bl["_roi_feat_lo"] = feat, argmax, feat_lo
         if on_before_params is not None:
             on_before_params()            # first parameter read of the step follows (fc6)
+        if self.x3:
+            # the update kernels refresh the high parts only: join every update and re-split the masters
+            if on_before_fc7 is not None:
+                on_before_fc7()
+                on_before_fc7 = None
+            if self.train:
+                self.sync_shadow()
+        rt = self.tf32 and not self.x3        # single-pass TF32: epilogues store operands rounded to the nearest TF32
         nS = len(stacks)
         drop6 = self._scratch("drop6", (R, nS * H), self.dtype)
         drop7 = self._scratch("drop7", (R, nS * H), self.dtype)
@@ -332,24 +366,30 @@ class WeblyHeadModel:
             m6 = torch.cat([dropout_masks[names[s][0]] for s in stacks], dim=1).contiguous()
             m7 = [dropout_masks[names[s][1]] for s in stacks]
         s0, s1 = stacks[0], stacks[-1] + 1
+        x3 = self.x3
         self._timed("fc6_fwd", lambda: ops.FC(
             feat, self.w["W6"][s0 * H:s1 * H], self.p["b6"][s0 * H:s1 * H], relu=True, dropout=use_drop,
             dropout_mask=m6, dropout_seed=(dropout_seed * 4 + 1) if (use_drop and m6 is None) else 0, out=drop6,
-            round_tf32=self.tf32, gate=self.fc6_gate if nS == self.S else None))
+            round_tf32=rt, gate=self.fc6_gate if (nS == self.S and not x3) else None,
+            X_lo=feat_lo, W_lo=self.wl["W6"][s0 * H:s1 * H] if x3 else None))
+        drop6_lo = self._lo("drop6", drop6)
         if on_before_fc7 is not None:
             on_before_fc7()               # first read of the fc7 / fc8 parameters follows
         if nS == self.S:      # all stacks: one launch ([S, R, H] views of the column blocks; nothing is copied)
             ops.FC(self._stacked(drop6, nS), self.w["W7"], self.p["b7"], relu=True, dropout=use_drop,
                    dropout_mask=None if m7 is None else torch.stack(m7),
                    dropout_seed=(dropout_seed * 4 + 2) if (use_drop and m7 is None) else 0,
-                   out=self._stacked(drop7, nS), round_tf32=self.tf32)
+                   out=self._stacked(drop7, nS), round_tf32=rt,
+                   X_lo=self._stacked(drop6_lo, nS) if x3 else None, W_lo=self.wl["W7"] if x3 else None)
         else:
             for i, s in enumerate(stacks):
                 ops.FC(drop6[:, i * H:(i + 1) * H], self.w["W7_%d" % s], self.p["b7_%d" % s], relu=True, dropout=use_drop,
                        dropout_mask=None if m7 is None else m7[i],
                        dropout_seed=(dropout_seed * 4 + 2 + s) if (use_drop and m7 is None) else 0,
-                       out=drop7[:, i * H:(i + 1) * H], round_tf32=self.tf32)
-        bl["drop6_cat"], bl["drop7_cat"] = drop6, drop7
+                       out=drop7[:, i * H:(i + 1) * H], round_tf32=rt,
+                       X_lo=drop6_lo[:, i * H:(i + 1) * H] if x3 else None, W_lo=self.wl["W7_%d" % s] if x3 else None)
+        drop7_lo = self._lo("drop7", drop7)
+        bl["drop6_cat"], bl["drop7_cat"], bl["_drop6_lo"], bl["_drop7_lo"] = drop6, drop7, drop6_lo, drop7_lo
         return drop6, drop7
 
     @staticmethod
@@ -365,11 +405,14 @@ class WeblyHeadModel:
         R = drop7.shape[0]
         ld = _round_up(C2, 8)
         logits = self._scratch("logits", (len(stacks), R, ld), torch.float32)
+        lo7 = self.blobs.get("_drop7_lo") if self.x3 else None
         if len(stacks) == self.S:
-            ops.FC(self._stacked(drop7, self.S), self.w["W8"], self.p["b8"], out=logits[:, :, :C2])
+            ops.FC(self._stacked(drop7, self.S), self.w["W8"], self.p["b8"], out=logits[:, :, :C2],
+                   X_lo=self._stacked(lo7, self.S) if self.x3 else None, W_lo=self.wl["W8"] if self.x3 else None)
         else:
             for i, s in enumerate(stacks):
-                ops.FC(drop7[:, i * H:(i + 1) * H], self.w["W8_%d" % s], self.p["b8_%d" % s], out=logits[i][:, :C2])
+                ops.FC(drop7[:, i * H:(i + 1) * H], self.w["W8_%d" % s], self.p["b8_%d" % s], out=logits[i][:, :C2],
+                       X_lo=lo7[:, i * H:(i + 1) * H] if self.x3 else None, W_lo=self.wl["W8_%d" % s] if self.x3 else None)
         self.blobs["fc8_logits"] = logits
         return logits
 
@@ -414,7 +457,11 @@ class WeblyHeadModel:
             ops.to_bf16(dlog.view(self.S * R, ld), out=dl.view(self.S * R, ld))
         else:
             dl = self._scratch("dlogits_lp", (self.S, R, ld), torch.float32)
-            ops.round_to_tf32(dlog.view(self.S * R, ld), out=dl.view(self.S * R, ld))
+            if self.x3:
+                dl_lo = self._scratch("dlogits_lo", (self.S, R, ld), torch.float32)
+                ops.split_tf32(dlog.view(self.S * R, ld), hi=dl.view(self.S * R, ld), lo=dl_lo.view(self.S * R, ld))
+            else:
+                ops.round_to_tf32(dlog.view(self.S * R, ld), out=dl.view(self.S * R, ld))
         d6 = self._scratch("d_fc6", (R, self.S * H), self.dtype)
         d7 = self._scratch("d_fc7", (R, self.S * H), self.dtype)
         # activation-gradient chain first (fc8 dX -> fc7 dX): it is the critical path to the fc6 weight
@@ -422,13 +469,22 @@ class WeblyHeadModel:
         S = self.S
         dl3, a7, a6 = dl[:, :, :C2], self._stacked(drop7, S), self._stacked(drop6, S)
         d73, d63 = self._stacked(d7, S), self._stacked(d6, S)
-        ops.FCGradientX(dl3, self.w["W8"], act_below=a7, dropout=self._dropped, out=d73, round_tf32=self.tf32)
-        ops.FCGradientX(d73, self.w["W7"], act_below=a6, dropout=self._dropped, out=d63, round_tf32=self.tf32)
+        x3, rt = self.x3, self.tf32 and not self.x3
+        dl3_lo = dl_lo[:, :, :C2] if x3 else None
+        ops.FCGradientX(dl3, self.w["W8"], act_below=a7, dropout=self._dropped, out=d73, round_tf32=rt,
+                        dY_lo=dl3_lo, W_lo=self.wl["W8"] if x3 else None)
+        d7_lo = self._lo("d_fc7", d7)
+        d73_lo = self._stacked(d7_lo, S) if x3 else None
+        ops.FCGradientX(d73, self.w["W7"], act_below=a6, dropout=self._dropped, out=d63, round_tf32=rt,
+                        dY_lo=d73_lo, W_lo=self.wl["W7"] if x3 else None)
+        d6_lo = self._lo("d_fc6", d6)
+        a7_lo = self._stacked(bl["_drop7_lo"], S) if x3 else None
+        a6_lo = self._stacked(bl["_drop6_lo"], S) if x3 else None
         if need_dX:
             # before the fc6 panels: a data-parallel exchange may refresh the W6 operands right behind them
             if bl["_argmax_roi_feat"] is None:
                 raise RuntimeError("need_dX requires freeze_conv_body=False (argmax is not kept otherwise)")
-            d_feat = ops.FCGradientX(d6, self.w["W6"], out_dtype=self.dtype)
+            d_feat = ops.FCGradientX(d6, self.w["W6"], out_dtype=self.dtype, dY_lo=d6_lo, W_lo=self.wl["W6"] if x3 else None)
             N, Hh, Ww, Cc = bl["conv5"].shape
             bl["d_conv5"] = ops.RoIPoolFGradient(bl["conv5"], bl["rois"], bl["_argmax_roi_feat"],
                                                  d_feat.view(R, self.roi_size, self.roi_size, Cc),
@@ -438,11 +494,12 @@ class WeblyHeadModel:
         for r0 in range(0, rows, step):
             r1 = min(rows, r0 + step)
             self._timed("fc6_bwd_w", lambda: ops.FCGradientW(d6[:, r0:r1], bl["roi_feat"], dW=self.g["W6"][r0:r1],
-                                                             db=self.g["b6"][r0:r1]))
+                                                             db=self.g["b6"][r0:r1],
+                                                             dY_lo=d6_lo[:, r0:r1] if x3 else None, X_lo=bl["_roi_feat_lo"]))
             if on_fc6_panel is not None:
                 on_fc6_panel(r0, r1)
-        ops.FCGradientW(dl3, a7, dW=self.g["W8"], db=self.g["b8"])
-        ops.FCGradientW(d73, a6, dW=self.g["W7"], db=self.g["b7"])
+        ops.FCGradientW(dl3, a7, dW=self.g["W8"], db=self.g["b8"], dY_lo=dl3_lo, X_lo=a7_lo)
+        ops.FCGradientW(d73, a6, dW=self.g["W7"], db=self.g["b7"], dY_lo=d73_lo, X_lo=a6_lo)
         if on_small_grads is not None:
             on_small_grads()
         return bl

@@ -420,7 +420,7 @@ def _same_stacks(who, *ss):
 
 
 def FC(X, W, b=None, *, relu=False, dropout_mask=None, dropout=False, dropout_seed=0, out=None, out_dtype=None,
-       round_tf32=False, gate=None):
+       round_tf32=False, gate=None, accumulate=False, X_lo=None, W_lo=None):
     """``FC([X, W, b] -> Y)`` with W [out, in] (Caffe2 layout), optionally fused with the
     ``Relu`` and ``Dropout(ratio=0.5, is_test=0)`` that follow it in the head
     (modeling/wsl_heads.py:674-679).  X may be a column slice of a wider matrix.  3-d operands
@@ -430,7 +430,23 @@ def FC(X, W, b=None, *, relu=False, dropout_mask=None, dropout=False, dropout_se
     ``gate`` (2-d operands only) = dict(flags=int32 CUDA tensor [groups * nflags], nflags, rows, seq, timeout_ms, status):
     rows ``[g*rows, (g+1)*rows)`` of W are read only once flags ``[g*nflags, (g+1)*nflags)`` have reached ``seq`` -- the
     data-parallel peer exchange's "operands of bucket g have landed" words (dp.P2PExchange), so the GEMM runs on the weights
-    that are there and meets the rest as they arrive."""
+    that are there and meets the rest as they arrive.
+
+    ``accumulate`` (float32 ``out``): the prior contents of ``out`` are added to X.W^T before bias / Relu / Dropout.
+    ``X_lo`` / ``W_lo`` (float32 operands, both or neither; see :func:`split_tf32`): the fp32 path -- X, W are the TF32 high
+    parts, and the product is summed from three tensor-core passes ``X_lo.W^T + X.W_lo^T + X.W^T`` (the epilogue runs in the last)."""
+    if (X_lo is None) != (W_lo is None):
+        raise RuntimeError("FC: pass both X_lo and W_lo (split-operand fp32 path) or neither")
+    if X_lo is not None:
+        if gate is not None or accumulate:
+            raise RuntimeError("FC: the split-operand path takes neither a gate nor accumulate")
+        if out is None:
+            out = torch.empty((X.shape[0], W.shape[0]) if X.dim() == 2 else (X.shape[0], X.shape[1], W.shape[1]),
+                              dtype=torch.float32, device=X.device)
+        FC(X_lo, W, out=out)
+        FC(X, W_lo, out=out, accumulate=True)
+        return FC(X, W, b, relu=relu, dropout_mask=dropout_mask, dropout=dropout, dropout_seed=dropout_seed, out=out,
+                  round_tf32=round_tf32, accumulate=True)
     S, M, K, lda, sA = _mat3(X, "X")
     S2, N, K2, ldw, sW = _mat3(W, "W")
     if K != K2 or X.dtype != W.dtype:
@@ -451,7 +467,9 @@ def FC(X, W, b=None, *, relu=False, dropout_mask=None, dropout=False, dropout_se
         raise RuntimeError("FC: dropout=True needs a dropout_mask or a non-zero dropout_seed")
     flags = (_lib.FC_RELU if relu else 0) | \
             (_lib.FC_DROPOUT if (dropout or dropout_mask is not None or dropout_seed) else 0) | \
-            (_lib.FC_ROUND_TF32 if round_tf32 else 0)
+            (_lib.FC_ROUND_TF32 if round_tf32 else 0) | (_lib.FC_ACCUMULATE if accumulate else 0)
+    if accumulate and (out is None or Y.dtype != torch.float32):
+        raise RuntimeError("FC: accumulate adds into a given float32 out")
     ldm = sm = 0
     if dropout_mask is not None:
         if dropout_mask.dtype != torch.uint8:
@@ -473,9 +491,23 @@ def FC(X, W, b=None, *, relu=False, dropout_mask=None, dropout=False, dropout_se
     return Y
 
 
-def FCGradientX(dY, W, *, act_below=None, mask_below=None, dropout=False, out=None, out_dtype=None, round_tf32=False):
+def FCGradientX(dY, W, *, act_below=None, mask_below=None, dropout=False, out=None, out_dtype=None, round_tf32=False,
+                accumulate=False, dY_lo=None, W_lo=None):
     """dX of ``FCGradient([X, W, dY] -> [dW, db, dX])`` fused with the ``DropoutGradient`` and
-    ``ReluGradient`` of the layer below: dX = (dY . W) * 2[dropout] * (act_below > 0).  3-d operands = stacks."""
+    ``ReluGradient`` of the layer below: dX = (dY . W) * 2[dropout] * (act_below > 0).  3-d operands = stacks.
+    ``accumulate`` / ``dY_lo`` + ``W_lo``: as in :func:`FC` (prior contents of ``out`` added before the gating; three passes)."""
+    if (dY_lo is None) != (W_lo is None):
+        raise RuntimeError("FCGradientX: pass both dY_lo and W_lo (split-operand fp32 path) or neither")
+    if dY_lo is not None:
+        if accumulate:
+            raise RuntimeError("FCGradientX: the split-operand path does not take accumulate")
+        if out is None:
+            out = torch.empty((dY.shape[0], W.shape[1]) if dY.dim() == 2 else (dY.shape[0], dY.shape[1], W.shape[2]),
+                              dtype=torch.float32, device=dY.device)
+        FCGradientX(dY_lo, W, out=out)
+        FCGradientX(dY, W_lo, out=out, accumulate=True)
+        return FCGradientX(dY, W, act_below=act_below, mask_below=mask_below, dropout=dropout, out=out, round_tf32=round_tf32,
+                           accumulate=True)
     S, M, N, lddy, sdY = _mat3(dY, "dY")
     S2, N2, K, ldw, sW = _mat3(W, "W")
     if N != N2 or dY.dtype != W.dtype:
@@ -487,7 +519,9 @@ def FCGradientX(dY, W, *, act_below=None, mask_below=None, dropout=False, out=No
     if K2 != K or M3 != M:
         raise RuntimeError("FCGradientX: out has the wrong shape")
     flags = (_lib.FC_RELU if act_below is not None else 0) | (_lib.FC_DROPOUT if (dropout or mask_below is not None) else 0) | \
-            (_lib.FC_ROUND_TF32 if round_tf32 else 0)
+            (_lib.FC_ROUND_TF32 if round_tf32 else 0) | (_lib.FC_ACCUMULATE if accumulate else 0)
+    if accumulate and (out is None or dX.dtype != torch.float32):
+        raise RuntimeError("FCGradientX: accumulate adds into a given float32 out")
     ldact, sact, act_dt, ldm, sm = 0, 0, F32, 0, 0
     if act_below is not None:
         S4, _, _, ldact, sact = _mat3(act_below, "act_below")
@@ -501,9 +535,16 @@ def FCGradientX(dY, W, *, act_below=None, mask_below=None, dropout=False, out=No
     return dX
 
 
-def FCGradientW(dY, X, *, dW=None, db=None, want_db=True, accumulate=False):
+def FCGradientW(dY, X, *, dW=None, db=None, want_db=True, accumulate=False, dY_lo=None, X_lo=None):
     """dW, db of ``FCGradient``: dW [N,K] = dY^T . X (float32), db [N] = column sums of dY.  3-d operands = stacks
-    (dW [S,N,K], db [S,N])."""
+    (dW [S,N,K], db [S,N]).  ``dY_lo`` + ``X_lo``: the split-operand fp32 path (see :func:`FC`): three accumulating passes
+    ``dY_lo^T.X + dY^T.X_lo + dY^T.X``; db sums the high and the low part of dY."""
+    if (dY_lo is None) != (X_lo is None):
+        raise RuntimeError("FCGradientW: pass both dY_lo and X_lo (split-operand fp32 path) or neither")
+    if dY_lo is not None:
+        dW, db = FCGradientW(dY_lo, X, dW=dW, db=db, want_db=want_db, accumulate=accumulate)
+        FCGradientW(dY, X_lo, dW=dW, want_db=False, accumulate=True)
+        return FCGradientW(dY, X, dW=dW, db=db, want_db=want_db, accumulate=True)
     S, M, N, lddy, sdY = _mat3(dY, "dY")
     S2, M2, K, lda, sA = _mat3(X, "X")
     if M != M2 or dY.dtype != X.dtype:
@@ -558,6 +599,22 @@ def round_to_tf32(src, out=None):
     _, _, ldd = _mat(dst, "dst")
     _lib.call("nawsod_round_to_tf32", _ptr(src), lds, rows, cols, _ptr(dst), ldd, _stream())
     return dst
+
+
+def split_tf32(src, hi=None, lo=None):
+    """float32 ``src`` -> (hi, lo): hi = nearest TF32 of src (``hi`` may be ``src``), lo = nearest TF32 of the exact remainder
+    -- the operand pair of the fp32 path's three-pass products (``FC(..., X_lo=, W_lo=)``)."""
+    rows, cols, lds = _mat(src, "src")
+    if src.dtype != torch.float32:
+        raise RuntimeError("split_tf32: source must be float32")
+    hi = torch.empty((rows, cols), dtype=torch.float32, device=src.device) if hi is None else hi
+    lo = torch.empty((rows, cols), dtype=torch.float32, device=src.device) if lo is None else lo
+    _, _, ldh = _mat(hi, "hi")
+    _, _, ldl = _mat(lo, "lo")
+    if hi.dtype != torch.float32 or lo.dtype != torch.float32 or tuple(hi.shape) != (rows, cols) or tuple(lo.shape) != (rows, cols):
+        raise RuntimeError("split_tf32: hi and lo must be float32 of the source's shape")
+    _lib.call("nawsod_split_tf32", _ptr(src), lds, rows, cols, _ptr(hi), ldh, _ptr(lo), ldl, _stream())
+    return hi, lo
 
 
 # --------------------------------------------------------------------------------------------

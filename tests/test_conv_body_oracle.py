@@ -136,7 +136,10 @@ def test_product_body_plumbing_on_stand_in_kernels(gold, monkeypatch, tag, dil):
     from nafwebsod_b200 import ops
     from nafwebsod_b200.conv_body import VGG16ConvBody, add_VGG16_conv5_body_origin
 
-    def conv(X, Wmat, b, *, dilation=1, relu=True, cols=None):
+    seen_implicit = []
+
+    def conv(X, Wmat, b, *, dilation=1, relu=True, cols=None, implicit=None):
+        seen_implicit.append((X.shape[3], implicit))
         cout, cp = Wmat.shape[0], X.shape[3]
         w = Wmat.float().reshape(cout, 3, 3, cp).permute(0, 3, 1, 2).contiguous()
         y = Fn.conv2d(X.float().permute(0, 3, 1, 2).contiguous(), w, b, padding=dilation, dilation=dilation)
@@ -159,5 +162,13 @@ def test_product_body_plumbing_on_stand_in_kernels(gold, monkeypatch, tag, dil):
     assert got.shape == want.shape
     rel = np.linalg.norm(got.astype(np.float64) - want) / np.linalg.norm(want.astype(np.float64))
     assert rel <= 1e-6, rel            # same torch functions at the same rounding points: equal up to the padded first layer's sum order
+    # the host-side choice of the convolution kernel: default = the library decides (None); never the implicit GEMM for the
+    # padded 8-plane first layer when forced on
+    assert all(imp is None for _, imp in seen_implicit)
+    del seen_implicit[:]
+    body.implicit = True
+    body.run()
+    assert [imp for _, imp in seen_implicit] == [cin % 64 == 0 for cin, _ in seen_implicit] and not seen_implicit[0][1]
+    body.implicit = None
     _, _, _ = body.run(keep=("pool4",))
     assert tuple(body.blobs["pool4"].shape[1:3]) == tuple(gold[tag + "_pool4"].shape[2:])

@@ -160,3 +160,63 @@ def test_fc_stacked_launch_equals_per_stack_launches(shape, dtype):
         rW, rb = ops.FCGradientW(dY[s], X[:, s * H:(s + 1) * H])
         assert torch.equal(dW[s], rW), ("bwd_w", s)
         assert torch.allclose(db[s], rb, rtol=1e-4, atol=1e-4), ("db", s)      # column sums use float atomics
+
+
+def test_split_tf32_is_an_exact_two_term_expansion():
+    """nawsod_split_tf32: hi = nearest TF32 (bit-equal to nawsod_round_to_tf32, in place allowed), lo = nearest TF32 of the
+    exact remainder: both carry 13 zero low bits, and hi + lo recovers src to 2^-21 relative."""
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    src = torch.randn(257, 1003, device="cuda", generator=g) * torch.exp(4 * torch.randn(257, 1003, device="cuda", generator=g))
+    src[0, :4] = torch.tensor([0.0, -0.0, 1.0, -3.5], device="cuda")
+    want_hi = ops.round_to_tf32(src)
+    buf = src.clone()
+    hi, lo = ops.split_tf32(buf, hi=buf)                       # in place
+    assert hi.data_ptr() == buf.data_ptr()
+    assert torch.equal(hi.view(torch.int32), want_hi.view(torch.int32) & ~0x1FFF)     # the TF32 value round_to_tf32 stores
+    for part in (hi, lo):
+        assert int((part.view(torch.int32) & 0x1FFF).abs().max()) == 0
+    err = (src.double() - hi.double() - lo.double()).abs()
+    assert bool((err <= src.double().abs() * 2.0 ** -21).all())
+    view = torch.zeros(16, 64, device="cuda")                   # column slices (leading dimensions) on every operand
+    hi2, lo2 = ops.split_tf32(src[:16, 8:40], hi=view[:, :32], lo=view[:, 32:])
+    assert torch.equal(view[:, :32], hi[:16, 8:40]) and torch.equal(view[:, 32:], lo[:16, 8:40])
+    with pytest.raises(RuntimeError):
+        ops.split_tf32(src, hi=src, lo=src)
+
+
+@pytest.mark.parametrize("shape", [(300, 520, 200), (777, 40, 4096), (2000, 1024, 1568)])
+def test_fc_split_operand_three_pass_reaches_fp32(shape):
+    """The fp32 path: operands as (high, low) TF32 pairs, three accumulating tensor-core passes per product (FC,
+    FCGradientX, FCGradientW incl. bias / ReLU / dropout epilogues, which run once on the summed product).  Against float64:
+    <= 2e-6 of the output scale, two orders below the single TF32 pass on the same data (printed)."""
+    ops = _ops()
+    M, N, K = shape
+    X, W, b, mask = _data(M, N, K, torch.float32, seed=3)
+    dY = torch.randn(M, N, device="cuda", generator=torch.Generator(device="cuda").manual_seed(9)) * 0.1
+    Xh, Xl = ops.split_tf32(X)
+    Wh, Wl = ops.split_tf32(W)
+    dYh, dYl = ops.split_tf32(dY)
+    X64, W64, dY64 = X.double(), W.double(), dY.double()
+    # forward with the whole epilogue
+    ref = torch.relu(X64 @ W64.T + b.double()) * 2.0 * mask.double()
+    y3 = ops.FC(Xh, Wh, b, relu=True, dropout_mask=mask, X_lo=Xl, W_lo=Wl)
+    y1 = ops.FC(Xh, Wh, b, relu=True, dropout_mask=mask)
+    e3, e1 = _rel(y3, ref), _rel(y1, ref)
+    # dX gated by an activation pattern
+    act = (torch.rand(M, K, device="cuda") < 0.5).float()
+    refx = (dY64 @ W64) * 2.0 * act.double()
+    dx3 = ops.FCGradientX(dYh, Wh, act_below=act, dropout=True, dY_lo=dYl, W_lo=Wl)
+    dx1 = ops.FCGradientX(dYh, Wh, act_below=act, dropout=True)
+    # dW, db (accumulating into a prior value)
+    prior = torch.randn(N, K, device="cuda") * 0.01
+    dW3, db3 = ops.FCGradientW(dYh, Xh, dW=prior.clone(), accumulate=True, db=torch.ones(N, device="cuda"), dY_lo=dYl, X_lo=Xl)
+    dW1, _ = ops.FCGradientW(dYh, Xh)
+    refw, refb = dY64.T @ X64 + prior.double(), dY64.sum(0) + 1.0
+    print("three-pass vs one-pass TF32 (max error / output scale): fwd %.1e / %.1e, dX %.1e / %.1e, dW %.1e / %.1e" % (
+        e3, e1, _rel(dx3, refx), _rel(dx1, refx), _rel(dW3, refw), _rel(dW1 + prior, refw)))
+    assert e3 <= 2e-6 and _rel(dx3, refx) <= 2e-6 and _rel(dW3, refw) <= 2e-6 and _rel(db3, refb) <= 2e-6
+    with pytest.raises(RuntimeError):
+        ops.FC(Xh, Wh, b, X_lo=Xl)                               # both low parts or neither
+    with pytest.raises(RuntimeError):
+        ops.FC(Xh.bfloat16(), Wh.bfloat16(), out=torch.empty(M, N, device="cuda", dtype=torch.bfloat16), accumulate=True)
