@@ -419,6 +419,15 @@ def _same_stacks(who, *ss):
     return S
 
 
+# Split-operand (fp32) products sum their dominant high x high term in reduction chunks of this many elements, added up by the
+# epilogue's round-to-nearest fp32 adds (FC_ACCUMULATE).  Measured on B200 (profiles/r2q_pytest_gpu.log): a tcgen05 kind::tf32
+# accumulation chain loses ~n_mma * 2^-25 of the running sum (the TMEM accumulator is updated with truncation, not rounding): 4e-6
+# of the output scale at K = 1568, 9e-6 at K = 4096, ~1e-4 at fc6's K = 25088 (3136 chained MMAs) -- two orders above the 2^-21 the
+# operand split itself leaves.  128 chained MMAs per chunk bound the loss at ~4e-6; the two low-order passes are 2^-11 smaller and
+# run unchunked.
+X3_CHUNK = 1024
+
+
 def FC(X, W, b=None, *, relu=False, dropout_mask=None, dropout=False, dropout_seed=0, out=None, out_dtype=None,
        round_tf32=False, gate=None, accumulate=False, X_lo=None, W_lo=None):
     """``FC([X, W, b] -> Y)`` with W [out, in] (Caffe2 layout), optionally fused with the
@@ -445,8 +454,13 @@ def FC(X, W, b=None, *, relu=False, dropout_mask=None, dropout=False, dropout_se
                               dtype=torch.float32, device=X.device)
         FC(X_lo, W, out=out)
         FC(X, W_lo, out=out, accumulate=True)
-        return FC(X, W, b, relu=relu, dropout_mask=dropout_mask, dropout=dropout, dropout_seed=dropout_seed, out=out,
-                  round_tf32=round_tf32, accumulate=True)
+        K = X.shape[-1]
+        for k0 in range(0, K, X3_CHUNK):             # high x high in reduction chunks (see X3_CHUNK)
+            k1 = min(K, k0 + X3_CHUNK)
+            if k1 < K:
+                FC(X[..., k0:k1], W[..., k0:k1], out=out, accumulate=True)
+        return FC(X[..., k0:K], W[..., k0:K], b, relu=relu, dropout_mask=dropout_mask, dropout=dropout, dropout_seed=dropout_seed,
+                  out=out, round_tf32=round_tf32, accumulate=True)
     S, M, K, lda, sA = _mat3(X, "X")
     S2, N, K2, ldw, sW = _mat3(W, "W")
     if K != K2 or X.dtype != W.dtype:
@@ -506,8 +520,13 @@ def FCGradientX(dY, W, *, act_below=None, mask_below=None, dropout=False, out=No
                               dtype=torch.float32, device=dY.device)
         FCGradientX(dY_lo, W, out=out)
         FCGradientX(dY, W_lo, out=out, accumulate=True)
-        return FCGradientX(dY, W, act_below=act_below, mask_below=mask_below, dropout=dropout, out=out, round_tf32=round_tf32,
-                           accumulate=True)
+        N = dY.shape[-1]
+        for n0 in range(0, N, X3_CHUNK):             # the reduction runs over the layer's outputs
+            n1 = min(N, n0 + X3_CHUNK)
+            if n1 < N:
+                FCGradientX(dY[..., n0:n1], W[..., n0:n1, :], out=out, accumulate=True)
+        return FCGradientX(dY[..., n0:N], W[..., n0:N, :], act_below=act_below, mask_below=mask_below, dropout=dropout, out=out,
+                           round_tf32=round_tf32, accumulate=True)
     S, M, N, lddy, sdY = _mat3(dY, "dY")
     S2, N2, K, ldw, sW = _mat3(W, "W")
     if N != N2 or dY.dtype != W.dtype:
@@ -544,7 +563,11 @@ def FCGradientW(dY, X, *, dW=None, db=None, want_db=True, accumulate=False, dY_l
     if dY_lo is not None:
         dW, db = FCGradientW(dY_lo, X, dW=dW, db=db, want_db=want_db, accumulate=accumulate)
         FCGradientW(dY, X_lo, dW=dW, want_db=False, accumulate=True)
-        return FCGradientW(dY, X, dW=dW, db=db, want_db=want_db, accumulate=True)
+        M = dY.shape[-2]
+        for m0 in range(0, M, X3_CHUNK):             # the reduction runs over the RoIs; each chunk adds its rows' column sums to db
+            m1 = min(M, m0 + X3_CHUNK)
+            FCGradientW(dY[..., m0:m1, :], X[..., m0:m1, :], dW=dW, db=db, want_db=want_db, accumulate=True)
+        return dW, db
     S, M, N, lddy, sdY = _mat3(dY, "dY")
     S2, M2, K, lda, sA = _mat3(X, "X")
     if M != M2 or dY.dtype != X.dtype:
