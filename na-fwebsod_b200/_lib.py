@@ -106,6 +106,11 @@ def load():
             fn.restype = res
             fn.argtypes = args
         _lib = lib
+        # NAWSOD_TUNING=key=value[,key=value...]: tuning knobs applied once at load time (measurement / test runs)
+        for kv in filter(None, os.environ.get("NAWSOD_TUNING", "").split(",")):
+            k, v = kv.split("=")
+            if lib.nawsod_set_tuning(k.strip().encode(), int(v)) != 0:
+                raise RuntimeError("NAWSOD_TUNING: %s" % lib.nawsod_last_error().decode())
     return _lib
 
 

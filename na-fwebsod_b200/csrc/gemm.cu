@@ -23,6 +23,9 @@
 namespace nawsod {
 namespace {
 
+// default of the gemm_pair tuning knob (0: one CTA per tile, 1: CTA pairs for BN = 256 tiles)
+constexpr long long kGemmPairDefault = 0;
+
 struct EpiParams {
   void* out; long long ldo; int out_dtype;
   const float* bias;
@@ -65,13 +68,22 @@ __device__ __forceinline__ void gate_wait(const uint32_t* flags, int n, uint32_t
   asm volatile("fence.proxy.async;" ::: "memory");     // the TMA loads that follow read what the flags guard
 }
 
-template <int BN, bool A_MN, bool B_MN, int ES>
+// PAIR: the CTA-pair form (cta_group::2, launched as (2,1,1) clusters): a pair owns a 256 x BN tile, CTA r of the pair stages rows
+// [r * 128, r * 128 + 128) of A and rows [r * BN/2, (r + 1) * BN/2) of B, the even CTA issues M = 256 MMAs for both, each CTA's TMEM
+// holds its own 128 rows of the accumulator and its epilogue warps store them.  Half the B bytes per FLOP through L2 and shared
+// memory, 32 KB instead of 48 KB per stage -> 6 stages instead of 4 of prefetch distance.
+template <int BN, bool A_MN, bool B_MN, int ES, bool PAIR = false>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const EpiParams ep_) {
-  using C = Cfg<BN, ES>;
+  using C = typename std::conditional<PAIR, CfgPair<BN, ES>, Cfg<BN, ES>>::type;
   const EpiParams& ep = ep_;
   constexpr int BK = C::BK;
   constexpr int ATOM = 128 / ES;                 // MN elements per 128-byte panel
+  constexpr int TILE_M = PAIR ? 2 * BLOCK_M : BLOCK_M;
+  constexpr int BNL = PAIR ? BN / 2 : BN;        // B rows this CTA stages
+  const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
+  const int cta = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int ncta = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + C::STAGES * C::STAGE_BYTES;
@@ -85,7 +97,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_m = (ep.M + BLOCK_M - 1) / BLOCK_M;
+  const int num_m = (ep.M + TILE_M - 1) / TILE_M;
   const int num_n = (ep.N + BN - 1) / BN;
   const int tiles_pb = num_m * num_n;
   const int num_tiles = tiles_pb * ep.nbatch;
@@ -95,15 +107,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < C::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    // the accumulator is released by the 4 epilogue warps of every CTA that holds a part of it
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), PAIR ? 8 : 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"(C::TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"(C::TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"(C::TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();                  // the peer's barriers and TMEM exist before anything targets them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_generic;
 
@@ -112,9 +131,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       int gate_open = -1;                        // row groups [0, gate_open] of W have been waited for
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      auto load = [&](uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+        if (PAIR) tma_load_3d_pair(dst, map, bar, c0, c1, c2);     // completes on the leader's barrier
+        else tma_load_3d(dst, map, bar, c0, c1, c2);
+      };
+      for (int tile = cta; tile < num_tiles; tile += ncta) {
         const int bi = tile / tiles_pb, tb = tile - bi * tiles_pb;
-        const int m0 = (tb % num_m) * BLOCK_M, n0 = (tb / num_m) * BN;
+        const int m0 = (tb % num_m) * TILE_M + static_cast<int>(crank) * BLOCK_M, n0 = (tb / num_m) * BN;
+        const int n0l = n0 + static_cast<int>(crank) * BNL;        // this CTA's share of the B tile
         if (ep.gate_flags) {                     // tiles arrive in ascending n0: groups open in order
           const int need = (min(n0 + BN, ep.N) - 1) / ep.gate_rows;
           for (; gate_open < need; ++gate_open)
@@ -123,17 +147,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t sa = smem_base + stage * C::STAGE_BYTES, sb = sa + C::A_BYTES;
-          mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
+          // pair: the leader's barrier counts both CTAs' bytes (a peer's complete_tx may precede the leader's expect_tx: the
+          // phase cannot complete before the leader's arrival)
+          if (!PAIR) mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
+          else if (crank == 0) mbar_expect_tx(full_bar(stage), 2 * C::STAGE_BYTES);
           const int k0 = kb * BK;
-          if (!A_MN) tma_load_3d(sa, &tmA, full_bar(stage), k0, m0, bi);
+          if (!A_MN) load(sa, &tmA, full_bar(stage), k0, m0, bi);
           else {
 #pragma unroll
-            for (int a = 0; a < BLOCK_M / ATOM; ++a) tma_load_3d(sa + a * BK * 128, &tmA, full_bar(stage), m0 + a * ATOM, k0, bi);
+            for (int a = 0; a < BLOCK_M / ATOM; ++a) load(sa + a * BK * 128, &tmA, full_bar(stage), m0 + a * ATOM, k0, bi);
           }
-          if (!B_MN) tma_load_3d(sb, &tmB, full_bar(stage), k0, n0, bi);
+          if (!B_MN) load(sb, &tmB, full_bar(stage), k0, n0l, bi);
           else {
 #pragma unroll
-            for (int a = 0; a < BN / ATOM; ++a) tma_load_3d(sb + a * BK * 128, &tmB, full_bar(stage), n0 + a * ATOM, k0, bi);
+            for (int a = 0; a < BNL / ATOM; ++a) load(sb + a * BK * 128, &tmB, full_bar(stage), n0l + a * ATOM, k0, bi);
           }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
@@ -141,8 +168,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(ES, A_MN, B_MN, BLOCK_M, BN);
+    if (lane == 0 && crank == 0) {               // pair: the even CTA issues for both
+      constexpr uint32_t idesc = make_idesc(ES, A_MN, B_MN, TILE_M, BN);
       // K-major: 8-row groups 1024 B apart (SBO), LBO unused; MN-major: 128-byte panels BK*128 B apart (LBO),
       // 8-row k-groups 1024 B apart (SBO)
       constexpr uint32_t a_lbo = A_MN ? BK * 128 : 16, b_lbo = B_MN ? BK * 128 : 16;
@@ -153,7 +180,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       constexpr uint32_t b_kstep = B_MN ? (C::UMMA_K * 128) >> 4 : 32 >> 4;
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = cta; tile < num_tiles; tile += ncta) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
@@ -163,12 +190,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const uint32_t sa = smem_base + stage * C::STAGE_BYTES, sb = sa + C::A_BYTES;
           const uint64_t adesc = make_smem_desc(sa, a_lbo, a_sbo, a_lay), bdesc = make_smem_desc(sb, b_lbo, b_sbo, b_lay);
 #pragma unroll
-          for (int k = 0; k < BK / C::UMMA_K; ++k)
-            tc_mma<ES>(tmem_d, adesc + (uint64_t)(k * a_kstep), bdesc + (uint64_t)(k * b_kstep), idesc, (kb | k) != 0);
-          tc_commit(empty_bar(stage));
+          for (int k = 0; k < BK / C::UMMA_K; ++k) {
+            if (PAIR) tc_mma_pair<ES>(tmem_d, adesc + (uint64_t)(k * a_kstep), bdesc + (uint64_t)(k * b_kstep), idesc, (kb | k) != 0);
+            else tc_mma<ES>(tmem_d, adesc + (uint64_t)(k * a_kstep), bdesc + (uint64_t)(k * b_kstep), idesc, (kb | k) != 0);
+          }
+          if (PAIR) tc_commit_pair(empty_bar(stage)); else tc_commit(empty_bar(stage));     // pair: frees the slot in both CTAs
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
-        tc_commit(tfull_bar(acc));
+        if (PAIR) tc_commit_pair(tfull_bar(acc)); else tc_commit(tfull_bar(acc));
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -181,9 +210,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const bool bias_vec = ep.bias && (reinterpret_cast<uintptr_t>(ep.bias) & 15u) == 0;
     const bool act_vec = ep.act && (reinterpret_cast<uintptr_t>(ep.act) & 15u) == 0 && (ep.ldact * 2) % 16 == 0;
     const bool mask_vec = ep.mask && (reinterpret_cast<uintptr_t>(ep.mask) & 15u) == 0 && ep.ldmask % 16 == 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = cta; tile < num_tiles; tile += ncta) {
       const int bi = tile / tiles_pb, tb = tile - bi * tiles_pb;
-      const int m0 = (tb % num_m) * BLOCK_M, n0 = (tb / num_m) * BN;
+      const int m0 = (tb % num_m) * TILE_M + static_cast<int>(crank) * BLOCK_M, n0 = (tb / num_m) * BN;
       // this problem's view of the epilogue operands, as scalars (a per-tile mutable copy of the whole parameter
       // struct proved fragile: one build kept reading the unshifted kernel parameters for stacks > 0)
       const size_t oes = ep.out_dtype == NAWSOD_F32 ? 4 : 2, aes = ep.act_dtype == NAWSOD_BF16 ? 2 : 4;
@@ -323,16 +352,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (lane == 0) { if (PAIR) mbar_arrive_leader(tempty_bar(acc)); else mbar_arrive(tempty_bar(acc)); }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();                  // the leader's MMAs read the peer's shared memory until the last tile is done
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::TMEM_COLS) : "memory");
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::TMEM_COLS) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::TMEM_COLS) : "memory");
   }
 }
 
@@ -403,30 +434,46 @@ __global__ void __launch_bounds__(256) cvt_bf16_kernel(const float* __restrict__
 // ------------------------------------------------------------------------------------------
 struct Operands { const void* A; long long lda, sA; const void* B; long long ldb, sB; };
 
-template <int BN, bool A_MN, bool B_MN, int ES>
+template <int BN, bool A_MN, bool B_MN, int ES, bool PAIR = false>
 int launch_gemm(const Operands& o, const EpiParams& ep, cudaStream_t st) {
-  using C = Cfg<BN, ES>;
+  using C = typename std::conditional<PAIR, CfgPair<BN, ES>, Cfg<BN, ES>>::type;
   constexpr int ATOM = 128 / ES;
+  constexpr int TILE_M = PAIR ? 2 * BLOCK_M : BLOCK_M;
   CUtensorMap tmA, tmB;
   int rc;
   // K-major operand: stored [MN, K]; box [BLOCK rows, BK].  MN-major operand: stored [K, MN]; box [BK rows, ATOM].
+  // (pair: a CTA stages BN / 2 rows of B per k-block)
   if (!A_MN) rc = make_tmap(&tmA, o.A, ES, ep.M, ep.K, o.lda, BLOCK_M, C::BK, false, ep.nbatch, o.sA);
   else rc = make_tmap(&tmA, o.A, ES, ep.K, ep.M, o.lda, C::BK, ATOM, ES == 4, ep.nbatch, o.sA);
   if (rc) return rc;
-  if (!B_MN) rc = make_tmap(&tmB, o.B, ES, ep.N, ep.K, o.ldb, BN, C::BK, false, ep.nbatch, o.sB);
+  if (!B_MN) rc = make_tmap(&tmB, o.B, ES, ep.N, ep.K, o.ldb, PAIR ? BN / 2 : BN, C::BK, false, ep.nbatch, o.sB);
   else rc = make_tmap(&tmB, o.B, ES, ep.K, ep.N, o.ldb, C::BK, ATOM, ES == 4, ep.nbatch, o.sB);
   if (rc) return rc;
-  auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, ES>;
+  auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, ES, PAIR>;
   static bool attr_set = false;
   if (!attr_set) {
     NAWSOD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
-  const int num_tiles = ((ep.M + BLOCK_M - 1) / BLOCK_M) * ((ep.N + BN - 1) / BN) * ep.nbatch;
+  const int num_tiles = ((ep.M + TILE_M - 1) / TILE_M) * ((ep.N + BN - 1) / BN) * ep.nbatch;
   // gemm_max_ctas: leave SMs to concurrently running collectives (a persistent one-CTA-per-SM grid
   // would otherwise wait behind them, or they behind it)
   const int cap = (int)get_tuning("gemm_max_ctas", 0);
-  const int grid = std::min(num_tiles, cap > 0 ? std::min(cap, sm_count()) : sm_count());
+  const int sms = cap > 0 ? std::min(cap, sm_count()) : sm_count();
+  if (PAIR) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * std::min(num_tiles, std::max(sms / 2, 1)));    // whole pairs: (2,1,1) clusters on the SMs of one TPC
+    cfg.blockDim = dim3(kNumThreads);
+    cfg.dynamicSmemBytes = C::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    NAWSOD_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, ep));
+    return NAWSOD_OK;
+  }
+  const int grid = std::min(num_tiles, sms);
   kern<<<grid, kNumThreads, C::SMEM_BYTES, st>>>(tmA, tmB, ep);
   NAWSOD_LAUNCH_OK();
   return NAWSOD_OK;
@@ -444,6 +491,12 @@ int dispatch_gemm(const Operands& o, EpiParams ep, int ab_dtype, cudaStream_t st
   }
   // BN = 256 for wide outputs; narrower tiles only when N itself is narrow (fc8: N = 2C)
   const int bn = ep.N > 128 ? 256 : (ep.N > 64 ? 128 : 64);
+  // gemm_pair: wide outputs on CTA pairs (cta_group::2) when the output has at least two 128-row blocks
+  const bool pair = bn == 256 && ep.M > BLOCK_M && get_tuning("gemm_pair", kGemmPairDefault) != 0;
+  if (pair) {
+    if (ab_dtype == NAWSOD_BF16) return launch_gemm<256, A_MN, B_MN, 2, true>(o, ep, st);
+    return launch_gemm<256, A_MN, B_MN, 4, true>(o, ep, st);
+  }
   if (ab_dtype == NAWSOD_BF16) {
     if (bn == 256) return launch_gemm<256, A_MN, B_MN, 2>(o, ep, st);
     if (bn == 128) return launch_gemm<128, A_MN, B_MN, 2>(o, ep, st);

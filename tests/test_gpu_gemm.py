@@ -224,3 +224,43 @@ def test_fc_split_operand_three_pass_reaches_fp32(shape):
         ops.FC(Xh, Wh, b, X_lo=Xl)                               # both low parts or neither
     with pytest.raises(RuntimeError):
         ops.FC(Xh.bfloat16(), Wh.bfloat16(), out=torch.empty(M, N, device="cuda", dtype=torch.bfloat16), accumulate=True)
+
+
+def _with_pair(on, fn):
+    from nafwebsod_b200 import _lib
+    _lib.set_tuning("gemm_pair", 1 if on else 0)
+    try:
+        return fn()
+    finally:
+        _lib.set_tuning("gemm_pair", 0)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("shape", [(256, 256, 64), (300, 520, 200), (1000, 300, 512), (4000, 4096, 1024), (2000, 8192, 1568)])
+def test_fc_cta_pair_equals_single_cta(shape, dtype):
+    """The CTA-pair form of the GEMM (tcgen05 cta_group::2: a (2,1,1) cluster owns a 256 x 256 tile, each CTA stages its 128
+    rows of A and half of the B tile, the even CTA issues M = 256 MMAs for both; tuning knob gemm_pair) walks K in the same
+    order with the same instruction shape per output element, so forward (bias + ReLU + dropout mask), dX (gated) and dW / db
+    -- K-major and MN-major operands, ragged M / N / K edges, stacked launches -- must equal the one-CTA kernel bit for bit."""
+    ops = _ops()
+    M, N, K = shape
+    X, W, b, mask = _data(M, N, K, dtype, seed=7)
+    g = torch.Generator(device="cuda").manual_seed(11)
+    dY = (torch.randn(M, N, device="cuda", generator=g) * 0.1).to(dtype)
+    act = (torch.rand(M, K, device="cuda", generator=g) < 0.5).to(dtype)
+
+    def run():
+        y = ops.FC(X, W, b, relu=True, dropout_mask=mask, out_dtype=torch.float32)
+        dx = ops.FCGradientX(dY, W, act_below=act, dropout=True, out_dtype=torch.float32)
+        dw, db = ops.FCGradientW(dY, X)
+        # two stacks in one launch (3-d operands)
+        Xs, Ws = torch.stack([X, X.flip(0)]), torch.stack([W, W.flip(0)])
+        ys = ops.FC(Xs, Ws, torch.stack([b, b]), relu=True, out_dtype=torch.float32)
+        torch.cuda.synchronize()
+        return y, dx, dw, db, ys
+    one = _with_pair(False, run)
+    two = _with_pair(True, run)
+    for name, a, c in zip(("fwd", "dX", "dW", "db", "stacked fwd"), one, two):
+        assert torch.equal(a, c), (name, (a - c).abs().max().item())
+    ref = torch.relu(X.float() @ W.float().T + b) * 2.0 * mask.float()
+    assert _rel(two[0], ref) <= (BF16_TOL if dtype == torch.bfloat16 else TF32_TOL)
