@@ -128,6 +128,7 @@ class GradientExchange:
             self.stream = torch.cuda.Stream(device=flat_grad.device, priority=-1)     # high priority
         self.in_flight = False
         self.bytes_out = 0      # gradient bytes handed to the collective (per step accounting by the caller)
+        self._done = {}         # tag -> events on the side stream behind that tag's buckets (partial joins, finish(tags=...))
 
     def _sliced(self, length, tag):
         return bucket_is_sliced(length, tag, self.world)
@@ -149,6 +150,10 @@ class GradientExchange:
         with ctx:
             if self.local:
                 self.update_fn(offset, length, tag, offset, length)
+                if self.cuda:
+                    done = torch.cuda.Event()
+                    done.record(self.stream)
+                    self._done.setdefault(tag, []).append(done)
                 return
             if not self.sharded:
                 dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group)
@@ -165,10 +170,18 @@ class GradientExchange:
                 dist.all_gather_into_tensor(self.out[offset: offset + length], self.out[so: so + sn], group=self.group)
 
     def finish(self, tags=None):
-        """Make the current (compute) stream wait for every outstanding bucket (``tags`` is accepted for interface parity
-        with P2PExchange.finish and ignored: the collectives of one stream complete in order anyway)."""
+        """Make the current (compute) stream wait for every outstanding bucket, or -- one GPU, ``tags`` given -- only for the
+        buckets of those tags: the next step's fc6 needs the fc6 panels and b6, not the fc7 / fc8 update still running behind
+        them.  (With collectives in flight ``tags`` is ignored: a full join, as before.)"""
         if self.cuda and self.in_flight:
-            torch.cuda.current_stream(self.flat.device).wait_stream(self.stream)
+            cur = torch.cuda.current_stream(self.flat.device)
+            if tags is not None and self.local:
+                for tag in tags:
+                    for ev in self._done.pop(tag, []):
+                        cur.wait_event(ev)
+                return                                # still in flight: a later finish() joins the rest
+            cur.wait_stream(self.stream)
+        self._done.clear()
         self.in_flight = False
 
 
@@ -687,6 +700,8 @@ class DataParallelHead:
                     ex.finish(tags=("biases_fc6",))
                 else:
                     ex.finish(tags=("fc6_panel", "biases_fc6"))     # all that fc6 reads; the rest lands while fc6 runs
+            elif self.sync == "local" and bias6 is not None:
+                ex.finish(tags=("fc6_panel", "biases_fc6"))      # the fc7 / fc8 update may still run while fc6 does
             else:
                 ex.finish()
             self._limit_gemm_grid(False)
@@ -696,6 +711,8 @@ class DataParallelHead:
                 ex.finish()                          # fc7 / fc8 weights and biases of the previous step
                 ex.poll()                            # a lost peer surfaces here, one step late, without a host sync
                 ex.begin_step()
+            elif self.sync == "local":
+                ex.finish()
 
         rows_total = m._slices["W6"][2][0]
 
