@@ -25,6 +25,8 @@ namespace {
 
 // default of the gemm_pair tuning knob (0: one CTA per tile, 1: CTA pairs for BN = 256 tiles; measured r2t: 4.43 -> 4.16 ms per step)
 constexpr long long kGemmPairDefault = 1;
+// default of the gemm_tma_store tuning knob (1: plain fp32 outputs -- the weight gradients -- are stored by the TMA)
+constexpr long long kGemmTmaStoreDefault = 0;
 
 struct EpiParams {
   void* out; long long ldo; int out_dtype;
@@ -45,7 +47,14 @@ struct EpiParams {
   // row group, so the GEMM starts on the weights that are there and meets the rest as they arrive.
   const uint32_t* gate_flags; int gate_nflags, gate_rows; uint32_t gate_seq;
   unsigned long long gate_timeout_ns; uint32_t* gate_status;
+  // 1: plain fp32 output (no bias / activation / mask; optionally ACCUMULATE) leaves through the TMA: each epilogue warp stages its
+  // 32 x 32 chunk in swizzled shared memory and one lane issues a bulk tensor store (reduce-add when accumulating) -- full
+  // 128-byte lines instead of 32 scattered 16-byte stores per instruction, and nothing queued in the LSU next to a concurrent
+  // update kernel's long-latency loads
+  int tma_store;
 };
+
+constexpr int kStagingBytes = 4 * 32 * 128;      // one 32-row x 128-byte box per epilogue warp
 
 // spin (one thread) until all n flags have reached `value` (sequence numbers wrap); a watchdog turns a lost peer into a status
 // word instead of a hung GPU
@@ -74,7 +83,8 @@ __device__ __forceinline__ void gate_wait(const uint32_t* flags, int n, uint32_t
 // memory, 32 KB instead of 48 KB per stage -> 6 stages instead of 4 of prefetch distance.
 template <int BN, bool A_MN, bool B_MN, int ES, bool PAIR = false>
 __global__ void __launch_bounds__(kNumThreads, 1)
-gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const EpiParams ep_) {
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmO, const EpiParams ep_) {
   using C = typename std::conditional<PAIR, CfgPair<BN, ES>, Cfg<BN, ES>>::type;
   const EpiParams& ep = ep_;
   constexpr int BK = C::BK;
@@ -86,7 +96,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int ncta = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + C::STAGES * C::STAGE_BYTES;
+  const uint32_t staging_base = smem_base + C::STAGES * C::STAGE_BYTES;     // 1024-byte aligned: the swizzle phase of a row is row & 7
+  const uint32_t bar_base = staging_base + kStagingBytes;
   // barrier layout (8 bytes each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then the TMEM pointer
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
@@ -106,6 +117,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (ep.tma_store) tma_prefetch_desc(&tmO);
     for (int s = 0; s < C::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     // the accumulator is released by the 4 epilogue warps of every CTA that holds a part of it
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), PAIR ? 8 : 4); }
@@ -234,6 +246,26 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         tc_wait_ld();
         const int n = n0 + c;
         const int ncols = min(32, ep.N - n);
+        if (ep.tma_store) {                       // warp-uniform
+          // row `lane` of the warp's 32 x 32 box: eight 16-byte chunks, chunk j at (j ^ (row & 7)) -- the 128B swizzle the
+          // tensor map undoes; a quarter-warp's eight rows then hit eight different bank groups
+          const uint32_t stg = staging_base + static_cast<uint32_t>(q) * (32 * 128);
+          if (lane == 0) tma_store_wait_read();   // the previous box of this warp has left shared memory
+          __syncwarp();
+          const uint32_t rowp = stg + static_cast<uint32_t>(lane) * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowp + ((j ^ (lane & 7)) << 4)),
+                         "r"(r[4 * j]), "r"(r[4 * j + 1]), "r"(r[4 * j + 2]), "r"(r[4 * j + 3]) : "memory");
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (ep.flags & NAWSOD_FC_ACCUMULATE) tma_reduce_add_3d(&tmO, stg, n, m0 + q * 32, bi);
+            else tma_store_3d(&tmO, stg, n, m0 + q * 32, bi);
+            tma_store_commit();
+          }
+          continue;
+        }
         if (row_ok) {
           float v[32];
 #pragma unroll
@@ -357,6 +389,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   }
 
+  if (ep.tma_store && warp >= 2 && lane == 0) tma_store_wait_all();          // this thread's bulk stores have been written
   tc_fence_before();
   __syncthreads();
   if (PAIR) cluster_sync_all();                  // the leader's MMAs read the peer's shared memory until the last tile is done
@@ -435,12 +468,13 @@ __global__ void __launch_bounds__(256) cvt_bf16_kernel(const float* __restrict__
 struct Operands { const void* A; long long lda, sA; const void* B; long long ldb, sB; };
 
 template <int BN, bool A_MN, bool B_MN, int ES, bool PAIR = false>
-int launch_gemm(const Operands& o, const EpiParams& ep, cudaStream_t st) {
+int launch_gemm(const Operands& o, const EpiParams& ep_in, cudaStream_t st) {
   using C = typename std::conditional<PAIR, CfgPair<BN, ES>, Cfg<BN, ES>>::type;
   constexpr int ATOM = 128 / ES;
   constexpr int TILE_M = PAIR ? 2 * BLOCK_M : BLOCK_M;
   CUtensorMap tmA, tmB;
   int rc;
+  EpiParams ep = ep_in;
   // K-major operand: stored [MN, K]; box [BLOCK rows, BK].  MN-major operand: stored [K, MN]; box [BK rows, ATOM].
   // (pair: a CTA stages BN / 2 rows of B per k-block)
   if (!A_MN) rc = make_tmap(&tmA, o.A, ES, ep.M, ep.K, o.lda, BLOCK_M, C::BK, false, ep.nbatch, o.sA);
@@ -449,10 +483,19 @@ int launch_gemm(const Operands& o, const EpiParams& ep, cudaStream_t st) {
   if (!B_MN) rc = make_tmap(&tmB, o.B, ES, ep.N, ep.K, o.ldb, PAIR ? BN / 2 : BN, C::BK, false, ep.nbatch, o.sB);
   else rc = make_tmap(&tmB, o.B, ES, ep.K, ep.N, o.ldb, C::BK, ATOM, ES == 4, ep.nbatch, o.sB);
   if (rc) return rc;
+  CUtensorMap tmO = tmA;                         // placeholder unless the output leaves through the TMA
+  ep.tma_store = 0;
+  if (ep.out_dtype == NAWSOD_F32 && !ep.bias && !ep.mask && !ep.act && !(ep.flags & ~NAWSOD_FC_ACCUMULATE) && aligned16(ep.out) &&
+      (ep.ldo * 4) % 16 == 0 && (ep.nbatch <= 1 || (ep.so * 4) % 16 == 0) && get_tuning("gemm_tma_store", kGemmTmaStoreDefault) != 0) {
+    // out [M, N] float, 32 x 32 boxes (128 bytes wide, 128B swizzle)
+    if (int rc2 = make_tmap(&tmO, ep.out, 4, ep.M, ep.N, ep.ldo, 32, 32, false, ep.nbatch, ep.so)) return rc2;
+    ep.tma_store = 1;
+  }
+  constexpr int kSmem = C::SMEM_BYTES + kStagingBytes;
   auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, ES, PAIR>;
   static bool attr_set = false;
   if (!attr_set) {
-    NAWSOD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    NAWSOD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     attr_set = true;
   }
   const int num_tiles = ((ep.M + TILE_M - 1) / TILE_M) * ((ep.N + BN - 1) / BN) * ep.nbatch;
@@ -464,17 +507,17 @@ int launch_gemm(const Operands& o, const EpiParams& ep, cudaStream_t st) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(2 * std::min(num_tiles, std::max(sms / 2, 1)));    // whole pairs: (2,1,1) clusters on the SMs of one TPC
     cfg.blockDim = dim3(kNumThreads);
-    cfg.dynamicSmemBytes = C::SMEM_BYTES;
+    cfg.dynamicSmemBytes = kSmem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    NAWSOD_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, ep));
+    NAWSOD_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmO, ep));
     return NAWSOD_OK;
   }
   const int grid = std::min(num_tiles, sms);
-  kern<<<grid, kNumThreads, C::SMEM_BYTES, st>>>(tmA, tmB, ep);
+  kern<<<grid, kNumThreads, kSmem, st>>>(tmA, tmB, tmO, ep);
   NAWSOD_LAUNCH_OK();
   return NAWSOD_OK;
 }

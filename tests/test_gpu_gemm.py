@@ -232,7 +232,7 @@ def _with_pair(on, fn):
     try:
         return fn()
     finally:
-        _lib.set_tuning("gemm_pair", 0)
+        _lib.set_tuning("gemm_pair", 1)           # the built-in default
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
@@ -267,3 +267,43 @@ def test_fc_cta_pair_equals_single_cta(shape, dtype):
             assert torch.equal(a, c), (name, (a - c).abs().max().item())
     ref = torch.relu(X.float() @ W.float().T + b) * 2.0 * mask.float()
     assert _rel(two[0], ref) <= (BF16_TOL if dtype == torch.bfloat16 else TF32_TOL)
+
+
+@pytest.mark.parametrize("pair", [0, 1])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("shape", [(256, 256, 64), (300, 520, 200), (1000, 304, 512), (4000, 1024, 4096), (2000, 40, 4096)])
+def test_fc_tma_store_epilogue_equals_register_stores(shape, dtype, pair):
+    """Plain fp32 outputs (the weight gradients; the partial passes of the three-pass fp32 path) may leave through the TMA:
+    every epilogue warp stages its 32 x 32 chunk in 128B-swizzled shared memory and one lane issues a bulk tensor store, or a
+    bulk reduce-add when accumulating (tuning knob gemm_tma_store).  Same values, same fp32 adds: bit-identical to the
+    register-store epilogue -- dW plain, accumulated onto a prior value, two stacks per launch, ragged edges (the tensor map
+    clips), on the one-CTA and the CTA-pair kernel."""
+    from nafwebsod_b200 import _lib
+    ops = _ops()
+    M, N, K = shape
+    X, W, b, mask = _data(M, N, K, dtype, seed=13)
+    g = torch.Generator(device="cuda").manual_seed(17)
+    dY = (torch.randn(M, N, device="cuda", generator=g) * 0.1).to(dtype)
+    prior = torch.randn(N, K, device="cuda", generator=g) * 0.01
+
+    def run():
+        dw, _ = ops.FCGradientW(dY, X, want_db=False)
+        acc = prior.clone()
+        ops.FCGradientW(dY, X, dW=acc, want_db=False, accumulate=True)
+        dws = torch.full((2, N, K), float("nan"), device="cuda")
+        ops.FCGradientW(torch.stack([dY, dY.flip(0)]), torch.stack([X, X.flip(0)]), dW=dws, want_db=False)
+        y = ops.FC(X, W, out_dtype=torch.float32)                   # forward without bias / activation: same epilogue
+        torch.cuda.synchronize()
+        return dw, acc, dws, y
+    res = []
+    try:
+        _lib.set_tuning("gemm_pair", pair)
+        for tma in (0, 1):
+            _lib.set_tuning("gemm_tma_store", tma)
+            res.append(run())
+    finally:
+        _lib.set_tuning("gemm_tma_store", 0)
+        _lib.set_tuning("gemm_pair", 1)
+    for name, a, c in zip(("dW", "dW accumulated", "stacked dW", "plain fwd"), res[0], res[1]):
+        assert torch.equal(a, c), (name, (a - c).abs().max().item())
+    assert _rel(res[1][0], dY.float().T @ X.float()) <= (BF16_TOL if dtype == torch.bfloat16 else TF32_TOL)
