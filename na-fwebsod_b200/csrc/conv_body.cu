@@ -18,6 +18,10 @@
 //   nawsod_maxpool2x2  MaxPool(kernel=2, pad=0, stride=1|2) on a channels-last bf16 map (Caffe2's floor output size:
 //                      (H - 2) / stride + 1); packed bf16x2 maxima, 16 bytes per thread.
 //
+// Measured and removed (profiles/r2w_microbench_convbody_pair0.log / _pair1.log): the CTA-pair form of this kernel (cta_group::2,
+// 16 x 16-pixel tiles, half of the weight tile per CTA; bit-identical outputs) -- 0.582 vs 0.566 ms for the 480 x 640 body, 0.873 vs
+// 0.869 ms for 688 x 912 (only conv3_3 on the large image gained, 53 -> 49 us): these layers are bound by tile count, short
+// reductions and the epilogue, not by the weight tile's bytes, unlike the FC GEMMs where pairs took 6 % off the step.
 // Measured (profiles/r2a_microbench_convbody.log -> r2*_microbench_convbody.log): the patch-matrix body ran 1.0 ms for a
 // 480 x 640 image (235 TFLOP/s, 14 % of the tensor peak: the patch matrix moves ~10x the layers' algorithmic bytes).
 #include <cuda.h>
@@ -29,8 +33,6 @@ namespace nawsod {
 namespace {
 
 constexpr int kThreads = 256;
-// default of the conv_pair tuning knob (1: the implicit-GEMM convolution runs on CTA pairs, tcgen05 cta_group::2)
-constexpr long long kConvPairDefault = 0;
 
 // one thread = one 16-byte vector (8 channels) of one tap of one output pixel
 __global__ void __launch_bounds__(kThreads) im2col3x3_kernel(const uint4* __restrict__ X, int N, int H, int W, int C8, int dil,
@@ -95,22 +97,10 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 
-// PAIR: CTA pairs (tcgen05 cta_group::2, (2,1,1) clusters; see gemm.cu): a pair owns a 16 x 16-pixel tile x BN channels, CTA r
-// stages the [8, 16, 64] box of pixel rows [8 r, 8 r + 8) and half of the weight tile, the even CTA issues M = 256 MMAs for both.
-__device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
-
-template <int BN, bool PAIR>
+template <int BN>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const ConvParams p) {
-  using C = typename std::conditional<PAIR, CfgPair<BN, 2>, Cfg<BN, 2>>::type;
-  constexpr int TILE_H = PAIR ? 2 * kTileH : kTileH;
-  const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
-  const int cta = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
-  const int ncta = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  using C = Cfg<BN, 2>;
   constexpr int BK = C::BK;                      // 64 channels = one 128-byte swizzle atom
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -124,7 +114,7 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tiles_w = (p.W + kTileW - 1) / kTileW, tiles_h = (p.H + TILE_H - 1) / TILE_H;
+  const int tiles_w = (p.W + kTileW - 1) / kTileW, tiles_h = (p.H + kTileH - 1) / kTileH;
   const int num_m = p.N * tiles_h * tiles_w;
   const int num_n = (p.Cout + BN - 1) / BN;
   const int num_tiles = num_m * num_n;
@@ -135,21 +125,15 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmW);
     for (int s = 0; s < C::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), PAIR ? 8 : 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    if (PAIR) {
-      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"(C::TMEM_COLS) : "memory");
-      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-    } else {
-      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"(C::TMEM_COLS) : "memory");
-      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"(C::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
-  if (PAIR) cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_generic;
 
@@ -160,7 +144,7 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     n0 = (tile / num_m) * BN;
     n = tm / (tiles_h * tiles_w);
     const int r = tm - n * tiles_h * tiles_w;
-    h0 = (r / tiles_w) * TILE_H + static_cast<int>(crank) * kTileH;     // pair: this CTA's 8 pixel rows of the 16
+    h0 = (r / tiles_w) * kTileH;
     w0 = (r % tiles_w) * kTileW;
   };
 
@@ -168,7 +152,7 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     // ================= TMA producer =================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = cta; tile < num_tiles; tile += ncta) {
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         int n, h0, w0, n0;
         tile_origin(tile, n, h0, w0, n0);
         for (int kb = 0; kb < num_kb; ++kb) {
@@ -176,15 +160,8 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
           const int dh = (tap / 3 - 1) * p.dil, dw = (tap % 3 - 1) * p.dil;
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t sa = smem_base + stage * C::STAGE_BYTES, sb = sa + C::A_BYTES;
-          // the shifted [8, 16, 64] box of the input map: rows / columns outside the image arrive as zeros (the padding)
-          if (PAIR) {
-            if (crank == 0) mbar_expect_tx(full_bar(stage), 2 * C::STAGE_BYTES);     // the even CTA's barrier counts both CTAs' bytes
-            tma_load_4d_pair(sa, &tmX, full_bar(stage), c0, w0 + dw, h0 + dh, n);
-            tma_load_3d_pair(sb, &tmW, full_bar(stage), kb * BK, n0 + static_cast<int>(crank) * (BN / 2), 0);
-            if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
-            continue;
-          }
           mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
+          // the shifted [8, 16, 64] box of the input map: rows / columns outside the image arrive as zeros (the padding)
           tma_load_4d(sa, &tmX, full_bar(stage), c0, w0 + dw, h0 + dh, n);
           tma_load_3d(sb, &tmW, full_bar(stage), kb * BK, n0, 0);
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
@@ -193,12 +170,12 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
-    if (lane == 0 && crank == 0) {
-      constexpr uint32_t idesc = make_idesc(2, false, false, PAIR ? 2 * BLOCK_M : BLOCK_M, BN);
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(2, false, false, BLOCK_M, BN);
       constexpr uint32_t kstep = 32 >> 4;
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int tile = cta; tile < num_tiles; tile += ncta) {
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
@@ -208,14 +185,12 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
           const uint32_t sa = smem_base + stage * C::STAGE_BYTES, sb = sa + C::A_BYTES;
           const uint64_t adesc = make_smem_desc(sa, 16, 1024, 2), bdesc = make_smem_desc(sb, 16, 1024, 2);
 #pragma unroll
-          for (int k = 0; k < BK / C::UMMA_K; ++k) {
-            if (PAIR) tc_mma_pair<2>(tmem_d, adesc + (uint64_t)(k * kstep), bdesc + (uint64_t)(k * kstep), idesc, (kb | k) != 0);
-            else tc_mma<2>(tmem_d, adesc + (uint64_t)(k * kstep), bdesc + (uint64_t)(k * kstep), idesc, (kb | k) != 0);
-          }
-          if (PAIR) tc_commit_pair(empty_bar(stage)); else tc_commit(empty_bar(stage));
+          for (int k = 0; k < BK / C::UMMA_K; ++k)
+            tc_mma<2>(tmem_d, adesc + (uint64_t)(k * kstep), bdesc + (uint64_t)(k * kstep), idesc, (kb | k) != 0);
+          tc_commit(empty_bar(stage));
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
-        if (PAIR) tc_commit_pair(tfull_bar(acc)); else tc_commit(tfull_bar(acc));
+        tc_commit(tfull_bar(acc));
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -223,7 +198,7 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     // ================= epilogue (warps 2..5): bias + Relu -> bf16, 16-byte stores =================
     const int q = warp & 3;
     int acc = 0; uint32_t acc_phase = 0;
-    for (int tile = cta; tile < num_tiles; tile += ncta) {
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       int n, h0, w0, n0;
       tile_origin(tile, n, h0, w0, n0);
       mbar_wait(tfull_bar(acc), acc_phase);
@@ -263,18 +238,16 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) { if (PAIR) mbar_arrive_leader(tempty_bar(acc)); else mbar_arrive(tempty_bar(acc)); }
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (PAIR) cluster_sync_all();
   if (warp == 1) {
     tc_fence_after();
-    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::TMEM_COLS) : "memory");
-    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::TMEM_COLS) : "memory");
   }
 }
 
@@ -293,33 +266,19 @@ int make_tmap_nhwc(CUtensorMap* map, const void* X, int N, int H, int W, int Cch
   return NAWSOD_OK;
 }
 
-template <int BN, bool PAIR = false>
+template <int BN>
 int launch_conv(const void* X, const void* Wm, const ConvParams& p, cudaStream_t st) {
-  using C = typename std::conditional<PAIR, CfgPair<BN, 2>, Cfg<BN, 2>>::type;
-  constexpr int TILE_H = PAIR ? 2 * kTileH : kTileH;
+  using C = Cfg<BN, 2>;
   CUtensorMap tmX, tmW;
   if (int rc = make_tmap_nhwc(&tmX, X, p.N, p.H, p.W, p.Cin)) return rc;
-  if (int rc = make_tmap(&tmW, Wm, 2, p.Cout, 9LL * p.Cin, 9LL * p.Cin, PAIR ? BN / 2 : BN, C::BK, false, 1, 0)) return rc;
-  auto kern = conv3x3_igemm_kernel<BN, PAIR>;
+  if (int rc = make_tmap(&tmW, Wm, 2, p.Cout, 9LL * p.Cin, 9LL * p.Cin, BN, C::BK, false, 1, 0)) return rc;
+  auto kern = conv3x3_igemm_kernel<BN>;
   static bool attr_set = false;
   if (!attr_set) {
     NAWSOD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
-  const int num_tiles = p.N * ((p.H + TILE_H - 1) / TILE_H) * ((p.W + kTileW - 1) / kTileW) * ((p.Cout + BN - 1) / BN);
-  if (PAIR) {
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(2 * std::min(num_tiles, std::max(sm_count() / 2, 1)));
-    cfg.blockDim = dim3(kNumThreads);
-    cfg.dynamicSmemBytes = C::SMEM_BYTES;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    NAWSOD_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tmX, tmW, p));
-    return NAWSOD_OK;
-  }
+  const int num_tiles = p.N * ((p.H + kTileH - 1) / kTileH) * ((p.W + kTileW - 1) / kTileW) * ((p.Cout + BN - 1) / BN);
   kern<<<std::min(num_tiles, sm_count()), kNumThreads, C::SMEM_BYTES, st>>>(tmX, tmW, p);
   NAWSOD_LAUNCH_OK();
   return NAWSOD_OK;
@@ -349,14 +308,6 @@ extern "C" int nawsod_conv3x3_relu(const void* X, int N, int H, int W, int Cin, 
   p.bias = bias; p.Y = static_cast<__nv_bfloat16*>(Y);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   // BN = 256 only when that still gives every SM a tile; small maps (conv5 at 1/8) take narrower tiles
-  if (get_tuning("conv_pair", kConvPairDefault) != 0) {
-    // CTA pairs: 16 x 16-pixel tiles; BN = 256 while that still gives every pair two tiles, else narrower
-    const long long mp = (long long)N * ((H + 2 * kTileH - 1) / (2 * kTileH)) * ((W + kTileW - 1) / kTileW);
-    if (Cout % 256 == 0 && mp * (Cout / 256) >= sm_count()) return launch_conv<256, true>(X, Wmat, p, st);
-    if (Cout % 128 == 0 && mp * (Cout / 128) >= sm_count() / 2) return launch_conv<128, true>(X, Wmat, p, st);
-    if (Cout % 64 == 0) return launch_conv<64, true>(X, Wmat, p, st);
-    return launch_conv<128, true>(X, Wmat, p, st);
-  }
   const long long mt = (long long)N * ((H + kTileH - 1) / kTileH) * ((W + kTileW - 1) / kTileW);
   if (Cout % 256 == 0 && mt * (Cout / 256) >= 2LL * sm_count()) return launch_conv<256>(X, Wmat, p, st);
   if (Cout % 128 == 0 && mt * (Cout / 128) >= sm_count()) return launch_conv<128>(X, Wmat, p, st);

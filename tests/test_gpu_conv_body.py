@@ -85,31 +85,6 @@ def test_implicit_gemm_equals_patch_matrix_gemm(shape, cout, dil):
         ops.Conv3x3Relu(x[..., :8].contiguous(), wm[:, :72].contiguous(), b, implicit=True)
 
 
-@pytest.mark.parametrize("shape,cout,dil", [((1, 19, 23, 64), 128, 1), ((2, 8, 16, 64), 64, 1), ((1, 37, 50, 512), 512, 2),
-                                            ((1, 120, 160, 256), 256, 1), ((1, 240, 320, 128), 128, 1), ((2, 9, 17, 128), 256, 2),
-                                            ((1, 3, 5, 64), 32, 1)])
-def test_implicit_gemm_on_cta_pairs_equals_one_cta(shape, cout, dil):
-    """The CTA-pair form of the convolution (tcgen05 cta_group::2: 16 x 16-pixel tiles, each CTA of a (2,1,1) cluster stages
-    8 pixel rows and half of the weight tile; knob conv_pair) equals the one-CTA kernel bit for bit -- whole and ragged tiles
-    (odd numbers of 8-row halves), BN = 64 / 128 / 256, both dilations, two images."""
-    from nafwebsod_b200 import _lib
-    ops = _ops()
-    N, H, W, cin = shape
-    rng = np.random.default_rng(H * W + cout + 1)
-    x = _bf16(np.maximum(rng.standard_normal(shape), 0)).cuda()
-    wm = _bf16(rng.standard_normal((cout, 9 * cin)) * np.sqrt(2.0 / (9 * cin))).cuda()
-    b = torch.from_numpy((rng.standard_normal(cout) * 0.05).astype(np.float32)).cuda()
-    out = []
-    try:
-        for pair in (0, 1):
-            _lib.set_tuning("conv_pair", pair)
-            out.append(ops.Conv3x3Relu(x, wm, b, dilation=dil, relu=True, implicit=True))
-            torch.cuda.synchronize()
-    finally:
-        _lib.set_tuning("conv_pair", 0)
-    assert torch.equal(out[0].view(torch.int16), out[1].view(torch.int16))
-
-
 @pytest.mark.parametrize("cin,cout,dil", [(64, 128, 1), (512, 512, 2), (8, 64, 1)])
 def test_conv3x3_relu_vs_oracle(cin, cout, dil):
     ops = _ops()
