@@ -8,7 +8,7 @@ OUT=gpurun_out; mkdir -p $OUT
 T0=$(date +%s); el() { echo "[$(( $(date +%s) - T0 )) s] $*"; }
 nvidia-smi topo -m > $OUT/${TAG}_topo.txt 2>&1
 el "pytest dp (world $N vs the oracle's reference schedule)"
-timeout 240 python -m pytest tests/test_gpu_zzzz_dp_oracle_schedule.py -m gpu -q -s --timeout 220 -p no:cacheprovider > $OUT/${TAG}_pytest_dp_n${N}.log 2>&1
+env ${NAWSOD_DP_TEST_ENV:-NAWSOD_X=0} timeout 240 python -m pytest tests/test_gpu_zzzz_dp_oracle_schedule.py -m gpu -q -s --timeout 220 -p no:cacheprovider > $OUT/${TAG}_pytest_dp_n${N}.log 2>&1
 echo "pytest exit $?" | tee -a $OUT/${TAG}_pytest_dp_n${N}.log; grep -a "worst relative\|passed\|failed\|Error" $OUT/${TAG}_pytest_dp_n${N}.log | tail -n 12
 run() {   # name, extra env (VAR=VALUE words), extra bench args
   local name="$1" envs="$2"; shift 2
@@ -36,6 +36,7 @@ for v in "$@"; do
     ce_p8)     run ce_p8 "NAWSOD_P2P_ENGINE=ce NAWSOD_P2P_PROFILE=1" --fc6-panels 8 ;;
     sm_p8)     run sm_p8 "NAWSOD_P2P_ENGINE=sm NAWSOD_P2P_PROFILE=1" --fc6-panels 8 ;;
     default)   run default "NAWSOD_P2P_PROFILE=1" ;;
+    tmapull)   run tmapull "NAWSOD_TUNING=sgd_pull_tma=1 NAWSOD_P2P_PROFILE=1" ;;
     sharded)   run sharded "NAWSOD_X=0" --dp-sync sharded ;;
     allreduce) run allreduce "NAWSOD_X=0" --dp-sync allreduce ;;
   esac
