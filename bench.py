@@ -330,7 +330,8 @@ def assemble_line(*, steps, warmup, world, R, S, bf16, noise, ms_total, ms_e2e, 
             traffic = tj.get("fc6_bwd_w_dram_bytes_per_launch")
     tensor_peak = peaks["tf_sustained"] * (1.0 if bf16 else 0.5)
     roofline = {
-        "kernel": "gemm_tcgen05_kernel<256,MN,MN> (fc6 weight gradient, dY^T.X, both stacks in one GEMM)",
+        "kernel": "gemm_tcgen05_kernel<256,MN,MN,pair> (fc6 weight gradient, dY^T.X, both stacks in one GEMM; CTA pairs, "
+                  "tcgen05 cta_group::2, TMA-store epilogue)",
         "bound": "tensor", "achieved": fc6_flops / (t_bww_total * 1e-3) / 1e12 if t_bww_total else None, "peak": tensor_peak,
         "unit": "TFLOP/s", "traffic": traffic, "traffic_source": "ncu --set full capture of one such launch (profiles/ncu_traffic.json)",
         "launches_per_step": n_panels,

@@ -11,8 +11,6 @@ namespace nawsod {
 namespace {
 
 constexpr int kMaxGradSources = 16;
-// default of the sgd_pull_tma tuning knob (1: the data-parallel owner's reduction pulls its peers' slices with TMA bulk copies)
-constexpr long long kSgdPullTmaDefault = 0;
 
 struct SgdArgs {
   const float* extra[kMaxGradSources - 1];   // further gradient contributions, summed onto g in order (data-parallel owner)
@@ -51,6 +49,10 @@ __device__ __forceinline__ void sgd_elem(float g, float& m, float& p, float& acc
   acc = ac;
 }
 
+// Measured and removed (profiles/r2y_pytest_pull.log, r2z_bench_n4_tmapull.json vs r2z_bench_n4_default.json): the same reduction
+// with the peers' slices pulled by TMA bulk copies (cp.async.bulk, 1 KB per source and stage, a <= 16 KB shared-memory ring so that
+// the CTA stays co-resident with the GEMM's 210 KB one) -- bit-identical, but 0.37 instead of 0.29 ms per fc6 panel at 4 GPUs
+// (step 4.71 vs 4.32 ms): one 14 KB ring per SM holds far fewer bytes in flight than the load-based kernel's registers do.
 // kPre: number of extra gradient sources whose loads are issued TOGETHER before the first add (0: the plain update; 7 / 15: the
 // data-parallel owner's reduction over up to 8 / 16 ranks).  The contributions may live in PEER memory (the pull exchange reads
 // the ranks' gradient slices in place over NVLink, ~1-2 us per load): a load -> add -> load chain would serialise that latency
@@ -115,87 +117,6 @@ __global__ void __launch_bounds__(256) sgd_kernel(const SgdArgs a) {
   }
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// The data-parallel owner's reduce + update with the other ranks' contributions PULLED BY THE TMA (tuning knob sgd_pull_tma):
-// one thread per CTA issues 1-D bulk copies (cp.async.bulk, 1 KB per source and stage) from the peers' gradient buffers --
-// mapped over NVLink -- into a small shared-memory ring, the CTA's 64 threads then add them in rank order and apply the update.
-// Against sgd_kernel<kPre>'s 16-byte loads: kilobyte requests on the link instead of 128-byte ones, no registers or LSU queue
-// entries held for the ~2 us a peer load takes (the weight-gradient GEMM running beside it issues its own stores and TMA
-// traffic through the same SM), and a ring small enough (<= 16 KB) to stay co-resident with the GEMM's 210 KB CTA.
-// Same adds in the same order: bit-identical to sgd_kernel.
-// ---------------------------------------------------------------------------------------------------------------
-constexpr int kPullThreads = 64;                 // one float4 per thread and stage
-constexpr int kPullChunk = kPullThreads * 16;    // bytes per source and stage
-constexpr int kPullSmemBudget = 16 * 1024;
-
-__device__ __forceinline__ uint32_t s_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-
-__global__ void __launch_bounds__(kPullThreads) sgd_pull_kernel(const SgdArgs a, const int stages) {
-  extern __shared__ __align__(128) unsigned char pull_smem[];
-  if (a.abort_flag && *reinterpret_cast<const volatile uint32_t*>(a.abort_flag) != 0u) return;
-  const int ne = a.n_extra, tid = threadIdx.x;
-  const uint32_t ring = s_u32(pull_smem);
-  const uint32_t bars = ring + static_cast<uint32_t>(stages * ne) * kPullChunk;      // 8-byte mbarriers, one per stage
-  const int64_t nchunks = a.n / (kPullThreads * 4);                                   // whole chunks; the host sends the tail to sgd_kernel
-  const float LR = __fmul_rn(a.lr[0], a.lr_mult);
-  if (tid == 0) {
-    for (int s = 0; s < stages; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bars + 8u * s));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async;" ::: "memory");          // the bulk copies read what the exchange's flags (acquired by the wait kernel) guard
-  }
-  __syncthreads();
-  auto issue = [&](int64_t chunk, int s) {                    // thread 0: ne bulk copies of one chunk into stage s
-    const uint32_t bar = bars + 8u * s;
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(static_cast<uint32_t>(ne * kPullChunk)) : "memory");
-    for (int e = 0; e < ne; ++e)
-      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                   ::"r"(ring + static_cast<uint32_t>(s * ne + e) * kPullChunk),
-                     "l"(reinterpret_cast<const unsigned char*>(a.extra[e]) + chunk * kPullChunk), "r"(kPullChunk), "r"(bar) : "memory");
-  };
-  const int64_t first = blockIdx.x, step = gridDim.x;
-  if (tid == 0)
-    for (int s = 0; s < stages; ++s)
-      if (first + s * step < nchunks) issue(first + s * step, s);
-  int64_t it = 0;
-  for (int64_t chunk = first; chunk < nchunks; chunk += step, ++it) {
-    const int s = static_cast<int>(it % stages);
-    const uint32_t parity = static_cast<uint32_t>(it / stages) & 1u;
-    const int64_t i = chunk * kPullThreads + tid;             // float4 index
-    float4 g = __ldcs(reinterpret_cast<const float4*>(a.g) + i);
-    float4 m = a.first_call ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldcs(reinterpret_cast<const float4*>(a.m) + i);
-    float4 p = __ldcs(reinterpret_cast<const float4*>(a.p) + i);
-    {
-      const uint32_t bar = bars + 8u * s;
-      uint32_t done;
-      do {
-        asm volatile("{\n.reg .pred q;\nmbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2;\nselp.u32 %0, 1, 0, q;\n}"
-                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-      } while (!done);
-    }
-    const float4* src = reinterpret_cast<const float4*>(pull_smem + static_cast<size_t>(s * ne) * kPullChunk) + tid;
-    for (int e = 0; e < ne; ++e) {                            // fixed (rank) order: the sum is deterministic
-      const float4 x = src[e * kPullThreads];
-      g.x = __fadd_rn(g.x, x.x); g.y = __fadd_rn(g.y, x.y); g.z = __fadd_rn(g.z, x.z); g.w = __fadd_rn(g.w, x.w);
-    }
-    float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
-    sgd_elem(g.x, m.x, p.x, c.x, a, LR);
-    sgd_elem(g.y, m.y, p.y, c.y, a, LR);
-    sgd_elem(g.z, m.z, p.z, c.z, a, LR);
-    sgd_elem(g.w, m.w, p.w, c.w, a, LR);
-    if (a.do_update || a.first_call) __stcs(reinterpret_cast<float4*>(a.m) + i, m);
-    if (a.do_update) {
-      __stcs(reinterpret_cast<float4*>(a.p) + i, p);
-      if (a.p_bf16) {
-        __nv_bfloat162 lo = __floats2bfloat162_rn(p.x, p.y), hi = __floats2bfloat162_rn(p.z, p.w);
-        reinterpret_cast<uint2*>(a.p_bf16)[i] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
-      }
-      if (a.p_tf32) reinterpret_cast<float4*>(a.p_tf32)[i] = make_float4(rna_tf32(p.x), rna_tf32(p.y), rna_tf32(p.z), rna_tf32(p.w));
-    }
-    __syncthreads();                                          // every thread has read stage s
-    if (tid == 0 && chunk + stages * step < nchunks) issue(chunk + stages * step, s);
-  }
-}
-
 }  // namespace
 }  // namespace nawsod
 
@@ -237,28 +158,6 @@ static int sgd_launch(const float* const* grads, int n_grads, float* m, const fl
   const int64_t cap = get_tuning("sgd_max_ctas", 0);
   const int blocks = (int)std::min<int64_t>((work + 255) / 256, cap > 0 ? cap : (int64_t)sm_count() * 16);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  // sgd_pull_tma: the owner's reduction pulls the other sources with TMA bulk copies (whole 256-element chunks; no accumulator)
-  if (a.n_extra >= 1 && !a.use_acc && a.do_update && n >= kPullThreads * 4 && get_tuning("sgd_pull_tma", kSgdPullTmaDefault) != 0) {
-    const int stages = std::max(2, std::min(8, kPullSmemBudget / (a.n_extra * kPullChunk)));
-    const int smem = stages * a.n_extra * kPullChunk + 8 * stages;
-    if (smem <= 48 * 1024) {
-      const int64_t nchunks = n / (kPullThreads * 4);
-      const int pull_blocks = (int)std::min<int64_t>(nchunks, cap > 0 ? cap : (int64_t)sm_count() * 8);
-      SgdArgs head = a;
-      head.n = nchunks * (kPullThreads * 4);
-      sgd_pull_kernel<<<pull_blocks, kPullThreads, smem, st>>>(head, stages);
-      NAWSOD_LAUNCH_OK();
-      const int64_t off = head.n;
-      if (off == n) return NAWSOD_OK;
-      a.g += off; a.m += off; a.p += off; a.n = n - off;      // the tail (< 256 elements) goes through the generic kernel
-      for (int e = 0; e < a.n_extra; ++e) a.extra[e] += off;
-      if (a.p_bf16) a.p_bf16 += off;
-      if (a.p_tf32) a.p_tf32 += off;
-      if (a.n_extra <= 7) sgd_kernel<7><<<1, 256, 0, st>>>(a); else sgd_kernel<15><<<1, 256, 0, st>>>(a);
-      NAWSOD_LAUNCH_OK();
-      return NAWSOD_OK;
-    }
-  }
   if (a.n_extra == 0) sgd_kernel<0><<<blocks, 256, 0, st>>>(a);
   else if (a.n_extra <= 7) sgd_kernel<7><<<blocks, 256, 0, st>>>(a);
   else sgd_kernel<15><<<blocks, 256, 0, st>>>(a);

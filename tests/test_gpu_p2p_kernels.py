@@ -65,41 +65,3 @@ def test_update_is_skipped_once_the_watchdog_word_is_set():
     ops.ACMWeightDecayMomentumSGDUpdate((g[0] + g[1]) + g[2], m1, lr, p1, None, gpu_num=3, weight_decay=5e-4, iter_count=2)
     torch.cuda.synchronize()
     assert torch.equal(m, m1) and torch.equal(p, p1)
-
-
-@pytest.mark.parametrize("n_src", [2, 4, 8])
-@pytest.mark.parametrize("n", [256 * 37, 256 * 4001 + 44, 200, 6422528])
-@pytest.mark.parametrize("shadow", [torch.bfloat16, torch.float32])
-def test_tma_pull_update_equals_the_load_based_kernel(n, n_src, shadow):
-    """The owner's reduce + update with the other sources pulled by TMA bulk copies into a shared-memory ring (tuning knob
-    sgd_pull_tma; csrc/sgd.cu: sgd_pull_kernel) adds the same contributions in the same order as the load-based kernel:
-    parameters, momenta and operand shadow bit for bit -- whole 256-element chunks, a tail, a slice shorter than a chunk
-    (falls through to the load-based kernel), the first call (momenta start from zero), and the watchdog's no-op."""
-    from nafwebsod_b200 import _lib, ops
-    g = torch.Generator(device="cuda").manual_seed(n + n_src)
-    pad = lambda k: torch.randn(k + 4, device="cuda", generator=g)[:k]
-    grads = [pad(n) for _ in range(n_src)]
-    lr = torch.tensor([1e-3], device="cuda")
-    kw = dict(momentum=0.9, gpu_num=n_src, lr_mult=1.0, weight_decay=5e-4)
-    p0, m0 = pad(n).clone(), pad(n).clone() * 0.01
-    out = {}
-    try:
-        for knob in (0, 1):
-            _lib.set_tuning("sgd_pull_tma", knob)
-            res = []
-            for it in (0, 3):
-                pp, mm, ss = p0.clone(), m0.clone(), torch.zeros(n, device="cuda", dtype=shadow)
-                ops.ACMWeightDecayMomentumSGDUpdateReduce(grads, mm, lr, pp, iter_count=it, p_shadow=ss, **kw)
-                res += [pp, mm, ss]
-            flag = torch.ones(1, dtype=torch.int32, device="cuda")
-            pp, mm = p0.clone(), m0.clone()
-            ops.ACMWeightDecayMomentumSGDUpdateReduce(grads, mm, lr, pp, iter_count=3, abort_flag=flag, **kw)
-            res += [pp, mm]
-            torch.cuda.synchronize()
-            out[knob] = res
-    finally:
-        _lib.set_tuning("sgd_pull_tma", 0)
-    for a, b in zip(out[0], out[1]):
-        assert torch.equal(a, b)
-    assert torch.equal(out[1][-2], p0) and torch.equal(out[1][-1], m0)         # aborted: untouched
-    assert not torch.equal(out[1][0], p0)

@@ -36,7 +36,6 @@ for v in "$@"; do
     ce_p8)     run ce_p8 "NAWSOD_P2P_ENGINE=ce NAWSOD_P2P_PROFILE=1" --fc6-panels 8 ;;
     sm_p8)     run sm_p8 "NAWSOD_P2P_ENGINE=sm NAWSOD_P2P_PROFILE=1" --fc6-panels 8 ;;
     default)   run default "NAWSOD_P2P_PROFILE=1" ;;
-    tmapull)   run tmapull "NAWSOD_TUNING=sgd_pull_tma=1 NAWSOD_P2P_PROFILE=1" ;;
     sharded)   run sharded "NAWSOD_X=0" --dp-sync sharded ;;
     allreduce) run allreduce "NAWSOD_X=0" --dp-sync allreduce ;;
   esac
