@@ -363,6 +363,13 @@ def assemble_line(*, steps, warmup, world, R, S, bf16, noise, ms_total, ms_e2e, 
                 "note": "same workload at the reference's sgemm accuracy: fp32 storage, every GEMM operand a TF32 (high, low) pair, "
                         "three kind::tf32 passes per product (rel <= 1e-4 vs the fp32 oracle at this size), resident inputs",
                 "ms_per_step": ms3, "rois_per_s": R * x3["steps"] / (x3["ms_total"] * 1e-3), "steps": x3["steps"]}
+        w1 = tf32.get("wsddn_bf16")
+        if w1:
+            ms1 = w1["ms_total"] / w1["steps"]
+            kernels["wsddn_step"] = {
+                "note": "single-stack head (plain WSDDN: clean stack only, unweighted loss), same inputs, bf16, resident inputs",
+                "ms_per_step": ms1, "rois_per_s": R * w1["steps"] / (w1["ms_total"] * 1e-3), "steps": w1["steps"],
+                "step_tensor_frac": _flops_per_roi(False) * R / (ms1 * 1e-3) / 1e12 / tensor_peak}
         kernels["tf32_step"] = {
             "note": "same workload, fp32 storage + kind::tf32 GEMMs (operands pre-rounded to nearest TF32), resident inputs",
             "ms_per_step": ms32, "rois_per_s": R * tf32["steps"] / (tf32["ms_total"] * 1e-3), "steps": tf32["steps"],
@@ -662,8 +669,13 @@ def gpu_arm(args):
         legs = {}
         # "tf32": one tensor-core pass per product; "fp32": operands as TF32 (high, low) pairs, three passes per product
         # (the reference's sgemm accuracy, tests/test_gpu_head.py::test_head_full_size_fp32_config2)
-        for precision, nsteps in (("tf32", args.steps), ("fp32", min(args.steps, 10))):
-            model = WeblyHeadModel(NUM_CLASSES, C5, 7, 4096, noise=noise, dtype=torch.float32, device=dev, precision=precision)
+        # "wsddn": the single-stack head (plain WSDDN: no noisy stack, no noise-aware weights) on the bench's own bf16 path --
+        # SURVEY.md 8d config 2 asks for both variants
+        variants = [("tf32", torch.float32, "tf32", noise, args.steps), ("fp32", torch.float32, "fp32", noise, min(args.steps, 10))]
+        if noise:
+            variants.append(("wsddn", torch.bfloat16, None, False, args.steps))
+        for precision, leg_dtype, leg_precision, leg_noise, nsteps in variants:
+            model = WeblyHeadModel(NUM_CLASSES, C5, 7, 4096, noise=leg_noise, dtype=leg_dtype, device=dev, precision=leg_precision)
             init_parameters()
             dp = DataParallelHead(model, fc6_panels=args.fc6_panels, sync=args.dp_sync)
             model.UpdateWorkspaceLr(1e-3)
@@ -680,6 +692,7 @@ def gpu_arm(args):
             dp.flush(); torch.cuda.synchronize()
         tf32 = legs["tf32"]
         tf32["fp32_three_pass"] = legs["fp32"]
+        tf32["wsddn_bf16"] = legs.get("wsddn")
         model, dp = main_model, main_dp
 
     if rank != 0:
