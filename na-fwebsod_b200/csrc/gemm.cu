@@ -11,13 +11,17 @@
 // core through the UMMA shared-memory descriptor (a_major / b_major bits) and loaded by TMA as
 // 128-byte-wide column panels.
 //
-// Kernel anatomy (192 threads, one CTA per SM, persistent over output tiles):
-//   warp 0      TMA producer: cp.async.bulk.tensor.2d into a kStages-deep 128B-swizzled smem ring
-//   warp 1      MMA issuer: one lane issues tcgen05.mma (M=128, N=BN, K=32 bytes) into a
-//               double-buffered TMEM accumulator (2 x BN fp32 columns); tcgen05.commit releases
-//               smem slots and publishes finished accumulators
-//   warps 2..5  epilogue: tcgen05.ld (32 lanes x 32 columns) -> bias / ReLU / dropout /
-//               ReLU-gradient -> bf16 or fp32 stores; overlaps the next tile's main loop
+// Kernel anatomy (192 threads, one CTA per SM, persistent over output tiles; CTA PAIRS -- (2,1,1) clusters, tcgen05
+// cta_group::2 -- for 256-wide tiles, see the PAIR template parameter):
+//   warp 0      TMA producer: cp.async.bulk.tensor.3d into a 128B-swizzled smem ring (4 stages of 48 KB; pairs: 6 stages of
+//               32 KB, each CTA staging its 128 rows of A and half of the B tile); optionally gated on the peer exchange's
+//               "operands have landed" flags (nawsod_fc_fwd_gated)
+//   warp 1      MMA issuer: one lane issues tcgen05.mma (M=128 or, for a pair, the even CTA issues M=256; N=BN, K=32 bytes)
+//               into a double-buffered TMEM accumulator (2 x BN fp32 columns); tcgen05.commit (multicast to both CTAs of a
+//               pair) releases smem slots and publishes finished accumulators
+//   warps 2..5  epilogue: tcgen05.ld (32 lanes x 32 columns) -> [prior output] / bias / ReLU / dropout / ReLU-gradient ->
+//               bf16 or fp32 stores; plain fp32 outputs (the weight gradients) are staged in swizzled smem and stored by the
+//               TMA (bulk tensor store, or reduce-add when accumulating); overlaps the next tile's main loop
 #include "gemm_tc.cuh"
 
 namespace nawsod {

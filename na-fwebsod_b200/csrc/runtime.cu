@@ -37,7 +37,7 @@ const char* nawsod_last_error(void) { return nawsod::g_err; }
 int nawsod_version(void) { return 100; }
 int nawsod_set_tuning(const char* key, int64_t value) {
   static const char* known[] = {"pool_slab_bytes", "pool_chunks", "pool_force_global", "pool_threads", "pool_generic", "pool_rowcache", "pool_rows2", "pool_skip_idle",
-                                "gemm_force_1cta", "gemm_pair", "gemm_tma_store", "gemm_max_ctas", "mil_ctas", "sgd_max_ctas", "p2p_ctas", nullptr};
+                                "gemm_pair", "gemm_tma_store", "gemm_max_ctas", "mil_ctas", "sgd_max_ctas", "p2p_ctas", nullptr};
   if (!key) { nawsod::set_error("nawsod_set_tuning: null key"); return NAWSOD_ERR_ARG; }
   for (int i = 0; known[i]; ++i)
     if (std::strcmp(known[i], key) == 0) {
