@@ -295,6 +295,13 @@ class P2PExchange:
         # b6's (tiny, replicated) update runs on a stream of its own: behind the last fc6 panel's update it would hold up
         # the next step's fc6, which reads b6 but meets the W6 panels through its in-kernel gate
         self.bias6_stream = torch.cuda.Stream(device=dev, priority=-1)
+        # Consecutive buckets alternate between two update streams: a bucket's chain on its stream is wait-for-the-W-flags ->
+        # reduce + update -> operand copies -> publish, and on ONE stream bucket k + 1's wait and update queued behind bucket
+        # k's operand copies (8 GPUs, profiles/r2x_bench_n8_default_p2p_timeline.txt: update 0.30-0.42 ms + publish 0.27-0.37 ms
+        # per fc6 panel, serialised: the last panel was published 1.5 ms after its gradient was ready).  The buckets touch
+        # disjoint slices, each joins the compute stream through its own event / flags, so their order is free.
+        self.ustreams = [self.stream] + [torch.cuda.Stream(device=dev, priority=-1)
+                                         for _ in range(max(0, int(os.environ.get("NAWSOD_P2P_USTREAMS", "2")) - 1))]
         # "ce": copy-engine transfers (default: no SM is taken from the GEMMs); "sm": one co-resident scatter kernel per bucket
         # and leg
         self.engine = os.environ.get("NAWSOD_P2P_ENGINE", "ce")
@@ -370,7 +377,7 @@ class P2PExchange:
                 if prof is not None:
                     prof.append(("sent", b, self._mark()))
         # update side: wait for the W contributions, reduce + SGD on the owned slice, publish the operands
-        ustream = self.bias6_stream if tag == "biases_fc6" else self.stream
+        ustream = self.bias6_stream if tag == "biases_fc6" else self.ustreams[b % len(self.ustreams)]
         ustream.wait_event(ev)
         so = offset if replicated else offset + rank * n
         with torch.cuda.stream(ustream):
