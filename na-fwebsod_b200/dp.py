@@ -300,8 +300,8 @@ class P2PExchange:
         # k's operand copies (8 GPUs, profiles/r2x_bench_n8_default_p2p_timeline.txt: update 0.30-0.42 ms + publish 0.27-0.37 ms
         # per fc6 panel, serialised: the last panel was published 1.5 ms after its gradient was ready).  The buckets touch
         # disjoint slices, each joins the compute stream through its own event / flags, so their order is free.
-        self.ustreams = [self.stream] + [torch.cuda.Stream(device=dev, priority=-1)
-                                         for _ in range(max(0, int(os.environ.get("NAWSOD_P2P_USTREAMS", "2")) - 1))]
+        self.ustreams = [self.stream]            # the second one is created LAST (below): the streams created so far keep the
+                                                 # creation order -- and with it the hardware queues -- of the measured runs
         # "ce": copy-engine transfers (default: no SM is taken from the GEMMs); "sm": one co-resident scatter kernel per bucket
         # and leg
         self.engine = os.environ.get("NAWSOD_P2P_ENGINE", "ce")
@@ -320,6 +320,8 @@ class P2PExchange:
         self._status_ev = None
         self._done = [None] * len(self.plan)     # per bucket: event on the update stream behind its publish
         self._joined = set()                     # buckets of the step in flight the compute stream has already joined
+        self.ustreams += [torch.cuda.Stream(device=dev, priority=-1)
+                          for _ in range(max(0, int(os.environ.get("NAWSOD_P2P_USTREAMS", "2")) - 1))]
 
     def _flag_ptrs(self, kind, b):
         W, nb = self.world, len(self.plan)
