@@ -27,11 +27,13 @@ On ONE GPU the same pipeline runs without a collective: each bucket's SGD update
 the side stream behind its producer GEMM and overlaps the remaining tensor-bound weight-gradient GEMMs.
 
 ``sync="p2p"`` is the same pipeline with the collectives replaced by the box's own hardware paths:
-every rank maps its peers' staging / flag / operand buffers (CUDA IPC over NVSwitch), the bulk data
-moves with the COPY ENGINES (so no SM is taken from the GEMMs and nothing has to be reserved), the
-owner's reduction is folded into its SGD kernel (``nawsod_sgd_update_reduce`` sums the W contributions
-in rank order -- deterministic -- while it updates), and cross-GPU ordering is a sequence number per
-(bucket, rank) published / awaited by one-warp kernels (``nawsod_p2p_signal`` / ``nawsod_p2p_wait``).
+every rank maps its peers' gradient / flag / operand (and, in push mode, staging) buffers (CUDA IPC over NVSwitch).  Reduce-scatter
+leg: the owner's SGD kernel reads the other ranks' gradient slices IN PLACE over NVLink and sums the W contributions in rank
+order -- deterministic -- while it updates (``nawsod_sgd_update_reduce``; "pull", the default beyond two ranks), or the copy
+engines push the slices into the owner's staging area first ("push").  Operand leg: the updated bf16 slice goes back to every
+peer with the COPY ENGINES (no SM is taken from the GEMMs).  Cross-GPU ordering is a sequence number per (bucket, rank)
+published / awaited by one-warp kernels (``nawsod_p2p_signal`` / ``nawsod_p2p_wait``, watchdog-bounded); the next step's fc6
+meets its weight panels inside the GEMM (``nawsod_fc_fwd_gated``), and consecutive buckets alternate between two update streams.
 
 ``sync="allreduce"`` keeps the reference's schedule (bucketed all-reduce, full SGD on every rank)
 for comparison.  torch.distributed (NCCL on the GPU box, gloo in the CPU tests) is the plumbing;
